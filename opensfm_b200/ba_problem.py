@@ -1,0 +1,201 @@
+"""Host-side SoA description of one bundle-adjustment problem.
+
+This is the bulk ("structure of arrays") form of what the reference builds one
+string-keyed call at a time through `bundle::BundleAdjuster::Add*`
+(opensfm/src/bundle/src/bundle_adjuster.cc:94-260) and keeps in
+`std::map<std::string, ...>` AoS containers (bundle/bundle_adjuster.h:306-313,
+bundle/data/*.h).  The CUDA engine uploads these arrays as they are; nothing
+here computes.
+
+Parameter conventions follow the reference:
+* camera parameters are stored [PROJ | DISTO | AFFINE]
+  (opensfm/src/geometry/src/camera.cc:9-178), e.g. perspective = [k1, k2, focal];
+* a pose is [rx, ry, rz, tx, ty, tz] = angle-axis of R(camera->world) and the
+  camera origin (bundle/data/pose.h:17,34-43);
+* a shot references (rig instance, camera, rig camera); the rig camera is used
+  only when it is non-trivial (`IsRigCameraUseful`, bundle_adjuster.cc:17-20).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import Optional
+
+import numpy as np
+
+# geometry::ProjectionType order (opensfm/src/geometry/camera_instances.h:8-20)
+PERSPECTIVE, BROWN, FISHEYE, FISHEYE_OPENCV, FISHEYE62, FISHEYE624, SPHERICAL, DUAL, RADIAL, SIMPLE_RADIAL = range(10)
+
+PROJECTION_NAMES = {
+    "perspective": PERSPECTIVE, "brown": BROWN, "fisheye": FISHEYE, "fisheye_opencv": FISHEYE_OPENCV,
+    "fisheye62": FISHEYE62, "fisheye624": FISHEYE624, "spherical": SPHERICAL, "equirectangular": SPHERICAL,
+    "dual": DUAL, "radial": RADIAL, "simple_radial": SIMPLE_RADIAL,
+}
+
+# Parameter names per model in storage order (geometry/src/camera.cc:9-178).
+CAMERA_PARAM_NAMES = {
+    PERSPECTIVE: ["k1", "k2", "focal"],
+    BROWN: ["k1", "k2", "k3", "p1", "p2", "focal", "aspect_ratio", "cx", "cy"],
+    FISHEYE: ["k1", "k2", "focal"],
+    FISHEYE_OPENCV: ["k1", "k2", "k3", "k4", "focal", "aspect_ratio", "cx", "cy"],
+    FISHEYE62: ["k1", "k2", "k3", "k4", "k5", "k6", "p1", "p2", "focal", "aspect_ratio", "cx", "cy"],
+    FISHEYE624: ["k1", "k2", "k3", "k4", "k5", "k6", "p1", "p2", "s0", "s1", "s2", "s3",
+                 "focal", "aspect_ratio", "cx", "cy"],
+    SPHERICAL: ["none"],
+    DUAL: ["transition", "k1", "k2", "focal"],
+    RADIAL: ["k1", "k2", "focal", "aspect_ratio", "cx", "cy"],
+    SIMPLE_RADIAL: ["k1", "focal", "aspect_ratio", "cx", "cy"],
+}
+
+LOSS_NAMES = ("TrivialLoss", "HuberLoss", "SoftLOneLoss", "CauchyLoss", "ArctanLoss")
+
+
+def camera_num_params(ptype: int) -> int:
+    return len(CAMERA_PARAM_NAMES[int(ptype)])
+
+
+def default_prior_sigma(ptype: int, focal_sd=1.0, aspect_ratio_sd=1.0, c_sd=1.0, k1_sd=1.0, k2_sd=1.0,
+                        p1_sd=1.0, p2_sd=1.0, k3_sd=1.0, k4_sd=1.0) -> np.ndarray:
+    """BundleAdjuster::GetDefaultCameraSigma (bundle_adjuster.cc:46-67): one sigma per stored
+    parameter.  The reference's map holds focal, aspect ratio, cx, cy, k1, k2, k3, p1, p2 and
+    transition (=1); every other parameter (k4, k5, k6, s0..s3, none) reads a default-inserted
+    0.0 from `std_dev_map[...]` (:64), i.e. scale 1/eps in DataPriorError (prior_error.h:31-35):
+    those parameters are pinned to their prior.  k4_sd is accepted and unused, as in the reference."""
+    del k4_sd
+    table = {"focal": focal_sd, "aspect_ratio": aspect_ratio_sd, "cx": c_sd, "cy": c_sd, "k1": k1_sd,
+             "k2": k2_sd, "k3": k3_sd, "p1": p1_sd, "p2": p2_sd, "transition": 1.0}
+    return np.array([table.get(n, 0.0) for n in CAMERA_PARAM_NAMES[int(ptype)]], dtype=np.float64)
+
+
+def prior_log_mask(ptype: int) -> np.ndarray:
+    """Focal and aspect ratio use a logarithmic prior (bundle_adjuster.cc:574-583)."""
+    return np.array([1 if n in ("focal", "aspect_ratio") else 0 for n in CAMERA_PARAM_NAMES[int(ptype)]],
+                    dtype=np.int32)
+
+
+@dataclass
+class BAProblem:
+    # cameras (K); parameters flattened, camera k owns cam_params[cam_off[k]:cam_off[k+1]]
+    cam_type: np.ndarray
+    cam_params: np.ndarray
+    cam_const: np.ndarray
+    cam_prior: np.ndarray
+    cam_prior_sigma: np.ndarray
+    cam_prior_log: np.ndarray
+    # rig instances (NI x 6)
+    inst: np.ndarray
+    inst_const: np.ndarray
+    inst_has_prior: np.ndarray
+    inst_prior_pos: np.ndarray
+    inst_prior_std: np.ndarray
+    # rig cameras (NR x 6)
+    rigcam: np.ndarray
+    rigcam_const: np.ndarray
+    # shots (S)
+    shot_inst: np.ndarray
+    shot_cam: np.ndarray
+    shot_rc: np.ndarray
+    shot_use_rc: np.ndarray
+    # points (P x 3)
+    points: np.ndarray
+    point_const: np.ndarray
+    # observations (N)
+    obs_shot: np.ndarray
+    obs_point: np.ndarray
+    obs_xy: np.ndarray
+    obs_sigma: np.ndarray
+    # solver options (defaults of bundle::BundleAdjuster(), bundle_adjuster.cc:24-44)
+    loss_name: str = "CauchyLoss"
+    loss_threshold: float = 1.0
+    max_iterations: int = 500
+    linear_solver_type: str = "SPARSE_SCHUR"
+    num_threads: int = 1
+
+    @property
+    def cam_off(self) -> np.ndarray:
+        sizes = np.array([camera_num_params(t) for t in self.cam_type], dtype=np.int32)
+        return np.concatenate([[0], np.cumsum(sizes)]).astype(np.int32)
+
+    @property
+    def num_observations(self) -> int:
+        return int(self.obs_shot.shape[0])
+
+    def copy(self) -> "BAProblem":
+        kw = {}
+        for k, v in self.__dict__.items():
+            kw[k] = v.copy() if isinstance(v, np.ndarray) else v
+        return BAProblem(**kw)
+
+    def validate(self) -> None:
+        K = len(self.cam_type)
+        ncp = int(self.cam_off[-1])
+        assert self.cam_params.shape == (ncp,)
+        assert self.cam_prior.shape == (ncp,) and self.cam_prior_sigma.shape == (ncp,)
+        assert self.cam_prior_log.shape == (ncp,)
+        assert len(self.cam_const) == K
+        NI, NR, S, P, N = len(self.inst), len(self.rigcam), len(self.shot_inst), len(self.points), len(self.obs_shot)
+        assert self.inst.shape == (NI, 6) and self.rigcam.shape == (NR, 6) and self.points.shape == (P, 3)
+        assert self.obs_xy.shape == (N, 2) and self.obs_sigma.shape == (N,)
+        if N:
+            assert self.obs_shot.min() >= 0 and self.obs_shot.max() < S
+            assert self.obs_point.min() >= 0 and self.obs_point.max() < P
+        if S:
+            assert self.shot_inst.max() < NI and self.shot_cam.max() < K and self.shot_rc.max() < max(NR, 1)
+        if self.loss_name not in LOSS_NAMES:
+            # bundle_adjuster.cc:427
+            raise RuntimeError("ceres::LossFunction with name %s not found." % self.loss_name)
+
+
+def make_problem(cam_type, cam_params_list, inst, points, obs_shot, obs_point, obs_xy, obs_sigma,
+                 shot_inst=None, shot_cam=None, rigcam=None, shot_rc=None, shot_use_rc=None,
+                 cam_const=None, inst_const=None, rigcam_const=None, point_const=None,
+                 cam_prior_list=None, prior_sd=None, inst_prior_pos=None, inst_prior_std=None,
+                 **options) -> BAProblem:
+    """Convenience builder: one camera/instance per shot unless told otherwise."""
+    cam_type = np.asarray(cam_type, dtype=np.int32)
+    K = len(cam_type)
+    inst = np.ascontiguousarray(inst, dtype=np.float64).reshape(-1, 6)
+    NI = len(inst)
+    if shot_inst is None:
+        shot_inst = np.arange(NI, dtype=np.int32)
+    S = len(shot_inst)
+    if shot_cam is None:
+        shot_cam = np.arange(S, dtype=np.int32) if K == S else np.zeros(S, dtype=np.int32)
+    if rigcam is None:
+        rigcam = np.zeros((1, 6))
+    rigcam = np.ascontiguousarray(rigcam, dtype=np.float64).reshape(-1, 6)
+    NR = len(rigcam)
+    if shot_rc is None:
+        shot_rc = np.zeros(S, dtype=np.int32)
+    if shot_use_rc is None:
+        shot_use_rc = np.zeros(S, dtype=np.int32)
+    cam_params = np.concatenate([np.asarray(p, dtype=np.float64) for p in cam_params_list])
+    cam_prior = cam_params.copy() if cam_prior_list is None else np.concatenate(
+        [np.asarray(p, dtype=np.float64) for p in cam_prior_list])
+    sd = prior_sd or {}
+    cam_prior_sigma = np.concatenate([default_prior_sigma(t, **sd) for t in cam_type])
+    cam_prior_log = np.concatenate([prior_log_mask(t) for t in cam_type])
+    points = np.ascontiguousarray(points, dtype=np.float64).reshape(-1, 3)
+    P = len(points)
+    has_prior = np.zeros(NI, dtype=np.int32)
+    if inst_prior_pos is None:
+        inst_prior_pos = np.zeros((NI, 3))
+        inst_prior_std = np.ones((NI, 3))
+    else:
+        has_prior[:] = 1
+    z = lambda n, a: np.zeros(n, dtype=np.int32) if a is None else np.asarray(a, dtype=np.int32)
+    pb = BAProblem(
+        cam_type=cam_type, cam_params=cam_params, cam_const=z(K, cam_const), cam_prior=cam_prior,
+        cam_prior_sigma=cam_prior_sigma, cam_prior_log=cam_prior_log,
+        inst=inst, inst_const=z(NI, inst_const), inst_has_prior=has_prior,
+        inst_prior_pos=np.ascontiguousarray(inst_prior_pos, dtype=np.float64),
+        inst_prior_std=np.ascontiguousarray(inst_prior_std, dtype=np.float64),
+        rigcam=rigcam, rigcam_const=np.ones(NR, dtype=np.int32) if rigcam_const is None else np.asarray(rigcam_const, dtype=np.int32),
+        shot_inst=np.asarray(shot_inst, dtype=np.int32), shot_cam=np.asarray(shot_cam, dtype=np.int32),
+        shot_rc=np.asarray(shot_rc, dtype=np.int32), shot_use_rc=np.asarray(shot_use_rc, dtype=np.int32),
+        points=points, point_const=z(P, point_const),
+        obs_shot=np.asarray(obs_shot, dtype=np.int32), obs_point=np.asarray(obs_point, dtype=np.int32),
+        obs_xy=np.ascontiguousarray(obs_xy, dtype=np.float64).reshape(-1, 2),
+        obs_sigma=np.ascontiguousarray(obs_sigma, dtype=np.float64),
+        **options)
+    pb.validate()
+    return pb
