@@ -1,0 +1,167 @@
+/* opensfm_b200 — C ABI of the B200-native hot paths of OpenSfM.
+ *
+ * Plain C, plain pointers and sizes; no torch / pybind types.  Every entry
+ * point returns 0 on success and a non-zero code on failure; the message of
+ * the last failure on the calling thread is osfm_last_error().
+ *
+ * Two paths:
+ *   MATCH  brute-force descriptor matching + Lowe ratio test, replacing
+ *          opensfm/matching.py:723-777 (cv2.BFMatcher.knnMatch k=2).
+ *   BA     bundle adjustment, replacing bundle::BundleAdjuster
+ *          (opensfm/src/bundle/bundle_adjuster.h:178-299,
+ *           opensfm/src/bundle/src/bundle_adjuster.cc) behind pybundle /
+ *          sfm::BAHelpers (opensfm/src/sfm/src/ba_helpers.cc:117,408,581).
+ *
+ * There is no CPU fallback: every call needs a CUDA device (sm_100a).
+ */
+#ifndef OPENSFM_B200_H_
+#define OPENSFM_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define OSFM_OK 0
+#define OSFM_ERR_CUDA 1
+#define OSFM_ERR_ARG 2
+#define OSFM_ERR_RUNTIME 3
+
+const char* osfm_last_error(void);
+int osfm_version(void);
+/* number of this library's kernels launched by the calling process so far */
+int64_t osfm_kernel_launch_count(void);
+
+/* ------------------------------------------------------------------------
+ * MATCH
+ * ---------------------------------------------------------------------- */
+typedef struct osfm_matcher osfm_matcher;
+
+/* A matcher owns one CUDA stream and its workspaces on `device`.  One matcher
+ * per host thread: matching.match_brute_force is called concurrently from
+ * joblib threads (opensfm/context.py:59-64). */
+int osfm_matcher_create(int device, osfm_matcher** out);
+int osfm_matcher_destroy(osfm_matcher* m);
+
+/* One-shot, host buffers: the drop-in for
+ *   matching.match_brute_force(f1, f2, config, maskij)            (matching.py:723-756)
+ *   matching.match_brute_force_symmetric(fi, fj, config, maskij)  (matching.py:759-777)
+ * f1: n1 x dim, f2: n2 x dim, row-major, float32 (L2, "BruteForce") or
+ * uint8 (Hamming, "BruteForce-Hamming", dim = bytes per descriptor).
+ * mask: NULL or n1 x n2 bytes, non-zero = allowed (matching.py:745).
+ * out_match[i] = matched index in f2 for row i of f1, or -1.  For the one-way
+ * call the reference's list is [(i, out_match[i]) for i ascending if >= 0]. */
+int osfm_bf_match_f32(osfm_matcher* m, const float* f1, int n1, const float* f2, int n2, int dim,
+                      double lowes_ratio, const uint8_t* mask, int symmetric, int32_t* out_match);
+int osfm_bf_match_u8(osfm_matcher* m, const uint8_t* f1, int n1, const uint8_t* f2, int n2, int nbytes,
+                     double lowes_ratio, const uint8_t* mask, int symmetric, int32_t* out_match);
+
+/* Resident descriptor sets + batched pair list: the drop-in for the pair loop of
+ * matching.match_images_with_pairs (matching.py:63-98).  Descriptors are
+ * uploaded once; a pair list is matched in one submission. */
+int osfm_matcher_add_f32(osfm_matcher* m, const float* desc, int n, int dim, int* out_id);
+int osfm_matcher_add_u8(osfm_matcher* m, const uint8_t* desc, int n, int nbytes, int* out_id);
+int osfm_matcher_remove(osfm_matcher* m, int id);
+int osfm_matcher_clear(osfm_matcher* m);
+/* Enqueue matching of npairs pairs (ids_a[p], ids_b[p]).  Results stay on the
+ * device until fetched.  Total result length = sum_p n(ids_a[p]). */
+int osfm_matcher_match_pairs_async(osfm_matcher* m, int npairs, const int* ids_a, const int* ids_b,
+                                   double lowes_ratio, int symmetric);
+int osfm_matcher_sync(osfm_matcher* m);
+/* Copy the last batch's results to the host: concatenated per pair, n(ids_a[p]) entries each. */
+int osfm_matcher_fetch(osfm_matcher* m, int32_t* out_match, int64_t capacity);
+/* Milliseconds spent on the device by the last batch (CUDA events on the matcher's stream). */
+int osfm_matcher_last_device_ms(osfm_matcher* m, float* ms_total, float* ms_distance_kernel);
+/* 0 = pick automatically, 1 = force the exact SIMT kernel, 2 = force the tcgen05 kernel
+ * (fails at match time if the descriptors are not exactly representable). */
+int osfm_matcher_set_kernel(osfm_matcher* m, int which);
+/* Which distance kernel the last batch used: 1 = SIMT, 2 = tcgen05. */
+int osfm_matcher_last_kernel(osfm_matcher* m);
+
+/* ------------------------------------------------------------------------
+ * BA
+ * ---------------------------------------------------------------------- */
+typedef struct osfm_ba osfm_ba;
+
+/* geometry::ProjectionType (opensfm/src/geometry/camera_instances.h:8-20) */
+enum {
+  OSFM_PERSPECTIVE = 0, OSFM_BROWN = 1, OSFM_FISHEYE = 2, OSFM_FISHEYE_OPENCV = 3, OSFM_FISHEYE62 = 4,
+  OSFM_FISHEYE624 = 5, OSFM_SPHERICAL = 6, OSFM_DUAL = 7, OSFM_RADIAL = 8, OSFM_SIMPLE_RADIAL = 9
+};
+/* ceres loss names accepted by CreateLossFunction (bundle_adjuster.cc:414-429) */
+enum { OSFM_LOSS_TRIVIAL = 0, OSFM_LOSS_HUBER = 1, OSFM_LOSS_SOFTLONE = 2, OSFM_LOSS_CAUCHY = 3, OSFM_LOSS_ARCTAN = 4 };
+
+int osfm_ba_create(int device, osfm_ba** out);
+int osfm_ba_destroy(osfm_ba* ba);
+int osfm_camera_num_params(int projection_type);
+
+/* Bulk SoA setters — replace the string-keyed AddCamera / AddRigInstance /
+ * AddRigCamera / AddPoint / AddPointProjectionObservation calls
+ * (bundle_adjuster.cc:94-260).  All arrays are host memory and are copied. */
+int osfm_ba_set_cameras(osfm_ba* ba, int n, const int32_t* type, const double* params /*flat*/,
+                        const int32_t* constant, const double* prior /*flat*/, const double* prior_sigma /*flat*/,
+                        const int32_t* prior_log /*flat*/);
+int osfm_ba_set_rig_instances(osfm_ba* ba, int n, const double* pose6, const int32_t* constant,
+                              const int32_t* has_position_prior, const double* prior_position3,
+                              const double* prior_std3);
+int osfm_ba_set_rig_cameras(osfm_ba* ba, int n, const double* pose6, const int32_t* constant);
+int osfm_ba_set_shots(osfm_ba* ba, int n, const int32_t* rig_instance, const int32_t* camera,
+                      const int32_t* rig_camera, const int32_t* use_rig_camera);
+int osfm_ba_set_points(osfm_ba* ba, int n, const double* xyz, const int32_t* constant);
+int osfm_ba_set_observations(osfm_ba* ba, int64_t n, const int32_t* shot, const int32_t* point,
+                             const double* xy, const double* std_deviation);
+/* SetPointProjectionLossFunction / SetMaxNumIterations / SetLinearSolverType
+ * (bundle_adjuster.cc:262-372).  linear_solver: "SPARSE_SCHUR", "DENSE_SCHUR",
+ * "ITERATIVE_SCHUR" are all served by Schur elimination + PCG; unknown names fail
+ * like ceres::StringToLinearSolverType (bundle_adjuster.cc:1105-1109). */
+int osfm_ba_set_options(osfm_ba* ba, int loss, double loss_threshold, int max_iterations,
+                        const char* linear_solver, int compute_reprojection_errors);
+/* Multi-GPU: this process holds shard `rank` of `world` (observations are
+ * sharded by point).  allreduce_sum(buf, count, user) must sum `count` doubles
+ * at device pointer `buf` across ranks on `stream` (NCCL); NULL when world == 1. */
+typedef int (*osfm_allreduce_fn)(void* device_buf, int64_t count, void* stream, void* user);
+int osfm_ba_set_distributed(osfm_ba* ba, int rank, int world, osfm_allreduce_fn fn, void* user);
+/* Use an externally owned stream (e.g. torch's current stream); NULL = own stream. */
+int osfm_ba_set_stream(osfm_ba* ba, void* cuda_stream);
+
+/* BundleAdjuster::Run (bundle_adjuster.cc:595-1121). */
+int osfm_ba_run(osfm_ba* ba);
+
+typedef struct {
+  int iterations;             /* LM iterations executed (successful + unsuccessful) */
+  int successful_steps;
+  int linear_solves;
+  int pcg_iterations;         /* total CG iterations */
+  int termination;            /* 0 CONVERGENCE, 1 NO_CONVERGENCE, 2 FAILURE */
+  double initial_cost, final_cost;
+  double time_run_s;          /* wall time of run() (ba_helpers.cc:749-753) */
+  double time_device_ms;      /* CUDA-event time of the LM loop */
+  double time_linearize_ms;   /* summed CUDA-event time of the linearise+accumulate kernel */
+  int64_t linearize_launches;
+  int64_t kernel_launches;
+  char message[128];
+} osfm_ba_summary;
+int osfm_ba_get_summary(osfm_ba* ba, osfm_ba_summary* out);
+
+int osfm_ba_get_cameras(osfm_ba* ba, double* params_flat);
+int osfm_ba_get_rig_instances(osfm_ba* ba, double* pose6);
+int osfm_ba_get_rig_cameras(osfm_ba* ba, double* pose6);
+int osfm_ba_get_points(osfm_ba* ba, double* xyz);
+/* ComputeReprojectionErrors (bundle_adjuster.cc:1196-1208): unscaled residuals,
+ * n x 3 (third column 0 for 2-D errors), observation order. */
+int osfm_ba_get_reprojection_errors(osfm_ba* ba, double* out_n_by_3);
+
+/* Single-observation evaluation on the device (test hook for the per-observation
+ * kernel; ReprojectionError2DAnalytic::Evaluate, projection_errors.h:67-207).
+ * Outputs: r[3], jac_camera[3*C], jac_instance[18], jac_rig_camera[18], jac_point[9]. */
+int osfm_ba_eval_observation(int device, int projection_type, const double* camera, const double* rig_instance,
+                             const double* rig_camera, int use_rig_camera, const double* point,
+                             const double* observed, double std_deviation, double* r, double* jac_camera,
+                             double* jac_instance, double* jac_rig_camera, double* jac_point, int* num_residuals);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OPENSFM_B200_H_ */

@@ -1,0 +1,1504 @@
+// Bundle adjustment on B200 (sm_100a): Levenberg-Marquardt with Schur
+// elimination of the points and PCG on the reduced camera system, all in fp64.
+//
+// Replaces bundle::BundleAdjuster::Run (opensfm/src/bundle/src/bundle_adjuster.cc:595-1121)
+// = problem assembly + ceres::Solve(SPARSE_SCHUR) + ComputeReprojectionErrors, for the
+// residual blocks the reference's default pipeline builds (sfm/src/ba_helpers.cc:581-763):
+// point projections with a shared robust loss, camera-intrinsics priors (log-scale focal /
+// aspect ratio), rig-instance position priors.  The LM rules are Ceres' (SURVEY.md §8c).
+//
+// HBM layout (SoA, observations sorted by point so that V_p, g_p, the Schur update
+// and the back-substitution of a point touch one contiguous range):
+//   obs_{shot,point,x,y,isig}[N]          observation records
+//   r[nres][N], Jc[nres*wc][N], Jp[nres*3][N]   robustified residual / Jacobian planes
+//   S[nc*nc], rhs[nc]                     reduced camera system (dense, symmetric)
+//   Vinv[6][npf], vectors[nc + 3 npf]     per-point inverse blocks, LM vectors
+//
+// Kernels: ba_linearize (per observation), ba_colnorm_grad, ba_schur (CTA per point:
+// U, g_c, V^-1 and W V^-1 W^T scattered to S with fp64 atomics), ba_finish_system,
+// PCG kernels (block-Jacobi), ba_backsub (warp per point), ba_model_change, ba_update.
+#include <chrono>
+#include <cmath>
+#include <string>
+#include <vector>
+
+#include "ba_models.cuh"
+#include "common.cuh"
+
+namespace osfm {
+
+// ---------------------------------------------------------------------------
+// Device-side problem view
+// ---------------------------------------------------------------------------
+struct BAView {
+  int K, NI, NR, S, P;
+  long long N;
+  int nc, npf;      // reduced camera-side dimension, free local points
+  int wc, nres;     // Jacobian plane counts
+  int loss;
+  double loss_a;
+  const int *cam_type, *cam_off, *cam_np, *cam_poff, *inst_poff, *rc_poff, *pt_poff;
+  const int *shot_inst, *shot_cam, *shot_rc, *shot_use_rc;
+  const int *obs_shot, *obs_point;
+  const double *obs_x, *obs_y, *obs_isig;
+  const long long* obs_orig;
+  const long long* pt_start;
+  double *r, *Jc, *Jp;
+};
+
+struct Params {
+  double *cam, *inst, *rc, *pts;
+};
+
+// scalar accumulators (device)
+struct Scalars {
+  double cost;
+  double model_change;
+  double step_norm2;
+  double x_norm2;
+  double grad_max_bits;  // max |g| via atomicMax on the bit pattern (non-negative doubles)
+  double pcg_rz[2];
+  double pcg_pAp;
+  double pcg_rr;
+  double pcg_bb;
+};
+
+__device__ __forceinline__ double block_reduce_sum(double v) {
+  __shared__ double sh[32];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+  for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  __syncthreads();
+  if (lane == 0) sh[w] = v;
+  __syncthreads();
+  const int nw = (blockDim.x + 31) >> 5;
+  v = threadIdx.x < nw ? sh[threadIdx.x] : 0.0;
+  if (w == 0) {
+#pragma unroll
+    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  }
+  return v;  // valid in thread 0
+}
+
+__device__ __forceinline__ void atomic_max_nonneg(double* addr, double v) {
+  atomicMax(reinterpret_cast<unsigned long long*>(addr), (unsigned long long)__double_as_longlong(v));
+}
+
+// ---------------------------------------------------------------------------
+// Per-observation kernels
+// ---------------------------------------------------------------------------
+// MODE 0: cost only (candidate evaluation).  MODE 1: residual + Jacobian planes (robustified).
+// MODE 2: unscaled reprojection errors (bundle_adjuster.cc:531-566), written in original order.
+template <int MODE>
+__global__ void __launch_bounds__(128) ba_linearize(BAView v, Params p, Scalars* sc, double* reproj) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  double cost = 0.0;
+  if (i < v.N) {
+    const int shot = v.obs_shot[i];
+    const int cam = v.shot_cam[shot];
+    const int type = v.cam_type[cam];
+    const int C = v.cam_np[cam];
+    const bool use_rc = v.shot_use_rc[shot] != 0;
+    const int pt = v.obs_point[i];
+    double camp[MAX_CAM_PARAMS], ri[6], rc[6], X[3];
+    for (int j = 0; j < C; ++j) camp[j] = p.cam[v.cam_off[cam] + j];
+#pragma unroll
+    for (int j = 0; j < 6; ++j) ri[j] = p.inst[6 * (size_t)v.shot_inst[shot] + j];
+    if (use_rc) {
+#pragma unroll
+      for (int j = 0; j < 6; ++j) rc[j] = p.rc[6 * (size_t)v.shot_rc[shot] + j];
+    }
+#pragma unroll
+    for (int j = 0; j < 3; ++j) X[j] = p.pts[3 * (size_t)pt + j];
+    const double ox = v.obs_x[i], oy = v.obs_y[i];
+    if (MODE == 2) {
+      double r[3] = {0.0, 0.0, 0.0};
+      observation_eval(type, camp, ri, rc, use_rc, X, ox, oy, 1.0, r, nullptr, nullptr, nullptr, nullptr);
+      const long long o = v.obs_orig[i];
+      reproj[3 * o] = r[0]; reproj[3 * o + 1] = r[1]; reproj[3 * o + 2] = r[2];
+    } else if (MODE == 0) {
+      double r[3];
+      const int nres = observation_eval(type, camp, ri, rc, use_rc, X, ox, oy, v.obs_isig[i], r, nullptr, nullptr,
+                                        nullptr, nullptr);
+      double s = r[0] * r[0] + r[1] * r[1];
+      if (nres == 3) s += r[2] * r[2];
+      double w;
+      cost = 0.5 * robust_loss(v.loss, v.loss_a, s, &w);
+    } else {
+      double r[3], jc[3 * MAX_CAM_PARAMS], jri[18], jrc[18], jp[9];
+      const int nres = observation_eval(type, camp, ri, rc, use_rc, X, ox, oy, v.obs_isig[i], r, jc, jri, jrc, jp);
+      double s = r[0] * r[0] + r[1] * r[1];
+      if (nres == 3) s += r[2] * r[2];
+      double w;
+      cost = 0.5 * robust_loss(v.loss, v.loss_a, s, &w);
+      const bool pfree = v.pt_poff[pt] >= 0;
+      const size_t N = (size_t)v.N;
+      for (int k = 0; k < v.nres; ++k) {
+        const bool live = k < nres;
+        v.r[k * N + i] = live ? w * r[k] : 0.0;
+        double* jcrow = v.Jc + (size_t)k * v.wc * N + i;
+        for (int j = 0; j < v.wc; ++j) {
+          double val = 0.0;
+          if (live) {
+            if (j < C) val = jc[k * C + j];
+            else if (j < C + 6) val = jri[k * 6 + (j - C)];
+            else if (use_rc && j < C + 12) val = jrc[k * 6 + (j - C - 6)];
+          }
+          jcrow[(size_t)j * N] = w * val;
+        }
+#pragma unroll
+        for (int j = 0; j < 3; ++j) v.Jp[((size_t)k * 3 + j) * N + i] = (live && pfree) ? w * jp[k * 3 + j] : 0.0;
+      }
+    }
+  }
+  if (MODE != 2) {
+    const double tot = block_reduce_sum(cost);
+    if (threadIdx.x == 0 && tot != 0.0) atomicAdd(&sc->cost, tot);
+  }
+}
+
+// Global column of local camera-side column j of an observation, or -1.
+struct ObsCols {
+  int g_cam, C, g_inst, g_rc;
+  __device__ __forceinline__ int col(int j) const {
+    if (j < C) return g_cam >= 0 ? g_cam + j : -1;
+    if (j < C + 6) return g_inst >= 0 ? g_inst + (j - C) : -1;
+    if (j < C + 12) return g_rc >= 0 ? g_rc + (j - C - 6) : -1;
+    return -1;
+  }
+};
+__device__ __forceinline__ ObsCols obs_cols(const BAView& v, long long i) {
+  const int shot = v.obs_shot[i];
+  const int cam = v.shot_cam[shot];
+  ObsCols oc;
+  oc.g_cam = v.cam_poff[cam];
+  oc.C = v.cam_np[cam];
+  oc.g_inst = v.inst_poff[v.shot_inst[shot]];
+  oc.g_rc = v.shot_use_rc[shot] ? v.rc_poff[v.shot_rc[shot]] : -2;  // -2: no rig-camera columns at all
+  return oc;
+}
+
+// Prior residual rows (camera prior bundle_adjuster.cc:568-593 / prior_error.h:78-95,
+// position prior bundle_adjuster.cc:745-778): row value, column, derivative.
+struct PriorView {
+  int n_cam_rows, n_pos_rows;
+  const int *cam_row_param, *cam_row_col, *cam_row_log;  // index into cam params / reduced column
+  const double *cam_row_prior, *cam_row_scale;
+  const int *pos_row_inst, *pos_row_axis, *pos_row_col;
+  const double *pos_row_prior, *pos_row_scale;
+};
+__device__ __forceinline__ void prior_row(const PriorView& pv, const Params& p, int row, double* r, int* col,
+                                          double* d) {
+  if (row < pv.n_cam_rows) {
+    const double val = p.cam[pv.cam_row_param[row]];
+    const double sc = pv.cam_row_scale[row];
+    *col = pv.cam_row_col[row];
+    if (pv.cam_row_log[row]) {
+      *r = sc * log(val / pv.cam_row_prior[row]);
+      *d = sc / val;
+    } else {
+      *r = sc * (val - pv.cam_row_prior[row]);
+      *d = sc;
+    }
+  } else {
+    const int q = row - pv.n_cam_rows;
+    const double sc = pv.pos_row_scale[q];
+    *col = pv.pos_row_col[q];
+    *r = sc * (p.inst[6 * (size_t)pv.pos_row_inst[q] + 3 + pv.pos_row_axis[q]] - pv.pos_row_prior[q]);
+    *d = sc;
+  }
+}
+
+__global__ void ba_prior_cost(PriorView pv, Params p, Scalars* sc) {
+  const int row = blockIdx.x * blockDim.x + threadIdx.x;
+  double c = 0.0;
+  if (row < pv.n_cam_rows + pv.n_pos_rows) {
+    double r, d;
+    int col;
+    prior_row(pv, p, row, &r, &col, &d);
+    c = 0.5 * r * r;
+  }
+  const double tot = block_reduce_sum(c);
+  if (threadIdx.x == 0 && tot != 0.0) atomicAdd(&sc->cost, tot);
+}
+
+// Squared column norms and gradient of the (unscaled, robustified) Jacobian.
+__global__ void __launch_bounds__(256) ba_colnorm_grad(BAView v, double* colnorm2, double* grad) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= v.N) return;
+  const size_t N = (size_t)v.N;
+  const ObsCols oc = obs_cols(v, i);
+  double r[3];
+  for (int k = 0; k < v.nres; ++k) r[k] = v.r[k * N + i];
+  for (int j = 0; j < v.wc; ++j) {
+    const int g = oc.col(j);
+    if (g < 0) continue;
+    double n2 = 0.0, gr = 0.0;
+    for (int k = 0; k < v.nres; ++k) {
+      const double a = v.Jc[((size_t)k * v.wc + j) * N + i];
+      n2 += a * a;
+      gr += a * r[k];
+    }
+    atomicAdd(&colnorm2[g], n2);
+    atomicAdd(&grad[g], gr);
+  }
+  const int pf = v.pt_poff[v.obs_point[i]];
+  if (pf >= 0) {
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      double n2 = 0.0, gr = 0.0;
+      for (int k = 0; k < v.nres; ++k) {
+        const double a = v.Jp[((size_t)k * 3 + j) * N + i];
+        n2 += a * a;
+        gr += a * r[k];
+      }
+      atomicAdd(&colnorm2[v.nc + 3 * pf + j], n2);
+      atomicAdd(&grad[v.nc + 3 * pf + j], gr);
+    }
+  }
+}
+
+__global__ void ba_prior_colnorm_grad(PriorView pv, Params p, double* colnorm2, double* grad) {
+  const int row = blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= pv.n_cam_rows + pv.n_pos_rows) return;
+  double r, d;
+  int col;
+  prior_row(pv, p, row, &r, &col, &d);
+  atomicAdd(&colnorm2[col], d * d);
+  atomicAdd(&grad[col], d * r);
+}
+
+// scale = 1 / (1 + sqrt(colnorm2))   (Ceres jacobi_scaling)
+__global__ void ba_make_scale(const double* colnorm2, double* scale, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) scale[i] = 1.0 / (1.0 + sqrt(colnorm2[i]));
+}
+// diag2 = clamp(colnorm2 * scale^2, 1e-6, 1e32) / radius ; also gradient max-norm
+__global__ void ba_make_diag(const double* colnorm2, const double* scale, double* diag, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) diag[i] = fmin(fmax(colnorm2[i] * scale[i] * scale[i], 1e-6), 1e32);
+}
+__global__ void ba_grad_max(const double* grad, int n, Scalars* sc) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  double v = i < n ? fabs(grad[i]) : 0.0;
+#pragma unroll
+  for (int o = 16; o; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+  if ((threadIdx.x & 31) == 0 && v > 0.0) atomic_max_nonneg(&sc->grad_max_bits, v);
+}
+
+// ---------------------------------------------------------------------------
+// Schur complement.  One CTA per point.
+//   U   += Jc_s^T Jc_s,  g_c += Jc_s^T r              (every observation)
+//   V    = sum Jp_s^T Jp_s + D_p ; g_p = sum Jp_s^T r   (free points)
+//   S   -= W_a V^-1 W_b^T,  rhs -= W_a V^-1 g_p         (all pairs a <= b, mirrored)
+// Only entries with global column g1 <= g2 are written (upper triangle); the
+// system is finished (all-reduce, priors, damping, mirror) by ba_finish_system.
+// Js = J diag(scale); diag = LM diagonal (already divided by the radius).
+// ---------------------------------------------------------------------------
+constexpr int SCHUR_THREADS = 128;
+constexpr int SCHUR_KC = 16;  // observations staged per chunk
+
+__global__ void __launch_bounds__(SCHUR_THREADS) ba_schur(BAView v, const double* __restrict__ scale,
+                                                          const double* __restrict__ diag, double inv_radius,
+                                                          double* __restrict__ Smat, double* __restrict__ rhs,
+                                                          double* __restrict__ Vinv, double* __restrict__ gpo) {
+  extern __shared__ double sm[];
+  const int wc = v.wc, nres = v.nres, nc = v.nc;
+  // smem: Ya[KC][wc][3], Wb[KC][wc][3], cols a/b [KC][wc] (int), red[...]
+  double* Ya = sm;
+  double* Wb = Ya + SCHUR_KC * wc * 3;
+  int* ca = reinterpret_cast<int*>(Wb + SCHUR_KC * wc * 3);
+  int* cb = ca + SCHUR_KC * wc;
+  __shared__ double sV[9], sVi[9], sg[3], sVig[3];
+
+  const int p = blockIdx.x;
+  const long long b0 = v.pt_start[p], e0 = v.pt_start[p + 1];
+  const int k = (int)(e0 - b0);
+  if (k == 0) return;
+  const int pf = v.pt_poff[p];
+  const size_t N = (size_t)v.N;
+  const int tid = threadIdx.x;
+
+  // ---- U and g_c: (obs, c1, c2 >= c1 in global order) ----
+  for (int idx = tid; idx < k * wc; idx += SCHUR_THREADS) {
+    const int a = idx / wc, c1 = idx % wc;
+    const long long i = b0 + a;
+    const ObsCols oc = obs_cols(v, i);
+    const int g1 = oc.col(c1);
+    if (g1 < 0) continue;
+    const double s1 = scale[g1];
+    double j1[3], rr[3];
+    for (int q = 0; q < nres; ++q) {
+      j1[q] = v.Jc[((size_t)q * wc + c1) * N + i] * s1;
+      rr[q] = v.r[q * N + i];
+    }
+    double g = 0.0;
+    for (int q = 0; q < nres; ++q) g += j1[q] * rr[q];
+    atomicAdd(&rhs[g1], g);
+    for (int c2 = 0; c2 < wc; ++c2) {
+      const int g2 = oc.col(c2);
+      if (g2 < g1) continue;  // also skips -1 / -2
+      const double s2 = scale[g2];
+      double val = 0.0;
+      for (int q = 0; q < nres; ++q) val += j1[q] * v.Jc[((size_t)q * wc + c2) * N + i] * s2;
+      atomicAdd(&Smat[(size_t)g1 * nc + g2], val);
+    }
+  }
+  if (pf < 0) return;
+
+  // ---- V, g_p ----
+  double acc[9];
+#pragma unroll
+  for (int j = 0; j < 9; ++j) acc[j] = 0.0;
+  const double sp0 = scale[nc + 3 * pf], sp1 = scale[nc + 3 * pf + 1], sp2 = scale[nc + 3 * pf + 2];
+  for (int a = tid; a < k; a += SCHUR_THREADS) {
+    const long long i = b0 + a;
+    for (int q = 0; q < nres; ++q) {
+      const double x = v.Jp[((size_t)q * 3 + 0) * N + i] * sp0;
+      const double y = v.Jp[((size_t)q * 3 + 1) * N + i] * sp1;
+      const double z = v.Jp[((size_t)q * 3 + 2) * N + i] * sp2;
+      const double rq = v.r[q * N + i];
+      acc[0] += x * x; acc[1] += x * y; acc[2] += x * z; acc[3] += y * y; acc[4] += y * z; acc[5] += z * z;
+      acc[6] += x * rq; acc[7] += y * rq; acc[8] += z * rq;
+    }
+  }
+  for (int j = 0; j < 9; ++j) {
+    const double t = block_reduce_sum(acc[j]);
+    if (tid == 0) sV[j] = t;
+  }
+  if (tid == 0) {
+    const double a = sV[0] + diag[nc + 3 * pf] * inv_radius, b = sV[1], c = sV[2];
+    const double d = sV[3] + diag[nc + 3 * pf + 1] * inv_radius, e = sV[4];
+    const double f = sV[5] + diag[nc + 3 * pf + 2] * inv_radius;
+    const double A = d * f - e * e, B = c * e - b * f, Cc = b * e - c * d;
+    const double id = 1.0 / (a * A + b * B + c * Cc);
+    sVi[0] = A * id; sVi[1] = B * id; sVi[2] = Cc * id;
+    sVi[3] = B * id; sVi[4] = (a * f - c * c) * id; sVi[5] = (b * c - a * e) * id;
+    sVi[6] = Cc * id; sVi[7] = sVi[5]; sVi[8] = (a * d - b * b) * id;
+    sg[0] = sV[6]; sg[1] = sV[7]; sg[2] = sV[8];
+    for (int j = 0; j < 3; ++j) sVig[j] = sVi[j * 3] * sg[0] + sVi[j * 3 + 1] * sg[1] + sVi[j * 3 + 2] * sg[2];
+    const size_t NP = (size_t)v.npf;
+    Vinv[0 * NP + pf] = sVi[0]; Vinv[1 * NP + pf] = sVi[1]; Vinv[2 * NP + pf] = sVi[2];
+    Vinv[3 * NP + pf] = sVi[4]; Vinv[4 * NP + pf] = sVi[5]; Vinv[5 * NP + pf] = sVi[8];
+    gpo[0 * NP + pf] = sg[0]; gpo[1 * NP + pf] = sg[1]; gpo[2 * NP + pf] = sg[2];
+  }
+  __syncthreads();
+
+  // ---- pairs, tiled KC x KC over (a-chunk <= b-chunk) ----
+  for (int a0 = 0; a0 < k; a0 += SCHUR_KC) {
+    const int na = min(SCHUR_KC, k - a0);
+    __syncthreads();
+    // stage Y_a = W_a V^-1 and the columns of chunk a; also rhs -= W_a V^-1 g_p
+    for (int idx = tid; idx < na * wc; idx += SCHUR_THREADS) {
+      const int a = idx / wc, c1 = idx % wc;
+      const long long i = b0 + a0 + a;
+      const ObsCols oc = obs_cols(v, i);
+      const int g1 = oc.col(c1);
+      ca[a * wc + c1] = g1;
+      double w0 = 0.0, w1 = 0.0, w2 = 0.0;
+      if (g1 >= 0) {
+        const double s1 = scale[g1];
+        for (int q = 0; q < nres; ++q) {
+          const double jc = v.Jc[((size_t)q * wc + c1) * N + i] * s1;
+          w0 += jc * v.Jp[((size_t)q * 3 + 0) * N + i] * sp0;
+          w1 += jc * v.Jp[((size_t)q * 3 + 1) * N + i] * sp1;
+          w2 += jc * v.Jp[((size_t)q * 3 + 2) * N + i] * sp2;
+        }
+        atomicAdd(&rhs[g1], -(w0 * sVig[0] + w1 * sVig[1] + w2 * sVig[2]));
+      }
+      double* y = Ya + (a * wc + c1) * 3;
+      y[0] = w0 * sVi[0] + w1 * sVi[3] + w2 * sVi[6];
+      y[1] = w0 * sVi[1] + w1 * sVi[4] + w2 * sVi[7];
+      y[2] = w0 * sVi[2] + w1 * sVi[5] + w2 * sVi[8];
+    }
+    for (int bb0 = a0; bb0 < k; bb0 += SCHUR_KC) {
+      const int nb = min(SCHUR_KC, k - bb0);
+      __syncthreads();
+      for (int idx = tid; idx < nb * wc; idx += SCHUR_THREADS) {
+        const int b = idx / wc, c2 = idx % wc;
+        const long long i = b0 + bb0 + b;
+        const ObsCols oc = obs_cols(v, i);
+        const int g2 = oc.col(c2);
+        cb[b * wc + c2] = g2;
+        double w0 = 0.0, w1 = 0.0, w2 = 0.0;
+        if (g2 >= 0) {
+          const double s2 = scale[g2];
+          for (int q = 0; q < nres; ++q) {
+            const double jc = v.Jc[((size_t)q * wc + c2) * N + i] * s2;
+            w0 += jc * v.Jp[((size_t)q * 3 + 0) * N + i] * sp0;
+            w1 += jc * v.Jp[((size_t)q * 3 + 1) * N + i] * sp1;
+            w2 += jc * v.Jp[((size_t)q * 3 + 2) * N + i] * sp2;
+          }
+        }
+        double* w = Wb + (b * wc + c2) * 3;
+        w[0] = w0; w[1] = w1; w[2] = w2;
+      }
+      __syncthreads();
+      // all (a, c1, b, c2) of this tile pair with global obs index a <= b
+      const int rowlen = nb * wc;
+      const int total = na * wc * rowlen;
+      for (int idx = tid; idx < total; idx += SCHUR_THREADS) {
+        const int ac = idx / rowlen, bc = idx % rowlen;
+        const int a = ac / wc, b = bc / wc;
+        const int ga = a0 + a, gb = bb0 + b;
+        if (gb < ga) continue;
+        const int g1 = ca[ac], g2 = cb[bc];
+        if (g1 < 0 || g2 < 0) continue;
+        const double* y = Ya + ac * 3;
+        const double* w = Wb + bc * 3;
+        double val = y[0] * w[0] + y[1] * w[1] + y[2] * w[2];
+        if (ga == gb) {
+          if (g2 < g1) continue;  // same observation: each (c1,c2) with g1 <= g2 once
+          atomicAdd(&Smat[(size_t)g1 * nc + g2], -val);
+        } else {
+          if (g1 == g2) val *= 2.0;  // (a,b) and (b,a) both land on the diagonal entry
+          const int lo = min(g1, g2), hi = max(g1, g2);
+          atomicAdd(&Smat[(size_t)lo * nc + hi], -val);
+        }
+      }
+    }
+  }
+}
+
+// After the (optional) all-reduce of the upper triangle: add priors and LM damping
+// to the diagonal, then mirror to the lower triangle.
+__global__ void ba_prior_system(PriorView pv, Params p, const double* scale, double* Smat, double* rhs, int nc) {
+  const int row = blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= pv.n_cam_rows + pv.n_pos_rows) return;
+  double r, d;
+  int col;
+  prior_row(pv, p, row, &r, &col, &d);
+  const double ds = d * scale[col];
+  atomicAdd(&Smat[(size_t)col * nc + col], ds * ds);
+  atomicAdd(&rhs[col], ds * r);
+}
+__global__ void ba_finish_system(double* Smat, const double* diag, double inv_radius, int nc) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  const int i = blockIdx.y;
+  if (j >= nc) return;
+  if (i == j) Smat[(size_t)i * nc + i] += diag[i] * inv_radius;
+  else if (j < i) Smat[(size_t)i * nc + j] = Smat[(size_t)j * nc + i];
+}
+
+// ---------------------------------------------------------------------------
+// PCG on S y = rhs with a block-Jacobi preconditioner (one block per parameter block).
+// ---------------------------------------------------------------------------
+constexpr int MAXB = 16;
+// Cholesky-inverts each diagonal block into Minv[b][MAXB*MAXB] (dense, row-major sz x sz).
+__global__ void pcg_factor_blocks(const double* __restrict__ Smat, int nc, const int* __restrict__ blk_off,
+                                  const int* __restrict__ blk_sz, int nblk, double* __restrict__ Minv) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= nblk) return;
+  const int o = blk_off[b], n = blk_sz[b];
+  double L[MAXB * MAXB];
+  for (int i = 0; i < n; ++i)
+    for (int j = 0; j <= i; ++j) L[i * MAXB + j] = Smat[(size_t)(o + i) * nc + o + j];
+  // in-place Cholesky (lower)
+  for (int j = 0; j < n; ++j) {
+    double d = L[j * MAXB + j];
+    for (int k = 0; k < j; ++k) d -= L[j * MAXB + k] * L[j * MAXB + k];
+    d = sqrt(fmax(d, 1e-300));
+    L[j * MAXB + j] = d;
+    for (int i = j + 1; i < n; ++i) {
+      double s = L[i * MAXB + j];
+      for (int k = 0; k < j; ++k) s -= L[i * MAXB + k] * L[j * MAXB + k];
+      L[i * MAXB + j] = s / d;
+    }
+  }
+  // inverse: solve L L^T X = I column by column
+  double* out = Minv + (size_t)b * MAXB * MAXB;
+  for (int c = 0; c < n; ++c) {
+    double y[MAXB];
+    for (int i = 0; i < n; ++i) {
+      double s = (i == c) ? 1.0 : 0.0;
+      for (int k = 0; k < i; ++k) s -= L[i * MAXB + k] * y[k];
+      y[i] = s / L[i * MAXB + i];
+    }
+    for (int i = n - 1; i >= 0; --i) {
+      double s = y[i];
+      for (int k = i + 1; k < n; ++k) s -= L[k * MAXB + i] * y[k];
+      y[i] = s / L[i * MAXB + i];
+    }
+    for (int i = 0; i < n; ++i) out[i * MAXB + c] = y[i];
+  }
+}
+
+// z = Minv r for the rows of one block; accumulates r.z into *rz and r.r into *rr
+__device__ __forceinline__ void apply_block(const double* Minv, const int* blk_off, const int* blk_sz, int b,
+                                            const double* r, double* z, double* rz, double* rr) {
+  const int o = blk_off[b], n = blk_sz[b];
+  const double* M = Minv + (size_t)b * MAXB * MAXB;
+  double a_rz = 0.0, a_rr = 0.0;
+  for (int i = 0; i < n; ++i) {
+    double s = 0.0;
+    for (int j = 0; j < n; ++j) s += M[i * MAXB + j] * r[o + j];
+    z[o + i] = s;
+    a_rz += s * r[o + i];
+    a_rr += r[o + i] * r[o + i];
+  }
+  *rz = a_rz;
+  *rr = a_rr;
+}
+
+__global__ void pcg_init(const double* rhs, double* x, double* r, double* z, double* p, int nc,
+                         const double* Minv, const int* blk_off, const int* blk_sz, int nblk, Scalars* sc) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  double rz = 0.0, rr = 0.0;
+  if (b < nblk) {
+    const int o = blk_off[b], n = blk_sz[b];
+    for (int i = 0; i < n; ++i) { x[o + i] = 0.0; r[o + i] = rhs[o + i]; }
+    apply_block(Minv, blk_off, blk_sz, b, r, z, &rz, &rr);
+    for (int i = 0; i < n; ++i) p[o + i] = z[o + i];
+  }
+  const double t1 = block_reduce_sum(rz);
+  const double t2 = block_reduce_sum(rr);
+  if (threadIdx.x == 0) {
+    atomicAdd(&sc->pcg_rz[0], t1);
+    atomicAdd(&sc->pcg_bb, t2);
+    atomicAdd(&sc->pcg_rr, t2);
+  }
+}
+
+// Ap = S p (one warp per row), pAp += p.Ap ; zeroes the next rz accumulator
+__global__ void __launch_bounds__(256) pcg_matvec(const double* __restrict__ Smat, const double* __restrict__ p,
+                                                  double* __restrict__ Ap, int nc, Scalars* sc, int it) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    sc->pcg_rz[(it + 1) & 1] = 0.0;
+    sc->pcg_rr = 0.0;
+  }
+  double s = 0.0;
+  if (row < nc) {
+    const double* Srow = Smat + (size_t)row * nc;
+    for (int j = lane; j < nc; j += 32) s += Srow[j] * p[j];
+#pragma unroll
+    for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) Ap[row] = s;
+  }
+  double contrib = (row < nc && lane == 0) ? s * p[row] : 0.0;
+  const double t = block_reduce_sum(contrib);
+  if (threadIdx.x == 0) atomicAdd(&sc->pcg_pAp, t);
+}
+
+// x += alpha p ; r -= alpha Ap ; z = Minv r ; rz_new, rr
+__global__ void pcg_update1(double* x, double* r, double* z, const double* p, const double* Ap,
+                            const double* Minv, const int* blk_off, const int* blk_sz, int nblk, Scalars* sc, int it) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  const double alpha = sc->pcg_rz[it & 1] / sc->pcg_pAp;
+  double rz = 0.0, rr = 0.0;
+  if (b < nblk) {
+    const int o = blk_off[b], n = blk_sz[b];
+    for (int i = 0; i < n; ++i) {
+      x[o + i] += alpha * p[o + i];
+      r[o + i] -= alpha * Ap[o + i];
+    }
+    apply_block(Minv, blk_off, blk_sz, b, r, z, &rz, &rr);
+  }
+  const double t1 = block_reduce_sum(rz);
+  const double t2 = block_reduce_sum(rr);
+  if (threadIdx.x == 0) {
+    atomicAdd(&sc->pcg_rz[(it + 1) & 1], t1);
+    atomicAdd(&sc->pcg_rr, t2);
+  }
+}
+// p = z + beta p ; reset pAp
+__global__ void pcg_update2(double* p, const double* z, int nc, Scalars* sc, int it) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const double beta = sc->pcg_rz[(it + 1) & 1] / sc->pcg_rz[it & 1];
+  if (i < nc) p[i] = z[i] + beta * p[i];
+  if (i == 0) sc->pcg_pAp = 0.0;  // read by pcg_update1 of this iteration (earlier kernel), reset for the next
+}
+
+// ---------------------------------------------------------------------------
+// Back-substitution: y_p = V^-1 (g_p - W^T y_c)  (scaled system), one warp per point.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) ba_backsub(BAView v, const double* __restrict__ scale,
+                                                  const double* __restrict__ Vinv, double* __restrict__ y) {
+  const int p = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (p >= v.P) return;
+  const int pf = v.pt_poff[p];
+  if (pf < 0) return;
+  const size_t N = (size_t)v.N;
+  const int nc = v.nc, wc = v.wc;
+  const double sp0 = scale[nc + 3 * pf], sp1 = scale[nc + 3 * pf + 1], sp2 = scale[nc + 3 * pf + 2];
+  double t0 = 0.0, t1 = 0.0, t2 = 0.0;
+  for (long long i = v.pt_start[p] + lane; i < v.pt_start[p + 1]; i += 32) {
+    const ObsCols oc = obs_cols(v, i);
+    for (int q = 0; q < v.nres; ++q) {
+      double e = v.r[q * N + i];
+      for (int j = 0; j < wc; ++j) {
+        const int g = oc.col(j);
+        if (g >= 0) e -= v.Jc[((size_t)q * wc + j) * N + i] * scale[g] * y[g];
+      }
+      t0 += v.Jp[((size_t)q * 3 + 0) * N + i] * sp0 * e;
+      t1 += v.Jp[((size_t)q * 3 + 1) * N + i] * sp1 * e;
+      t2 += v.Jp[((size_t)q * 3 + 2) * N + i] * sp2 * e;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) {
+    t0 += __shfl_xor_sync(0xffffffffu, t0, o);
+    t1 += __shfl_xor_sync(0xffffffffu, t1, o);
+    t2 += __shfl_xor_sync(0xffffffffu, t2, o);
+  }
+  if (lane == 0) {
+    const size_t NP = (size_t)v.npf;
+    const double a = Vinv[0 * NP + pf], b = Vinv[1 * NP + pf], c = Vinv[2 * NP + pf];
+    const double d = Vinv[3 * NP + pf], e = Vinv[4 * NP + pf], f = Vinv[5 * NP + pf];
+    y[nc + 3 * pf + 0] = a * t0 + b * t1 + c * t2;
+    y[nc + 3 * pf + 1] = b * t0 + d * t1 + e * t2;
+    y[nc + 3 * pf + 2] = c * t0 + e * t1 + f * t2;
+  }
+}
+
+// Ceres: model_cost_change = -sum m (r + m/2), m = Js step ; step = -y
+__global__ void __launch_bounds__(256) ba_model_change(BAView v, const double* __restrict__ scale,
+                                                       const double* __restrict__ y, Scalars* sc) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  double tot = 0.0;
+  if (i < v.N) {
+    const size_t N = (size_t)v.N;
+    const int nc = v.nc, wc = v.wc;
+    const ObsCols oc = obs_cols(v, i);
+    const int pf = v.pt_poff[v.obs_point[i]];
+    for (int q = 0; q < v.nres; ++q) {
+      double m = 0.0;
+      for (int j = 0; j < wc; ++j) {
+        const int g = oc.col(j);
+        if (g >= 0) m -= v.Jc[((size_t)q * wc + j) * N + i] * scale[g] * y[g];
+      }
+      if (pf >= 0) {
+#pragma unroll
+        for (int j = 0; j < 3; ++j) m -= v.Jp[((size_t)q * 3 + j) * N + i] * scale[nc + 3 * pf + j] * y[nc + 3 * pf + j];
+      }
+      tot += -m * (v.r[q * N + i] + 0.5 * m);
+    }
+  }
+  const double t = block_reduce_sum(tot);
+  if (threadIdx.x == 0 && t != 0.0) atomicAdd(&sc->model_change, t);
+}
+__global__ void ba_prior_model_change(PriorView pv, Params p, const double* scale, const double* y, Scalars* sc) {
+  const int row = blockIdx.x * blockDim.x + threadIdx.x;
+  double tot = 0.0;
+  if (row < pv.n_cam_rows + pv.n_pos_rows) {
+    double r, d;
+    int col;
+    prior_row(pv, p, row, &r, &col, &d);
+    const double m = -d * scale[col] * y[col];
+    tot = -m * (r + 0.5 * m);
+  }
+  const double t = block_reduce_sum(tot);
+  if (threadIdx.x == 0 && t != 0.0) atomicAdd(&sc->model_change, t);
+}
+
+// candidate = x - scale * y ; accumulates |delta|^2 and |x|^2 (free parameters only).
+// which: 0 cameras, 1 instances, 2 rig cameras, 3 points.
+__global__ void ba_update(int which, int count, const int* __restrict__ poff, const int* __restrict__ off,
+                          const int* __restrict__ np, int stride, int base, const double* __restrict__ src,
+                          double* __restrict__ dst, const double* __restrict__ scale, const double* __restrict__ y,
+                          Scalars* sc, int accumulate_norms) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  double sn = 0.0, xn = 0.0;
+  if (b < count) {
+    const int o = which == 0 ? off[b] : b * stride;
+    const int n = which == 0 ? np[b] : stride;
+    const int g = poff[b];
+    for (int j = 0; j < n; ++j) {
+      double val = src[o + j];
+      if (g >= 0) {
+        const int gi = which == 3 ? base + 3 * g + j : g + j;
+        const double d = -scale[gi] * y[gi];
+        xn += val * val;
+        sn += d * d;
+        val += d;
+      }
+      dst[o + j] = val;
+    }
+  }
+  if (accumulate_norms) {
+    const double t1 = block_reduce_sum(sn);
+    const double t2 = block_reduce_sum(xn);
+    if (threadIdx.x == 0) {
+      if (t1 != 0.0) atomicAdd(&sc->step_norm2, t1);
+      if (t2 != 0.0) atomicAdd(&sc->x_norm2, t2);
+    }
+  }
+}
+
+// single-observation device evaluation (test hook)
+__global__ void ba_eval_one(int type, const double* in, int use_rc, double* out, int* nres_out) {
+  // in: cam[16] ri[6] rc[6] X[3] obs[2] isig[1]
+  double r[3] = {0, 0, 0}, jc[3 * MAX_CAM_PARAMS], jri[18], jrc[18], jp[9];
+  for (int i = 0; i < 18; ++i) jrc[i] = 0.0;
+  const int nres = observation_eval(type, in, in + 16, in + 22, use_rc != 0, in + 28, in[31], in[32], in[33], r, jc,
+                                    jri, jrc, jp);
+  *nres_out = nres;
+  for (int i = 0; i < 3; ++i) out[i] = r[i];
+  for (int i = 0; i < 48; ++i) out[3 + i] = jc[i];
+  for (int i = 0; i < 18; ++i) out[51 + i] = jri[i];
+  for (int i = 0; i < 18; ++i) out[69 + i] = jrc[i];
+  for (int i = 0; i < 9; ++i) out[87 + i] = jp[i];
+}
+
+// ---------------------------------------------------------------------------
+// Host side
+// ---------------------------------------------------------------------------
+template <class T>
+static void upload(DevBuf<T>& d, const std::vector<T>& h, cudaStream_t st) {
+  d.reserve(std::max<size_t>(h.size(), 1));
+  if (!h.empty()) OSFM_CUDA(cudaMemcpyAsync(d.p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice, st));
+}
+
+struct BA {
+  int device = 0;
+  cudaStream_t own_stream = nullptr, stream = nullptr;
+  // host copies of the problem
+  std::vector<int> cam_type, cam_const, cam_prior_log;
+  std::vector<double> cam_params, cam_prior, cam_prior_sigma;
+  std::vector<double> inst, inst_prior_pos, inst_prior_std;
+  std::vector<int> inst_const, inst_has_prior;
+  std::vector<double> rc;
+  std::vector<int> rc_const;
+  std::vector<int> shot_inst, shot_cam, shot_rc, shot_use_rc;
+  std::vector<double> pts;
+  std::vector<int> pt_const;
+  std::vector<int> obs_shot, obs_point;
+  std::vector<double> obs_xy, obs_sigma;
+  // options (defaults of bundle::BundleAdjuster(), bundle_adjuster.cc:24-44)
+  int loss = OSFM_LOSS_CAUCHY;
+  double loss_a = 1.0;
+  int max_iterations = 500;
+  bool compute_reproj = true;
+  int rank = 0, world = 1;
+  osfm_allreduce_fn allreduce = nullptr;
+  void* allreduce_user = nullptr;
+  // results
+  std::vector<double> reproj;
+  osfm_ba_summary summary{};
+  bool has_run = false;
+
+  // device state
+  DevBuf<int> d_cam_type, d_cam_off, d_cam_np, d_cam_poff, d_inst_poff, d_rc_poff, d_pt_poff;
+  DevBuf<int> d_shot_inst, d_shot_cam, d_shot_rc, d_shot_use_rc, d_obs_shot, d_obs_point;
+  DevBuf<double> d_obs_x, d_obs_y, d_obs_isig;
+  DevBuf<long long> d_obs_orig, d_pt_start;
+  DevBuf<double> d_cam[2], d_inst[2], d_rc[2], d_pts[2];
+  DevBuf<double> d_r, d_Jc, d_Jp, d_S, d_rhs, d_Vinv, d_gp;
+  DevBuf<double> d_scale, d_colnorm2, d_grad, d_diag, d_y;
+  DevBuf<double> d_px, d_pr, d_pz, d_pp, d_pAp, d_Minv, d_reproj, d_full_pts;
+  DevBuf<int> d_blk_off, d_blk_sz;
+  DevBuf<int> d_pr_cam_param, d_pr_cam_col, d_pr_cam_log, d_pr_pos_inst, d_pr_pos_axis, d_pr_pos_col;
+  DevBuf<double> d_pr_cam_prior, d_pr_cam_scale, d_pr_pos_prior, d_pr_pos_scale;
+  DevBuf<Scalars> d_sc;
+  PinnedBuf<Scalars> h_sc;
+  DevBuf<double> d_eval;
+
+  explicit BA(int dev) : device(dev) {
+    OSFM_CUDA(cudaSetDevice(device));
+    OSFM_CUDA(cudaStreamCreateWithFlags(&own_stream, cudaStreamNonBlocking));
+    stream = own_stream;
+    h_sc.reserve(1);
+  }
+  ~BA() {
+    cudaSetDevice(device);
+    if (own_stream) cudaStreamDestroy(own_stream);
+  }
+
+  Scalars read_scalars() {
+    OSFM_CUDA(cudaMemcpyAsync(h_sc.p, d_sc.p, sizeof(Scalars), cudaMemcpyDeviceToHost, stream));
+    OSFM_CUDA(cudaStreamSynchronize(stream));
+    return *h_sc.p;
+  }
+  void allreduce_dev(double* buf, long long count) {
+    if (world > 1) {
+      if (!allreduce) throw ArgError("world > 1 but no all-reduce callback set");
+      if (allreduce(buf, count, stream, allreduce_user) != 0) throw std::runtime_error("all-reduce callback failed");
+    }
+  }
+  void run();
+};
+
+static int grid_for(long long n, int threads) { return (int)std::max<long long>(1, (n + threads - 1) / threads); }
+
+void BA::run() {
+  OSFM_CUDA(cudaSetDevice(device));
+  const auto t_start = std::chrono::high_resolution_clock::now();
+  const int K = (int)cam_type.size(), NI = (int)inst_const.size(), NR = (int)rc_const.size();
+  const int S = (int)shot_inst.size(), Pfull = (int)pt_const.size();
+  const long long Nfull = (long long)obs_shot.size();
+  if (K == 0 && Nfull > 0) throw ArgError("observations but no cameras");
+  int64_t launches0 = g_kernel_launches.load();
+
+  // ---- validation (errors mirror the reference's: missing ids -> runtime_error) ----
+  for (int s = 0; s < S; ++s) {
+    if (shot_inst[s] < 0 || shot_inst[s] >= NI) throw ArgError("shot references a rig instance that doesn't exist");
+    if (shot_cam[s] < 0 || shot_cam[s] >= K) throw ArgError("shot references a camera that doesn't exist");
+    if (shot_use_rc[s] && (shot_rc[s] < 0 || shot_rc[s] >= NR))
+      throw ArgError("shot references a rig camera that doesn't exist");
+  }
+  for (long long i = 0; i < Nfull; ++i) {
+    if (obs_shot[i] < 0 || obs_shot[i] >= S) throw ArgError("observation references a shot that doesn't exist");
+    if (obs_point[i] < 0 || obs_point[i] >= Pfull) throw ArgError("observation references a point that doesn't exist");
+  }
+
+  // ---- layout of the reduced vector: [free cameras | free instances | free rig cameras] ----
+  std::vector<int> cam_off(K + 1, 0), cam_np(K), cam_poff(K), inst_poff(NI), rc_poff(std::max(NR, 1), -1);
+  std::vector<int> blk_off, blk_sz;
+  int off = 0;
+  for (int k = 0; k < K; ++k) {
+    cam_np[k] = model_num_params(cam_type[k]);
+    cam_off[k + 1] = cam_off[k] + cam_np[k];
+  }
+  for (int k = 0; k < K; ++k) {
+    cam_poff[k] = cam_const[k] ? -1 : off;
+    if (!cam_const[k]) { blk_off.push_back(off); blk_sz.push_back(cam_np[k]); off += cam_np[k]; }
+  }
+  for (int i = 0; i < NI; ++i) {
+    inst_poff[i] = inst_const[i] ? -1 : off;
+    if (!inst_const[i]) { blk_off.push_back(off); blk_sz.push_back(6); off += 6; }
+  }
+  for (int i = 0; i < NR; ++i) {
+    rc_poff[i] = rc_const[i] ? -1 : off;
+    if (!rc_const[i]) { blk_off.push_back(off); blk_sz.push_back(6); off += 6; }
+  }
+  const int nc = off;
+  const int nblk = (int)blk_off.size();
+
+  // ---- shard points over ranks (p % world == rank), sort observations by point ----
+  std::vector<int> local_of(Pfull, -1), global_of;
+  for (int p = 0; p < Pfull; ++p)
+    if (p % world == rank) { local_of[p] = (int)global_of.size(); global_of.push_back(p); }
+  const int P = (int)global_of.size();
+  std::vector<long long> pt_start(P + 1, 0);
+  for (long long i = 0; i < Nfull; ++i) {
+    const int lp = local_of[obs_point[i]];
+    if (lp >= 0) pt_start[lp + 1]++;
+  }
+  for (int p = 0; p < P; ++p) pt_start[p + 1] += pt_start[p];
+  const long long N = pt_start[P];
+  std::vector<long long> fill(pt_start.begin(), pt_start.end() - 1), obs_orig(N);
+  std::vector<int> s_shot(N), s_point(N);
+  std::vector<double> s_x(N), s_y(N), s_isig(N);
+  for (long long i = 0; i < Nfull; ++i) {
+    const int lp = local_of[obs_point[i]];
+    if (lp < 0) continue;
+    const long long d = fill[lp]++;
+    obs_orig[d] = i; s_shot[d] = obs_shot[i]; s_point[d] = lp;
+    s_x[d] = obs_xy[2 * i]; s_y[d] = obs_xy[2 * i + 1];
+    s_isig[d] = 1.0 / obs_sigma[i];  // projection_errors.h:21
+  }
+  std::vector<int> pt_poff(std::max(P, 1), -1);
+  std::vector<double> lpts(3 * (size_t)std::max(P, 1), 0.0);
+  int npf = 0;
+  for (int p = 0; p < P; ++p) {
+    pt_poff[p] = pt_const[global_of[p]] ? -1 : npf++;
+    for (int j = 0; j < 3; ++j) lpts[3 * (size_t)p + j] = pts[3 * (size_t)global_of[p] + j];
+  }
+  const int n = nc + 3 * npf;
+  int wc = 0, nres = 2;
+  for (int s = 0; s < S; ++s) {
+    wc = std::max(wc, cam_np[shot_cam[s]] + 6 + (shot_use_rc[s] ? 6 : 0));
+    if (cam_type[shot_cam[s]] == PT_SPHERICAL) nres = 3;
+  }
+  wc = std::max(wc, 1);
+
+  // ---- prior rows (rank 0 adds them; Ceres drops residuals of constant blocks) ----
+  std::vector<int> pr_cam_param, pr_cam_col, pr_cam_log, pr_pos_inst, pr_pos_axis, pr_pos_col;
+  std::vector<double> pr_cam_prior, pr_cam_scale, pr_pos_prior, pr_pos_scale;
+  for (int k = 0; k < K; ++k) {
+    if (cam_poff[k] < 0) continue;
+    for (int j = 0; j < cam_np[k]; ++j) {
+      const int idx = cam_off[k] + j;
+      pr_cam_param.push_back(idx);
+      pr_cam_col.push_back(cam_poff[k] + j);
+      pr_cam_log.push_back(cam_prior_log[idx]);
+      pr_cam_prior.push_back(cam_prior[idx]);
+      pr_cam_scale.push_back(1.0 / std::max(cam_prior_sigma[idx], DBL_EPSILON));  // prior_error.h:31-35
+    }
+  }
+  for (int i = 0; i < NI; ++i) {
+    if (!inst_has_prior[i] || inst_poff[i] < 0) continue;
+    for (int j = 0; j < 3; ++j) {
+      pr_pos_inst.push_back(i); pr_pos_axis.push_back(j); pr_pos_col.push_back(inst_poff[i] + 3 + j);
+      pr_pos_prior.push_back(inst_prior_pos[3 * (size_t)i + j]);
+      pr_pos_scale.push_back(1.0 / std::max(inst_prior_std[3 * (size_t)i + j], DBL_EPSILON));
+    }
+  }
+  const int npr = (int)(pr_cam_param.size() + pr_pos_inst.size());
+  const bool add_priors = rank == 0;
+
+  // ---- upload ----
+  upload(d_cam_type, cam_type, stream); upload(d_cam_off, cam_off, stream); upload(d_cam_np, cam_np, stream);
+  upload(d_cam_poff, cam_poff, stream); upload(d_inst_poff, inst_poff, stream); upload(d_rc_poff, rc_poff, stream);
+  upload(d_pt_poff, pt_poff, stream);
+  upload(d_shot_inst, shot_inst, stream); upload(d_shot_cam, shot_cam, stream); upload(d_shot_rc, shot_rc, stream);
+  upload(d_shot_use_rc, shot_use_rc, stream);
+  upload(d_obs_shot, s_shot, stream); upload(d_obs_point, s_point, stream);
+  upload(d_obs_x, s_x, stream); upload(d_obs_y, s_y, stream); upload(d_obs_isig, s_isig, stream);
+  upload(d_obs_orig, obs_orig, stream); upload(d_pt_start, pt_start, stream);
+  std::vector<double> rc_h = rc;
+  if (rc_h.empty()) rc_h.assign(6, 0.0);
+  for (int b = 0; b < 2; ++b) {
+    upload(d_cam[b], cam_params, stream); upload(d_inst[b], inst, stream); upload(d_rc[b], rc_h, stream);
+    upload(d_pts[b], lpts, stream);
+  }
+  upload(d_blk_off, blk_off, stream); upload(d_blk_sz, blk_sz, stream);
+  upload(d_pr_cam_param, pr_cam_param, stream); upload(d_pr_cam_col, pr_cam_col, stream);
+  upload(d_pr_cam_log, pr_cam_log, stream); upload(d_pr_cam_prior, pr_cam_prior, stream);
+  upload(d_pr_cam_scale, pr_cam_scale, stream); upload(d_pr_pos_inst, pr_pos_inst, stream);
+  upload(d_pr_pos_axis, pr_pos_axis, stream); upload(d_pr_pos_col, pr_pos_col, stream);
+  upload(d_pr_pos_prior, pr_pos_prior, stream); upload(d_pr_pos_scale, pr_pos_scale, stream);
+  const size_t Nz = (size_t)std::max<long long>(N, 1);
+  d_r.reserve(nres * Nz); d_Jc.reserve((size_t)nres * wc * Nz); d_Jp.reserve((size_t)nres * 3 * Nz);
+  d_S.reserve((size_t)std::max(nc, 1) * std::max(nc, 1)); d_rhs.reserve(std::max(nc, 1));
+  d_Vinv.reserve(6 * (size_t)std::max(npf, 1)); d_gp.reserve(3 * (size_t)std::max(npf, 1));
+  const size_t nz = (size_t)std::max(n, 1);
+  d_scale.reserve(nz); d_colnorm2.reserve(nz); d_grad.reserve(nz); d_diag.reserve(nz); d_y.reserve(nz);
+  d_px.reserve(std::max(nc, 1)); d_pr.reserve(std::max(nc, 1)); d_pz.reserve(std::max(nc, 1));
+  d_pp.reserve(std::max(nc, 1)); d_pAp.reserve(std::max(nc, 1));
+  d_Minv.reserve((size_t)std::max(nblk, 1) * MAXB * MAXB);
+  d_sc.reserve(1);
+
+  BAView v{};
+  v.K = K; v.NI = NI; v.NR = NR; v.S = S; v.P = P; v.N = N; v.nc = nc; v.npf = npf; v.wc = wc; v.nres = nres;
+  v.loss = loss; v.loss_a = loss_a;
+  v.cam_type = d_cam_type.p; v.cam_off = d_cam_off.p; v.cam_np = d_cam_np.p; v.cam_poff = d_cam_poff.p;
+  v.inst_poff = d_inst_poff.p; v.rc_poff = d_rc_poff.p; v.pt_poff = d_pt_poff.p;
+  v.shot_inst = d_shot_inst.p; v.shot_cam = d_shot_cam.p; v.shot_rc = d_shot_rc.p; v.shot_use_rc = d_shot_use_rc.p;
+  v.obs_shot = d_obs_shot.p; v.obs_point = d_obs_point.p; v.obs_x = d_obs_x.p; v.obs_y = d_obs_y.p;
+  v.obs_isig = d_obs_isig.p; v.obs_orig = d_obs_orig.p; v.pt_start = d_pt_start.p;
+  v.r = d_r.p; v.Jc = d_Jc.p; v.Jp = d_Jp.p;
+  PriorView pv{};
+  pv.n_cam_rows = add_priors ? (int)pr_cam_param.size() : 0;
+  pv.n_pos_rows = add_priors ? (int)pr_pos_inst.size() : 0;
+  pv.cam_row_param = d_pr_cam_param.p; pv.cam_row_col = d_pr_cam_col.p; pv.cam_row_log = d_pr_cam_log.p;
+  pv.cam_row_prior = d_pr_cam_prior.p; pv.cam_row_scale = d_pr_cam_scale.p;
+  pv.pos_row_inst = d_pr_pos_inst.p; pv.pos_row_axis = d_pr_pos_axis.p; pv.pos_row_col = d_pr_pos_col.p;
+  pv.pos_row_prior = d_pr_pos_prior.p; pv.pos_row_scale = d_pr_pos_scale.p;
+  const int npr_local = pv.n_cam_rows + pv.n_pos_rows;
+  (void)npr;
+
+  int cur = 0;  // index of the accepted parameter set
+  auto params_of = [&](int b) { return Params{d_cam[b].p, d_inst[b].p, d_rc[b].p, d_pts[b].p}; };
+
+  cudaEvent_t ev0, ev1, evl0, evl1;
+  OSFM_CUDA(cudaEventCreate(&ev0)); OSFM_CUDA(cudaEventCreate(&ev1));
+  OSFM_CUDA(cudaEventCreate(&evl0)); OSFM_CUDA(cudaEventCreate(&evl1));
+  double lin_ms = 0.0;
+  long long lin_launches = 0;
+
+  // cost at parameter set b (sum over ranks)
+  auto eval_cost = [&](int b) -> double {
+    OSFM_CUDA(cudaMemsetAsync(&d_sc.p->cost, 0, sizeof(double), stream));
+    if (N > 0) {
+      ba_linearize<0><<<grid_for(N, 128), 128, 0, stream>>>(v, params_of(b), d_sc.p, nullptr);
+      OSFM_LAUNCH_CHECK();
+    }
+    if (npr_local > 0) {
+      ba_prior_cost<<<grid_for(npr_local, 128), 128, 0, stream>>>(pv, params_of(b), d_sc.p);
+      OSFM_LAUNCH_CHECK();
+    }
+    allreduce_dev(&d_sc.p->cost, 1);
+    return read_scalars().cost;
+  };
+  // residual + Jacobian planes, column norms, gradient at parameter set b
+  auto linearize = [&](int b, double* grad_max) -> double {
+    OSFM_CUDA(cudaMemsetAsync(d_sc.p, 0, sizeof(Scalars), stream));
+    OSFM_CUDA(cudaMemsetAsync(d_colnorm2.p, 0, sizeof(double) * nz, stream));
+    OSFM_CUDA(cudaMemsetAsync(d_grad.p, 0, sizeof(double) * nz, stream));
+    if (N > 0) {
+      OSFM_CUDA(cudaEventRecord(evl0, stream));
+      ba_linearize<1><<<grid_for(N, 128), 128, 0, stream>>>(v, params_of(b), d_sc.p, nullptr);
+      OSFM_LAUNCH_CHECK();
+      OSFM_CUDA(cudaEventRecord(evl1, stream));
+      ba_colnorm_grad<<<grid_for(N, 256), 256, 0, stream>>>(v, d_colnorm2.p, d_grad.p);
+      OSFM_LAUNCH_CHECK();
+    }
+    if (npr_local > 0) {
+      ba_prior_cost<<<grid_for(npr_local, 128), 128, 0, stream>>>(pv, params_of(b), d_sc.p);
+      OSFM_LAUNCH_CHECK();
+      ba_prior_colnorm_grad<<<grid_for(npr_local, 128), 128, 0, stream>>>(pv, params_of(b), d_colnorm2.p, d_grad.p);
+      OSFM_LAUNCH_CHECK();
+    }
+    if (world > 1) {
+      allreduce_dev(&d_sc.p->cost, 1);
+      if (nc > 0) { allreduce_dev(d_colnorm2.p, nc); allreduce_dev(d_grad.p, nc); }
+    }
+    if (n > 0) {
+      ba_grad_max<<<grid_for(n, 256), 256, 0, stream>>>(d_grad.p, n, d_sc.p);
+      OSFM_LAUNCH_CHECK();
+    }
+    const Scalars s = read_scalars();
+    if (N > 0) {
+      float ms = 0.f;
+      OSFM_CUDA(cudaEventElapsedTime(&ms, evl0, evl1));
+      lin_ms += ms;
+      lin_launches++;
+    }
+    double gm = s.grad_max_bits;
+    if (world > 1) {
+      // max over ranks of the local point-gradient maxima: sum of one-hot slots
+      std::vector<double> slots(world, 0.0);
+      slots[rank] = gm;
+      DevBuf<double> tmp;
+      tmp.reserve(world);
+      OSFM_CUDA(cudaMemcpyAsync(tmp.p, slots.data(), sizeof(double) * world, cudaMemcpyHostToDevice, stream));
+      allreduce_dev(tmp.p, world);
+      OSFM_CUDA(cudaMemcpyAsync(slots.data(), tmp.p, sizeof(double) * world, cudaMemcpyDeviceToHost, stream));
+      OSFM_CUDA(cudaStreamSynchronize(stream));
+      for (double x : slots) gm = std::max(gm, x);
+    }
+    *grad_max = gm;
+    return s.cost;
+  };
+
+  // ---- Levenberg-Marquardt (Ceres trust_region_minimizer / levenberg_marquardt_strategy) ----
+  OSFM_CUDA(cudaEventRecord(ev0, stream));
+  double radius = 1e4;
+  const double max_radius = 1e16, min_radius = 1e-32, min_rel_decrease = 1e-3;
+  const double ftol = 1e-6, gtol = 1e-10, ptol = 1e-8;
+  double decrease_factor = 2.0;
+  bool reuse_diagonal = false;
+  int n_invalid = 0, it = 0, n_success = 0, n_solves = 0, pcg_total = 0;
+  int termination = 1;
+  std::string message = "Maximum number of iterations reached.";
+
+  double grad_max = 0.0;
+  double cost = linearize(cur, &grad_max);
+  const double initial_cost = cost;
+  if (n > 0) {
+    ba_make_scale<<<grid_for(n, 256), 256, 0, stream>>>(d_colnorm2.p, d_scale.p, n);
+    OSFM_LAUNCH_CHECK();
+  }
+  // |x| of the free parameters
+  auto x_norm_of = [&](int b) -> double {
+    OSFM_CUDA(cudaMemsetAsync(&d_sc.p->x_norm2, 0, sizeof(double), stream));
+    OSFM_CUDA(cudaMemsetAsync(d_y.p, 0, sizeof(double) * nz, stream));
+    Params pp = params_of(b);
+    if (K) { ba_update<<<grid_for(K, 128), 128, 0, stream>>>(0, K, d_cam_poff.p, d_cam_off.p, d_cam_np.p, 0, 0, pp.cam, pp.cam, d_scale.p, d_y.p, d_sc.p, rank == 0); OSFM_LAUNCH_CHECK(); }
+    if (NI) { ba_update<<<grid_for(NI, 128), 128, 0, stream>>>(1, NI, d_inst_poff.p, nullptr, nullptr, 6, 0, pp.inst, pp.inst, d_scale.p, d_y.p, d_sc.p, rank == 0); OSFM_LAUNCH_CHECK(); }
+    if (NR) { ba_update<<<grid_for(NR, 128), 128, 0, stream>>>(2, NR, d_rc_poff.p, nullptr, nullptr, 6, 0, pp.rc, pp.rc, d_scale.p, d_y.p, d_sc.p, rank == 0); OSFM_LAUNCH_CHECK(); }
+    if (P) { ba_update<<<grid_for(P, 128), 128, 0, stream>>>(3, P, d_pt_poff.p, nullptr, nullptr, 3, nc, pp.pts, pp.pts, d_scale.p, d_y.p, d_sc.p, 1); OSFM_LAUNCH_CHECK(); }
+    allreduce_dev(&d_sc.p->x_norm2, 1);
+    return std::sqrt(read_scalars().x_norm2);
+  };
+  double x_norm = n > 0 ? x_norm_of(cur) : 0.0;
+
+  if (grad_max <= gtol || n == 0) {
+    termination = 0;
+    message = n == 0 ? "No free parameters." : "Gradient tolerance reached.";
+  }
+  while (termination == 1) {
+    if (it >= max_iterations) break;
+    if (radius < min_radius) { termination = 0; message = "Minimum trust region radius reached."; break; }
+    ++it;
+    if (!reuse_diagonal) {
+      ba_make_diag<<<grid_for(n, 256), 256, 0, stream>>>(d_colnorm2.p, d_scale.p, d_diag.p, n);
+      OSFM_LAUNCH_CHECK();
+    }
+    const double inv_radius = 1.0 / radius;
+    // --- reduced camera system ---
+    if (nc > 0) {
+      OSFM_CUDA(cudaMemsetAsync(d_S.p, 0, sizeof(double) * (size_t)nc * nc, stream));
+      OSFM_CUDA(cudaMemsetAsync(d_rhs.p, 0, sizeof(double) * nc, stream));
+    }
+    if (P > 0) {
+      const size_t smem = (size_t)SCHUR_KC * wc * (2 * 3 * sizeof(double) + 2 * sizeof(int));
+      ba_schur<<<P, SCHUR_THREADS, smem, stream>>>(v, d_scale.p, d_diag.p, inv_radius, d_S.p, d_rhs.p, d_Vinv.p, d_gp.p);
+      OSFM_LAUNCH_CHECK();
+    }
+    bool ok = true;
+    int pcg_it = 0;
+    OSFM_CUDA(cudaMemsetAsync(d_y.p, 0, sizeof(double) * nz, stream));
+    if (nc > 0) {
+      if (world > 1) { allreduce_dev(d_S.p, (long long)nc * nc); allreduce_dev(d_rhs.p, nc); }
+      {
+        // S_g stays a pure partial sum through the all-reduce; every rank then adds the (replicated)
+        // prior rows and the damping to its copy of the reduced system.
+        PriorView pall = pv;
+        pall.n_cam_rows = (int)pr_cam_param.size();
+        pall.n_pos_rows = (int)pr_pos_inst.size();
+        const int nall = pall.n_cam_rows + pall.n_pos_rows;
+        if (nall > 0) {
+          ba_prior_system<<<grid_for(nall, 128), 128, 0, stream>>>(pall, params_of(cur), d_scale.p, d_S.p, d_rhs.p, nc);
+          OSFM_LAUNCH_CHECK();
+        }
+      }
+      dim3 fg((nc + 255) / 256, nc);
+      ba_finish_system<<<fg, 256, 0, stream>>>(d_S.p, d_diag.p, inv_radius, nc);
+      OSFM_LAUNCH_CHECK();
+      // --- PCG ---
+      pcg_factor_blocks<<<grid_for(nblk, 64), 64, 0, stream>>>(d_S.p, nc, d_blk_off.p, d_blk_sz.p, nblk, d_Minv.p);
+      OSFM_LAUNCH_CHECK();
+      OSFM_CUDA(cudaMemsetAsync(&d_sc.p->pcg_rz[0], 0, sizeof(double) * 5, stream));
+      pcg_init<<<grid_for(nblk, 128), 128, 0, stream>>>(d_rhs.p, d_px.p, d_pr.p, d_pz.p, d_pp.p, nc, d_Minv.p,
+                                                        d_blk_off.p, d_blk_sz.p, nblk, d_sc.p);
+      OSFM_LAUNCH_CHECK();
+      Scalars s0 = read_scalars();
+      const double bb = s0.pcg_bb;
+      const double tol2 = 1e-20 * bb;  // |r| <= 1e-10 |b|
+      const int max_pcg = std::min(2 * nc + 100, 5000);
+      const int check_every = 8;
+      if (!(bb > 0.0)) { /* rhs == 0: y_c = 0 */ }
+      else {
+        bool done = false;
+        while (!done && pcg_it < max_pcg) {
+          for (int q = 0; q < check_every; ++q, ++pcg_it) {
+            pcg_matvec<<<grid_for((long long)nc * 32, 256), 256, 0, stream>>>(d_S.p, d_pp.p, d_pAp.p, nc, d_sc.p, pcg_it);
+            OSFM_LAUNCH_CHECK();
+            pcg_update1<<<grid_for(nblk, 128), 128, 0, stream>>>(d_px.p, d_pr.p, d_pz.p, d_pp.p, d_pAp.p, d_Minv.p,
+                                                                d_blk_off.p, d_blk_sz.p, nblk, d_sc.p, pcg_it);
+            OSFM_LAUNCH_CHECK();
+            pcg_update2<<<grid_for(nc, 256), 256, 0, stream>>>(d_pp.p, d_pz.p, nc, d_sc.p, pcg_it);
+            OSFM_LAUNCH_CHECK();
+          }
+          const Scalars s = read_scalars();
+          if (!(s.pcg_rr == s.pcg_rr)) { ok = false; break; }
+          if (s.pcg_rr <= tol2) done = true;
+        }
+      }
+      pcg_total += pcg_it;
+      OSFM_CUDA(cudaMemcpyAsync(d_y.p, d_px.p, sizeof(double) * nc, cudaMemcpyDeviceToDevice, stream));
+    }
+    ++n_solves;
+    // --- back-substitution, model cost change ---
+    if (P > 0 && npf > 0) {
+      ba_backsub<<<grid_for((long long)P * 32, 256), 256, 0, stream>>>(v, d_scale.p, d_Vinv.p, d_y.p);
+      OSFM_LAUNCH_CHECK();
+    }
+    OSFM_CUDA(cudaMemsetAsync(&d_sc.p->model_change, 0, sizeof(double) * 3, stream));  // model_change, step_norm2, x_norm2
+    if (N > 0) {
+      ba_model_change<<<grid_for(N, 256), 256, 0, stream>>>(v, d_scale.p, d_y.p, d_sc.p);
+      OSFM_LAUNCH_CHECK();
+    }
+    if (npr_local > 0) {
+      ba_prior_model_change<<<grid_for(npr_local, 128), 128, 0, stream>>>(pv, params_of(cur), d_scale.p, d_y.p, d_sc.p);
+      OSFM_LAUNCH_CHECK();
+    }
+    // --- candidate point ---
+    const int cand = cur ^ 1;
+    {
+      Params a = params_of(cur), b = params_of(cand);
+      if (K) { ba_update<<<grid_for(K, 128), 128, 0, stream>>>(0, K, d_cam_poff.p, d_cam_off.p, d_cam_np.p, 0, 0, a.cam, b.cam, d_scale.p, d_y.p, d_sc.p, rank == 0); OSFM_LAUNCH_CHECK(); }
+      if (NI) { ba_update<<<grid_for(NI, 128), 128, 0, stream>>>(1, NI, d_inst_poff.p, nullptr, nullptr, 6, 0, a.inst, b.inst, d_scale.p, d_y.p, d_sc.p, rank == 0); OSFM_LAUNCH_CHECK(); }
+      if (NR) { ba_update<<<grid_for(NR, 128), 128, 0, stream>>>(2, NR, d_rc_poff.p, nullptr, nullptr, 6, 0, a.rc, b.rc, d_scale.p, d_y.p, d_sc.p, rank == 0); OSFM_LAUNCH_CHECK(); }
+      if (P) { ba_update<<<grid_for(P, 128), 128, 0, stream>>>(3, P, d_pt_poff.p, nullptr, nullptr, 3, nc, a.pts, b.pts, d_scale.p, d_y.p, d_sc.p, 1); OSFM_LAUNCH_CHECK(); }
+    }
+    if (world > 1) allreduce_dev(&d_sc.p->model_change, 3);
+    const Scalars sm = read_scalars();
+    const double model_change = sm.model_change;
+    const double step_norm = std::sqrt(sm.step_norm2);
+    if (!ok || !(model_change > 0.0) || !std::isfinite(step_norm)) {
+      if (++n_invalid >= 5) { termination = 2; message = "Too many consecutive invalid steps."; break; }
+      radius *= 0.5;
+      reuse_diagonal = true;
+      continue;
+    }
+    n_invalid = 0;
+    const double cand_cost = eval_cost(cand);
+    if (step_norm <= ptol * (x_norm + ptol)) { termination = 0; message = "Parameter tolerance reached."; break; }
+    const double cost_change = cost - cand_cost;
+    if (std::fabs(cost_change) <= ftol * cost) { termination = 0; message = "Function tolerance reached."; break; }
+    const double rel = cost_change / model_change;
+    if (rel > min_rel_decrease) {
+      cur = cand;
+      cost = linearize(cur, &grad_max);
+      x_norm = x_norm_of(cur);
+      radius = std::min(max_radius, radius / std::max(1.0 / 3.0, 1.0 - std::pow(2.0 * rel - 1.0, 3)));
+      decrease_factor = 2.0;
+      reuse_diagonal = false;
+      ++n_success;
+      if (grad_max <= gtol) { termination = 0; message = "Gradient tolerance reached."; break; }
+    } else {
+      radius /= decrease_factor;
+      decrease_factor *= 2.0;
+      reuse_diagonal = true;
+    }
+  }
+  OSFM_CUDA(cudaEventRecord(ev1, stream));
+  const double final_cost = eval_cost(cur);
+
+  // ---- results back to the host ----
+  OSFM_CUDA(cudaMemcpyAsync(cam_params.data(), d_cam[cur].p, sizeof(double) * cam_params.size(), cudaMemcpyDeviceToHost, stream));
+  OSFM_CUDA(cudaMemcpyAsync(inst.data(), d_inst[cur].p, sizeof(double) * inst.size(), cudaMemcpyDeviceToHost, stream));
+  if (!rc.empty())
+    OSFM_CUDA(cudaMemcpyAsync(rc.data(), d_rc[cur].p, sizeof(double) * rc.size(), cudaMemcpyDeviceToHost, stream));
+  std::vector<double> lp(3 * (size_t)std::max(P, 1));
+  OSFM_CUDA(cudaMemcpyAsync(lp.data(), d_pts[cur].p, sizeof(double) * 3 * (size_t)P, cudaMemcpyDeviceToHost, stream));
+  reproj.assign(3 * (size_t)Nfull, 0.0);
+  if (compute_reproj && Nfull > 0) {
+    d_reproj.reserve(3 * (size_t)Nfull);
+    OSFM_CUDA(cudaMemsetAsync(d_reproj.p, 0, sizeof(double) * 3 * (size_t)Nfull, stream));
+    if (N > 0) {
+      ba_linearize<2><<<grid_for(N, 128), 128, 0, stream>>>(v, params_of(cur), d_sc.p, d_reproj.p);
+      OSFM_LAUNCH_CHECK();
+    }
+    allreduce_dev(d_reproj.p, 3 * Nfull);
+    OSFM_CUDA(cudaMemcpyAsync(reproj.data(), d_reproj.p, sizeof(double) * 3 * (size_t)Nfull, cudaMemcpyDeviceToHost, stream));
+  }
+  OSFM_CUDA(cudaStreamSynchronize(stream));
+  if (world > 1) {
+    std::vector<double> full(3 * (size_t)Pfull, 0.0);
+    for (int p = 0; p < P; ++p)
+      for (int j = 0; j < 3; ++j) full[3 * (size_t)global_of[p] + j] = lp[3 * (size_t)p + j];
+    d_full_pts.reserve(full.size());
+    OSFM_CUDA(cudaMemcpyAsync(d_full_pts.p, full.data(), sizeof(double) * full.size(), cudaMemcpyHostToDevice, stream));
+    allreduce_dev(d_full_pts.p, (long long)full.size());
+    OSFM_CUDA(cudaMemcpyAsync(pts.data(), d_full_pts.p, sizeof(double) * full.size(), cudaMemcpyDeviceToHost, stream));
+    OSFM_CUDA(cudaStreamSynchronize(stream));
+  } else {
+    for (int p = 0; p < P; ++p)
+      for (int j = 0; j < 3; ++j) pts[3 * (size_t)global_of[p] + j] = lp[3 * (size_t)p + j];
+  }
+  float dev_ms = 0.f;
+  OSFM_CUDA(cudaEventElapsedTime(&dev_ms, ev0, ev1));
+  cudaEventDestroy(ev0); cudaEventDestroy(ev1); cudaEventDestroy(evl0); cudaEventDestroy(evl1);
+
+  summary = osfm_ba_summary{};
+  summary.iterations = it;
+  summary.successful_steps = n_success;
+  summary.linear_solves = n_solves;
+  summary.pcg_iterations = pcg_total;
+  summary.termination = termination;
+  summary.initial_cost = initial_cost;
+  summary.final_cost = final_cost;
+  summary.time_device_ms = dev_ms;
+  summary.time_linearize_ms = lin_ms;
+  summary.linearize_launches = lin_launches;
+  summary.kernel_launches = g_kernel_launches.load() - launches0;
+  snprintf(summary.message, sizeof(summary.message), "%s", message.c_str());
+  summary.time_run_s =
+      std::chrono::duration<double>(std::chrono::high_resolution_clock::now() - t_start).count();
+  has_run = true;
+}
+
+}  // namespace osfm
+
+// ---------------------------------------------------------------------------
+// C ABI
+// ---------------------------------------------------------------------------
+struct osfm_ba {
+  osfm::BA impl;
+  explicit osfm_ba(int dev) : impl(dev) {}
+};
+using osfm::ArgError;
+
+extern "C" {
+
+int osfm_camera_num_params(int projection_type) {
+  if (projection_type < 0 || projection_type > 9) return -1;
+  return osfm::model_num_params(projection_type);
+}
+
+int osfm_ba_create(int device, osfm_ba** out) {
+  OSFM_API_BEGIN
+  if (!out) throw ArgError("null out");
+  int count = 0;
+  OSFM_CUDA(cudaGetDeviceCount(&count));
+  if (device < 0 || device >= count) throw ArgError("no such CUDA device");
+  *out = new osfm_ba(device);
+  OSFM_API_END
+}
+int osfm_ba_destroy(osfm_ba* ba) {
+  OSFM_API_BEGIN
+  delete ba;
+  OSFM_API_END
+}
+#define OSFM_BA_CHECK if (!ba) throw ArgError("null ba handle");
+
+int osfm_ba_set_cameras(osfm_ba* ba, int n, const int32_t* type, const double* params, const int32_t* constant,
+                        const double* prior, const double* prior_sigma, const int32_t* prior_log) {
+  OSFM_API_BEGIN
+  OSFM_BA_CHECK
+  auto& b = ba->impl;
+  if (n < 0 || (n > 0 && (!type || !params || !constant || !prior || !prior_sigma || !prior_log)))
+    throw ArgError("bad camera arrays");
+  int total = 0;
+  for (int k = 0; k < n; ++k) {
+    if (type[k] < 0 || type[k] > 9) throw ArgError("Invalid ProjectionType");  // camera_instances.h:232
+    total += osfm::model_num_params(type[k]);
+  }
+  b.cam_type.assign(type, type + n);
+  b.cam_const.assign(constant, constant + n);
+  b.cam_params.assign(params, params + total);
+  b.cam_prior.assign(prior, prior + total);
+  b.cam_prior_sigma.assign(prior_sigma, prior_sigma + total);
+  b.cam_prior_log.assign(prior_log, prior_log + total);
+  OSFM_API_END
+}
+int osfm_ba_set_rig_instances(osfm_ba* ba, int n, const double* pose6, const int32_t* constant,
+                              const int32_t* has_position_prior, const double* prior_position3,
+                              const double* prior_std3) {
+  OSFM_API_BEGIN
+  OSFM_BA_CHECK
+  auto& b = ba->impl;
+  if (n < 0 || (n > 0 && (!pose6 || !constant))) throw ArgError("bad rig instance arrays");
+  b.inst.assign(pose6, pose6 + 6 * (size_t)n);
+  b.inst_const.assign(constant, constant + n);
+  b.inst_has_prior.assign(n, 0);
+  b.inst_prior_pos.assign(3 * (size_t)n, 0.0);
+  b.inst_prior_std.assign(3 * (size_t)n, 1.0);
+  if (has_position_prior) {
+    if (!prior_position3 || !prior_std3) throw ArgError("position prior arrays missing");
+    b.inst_has_prior.assign(has_position_prior, has_position_prior + n);
+    b.inst_prior_pos.assign(prior_position3, prior_position3 + 3 * (size_t)n);
+    b.inst_prior_std.assign(prior_std3, prior_std3 + 3 * (size_t)n);
+  }
+  OSFM_API_END
+}
+int osfm_ba_set_rig_cameras(osfm_ba* ba, int n, const double* pose6, const int32_t* constant) {
+  OSFM_API_BEGIN
+  OSFM_BA_CHECK
+  if (n < 0 || (n > 0 && (!pose6 || !constant))) throw ArgError("bad rig camera arrays");
+  ba->impl.rc.assign(pose6, pose6 + 6 * (size_t)n);
+  ba->impl.rc_const.assign(constant, constant + n);
+  OSFM_API_END
+}
+int osfm_ba_set_shots(osfm_ba* ba, int n, const int32_t* rig_instance, const int32_t* camera,
+                      const int32_t* rig_camera, const int32_t* use_rig_camera) {
+  OSFM_API_BEGIN
+  OSFM_BA_CHECK
+  if (n < 0 || (n > 0 && (!rig_instance || !camera || !rig_camera || !use_rig_camera))) throw ArgError("bad shot arrays");
+  ba->impl.shot_inst.assign(rig_instance, rig_instance + n);
+  ba->impl.shot_cam.assign(camera, camera + n);
+  ba->impl.shot_rc.assign(rig_camera, rig_camera + n);
+  ba->impl.shot_use_rc.assign(use_rig_camera, use_rig_camera + n);
+  OSFM_API_END
+}
+int osfm_ba_set_points(osfm_ba* ba, int n, const double* xyz, const int32_t* constant) {
+  OSFM_API_BEGIN
+  OSFM_BA_CHECK
+  if (n < 0 || (n > 0 && (!xyz || !constant))) throw ArgError("bad point arrays");
+  ba->impl.pts.assign(xyz, xyz + 3 * (size_t)n);
+  ba->impl.pt_const.assign(constant, constant + n);
+  OSFM_API_END
+}
+int osfm_ba_set_observations(osfm_ba* ba, int64_t n, const int32_t* shot, const int32_t* point, const double* xy,
+                             const double* std_deviation) {
+  OSFM_API_BEGIN
+  OSFM_BA_CHECK
+  if (n < 0 || (n > 0 && (!shot || !point || !xy || !std_deviation))) throw ArgError("bad observation arrays");
+  ba->impl.obs_shot.assign(shot, shot + n);
+  ba->impl.obs_point.assign(point, point + n);
+  ba->impl.obs_xy.assign(xy, xy + 2 * n);
+  ba->impl.obs_sigma.assign(std_deviation, std_deviation + n);
+  OSFM_API_END
+}
+int osfm_ba_set_options(osfm_ba* ba, int loss, double loss_threshold, int max_iterations, const char* linear_solver,
+                        int compute_reprojection_errors) {
+  OSFM_API_BEGIN
+  OSFM_BA_CHECK
+  if (loss < 0 || loss > 4) throw ArgError("ceres::LossFunction with that name not found.");  // bundle_adjuster.cc:427
+  if (linear_solver) {
+    const std::string s(linear_solver);
+    // ceres::StringToLinearSolverType names (bundle_adjuster.cc:1105-1109)
+    static const char* known[] = {"DENSE_NORMAL_CHOLESKY", "DENSE_QR", "SPARSE_NORMAL_CHOLESKY", "DENSE_SCHUR",
+                                  "SPARSE_SCHUR", "ITERATIVE_SCHUR", "CGNR"};
+    bool found = false;
+    for (const char* k : known) found |= (s == k);
+    if (!found) throw std::runtime_error("Linear solver type " + s + " doesn't exist.");
+  }
+  ba->impl.loss = loss;
+  ba->impl.loss_a = loss_threshold;
+  ba->impl.max_iterations = max_iterations;
+  ba->impl.compute_reproj = compute_reprojection_errors != 0;
+  OSFM_API_END
+}
+int osfm_ba_set_distributed(osfm_ba* ba, int rank, int world, osfm_allreduce_fn fn, void* user) {
+  OSFM_API_BEGIN
+  OSFM_BA_CHECK
+  if (world < 1 || rank < 0 || rank >= world) throw ArgError("bad rank/world");
+  if (world > 1 && !fn) throw ArgError("world > 1 needs an all-reduce callback");
+  ba->impl.rank = rank; ba->impl.world = world; ba->impl.allreduce = fn; ba->impl.allreduce_user = user;
+  OSFM_API_END
+}
+int osfm_ba_set_stream(osfm_ba* ba, void* cuda_stream) {
+  OSFM_API_BEGIN
+  OSFM_BA_CHECK
+  ba->impl.stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : ba->impl.own_stream;
+  OSFM_API_END
+}
+int osfm_ba_run(osfm_ba* ba) {
+  OSFM_API_BEGIN
+  OSFM_BA_CHECK
+  ba->impl.run();
+  OSFM_API_END
+}
+int osfm_ba_get_summary(osfm_ba* ba, osfm_ba_summary* out) {
+  OSFM_API_BEGIN
+  OSFM_BA_CHECK
+  if (!out) throw ArgError("null out");
+  *out = ba->impl.summary;
+  OSFM_API_END
+}
+int osfm_ba_get_cameras(osfm_ba* ba, double* params_flat) {
+  OSFM_API_BEGIN
+  OSFM_BA_CHECK
+  std::copy(ba->impl.cam_params.begin(), ba->impl.cam_params.end(), params_flat);
+  OSFM_API_END
+}
+int osfm_ba_get_rig_instances(osfm_ba* ba, double* pose6) {
+  OSFM_API_BEGIN
+  OSFM_BA_CHECK
+  std::copy(ba->impl.inst.begin(), ba->impl.inst.end(), pose6);
+  OSFM_API_END
+}
+int osfm_ba_get_rig_cameras(osfm_ba* ba, double* pose6) {
+  OSFM_API_BEGIN
+  OSFM_BA_CHECK
+  std::copy(ba->impl.rc.begin(), ba->impl.rc.end(), pose6);
+  OSFM_API_END
+}
+int osfm_ba_get_points(osfm_ba* ba, double* xyz) {
+  OSFM_API_BEGIN
+  OSFM_BA_CHECK
+  std::copy(ba->impl.pts.begin(), ba->impl.pts.end(), xyz);
+  OSFM_API_END
+}
+int osfm_ba_get_reprojection_errors(osfm_ba* ba, double* out_n_by_3) {
+  OSFM_API_BEGIN
+  OSFM_BA_CHECK
+  if (!ba->impl.has_run) throw std::runtime_error("run() has not been called");
+  std::copy(ba->impl.reproj.begin(), ba->impl.reproj.end(), out_n_by_3);
+  OSFM_API_END
+}
+
+int osfm_ba_eval_observation(int device, int projection_type, const double* camera, const double* rig_instance,
+                             const double* rig_camera, int use_rig_camera, const double* point,
+                             const double* observed, double std_deviation, double* r, double* jac_camera,
+                             double* jac_instance, double* jac_rig_camera, double* jac_point, int* num_residuals) {
+  OSFM_API_BEGIN
+  if (projection_type < 0 || projection_type > 9) throw ArgError("Invalid ProjectionType");
+  OSFM_CUDA(cudaSetDevice(device));
+  const int C = osfm::model_num_params(projection_type);
+  double in[34] = {0};
+  for (int i = 0; i < C; ++i) in[i] = camera[i];
+  for (int i = 0; i < 6; ++i) in[16 + i] = rig_instance[i];
+  for (int i = 0; i < 6; ++i) in[22 + i] = rig_camera ? rig_camera[i] : 0.0;
+  for (int i = 0; i < 3; ++i) in[28 + i] = point[i];
+  in[31] = observed[0]; in[32] = observed[1]; in[33] = 1.0 / std_deviation;
+  double *d_in = nullptr, *d_out = nullptr;
+  int* d_n = nullptr;
+  OSFM_CUDA(cudaMalloc(&d_in, sizeof(in)));
+  OSFM_CUDA(cudaMalloc(&d_out, sizeof(double) * 96));
+  OSFM_CUDA(cudaMalloc(&d_n, sizeof(int)));
+  OSFM_CUDA(cudaMemcpy(d_in, in, sizeof(in), cudaMemcpyHostToDevice));
+  osfm::ba_eval_one<<<1, 1>>>(projection_type, d_in, use_rig_camera, d_out, d_n);
+  OSFM_LAUNCH_CHECK();
+  double out[96];
+  int nres = 0;
+  OSFM_CUDA(cudaMemcpy(out, d_out, sizeof(out), cudaMemcpyDeviceToHost));
+  OSFM_CUDA(cudaMemcpy(&nres, d_n, sizeof(int), cudaMemcpyDeviceToHost));
+  cudaFree(d_in); cudaFree(d_out); cudaFree(d_n);
+  for (int i = 0; i < nres; ++i) r[i] = out[i];
+  for (int i = 0; i < nres * C; ++i) jac_camera[i] = out[3 + i];
+  for (int i = 0; i < nres * 6; ++i) jac_instance[i] = out[51 + i];
+  for (int i = 0; i < nres * 6; ++i) jac_rig_camera[i] = out[69 + i];
+  for (int i = 0; i < nres * 3; ++i) jac_point[i] = out[87 + i];
+  if (num_residuals) *num_residuals = nres;
+  OSFM_API_END
+}
+
+}  // extern "C"

@@ -1,0 +1,578 @@
+// Brute-force descriptor matching on B200 (sm_100a).
+//
+// Replaces the OpenCV call under opensfm/matching.py:723-777
+// (`cv2.DescriptorMatcher.knnMatch(k=2)` + Lowe ratio test) for float32 L2
+// ("BruteForce") and uint8 Hamming ("BruteForce-Hamming") descriptors.
+//
+// Semantics reproduced from cv2 (pinned by tests against live cv2):
+//  * L2 candidates are ranked by sqrt(float32 sum of squared differences);
+//    Hamming by the integer bit count;
+//  * ties -> lowest train index (cv2 inserts with a strict `<`);
+//  * masked-out trains are skipped; a query with < 2 candidates has no match
+//    (matching.py:752);
+//  * ratio test `m.distance < ratio * n.distance` in double on the float32
+//    distances (matching.py:754).
+//
+// Kernels in this file:
+//  bf_top2_simt<U8>   exact SIMT tile kernel (any float32 values, masks, Hamming)
+//  bf_top2_finalize   merge train chunks per query + ratio test
+//  bf_symmetric       keep (i,j) iff j's match is i (matching.py:775-777)
+// The tcgen05 tensor-core distance kernel lives in match_tc.cu.
+#include <algorithm>
+#include <cmath>
+#include <map>
+#include <mutex>
+#include <vector>
+
+#include "common.cuh"
+#include "match_common.cuh"
+
+namespace osfm {
+
+// ---------------------------------------------------------------------------
+// SIMT tile kernel
+// ---------------------------------------------------------------------------
+constexpr int BM = 64;       // queries per CTA tile
+constexpr int BN = 64;       // trains per inner tile
+constexpr int DK = 16;       // elements (float or u32 word) per k-step
+constexpr int LDS_STRIDE = 68;
+
+template <bool U8>
+__global__ void __launch_bounds__(256) bf_top2_simt(const MatchJob* __restrict__ jobs,
+                                                    const int* __restrict__ tile_prefix, int njobs,
+                                                    Top2* __restrict__ partial) {
+  using Elem = typename std::conditional<U8, uint32_t, float>::type;
+  using Acc = typename std::conditional<U8, int, float>::type;
+  __shared__ __align__(16) Elem As[DK][LDS_STRIDE];
+  __shared__ __align__(16) Elem Bs[DK][LDS_STRIDE];
+  __shared__ Top2 cand[BM][16];
+
+  // locate the job of this CTA (binary search over the tile prefix sums)
+  int lo = 0, hi = njobs - 1;
+  const int cta = blockIdx.x;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (tile_prefix[mid] <= cta) lo = mid; else hi = mid - 1;
+  }
+  const MatchJob job = jobs[lo];
+  const int local = cta - tile_prefix[lo];
+  const int qtile = local / job.nchunks;
+  const int chunk = local % job.nchunks;
+  const int q0 = qtile * BM;
+  const int t_begin = chunk * job.chunk_len;
+  const int t_end = min(job.nt, t_begin + job.chunk_len);
+  const int D = job.dim_padded;  // elements per row (multiple of DK)
+  const Elem* __restrict__ Q = static_cast<const Elem*>(job.q);
+  const Elem* __restrict__ T = static_cast<const Elem*>(job.t);
+
+  const int tid = threadIdx.x;
+  const int ty = tid >> 4, tx = tid & 15;
+
+  Top2 best[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) best[i] = top2_empty();
+
+  for (int t0 = t_begin; t0 < t_end; t0 += BN) {
+    Acc acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[i][j] = 0;
+
+    for (int k0 = 0; k0 < D; k0 += DK) {
+      // 64 rows x 16 elems = 256 x 16-byte vectors per operand: one per thread
+      {
+        const int row = tid & 63, kq = tid >> 6;  // kq 0..3 -> elems kq*4..kq*4+3
+        const int gq = q0 + row, gt = t0 + row;
+        uint4 va = make_uint4(0, 0, 0, 0), vb = make_uint4(0, 0, 0, 0);
+        if (gq < job.nq) va = *reinterpret_cast<const uint4*>(Q + (size_t)gq * D + k0 + kq * 4);
+        if (gt < t_end) vb = *reinterpret_cast<const uint4*>(T + (size_t)gt * D + k0 + kq * 4);
+        const Elem* ea = reinterpret_cast<const Elem*>(&va);
+        const Elem* eb = reinterpret_cast<const Elem*>(&vb);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          As[kq * 4 + e][row] = ea[e];
+          Bs[kq * 4 + e][row] = eb[e];
+        }
+      }
+      __syncthreads();
+#pragma unroll
+      for (int k = 0; k < DK; ++k) {
+        const uint4 a4 = *reinterpret_cast<const uint4*>(&As[k][ty * 4]);
+        const uint4 b4 = *reinterpret_cast<const uint4*>(&Bs[k][tx * 4]);
+        const Elem* a = reinterpret_cast<const Elem*>(&a4);
+        const Elem* b = reinterpret_cast<const Elem*>(&b4);
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            if constexpr (U8) {
+              acc[i][j] += __popc(a[i] ^ b[j]);
+            } else {
+              const float d = a[i] - b[j];
+              acc[i][j] = fmaf(d, d, acc[i][j]);
+            }
+          }
+      }
+      __syncthreads();
+    }
+    // fold this tile's 4x4 results into the thread-local top-2 of each row
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int gq = q0 + ty * 4 + i;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int gt = t0 + tx * 4 + j;
+        if (gq >= job.nq || gt >= t_end) continue;
+        if (job.mask && job.mask[(size_t)gq * job.mask_sq + (size_t)gt * job.mask_st] == 0) continue;
+        float s;
+        if constexpr (U8) s = (float)acc[i][j]; else s = __fsqrt_rn(acc[i][j]);
+        top2_insert(best[i], s, gt);
+      }
+    }
+  }
+  // merge the 16 threads that share a query row
+#pragma unroll
+  for (int i = 0; i < 4; ++i) cand[ty * 4 + i][tx] = best[i];
+  __syncthreads();
+  if (tid < BM) {
+    const int gq = q0 + tid;
+    if (gq < job.nq) {
+      Top2 m = top2_empty();
+      for (int x = 0; x < 16; ++x) top2_merge(m, cand[tid][x]);
+      partial[job.partial_off + (size_t)chunk * job.nq + gq] = m;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Merge chunks + ratio test.  grid = (ceil(max_nq/256), njobs)
+// ---------------------------------------------------------------------------
+__global__ void bf_top2_finalize(const MatchJob* __restrict__ jobs, const Top2* __restrict__ partial,
+                                 int32_t* __restrict__ match_buf, double ratio) {
+  const MatchJob job = jobs[blockIdx.y];
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= job.nq) return;
+  Top2 m = top2_empty();
+  for (int c = 0; c < job.nchunks; ++c) top2_merge(m, partial[job.partial_off + (size_t)c * job.nq + q]);
+  int out = -1;
+  // matching.py:752-755: two candidates and m.distance < ratio * n.distance (double)
+  if (m.i1 >= 0 && m.i2 >= 0 && (double)m.s1 < ratio * (double)m.s2) out = m.i1;
+  match_buf[job.match_off + q] = out;
+}
+
+// matching.py:775-777: intersect matches_ij with the transposed matches_ji.
+// grid = (ceil(max_na/256), npairs); job 2p is a->b, job 2p+1 is b->a.
+__global__ void bf_symmetric(const MatchJob* __restrict__ jobs, const int32_t* __restrict__ match_buf,
+                             int32_t* __restrict__ out, const long long* __restrict__ out_off) {
+  const MatchJob fwd = jobs[2 * blockIdx.y];
+  const MatchJob bwd = jobs[2 * blockIdx.y + 1];
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= fwd.nq) return;
+  const int j = match_buf[fwd.match_off + q];
+  int res = -1;
+  if (j >= 0 && match_buf[bwd.match_off + j] == q) res = j;
+  out[out_off[blockIdx.y] + q] = res;
+}
+
+// ---------------------------------------------------------------------------
+// Descriptor upload helpers
+// ---------------------------------------------------------------------------
+// Pads rows to dim_padded with zeros (distance-neutral).  One thread per padded element.
+template <class T>
+__global__ void pad_rows_kernel(const T* __restrict__ src, int n, int dim, T* __restrict__ dst, int dim_padded) {
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (size_t)n * dim_padded) return;
+  const int r = idx / dim_padded, c = idx % dim_padded;
+  dst[idx] = c < dim ? src[(size_t)r * dim + c] : T(0);
+}
+
+// ---------------------------------------------------------------------------
+// Matcher object
+// ---------------------------------------------------------------------------
+Matcher::Matcher(int dev) : device(dev) {
+  OSFM_CUDA(cudaSetDevice(device));
+  OSFM_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+  for (auto& e : ev) OSFM_CUDA(cudaEventCreate(&e));
+  cudaDeviceProp prop;
+  OSFM_CUDA(cudaGetDeviceProperties(&prop, device));
+  num_sms = prop.multiProcessorCount;
+}
+
+Matcher::~Matcher() {
+  cudaSetDevice(device);
+  for (auto& kv : sets) free_set(kv.second);
+  for (auto& e : ev) cudaEventDestroy(e);
+  cudaStreamDestroy(stream);
+}
+
+void Matcher::free_set(DescSet& s) {
+  if (s.data) cudaFree(s.data);
+  if (s.tc_data) cudaFree(s.tc_data);
+  s.data = nullptr;
+  s.tc_data = nullptr;
+  s.tc_ok = false;
+}
+
+int Matcher::add(const void* host, int n, int dim, bool u8) {
+  if (n < 0 || dim <= 0) throw ArgError("descriptor matrix must be n x dim with dim > 0");
+  if (!host && n > 0) throw ArgError("null descriptor pointer");
+  OSFM_CUDA(cudaSetDevice(device));
+  DescSet s;
+  s.n = n;
+  s.dim = dim;
+  s.u8 = u8;
+  const size_t esz = u8 ? 1 : 4;
+  // padded row length in bytes: multiple of DK elements (64 B for both types)
+  const int row_bytes = (int)(((size_t)dim * esz + 63) / 64 * 64);
+  s.dim_padded = row_bytes / (u8 ? 4 : 4);  // in 4-byte elements
+  s.row_bytes = row_bytes;
+  const size_t bytes = (size_t)std::max(n, 1) * row_bytes;
+  OSFM_CUDA(cudaMalloc(&s.data, bytes));
+  if (n > 0) {
+    staging.reserve((size_t)n * dim * esz);
+    OSFM_CUDA(cudaMemcpyAsync(staging.p, host, (size_t)n * dim * esz, cudaMemcpyHostToDevice, stream));
+    const size_t total = (size_t)n * row_bytes / esz;
+    const int threads = 256;
+    const unsigned blocks = (unsigned)((total + threads - 1) / threads);
+    if (u8)
+      pad_rows_kernel<uint8_t><<<blocks, threads, 0, stream>>>(staging.p, n, dim, (uint8_t*)s.data, row_bytes);
+    else
+      pad_rows_kernel<float><<<blocks, threads, 0, stream>>>((const float*)staging.p, n, dim, (float*)s.data,
+                                                             row_bytes / 4);
+    OSFM_LAUNCH_CHECK();
+    if (!u8) prepare_tc(s);  // bf16 operand copy + exactness flag (match_tc.cu)
+    OSFM_CUDA(cudaStreamSynchronize(stream));
+  }
+  const int id = next_id++;
+  sets[id] = s;
+  return id;
+}
+
+void Matcher::remove(int id) {
+  auto it = sets.find(id);
+  if (it == sets.end()) throw ArgError("unknown descriptor set id");
+  OSFM_CUDA(cudaSetDevice(device));
+  OSFM_CUDA(cudaStreamSynchronize(stream));
+  free_set(it->second);
+  sets.erase(it);
+}
+
+void Matcher::clear() {
+  OSFM_CUDA(cudaSetDevice(device));
+  OSFM_CUDA(cudaStreamSynchronize(stream));
+  for (auto& kv : sets) free_set(kv.second);
+  sets.clear();
+}
+
+void Matcher::match_pairs_async(int npairs, const int* ids_a, const int* ids_b, double ratio, bool symmetric,
+                                const uint8_t* dmask) {
+  OSFM_CUDA(cudaSetDevice(device));
+  if (npairs < 0) throw ArgError("npairs < 0");
+  if (npairs > 30000) throw ArgError("at most 30000 pairs per submission");
+  const int ndir = symmetric ? 2 : 1;
+  const int njobs = npairs * ndir;
+  h_jobs.assign(njobs, MatchJob());
+  h_prefix.assign(njobs + 1, 0);
+  h_out_off.assign(npairs + 1, 0);
+  bool any_u8 = false, any_f32 = false, all_tc = true;
+  long long total_qtiles = 0;
+  int max_nq = 0;
+  for (int p = 0; p < npairs; ++p) {
+    auto ia = sets.find(ids_a[p]), ib = sets.find(ids_b[p]);
+    if (ia == sets.end() || ib == sets.end()) throw ArgError("unknown descriptor set id in pair list");
+    const DescSet& A = ia->second;
+    const DescSet& B = ib->second;
+    // matching.py:737: assert f1.dtype.type == f2.dtype.type
+    if (A.u8 != B.u8 || A.dim != B.dim) throw ArgError("descriptor sets of a pair differ in dtype or dimension");
+    any_u8 |= A.u8;
+    any_f32 |= !A.u8;
+    all_tc &= (!A.u8 && A.tc_ok && B.tc_ok);
+    h_out_off[p + 1] = h_out_off[p] + A.n;
+    for (int d = 0; d < ndir; ++d) {
+      MatchJob& j = h_jobs[p * ndir + d];
+      const DescSet& Qs = d == 0 ? A : B;
+      const DescSet& Ts = d == 0 ? B : A;
+      j.q = Qs.data; j.t = Ts.data;
+      j.q_tc = Qs.tc_q; j.t_tc = Ts.tc_t;
+      j.q_norm = Qs.tc_norm; j.t_norm = Ts.tc_norm;
+      j.nq = Qs.n; j.nt = Ts.n;
+      j.dim = A.dim;
+      j.dim_padded = A.dim_padded;
+      j.qtiles = (j.nq + BM - 1) / BM;
+      j.mask = dmask;
+      if (dmask) {
+        // forward: mask[q*n2 + t]; backward reads the transpose (matching.py:774)
+        j.mask_sq = d == 0 ? B.n : 1;
+        j.mask_st = d == 0 ? 1 : B.n;
+      }
+      total_qtiles += j.qtiles;
+      max_nq = std::max(max_nq, j.nq);
+    }
+  }
+  if (any_u8 && any_f32) throw ArgError("mixed float32 / uint8 pairs in one submission");
+  // kernel choice
+  int use = 1;
+  if (kernel_choice == 2) {
+    if (!all_tc || dmask) throw ArgError("tcgen05 kernel forced but descriptors are not bf16-exact or a mask is set");
+    use = 2;
+  } else if (kernel_choice == 0 && all_tc && !dmask && any_f32 && tc_available()) {
+    use = 2;
+  }
+  last_kernel = use;
+  last_total_results = h_out_off[npairs];
+  last_npairs = npairs;
+
+  // split the train dimension when there are too few query tiles to fill the GPU
+  const int tile_m = use == 2 ? tc_tile_m() : BM;
+  const int chunk_unit = use == 2 ? tc_tile_n() : BN;
+  long long tiles_total = 0;
+  if (use == 2) {
+    total_qtiles = 0;
+    for (auto& j : h_jobs) { j.qtiles = (j.nq + tile_m - 1) / tile_m; total_qtiles += j.qtiles; }
+  }
+  const long long target = (long long)num_sms * (use == 2 ? 2 : 4);
+  long long partial_total = 0, match_total = 0;
+  for (int i = 0; i < njobs; ++i) {
+    MatchJob& j = h_jobs[i];
+    int nchunks = 1;
+    if (total_qtiles < target && total_qtiles > 0) {
+      const int want = (int)((target + total_qtiles - 1) / total_qtiles);
+      const int maxc = std::max(1, (j.nt + chunk_unit - 1) / chunk_unit);
+      nchunks = std::min(want, maxc);
+    }
+    int chunk_len = (j.nt + nchunks - 1) / nchunks;
+    chunk_len = std::max(chunk_unit, (chunk_len + chunk_unit - 1) / chunk_unit * chunk_unit);
+    nchunks = std::max(1, (j.nt + chunk_len - 1) / chunk_len);
+    j.nchunks = nchunks;
+    j.chunk_len = chunk_len;
+    j.partial_off = partial_total;
+    partial_total += (long long)nchunks * j.nq;
+    const bool direct = !symmetric;  // one-way: the forward match buffer is the result
+    j.match_off = match_total;
+    (void)direct;
+    match_total += j.nq;
+    h_prefix[i] = (int)tiles_total;
+    tiles_total += (long long)j.qtiles * nchunks;
+    if (tiles_total > 0x7fffffffLL) throw ArgError("too many tiles in one submission");
+  }
+  h_prefix[njobs] = (int)tiles_total;
+
+  d_jobs.reserve(njobs + 1);
+  d_prefix.reserve(njobs + 1);
+  d_out_off.reserve(npairs + 1);
+  d_partial.reserve(std::max<long long>(partial_total, 1));
+  d_match.reserve(std::max<long long>(match_total, 1));
+  d_out.reserve(std::max<long long>(last_total_results, 1));
+  p_jobs.reserve(njobs + 1);
+  p_prefix.reserve(njobs + 1);
+  p_out_off.reserve(npairs + 1);
+  // previous batch may still be reading the pinned staging buffers
+  OSFM_CUDA(cudaStreamSynchronize(stream));
+  std::copy(h_jobs.begin(), h_jobs.end(), p_jobs.p);
+  std::copy(h_prefix.begin(), h_prefix.end(), p_prefix.p);
+  std::copy(h_out_off.begin(), h_out_off.end(), p_out_off.p);
+
+  OSFM_CUDA(cudaEventRecord(ev[0], stream));
+  if (njobs > 0) {
+    OSFM_CUDA(cudaMemcpyAsync(d_jobs.p, p_jobs.p, sizeof(MatchJob) * njobs, cudaMemcpyHostToDevice, stream));
+    OSFM_CUDA(cudaMemcpyAsync(d_prefix.p, p_prefix.p, sizeof(int) * (njobs + 1), cudaMemcpyHostToDevice, stream));
+    OSFM_CUDA(cudaMemcpyAsync(d_out_off.p, p_out_off.p, sizeof(long long) * (npairs + 1), cudaMemcpyHostToDevice,
+                              stream));
+  }
+  OSFM_CUDA(cudaEventRecord(ev[1], stream));
+  if (tiles_total > 0) {
+    if (use == 2) {
+      launch_tc(*this, njobs, (int)tiles_total);
+    } else if (any_u8) {
+      bf_top2_simt<true><<<(unsigned)tiles_total, 256, 0, stream>>>(d_jobs.p, d_prefix.p, njobs, d_partial.p);
+      OSFM_LAUNCH_CHECK();
+    } else {
+      bf_top2_simt<false><<<(unsigned)tiles_total, 256, 0, stream>>>(d_jobs.p, d_prefix.p, njobs, d_partial.p);
+      OSFM_LAUNCH_CHECK();
+    }
+  }
+  OSFM_CUDA(cudaEventRecord(ev[2], stream));
+  if (njobs > 0 && max_nq > 0) {
+    dim3 grid((max_nq + 255) / 256, njobs);
+    bf_top2_finalize<<<grid, 256, 0, stream>>>(d_jobs.p, d_partial.p, d_match.p, ratio);
+    OSFM_LAUNCH_CHECK();
+    if (symmetric) {
+      dim3 g2((max_nq + 255) / 256, npairs);
+      bf_symmetric<<<g2, 256, 0, stream>>>(d_jobs.p, d_match.p, d_out.p, d_out_off.p);
+      OSFM_LAUNCH_CHECK();
+    }
+  }
+  results_in_match_buf = !symmetric;
+  OSFM_CUDA(cudaEventRecord(ev[3], stream));
+}
+
+void Matcher::sync() {
+  OSFM_CUDA(cudaSetDevice(device));
+  OSFM_CUDA(cudaStreamSynchronize(stream));
+}
+
+void Matcher::fetch(int32_t* out, int64_t capacity) {
+  OSFM_CUDA(cudaSetDevice(device));
+  if (capacity < last_total_results) throw ArgError("output buffer too small for the last batch");
+  if (last_total_results > 0) {
+    // one-way results are laid out per job == per pair in d_match (match_off == out_off)
+    const int32_t* src = results_in_match_buf ? d_match.p : d_out.p;
+    OSFM_CUDA(cudaMemcpyAsync(out, src, sizeof(int32_t) * last_total_results, cudaMemcpyDeviceToHost, stream));
+  }
+  OSFM_CUDA(cudaStreamSynchronize(stream));
+}
+
+void Matcher::last_ms(float* total, float* kernel) {
+  OSFM_CUDA(cudaSetDevice(device));
+  OSFM_CUDA(cudaEventSynchronize(ev[3]));
+  if (total) OSFM_CUDA(cudaEventElapsedTime(total, ev[0], ev[3]));
+  if (kernel) OSFM_CUDA(cudaEventElapsedTime(kernel, ev[1], ev[2]));
+}
+
+void Matcher::one_shot(const void* f1, int n1, const void* f2, int n2, int dim, bool u8, double ratio,
+                       const uint8_t* mask, bool symmetric, int32_t* out) {
+  if (n1 < 0 || n2 < 0) throw ArgError("negative descriptor count");
+  if (!out && n1 > 0) throw ArgError("null output");
+  const int a = add(f1, n1, dim, u8);
+  int b = -1;
+  try {
+    b = add(f2, n2, dim, u8);
+    const uint8_t* dmask = nullptr;
+    if (mask && n1 > 0 && n2 > 0) {
+      mask_buf.reserve((size_t)n1 * n2);
+      OSFM_CUDA(cudaMemcpyAsync(mask_buf.p, mask, (size_t)n1 * n2, cudaMemcpyHostToDevice, stream));
+      dmask = mask_buf.p;
+    }
+    match_pairs_async(1, &a, &b, ratio, symmetric, dmask);
+    fetch(out, n1);
+  } catch (...) {
+    if (b >= 0) remove(b);
+    remove(a);
+    throw;
+  }
+  remove(b);
+  remove(a);
+}
+
+}  // namespace osfm
+
+// ---------------------------------------------------------------------------
+// C ABI
+// ---------------------------------------------------------------------------
+using osfm::Matcher;
+struct osfm_matcher {
+  Matcher impl;
+  std::mutex mu;
+  explicit osfm_matcher(int dev) : impl(dev) {}
+};
+
+extern "C" {
+
+int osfm_matcher_create(int device, osfm_matcher** out) {
+  OSFM_API_BEGIN
+  if (!out) throw osfm::ArgError("null out");
+  int count = 0;
+  OSFM_CUDA(cudaGetDeviceCount(&count));
+  if (device < 0 || device >= count) throw osfm::ArgError("no such CUDA device");
+  *out = new osfm_matcher(device);
+  OSFM_API_END
+}
+
+int osfm_matcher_destroy(osfm_matcher* m) {
+  OSFM_API_BEGIN
+  delete m;
+  OSFM_API_END
+}
+
+#define OSFM_M_LOCK                                   \
+  if (!m) throw osfm::ArgError("null matcher");       \
+  std::lock_guard<std::mutex> lock(m->mu);
+
+int osfm_bf_match_f32(osfm_matcher* m, const float* f1, int n1, const float* f2, int n2, int dim,
+                      double lowes_ratio, const uint8_t* mask, int symmetric, int32_t* out_match) {
+  OSFM_API_BEGIN
+  OSFM_M_LOCK
+  m->impl.one_shot(f1, n1, f2, n2, dim, false, lowes_ratio, mask, symmetric != 0, out_match);
+  OSFM_API_END
+}
+
+int osfm_bf_match_u8(osfm_matcher* m, const uint8_t* f1, int n1, const uint8_t* f2, int n2, int nbytes,
+                     double lowes_ratio, const uint8_t* mask, int symmetric, int32_t* out_match) {
+  OSFM_API_BEGIN
+  OSFM_M_LOCK
+  m->impl.one_shot(f1, n1, f2, n2, nbytes, true, lowes_ratio, mask, symmetric != 0, out_match);
+  OSFM_API_END
+}
+
+int osfm_matcher_add_f32(osfm_matcher* m, const float* desc, int n, int dim, int* out_id) {
+  OSFM_API_BEGIN
+  OSFM_M_LOCK
+  if (!out_id) throw osfm::ArgError("null out_id");
+  *out_id = m->impl.add(desc, n, dim, false);
+  OSFM_API_END
+}
+
+int osfm_matcher_add_u8(osfm_matcher* m, const uint8_t* desc, int n, int nbytes, int* out_id) {
+  OSFM_API_BEGIN
+  OSFM_M_LOCK
+  if (!out_id) throw osfm::ArgError("null out_id");
+  *out_id = m->impl.add(desc, n, nbytes, true);
+  OSFM_API_END
+}
+
+int osfm_matcher_remove(osfm_matcher* m, int id) {
+  OSFM_API_BEGIN
+  OSFM_M_LOCK
+  m->impl.remove(id);
+  OSFM_API_END
+}
+
+int osfm_matcher_clear(osfm_matcher* m) {
+  OSFM_API_BEGIN
+  OSFM_M_LOCK
+  m->impl.clear();
+  OSFM_API_END
+}
+
+int osfm_matcher_match_pairs_async(osfm_matcher* m, int npairs, const int* ids_a, const int* ids_b,
+                                   double lowes_ratio, int symmetric) {
+  OSFM_API_BEGIN
+  OSFM_M_LOCK
+  if (npairs > 0 && (!ids_a || !ids_b)) throw osfm::ArgError("null pair list");
+  m->impl.match_pairs_async(npairs, ids_a, ids_b, lowes_ratio, symmetric != 0, nullptr);
+  OSFM_API_END
+}
+
+int osfm_matcher_sync(osfm_matcher* m) {
+  OSFM_API_BEGIN
+  OSFM_M_LOCK
+  m->impl.sync();
+  OSFM_API_END
+}
+
+int osfm_matcher_fetch(osfm_matcher* m, int32_t* out_match, int64_t capacity) {
+  OSFM_API_BEGIN
+  OSFM_M_LOCK
+  m->impl.fetch(out_match, capacity);
+  OSFM_API_END
+}
+
+int osfm_matcher_last_device_ms(osfm_matcher* m, float* ms_total, float* ms_distance_kernel) {
+  OSFM_API_BEGIN
+  OSFM_M_LOCK
+  m->impl.last_ms(ms_total, ms_distance_kernel);
+  OSFM_API_END
+}
+
+int osfm_matcher_set_kernel(osfm_matcher* m, int which) {
+  OSFM_API_BEGIN
+  OSFM_M_LOCK
+  if (which < 0 || which > 2) throw osfm::ArgError("kernel must be 0, 1 or 2");
+  m->impl.kernel_choice = which;
+  OSFM_API_END
+}
+
+int osfm_matcher_last_kernel(osfm_matcher* m) { return m ? m->impl.last_kernel : 0; }
+
+}  // extern "C"

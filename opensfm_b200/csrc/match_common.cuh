@@ -1,0 +1,130 @@
+// Types shared by the SIMT and tcgen05 matching kernels.
+#pragma once
+#include <cuda_bf16.h>
+
+#include <map>
+#include <vector>
+
+#include "common.cuh"
+
+namespace osfm {
+
+// Running two-nearest list of one query, in cv2's ranking space:
+// s = sqrt(float32 d^2) for L2, bit count for Hamming; i = train index or -1.
+struct Top2 {
+  float s1;
+  int i1;
+  float s2;
+  int i2;
+};
+
+__host__ __device__ inline Top2 top2_empty() {
+  Top2 t;
+  t.s1 = __builtin_huge_valf();
+  t.s2 = __builtin_huge_valf();
+  t.i1 = -1;
+  t.i2 = -1;
+  return t;
+}
+
+// Insert candidate (s, i); order is lexicographic (distance, index), which is
+// what cv2's stable insertion with a strict `<` produces when trains are
+// visited in increasing index order.
+__host__ __device__ inline void top2_insert(Top2& t, float s, int i) {
+  if (s < t.s1 || (s == t.s1 && (unsigned)i < (unsigned)t.i1)) {
+    t.s2 = t.s1; t.i2 = t.i1;
+    t.s1 = s; t.i1 = i;
+  } else if (s < t.s2 || (s == t.s2 && (unsigned)i < (unsigned)t.i2)) {
+    t.s2 = s; t.i2 = i;
+  }
+}
+
+__host__ __device__ inline void top2_merge(Top2& t, const Top2& o) {
+  if (o.i1 >= 0) top2_insert(t, o.s1, o.i1);
+  if (o.i2 >= 0) top2_insert(t, o.s2, o.i2);
+}
+
+// One direction of one image pair.
+struct MatchJob {
+  const void* q;  // queries, padded rows (float32 or packed uint8 words)
+  const void* t;  // trains
+  const __nv_bfloat16* q_tc;  // tcgen05 operand copies (blocked core-matrix layout), or null
+  const __nv_bfloat16* t_tc;
+  const float* q_norm;        // |q_i|^2 (tcgen05 path)
+  const float* t_norm;
+  int nq, nt;
+  int dim, dim_padded;  // dim_padded: 4-byte elements per padded row
+  int qtiles;
+  int nchunks, chunk_len;
+  long long partial_off;  // Top2 partial[partial_off + chunk * nq + q]
+  long long match_off;    // int32 match[match_off + q]
+  const uint8_t* mask;
+  long long mask_sq, mask_st;
+};
+
+struct DescSet {
+  void* data = nullptr;
+  int n = 0, dim = 0, dim_padded = 0, row_bytes = 0;
+  bool u8 = false;
+  // tcgen05 operands (float32 sets with integer values in [0,255] and dim <= 128 only)
+  void* tc_data = nullptr;  // one allocation: [A-role | B-role | norms]
+  const __nv_bfloat16* tc_q = nullptr;
+  const __nv_bfloat16* tc_t = nullptr;
+  const float* tc_norm = nullptr;
+  bool tc_ok = false;
+  int rows_padded = 0;
+};
+
+struct Matcher {
+  int device;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev[4];
+  int num_sms = 148;
+  int next_id = 1;
+  int kernel_choice = 0;
+  int last_kernel = 0;
+  long long last_total_results = 0;
+  int last_npairs = 0;
+  bool results_in_match_buf = true;
+  std::map<int, DescSet> sets;
+  std::vector<MatchJob> h_jobs;
+  std::vector<int> h_prefix;
+  std::vector<long long> h_out_off;
+  DevBuf<MatchJob> d_jobs;
+  DevBuf<int> d_prefix;
+  DevBuf<long long> d_out_off;
+  DevBuf<Top2> d_partial;
+  DevBuf<int32_t> d_match, d_out;
+  DevBuf<uint8_t> staging, mask_buf;
+  DevBuf<int> d_flags;
+  PinnedBuf<MatchJob> p_jobs;
+  PinnedBuf<int> p_prefix;
+  PinnedBuf<long long> p_out_off;
+
+  explicit Matcher(int dev);
+  ~Matcher();
+  Matcher(const Matcher&) = delete;
+  Matcher& operator=(const Matcher&) = delete;
+
+  int add(const void* host, int n, int dim, bool u8);
+  void remove(int id);
+  void clear();
+  void free_set(DescSet& s);
+  void match_pairs_async(int npairs, const int* ids_a, const int* ids_b, double ratio, bool symmetric,
+                         const uint8_t* dmask);
+  void sync();
+  void fetch(int32_t* out, int64_t capacity);
+  void last_ms(float* total, float* kernel);
+  void one_shot(const void* f1, int n1, const void* f2, int n2, int dim, bool u8, double ratio,
+                const uint8_t* mask, bool symmetric, int32_t* out);
+  // match_tc.cu
+  void prepare_tc(DescSet& s);
+};
+
+// match_tc.cu
+bool tc_available();
+int tc_tile_m();
+int tc_tile_n();
+void launch_tc(Matcher& m, int njobs, int ntiles);
+
+}  // namespace osfm

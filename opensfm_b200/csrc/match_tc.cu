@@ -1,0 +1,449 @@
+// tcgen05 tensor-core distance kernel for brute-force L2 matching (sm_100a).
+//
+// The N x M x 128 contraction of opensfm/matching.py:742-747 (cv2 knnMatch)
+// is a dense GEMM: d2(i,j) = |a_i|^2 + |b_j|^2 - 2 a_i.b_j.  For descriptors
+// whose values are integers in [0,255] (HAHOG / SIFT as OpenSfM stores them,
+// opensfm/features.py:526-534, and the synthetic scenes) every product and
+// partial sum is an integer below 2^24, so bf16 operands with fp32 accumulation
+// reproduce the float32 sum of squared differences of cv2 bit for bit.
+//
+// Operand layout (built once per descriptor set by prepare_tc):
+//   K = 144 = 128 descriptor dims + 16 augmentation columns.
+//   A role (queries):  [ a_i            | 1, 1, 1, 0 ... ]
+//   B role (trains):   [ -2 b_j         | hi, mid, lo of |b_j|^2, 0 ... ]
+//   => accumulator(i,j) = |b_j|^2 - 2 a_i.b_j = d2(i,j) - |a_i|^2   (exact)
+//   so the epilogue needs no per-column add: ranking within a query row is
+//   the ranking of the accumulator itself.
+// Rows are stored in HBM already in the UMMA canonical K-major no-swizzle
+// ("interleave") core-matrix order: [row/8][k/8][row%8][k%8] bf16, 128 bytes
+// per core matrix, so one tile is a single contiguous range and is staged with
+// one cp.async.bulk (TMA engine) per operand tile; LBO = 128 B, SBO = 18*128 B.
+//
+// Kernel: persistent, 1 CTA / SM, 6 warps:
+//   warp 0  bulk-copy producer (Q tile double-buffered per task, T tiles 2 stages)
+//   warp 1  TMEM alloc + single-thread tcgen05.mma issue (M=128, N=256, K=16 x 9)
+//   warps 2-5  epilogue: tcgen05.ld the 128x256 fp32 accumulator (double-buffered
+//           in TMEM, 2 x 256 columns) and keep a running top-2 per query row with
+//           a group-min threshold filter (~1 instruction / element); the exact
+//           cv2 ranking (sqrt'd float32 distance, ties -> lowest index) is applied
+//           only to the rare elements that pass the filter.
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+#include "match_common.cuh"
+
+namespace osfm {
+
+constexpr int TC_M = 128;
+constexpr int TC_N = 256;
+constexpr int TC_KD = 128;               // descriptor dims carried
+constexpr int TC_KP = 144;               // padded K (9 x UMMA_K)
+constexpr int TC_KCH = TC_KP / 8;        // 16-byte K chunks per row
+constexpr int TC_ROW_BYTES = TC_KP * 2;  // 288
+constexpr int TC_Q_BYTES = TC_M * TC_ROW_BYTES;  // 36864
+constexpr int TC_T_BYTES = TC_N * TC_ROW_BYTES;  // 73728
+constexpr int TC_SBO = TC_KCH * 128;     // bytes between 8-row groups
+constexpr int TC_LBO = 128;              // bytes between K-adjacent core matrices
+constexpr int TC_STAGES = 2;
+constexpr int TC_THREADS = 192;
+constexpr int TC_SMEM = 2 * TC_Q_BYTES + TC_STAGES * TC_T_BYTES;  // 221184
+
+int tc_tile_m() { return TC_M; }
+int tc_tile_n() { return TC_N; }
+
+bool tc_available() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return false;
+  int major = 0;
+  cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+  return major == 10;
+}
+
+// ---------------------------------------------------------------------------
+// Operand preparation
+// ---------------------------------------------------------------------------
+// flags[0] |= 1 if any value is not an integer in [0,255]
+__global__ void tc_check_exact(const float* __restrict__ src, size_t count, int* __restrict__ flags) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  bool bad = false;
+  if (i < count) {
+    const float v = src[i];
+    bad = !(v >= 0.0f && v <= 255.0f && v == floorf(v));
+  }
+  if (__syncthreads_or(bad) && threadIdx.x == 0) atomicOr(flags, 1);
+}
+
+// one warp per row: |x|^2 (exact integer in fp32 for the accepted inputs)
+__global__ void tc_row_norms(const float* __restrict__ src, int n, int dim, int rows_padded,
+                             float* __restrict__ norm) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows_padded) return;
+  float s = 0.0f;
+  if (row < n)
+    for (int k = lane; k < dim; k += 32) {
+      const float v = src[(size_t)row * dim + k];
+      s = fmaf(v, v, s);
+    }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (lane == 0) norm[row] = s;
+}
+
+// one thread per (row, 16-byte K chunk): writes both operand roles
+__global__ void tc_build_operands(const float* __restrict__ src, int n, int dim, int rows_padded,
+                                  const float* __restrict__ norm, __nv_bfloat16* __restrict__ qa,
+                                  __nv_bfloat16* __restrict__ tb) {
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (size_t)rows_padded * TC_KCH) return;
+  const int row = idx / TC_KCH, c = idx % TC_KCH;
+  const size_t off = ((size_t)(row >> 3) * TC_KCH + c) * 64 + (row & 7) * 8;
+  __align__(16) __nv_bfloat16 a[8], b[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    a[e] = __float2bfloat16(0.0f);
+    b[e] = __float2bfloat16(0.0f);
+  }
+  if (c < TC_KD / 8) {
+    if (row < n) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const int k = c * 8 + e;
+        const float v = k < dim ? src[(size_t)row * dim + k] : 0.0f;
+        a[e] = __float2bfloat16(v);
+        b[e] = __float2bfloat16(-2.0f * v);
+      }
+    }
+  } else if (c == TC_KD / 8) {
+    if (row < n) {
+      a[0] = a[1] = a[2] = __float2bfloat16(1.0f);
+      const float nb = norm[row];
+      const __nv_bfloat16 hi = __float2bfloat16(nb);
+      const float r1 = nb - __bfloat162float(hi);
+      const __nv_bfloat16 mid = __float2bfloat16(r1);
+      const float r2 = r1 - __bfloat162float(mid);
+      b[0] = hi; b[1] = mid; b[2] = __float2bfloat16(r2);
+    } else {
+      // padding trains can never be selected: accumulator = +inf for real queries
+      a[0] = a[1] = a[2] = __float2bfloat16(0.0f);
+      b[0] = __float2bfloat16(__builtin_huge_valf());
+    }
+  }
+  *reinterpret_cast<uint4*>(qa + off) = *reinterpret_cast<const uint4*>(a);
+  *reinterpret_cast<uint4*>(tb + off) = *reinterpret_cast<const uint4*>(b);
+}
+
+void Matcher::prepare_tc(DescSet& s) {
+  s.tc_ok = false;
+  if (s.u8 || s.dim > TC_KD || s.n == 0 || !tc_available()) return;
+  // staging.p still holds the dense float32 upload (n x dim) on this stream
+  const float* src = reinterpret_cast<const float*>(staging.p);
+  d_flags.reserve(4);
+  OSFM_CUDA(cudaMemsetAsync(d_flags.p, 0, sizeof(int), stream));
+  const size_t count = (size_t)s.n * s.dim;
+  tc_check_exact<<<(unsigned)((count + 255) / 256), 256, 0, stream>>>(src, count, d_flags.p);
+  OSFM_LAUNCH_CHECK();
+  int flag = 0;
+  OSFM_CUDA(cudaMemcpyAsync(&flag, d_flags.p, sizeof(int), cudaMemcpyDeviceToHost, stream));
+  OSFM_CUDA(cudaStreamSynchronize(stream));
+  if (flag) return;  // not bf16-exact: the exact SIMT kernel serves this set
+  const int rows_padded = (s.n + TC_N - 1) / TC_N * TC_N;
+  s.rows_padded = rows_padded;
+  const size_t op_bytes = (size_t)rows_padded * TC_ROW_BYTES;
+  OSFM_CUDA(cudaMalloc(&s.tc_data, 2 * op_bytes + (size_t)rows_padded * sizeof(float)));
+  __nv_bfloat16* qa = reinterpret_cast<__nv_bfloat16*>(s.tc_data);
+  __nv_bfloat16* tb = reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<char*>(s.tc_data) + op_bytes);
+  float* norm = reinterpret_cast<float*>(reinterpret_cast<char*>(s.tc_data) + 2 * op_bytes);
+  tc_row_norms<<<(rows_padded + 7) / 8, 256, 0, stream>>>(src, s.n, s.dim, rows_padded, norm);
+  OSFM_LAUNCH_CHECK();
+  const size_t items = (size_t)rows_padded * TC_KCH;
+  tc_build_operands<<<(unsigned)((items + 255) / 256), 256, 0, stream>>>(src, s.n, s.dim, rows_padded, norm, qa, tb);
+  OSFM_LAUNCH_CHECK();
+  s.tc_q = qa;
+  s.tc_t = tb;
+  s.tc_norm = norm;
+  s.tc_ok = true;
+}
+
+// ---------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// Bounded wait: a protocol bug must surface as a trapped kernel, never as a hung GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int* err_flag) {
+  const uint32_t addr = smem_u32(bar);
+  const long long t0 = clock64();
+  for (;;) {
+    uint32_t done;
+    asm volatile(
+        "{\n.reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n}\n"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (done) return;
+    if (clock64() - t0 > 4000000000LL) {
+      atomicExch(err_flag, 1);
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void bulk_copy_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(smem_dst)),
+               "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n.reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// K-major, no swizzle (cute::UMMA::SmemDescriptor: start>>4 @0, LBO>>4 @16, SBO>>4 @32, version=1 @46)
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3fff);
+  d |= (uint64_t)((TC_LBO >> 4) & 0x3fff) << 16;
+  d |= (uint64_t)((TC_SBO >> 4) & 0x3fff) << 32;
+  d |= (uint64_t)1 << 46;
+  return d;
+}
+// cute::UMMA::InstrDescriptor: c_format F32 (1) @4, a/b format BF16 (1) @7/@10, K-major both,
+// n_dim = N>>3 @17, m_dim = M>>4 @24
+constexpr uint32_t TC_IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TC_N >> 3) << 17) |
+                              ((uint32_t)(TC_M >> 4) << 24);
+
+#define OSFM_TMEM_LD32(taddr, v)                                                                           \
+  asm volatile(                                                                                            \
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "                                                            \
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26," \
+      "%27,%28,%29,%30,%31}, [%32];"                                                                       \
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),    \
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]),           \
+        "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]),         \
+        "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]),         \
+        "=r"(v[29]), "=r"(v[30]), "=r"(v[31])                                                              \
+      : "r"(taddr)                                                                                         \
+      : "memory")
+
+struct TcTask {
+  MatchJob job;
+  int q0, t_begin, ntiles, chunk;
+};
+
+__device__ __forceinline__ TcTask tc_decode(const MatchJob* jobs, const int* tile_prefix, int njobs, int task) {
+  int lo = 0, hi = njobs - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (tile_prefix[mid] <= task) lo = mid; else hi = mid - 1;
+  }
+  TcTask t;
+  t.job = jobs[lo];
+  const int local = task - tile_prefix[lo];
+  const int qtile = local / t.job.nchunks;
+  t.chunk = local % t.job.nchunks;
+  t.q0 = qtile * TC_M;
+  t.t_begin = t.chunk * t.job.chunk_len;
+  const int t_end = min(t.job.nt, t.t_begin + t.job.chunk_len);
+  t.ntiles = (t_end - t.t_begin + TC_N - 1) / TC_N;
+  return t;
+}
+
+// Epilogue state of one query row (ranking space of cv2 + the accumulator value of slot 2).
+struct RowState {
+  float s1, q1, s2, q2;
+  int i1, i2;
+};
+
+// Exact insertion for an element that passed the threshold filter (rare).
+__device__ __forceinline__ void row_insert(RowState& st, float v, int idx, float na) {
+  const float s = __fsqrt_rn(fmaxf(v + na, 0.0f));
+  if (s < st.s1) {
+    st.s2 = st.s1; st.q2 = st.q1; st.i2 = st.i1;
+    st.s1 = s; st.q1 = v; st.i1 = idx;
+  } else if (s < st.s2) {
+    st.s2 = s; st.q2 = v; st.i2 = idx;
+  }
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+    bf_top2_tc(const MatchJob* __restrict__ jobs, const int* __restrict__ tile_prefix, int njobs, int ntasks,
+               Top2* __restrict__ partial, int* __restrict__ err_flag) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ __align__(8) uint64_t bar_qfull[2], bar_qempty[2], bar_full[TC_STAGES], bar_empty[TC_STAGES],
+      bar_accfull[2], bar_accempty[2];
+  __shared__ uint32_t tmem_base_smem;
+
+  uint8_t* q_smem[2] = {smem, smem + TC_Q_BYTES};
+  uint8_t* t_smem[TC_STAGES];
+#pragma unroll
+  for (int s = 0; s < TC_STAGES; ++s) t_smem[s] = smem + 2 * TC_Q_BYTES + s * TC_T_BYTES;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&bar_qfull[i], 1);
+      mbar_init(&bar_qempty[i], 1);
+      mbar_init(&bar_accfull[i], 1);
+      mbar_init(&bar_accempty[i], 4);  // one arrival per epilogue warp
+    }
+    for (int i = 0; i < TC_STAGES; ++i) {
+      mbar_init(&bar_full[i], 1);
+      mbar_init(&bar_empty[i], 1);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&tmem_base_smem))
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_smem;
+
+  if (warp == 0) {
+    // ===== bulk-copy producer =====
+    if (lane == 0) {
+      int stage = 0, ph = 0, n = 0;
+      for (int task = blockIdx.x; task < ntasks; task += gridDim.x, ++n) {
+        const TcTask t = tc_decode(jobs, tile_prefix, njobs, task);
+        const int b = n & 1, qph = (n >> 1) & 1;
+        mbar_wait(&bar_qempty[b], qph ^ 1, err_flag);
+        mbar_expect_tx(&bar_qfull[b], TC_Q_BYTES);
+        bulk_copy_g2s(q_smem[b], reinterpret_cast<const uint8_t*>(t.job.q_tc) + (size_t)t.q0 * TC_ROW_BYTES,
+                      TC_Q_BYTES, &bar_qfull[b]);
+        for (int i = 0; i < t.ntiles; ++i) {
+          mbar_wait(&bar_empty[stage], ph ^ 1, err_flag);
+          mbar_expect_tx(&bar_full[stage], TC_T_BYTES);
+          bulk_copy_g2s(t_smem[stage],
+                        reinterpret_cast<const uint8_t*>(t.job.t_tc) + (size_t)(t.t_begin + i * TC_N) * TC_ROW_BYTES,
+                        TC_T_BYTES, &bar_full[stage]);
+          if (++stage == TC_STAGES) { stage = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      int stage = 0, ph = 0, n = 0, tilecount = 0;
+      for (int task = blockIdx.x; task < ntasks; task += gridDim.x, ++n) {
+        const TcTask t = tc_decode(jobs, tile_prefix, njobs, task);
+        const int b = n & 1, qph = (n >> 1) & 1;
+        mbar_wait(&bar_qfull[b], qph, err_flag);
+        const uint64_t adesc0 = make_smem_desc(smem_u32(q_smem[b]));
+        for (int i = 0; i < t.ntiles; ++i, ++tilecount) {
+          const int a = tilecount & 1, aph = (tilecount >> 1) & 1;
+          mbar_wait(&bar_accempty[a], aph ^ 1, err_flag);
+          mbar_wait(&bar_full[stage], ph, err_flag);
+          tc_fence_after();
+          const uint64_t bdesc0 = make_smem_desc(smem_u32(t_smem[stage]));
+          const uint32_t d_tmem = tmem_base + (uint32_t)a * TC_N;
+#pragma unroll
+          for (int k = 0; k < TC_KP / 16; ++k) {
+            // one UMMA_K = 16 bf16 = two core matrices = 256 bytes along K
+            const uint64_t koff = (uint64_t)((k * 2 * TC_LBO) >> 4);
+            tc_mma_bf16(d_tmem, adesc0 + koff, bdesc0 + koff, TC_IDESC, k > 0 ? 1u : 0u);
+          }
+          tc_commit(&bar_empty[stage]);   // smem stage reusable when these MMAs retire
+          tc_commit(&bar_accfull[a]);     // accumulator complete
+          if (++stage == TC_STAGES) { stage = 0; ph ^= 1; }
+        }
+        tc_commit(&bar_qempty[b]);  // Q buffer reusable after the task's last MMA
+      }
+    }
+  } else {
+    // ===== epilogue: warps 2..5 own TMEM lane quarters (warp % 4) =====
+    const int quarter = warp & 3;
+    const int row_in_tile = quarter * 32 + lane;
+    int tilecount = 0;
+    for (int task = blockIdx.x; task < ntasks; task += gridDim.x) {
+      const TcTask t = tc_decode(jobs, tile_prefix, njobs, task);
+      const int gq = t.q0 + row_in_tile;
+      const float na = gq < t.job.nq ? t.job.q_norm[gq] : 0.0f;
+      RowState st;
+      st.s1 = st.s2 = st.q1 = st.q2 = __builtin_huge_valf();
+      st.i1 = st.i2 = -1;
+      for (int i = 0; i < t.ntiles; ++i, ++tilecount) {
+        const int a = tilecount & 1, aph = (tilecount >> 1) & 1;
+        mbar_wait(&bar_accfull[a], aph, err_flag);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)a * TC_N;
+        const int col_base = t.t_begin + i * TC_N;
+#pragma unroll 1
+        for (int cb = 0; cb < TC_N / 32; ++cb) {
+          uint32_t v[32];
+          OSFM_TMEM_LD32(taddr + cb * 32, v);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            float m = __uint_as_float(v[g * 8]);
+#pragma unroll
+            for (int e = 1; e < 8; ++e) m = fminf(m, __uint_as_float(v[g * 8 + e]));
+            if (m < st.q2) {
+#pragma unroll
+              for (int e = 0; e < 8; ++e) {
+                const float x = __uint_as_float(v[g * 8 + e]);
+                if (x < st.q2) row_insert(st, x, col_base + cb * 32 + g * 8 + e, na);
+              }
+            }
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bar_accempty[a]);
+      }
+      if (gq < t.job.nq) {
+        Top2 out;
+        out.s1 = st.s1; out.i1 = st.i1; out.s2 = st.s2; out.i2 = st.i2;
+        partial[t.job.partial_off + (size_t)t.chunk * t.job.nq + gq] = out;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+  }
+}
+
+void launch_tc(Matcher& m, int njobs, int ntasks) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    OSFM_CUDA(cudaFuncSetAttribute(bf_top2_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
+    attr_set = true;
+  }
+  m.d_flags.reserve(4);
+  OSFM_CUDA(cudaMemsetAsync(m.d_flags.p + 1, 0, sizeof(int), m.stream));
+  const int grid = std::min(ntasks, m.num_sms);
+  bf_top2_tc<<<grid, TC_THREADS, TC_SMEM, m.stream>>>(m.d_jobs.p, m.d_prefix.p, njobs, ntasks, m.d_partial.p,
+                                                     m.d_flags.p + 1);
+  OSFM_LAUNCH_CHECK();
+}
+
+}  // namespace osfm

@@ -1,0 +1,183 @@
+"""Drop-in brute-force matching: the `opensfm.matching` names this engine replaces.
+
+    match_brute_force(f1, f2, config, maskij=None)            opensfm/matching.py:723-756
+    match_brute_force_symmetric(fi, fj, config, maskij=None)  opensfm/matching.py:759-777
+    match_images_with_pairs-style batch: `PairMatcher`        opensfm/matching.py:63-98
+
+Same argument meaning, same return types (lists of (queryIdx, trainIdx) tuples),
+same dtype dispatch (uint8 -> Hamming, else L2, matching.py:738-742).  All
+arithmetic happens in the CUDA library (opensfm_b200/csrc/match*.cu) through the
+C ABI; there is no CPU path here.
+
+Thread safety: the reference calls these from a joblib *threading* pool
+(opensfm/context.py:59-64).  Each Python thread gets its own matcher (own CUDA
+stream); ctypes releases the GIL for the duration of the call.
+"""
+from __future__ import annotations
+
+import ctypes
+import threading
+from typing import Any, Dict, Iterable, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import _lib
+
+_tls = threading.local()
+
+
+class _Matcher:
+    def __init__(self, device: int = 0):
+        L = _lib.load()
+        h = ctypes.c_void_p()
+        _lib.check(L.osfm_matcher_create(int(device), ctypes.byref(h)))
+        self.h = h
+        self.device = device
+        self.L = L
+
+    def __del__(self):
+        try:
+            self.L.osfm_matcher_destroy(self.h)
+        except Exception:
+            pass
+
+
+def _thread_matcher(device: int = 0) -> _Matcher:
+    key = "m%d" % device
+    m = getattr(_tls, key, None)
+    if m is None:
+        m = _Matcher(device)
+        setattr(_tls, key, m)
+    return m
+
+
+def _prep(f: np.ndarray) -> np.ndarray:
+    if f.dtype.type == np.uint8:
+        return np.ascontiguousarray(f)
+    return np.ascontiguousarray(f, dtype=np.float32)
+
+
+def _match_raw(f1: np.ndarray, f2: np.ndarray, ratio: float, maskij: Optional[np.ndarray], symmetric: bool,
+               device: int = 0) -> np.ndarray:
+    assert f1.dtype.type == f2.dtype.type  # matching.py:737
+    if f1.ndim != 2 or f2.ndim != 2 or (f1.shape[0] and f2.shape[0] and f1.shape[1] != f2.shape[1]):
+        raise ValueError("descriptor matrices must be 2-D with equal row length")
+    a, b = _prep(f1), _prep(f2)
+    n1, n2 = a.shape[0], b.shape[0]
+    out = np.full(n1, -1, dtype=np.int32)
+    if n1 == 0 or n2 == 0:
+        return out
+    dim = a.shape[1]
+    mask = None
+    mask_p = None
+    if maskij is not None:
+        mask = np.ascontiguousarray(np.asarray(maskij).astype(np.uint8))  # matching.py:745
+        if mask.shape != (n1, n2):
+            raise ValueError("maskij must be len(f1) x len(f2)")
+        mask_p = mask.ctypes.data_as(ctypes.c_void_p)
+    m = _thread_matcher(device)
+    fn = m.L.osfm_bf_match_u8 if a.dtype == np.uint8 else m.L.osfm_bf_match_f32
+    _lib.check(fn(m.h, a.ctypes.data_as(ctypes.c_void_p), n1, b.ctypes.data_as(ctypes.c_void_p), n2, dim,
+                  float(ratio), mask_p, int(symmetric), out.ctypes.data_as(ctypes.c_void_p)))
+    return out
+
+
+def match_brute_force(f1: np.ndarray, f2: np.ndarray, config: Dict[str, Any],
+                      maskij: Optional[np.ndarray] = None) -> List[Tuple[int, int]]:
+    """Brute force matching and Lowe's ratio filtering (matching.py:723-756)."""
+    idx = _match_raw(f1, f2, config["lowes_ratio"], maskij, False)
+    q = np.nonzero(idx >= 0)[0]
+    return [(int(i), int(idx[i])) for i in q]
+
+
+def match_brute_force_symmetric(fi: np.ndarray, fj: np.ndarray, config: Dict[str, Any],
+                                maskij: Optional[np.ndarray] = None) -> List[Tuple[int, int]]:
+    """Match in both directions and keep consistent matches (matching.py:759-777).
+    The reference returns `list(set & set)` (arbitrary order); this returns them sorted by i."""
+    idx = _match_raw(fi, fj, config["lowes_ratio"], maskij, True)
+    q = np.nonzero(idx >= 0)[0]
+    return [(int(i), int(idx[i])) for i in q]
+
+
+class PairMatcher:
+    """Descriptors resident in HBM + a pair list matched in one submission.
+
+    The batched form of the per-pair loop in `match_images_with_pairs`
+    (matching.py:63-98): upload every image's descriptors once (`add`), then
+    `match_pairs([(im1, im2), ...])` returns {(im1, im2): ndarray[K, 2]} like the
+    reference's result dict.
+    """
+
+    def __init__(self, device: int = 0, kernel: int = 0):
+        self._m = _Matcher(device)
+        self._ids: Dict[Any, int] = {}
+        self._n: Dict[Any, int] = {}
+        self._keep: Dict[Any, np.ndarray] = {}
+        if kernel:
+            _lib.check(self._m.L.osfm_matcher_set_kernel(self._m.h, int(kernel)))
+
+    def add(self, key: Any, desc: np.ndarray) -> None:
+        d = _prep(desc)
+        out = ctypes.c_int()
+        fn = self._m.L.osfm_matcher_add_u8 if d.dtype == np.uint8 else self._m.L.osfm_matcher_add_f32
+        _lib.check(fn(self._m.h, d.ctypes.data_as(ctypes.c_void_p), d.shape[0], d.shape[1], ctypes.byref(out)))
+        if key in self._ids:
+            _lib.check(self._m.L.osfm_matcher_remove(self._m.h, self._ids[key]))
+        self._ids[key] = out.value
+        self._n[key] = d.shape[0]
+
+    def submit(self, pairs: Sequence[Tuple[Any, Any]], lowes_ratio: float, symmetric: bool = True) -> None:
+        ia = np.array([self._ids[a] for a, _ in pairs], dtype=np.int32)
+        ib = np.array([self._ids[b] for _, b in pairs], dtype=np.int32)
+        self._pairs = list(pairs)
+        _lib.check(self._m.L.osfm_matcher_match_pairs_async(
+            self._m.h, len(pairs), ia.ctypes.data_as(ctypes.c_void_p), ib.ctypes.data_as(ctypes.c_void_p),
+            float(lowes_ratio), int(symmetric)))
+
+    def sync(self) -> None:
+        _lib.check(self._m.L.osfm_matcher_sync(self._m.h))
+
+    def fetch_raw(self) -> np.ndarray:
+        total = sum(self._n[a] for a, _ in self._pairs)
+        out = np.empty(max(total, 1), dtype=np.int32)
+        _lib.check(self._m.L.osfm_matcher_fetch(self._m.h, out.ctypes.data_as(ctypes.c_void_p), total))
+        return out[:total]
+
+    def device_ms(self) -> Tuple[float, float]:
+        a, b = ctypes.c_float(), ctypes.c_float()
+        _lib.check(self._m.L.osfm_matcher_last_device_ms(self._m.h, ctypes.byref(a), ctypes.byref(b)))
+        return a.value, b.value
+
+    def last_kernel(self) -> int:
+        return self._m.L.osfm_matcher_last_kernel(self._m.h)
+
+    def match_pairs(self, pairs: Sequence[Tuple[Any, Any]], config: Dict[str, Any],
+                    symmetric: Optional[bool] = None) -> Dict[Tuple[Any, Any], np.ndarray]:
+        if symmetric is None:
+            symmetric = bool(config.get("symmetric_matching", True))  # config.py:101
+        self.submit(pairs, config["lowes_ratio"], symmetric)
+        raw = self.fetch_raw()
+        res: Dict[Tuple[Any, Any], np.ndarray] = {}
+        off = 0
+        for a, b in self._pairs:
+            n = self._n[a]
+            idx = raw[off:off + n]
+            off += n
+            q = np.nonzero(idx >= 0)[0]
+            res[(a, b)] = np.stack([q, idx[q]], axis=1).astype(np.int64) if len(q) else np.zeros((0, 2), dtype=np.int64)
+        return res
+
+
+def shard_pairs(pairs: Sequence[Tuple[Any, Any]], sizes: Dict[Any, int], world: int) -> List[List[Tuple[Any, Any]]]:
+    """Split a pair list over `world` GPUs, balancing sum(N_i * M_i) (greedy LPT).
+
+    Image pairs are independent units (matching.py:83 maps a pure function over
+    them), so multi-GPU matching needs no collective: each rank matches its shard."""
+    order = sorted(range(len(pairs)), key=lambda i: -(sizes[pairs[i][0]] * sizes[pairs[i][1]]))
+    load = [0] * world
+    shards: List[List[int]] = [[] for _ in range(world)]
+    for i in order:
+        r = min(range(world), key=lambda k: load[k])
+        shards[r].append(i)
+        load[r] += sizes[pairs[i][0]] * sizes[pairs[i][1]]
+    return [[pairs[i] for i in sorted(s)] for s in shards]

@@ -1,0 +1,105 @@
+"""ORACLE — TEST INFRASTRUCTURE ONLY.  Not part of the shipped product.
+
+Two checkers for the brute-force matcher:
+
+1. `match_brute_force` / `match_brute_force_symmetric`: the reference code path
+   itself, restated line for line from opensfm/matching.py:723-777 around the
+   live `cv2` (4.13.0 in this image; reference pins opencv-python>=4.8,
+   pyproject.toml:31).  cv2 is importable here and on the GPU box, so this is
+   the *real reference* for the matcher ("kind": "reference" in bench.py).
+
+2. `knn2_numpy` / `match_brute_force_numpy`: a numpy restatement of what
+   cv2.BFMatcher.knnMatch(k=2) computes (OpenCV is a third-party dependency not
+   under /root/reference; algorithm restated from its published behaviour,
+   modules/core/src/batch_distance.cpp): for every query the two smallest
+   `sqrt(float32 sum of squared differences)` (L2) or integer Hamming counts,
+   ties resolved to the lowest train index (stable insertion with strict `<`),
+   masked-out trains skipped, queries with fewer than two candidates dropped by
+   matching.py:752.  It is pinned against cv2 in tests/test_match_oracle.py.
+
+Only tests/, __graft_entry__.smoke() and bench.py's CPU legs may import this.
+"""
+from __future__ import annotations
+
+from typing import Any, Dict, List, Optional, Tuple
+
+import numpy as np
+
+
+def match_brute_force(f1: np.ndarray, f2: np.ndarray, config: Dict[str, Any],
+                      maskij: Optional[np.ndarray] = None) -> List[Tuple[int, int]]:
+    """opensfm/matching.py:723-756 (cv2 knnMatch k=2 + Lowe ratio)."""
+    import cv2
+
+    assert f1.dtype.type == f2.dtype.type
+    if f1.dtype.type == np.uint8:
+        matcher_type = "BruteForce-Hamming"
+    else:
+        matcher_type = "BruteForce"
+    matcher = cv2.DescriptorMatcher_create(matcher_type)
+    matcher.add([f2])
+    if maskij is not None:
+        matches = matcher.knnMatch(f1, k=2, masks=np.array([maskij]).astype(np.uint8))
+    else:
+        matches = matcher.knnMatch(f1, k=2)
+    ratio = config["lowes_ratio"]
+    good_matches = []
+    for match in matches:
+        if match and len(match) == 2:
+            m, n = match
+            if m.distance < ratio * n.distance:
+                good_matches.append(m)
+    return [(mm.queryIdx, mm.trainIdx) for mm in good_matches]
+
+
+def match_brute_force_symmetric(fi: np.ndarray, fj: np.ndarray, config: Dict[str, Any],
+                                maskij: Optional[np.ndarray] = None) -> List[Tuple[int, int]]:
+    """opensfm/matching.py:759-777."""
+    matches_ij = [(a, b) for a, b in match_brute_force(fi, fj, config, maskij)]
+    maskijT = maskij.T if maskij is not None else None
+    matches_ji = [(b, a) for a, b in match_brute_force(fj, fi, config, maskijT)]
+    return list(set(matches_ij).intersection(set(matches_ji)))
+
+
+def distance_matrix(f1: np.ndarray, f2: np.ndarray) -> np.ndarray:
+    """float32 distances as cv2 returns them: sqrt of the float32 sum of squared
+    differences (exact for integer-valued descriptors), or Hamming bit counts."""
+    if f1.dtype == np.uint8:
+        x = np.bitwise_xor(f1[:, None, :], f2[None, :, :])
+        return np.unpackbits(x, axis=2).sum(axis=2).astype(np.float32)
+    a = f1.astype(np.float64)
+    b = f2.astype(np.float64)
+    d2 = (a * a).sum(1)[:, None] + (b * b).sum(1)[None, :] - 2.0 * (a @ b.T)
+    d2 = np.maximum(d2, 0.0).astype(np.float32)
+    return np.sqrt(d2)
+
+
+def knn2_numpy(f1: np.ndarray, f2: np.ndarray, maskij: Optional[np.ndarray] = None):
+    """(idx1, d1, idx2, d2) per query; idx -1 where fewer candidates exist."""
+    d = distance_matrix(f1, f2).astype(np.float64)
+    if maskij is not None:
+        d = np.where(maskij.astype(bool), d, np.inf)
+    n, m = d.shape
+    order = np.argsort(d, axis=1, kind="stable")[:, :2]
+    if m < 2:
+        order = np.concatenate([order, np.zeros((n, 2 - m), dtype=order.dtype)], axis=1)
+    rows = np.arange(n)
+    d1 = d[rows, order[:, 0]] if m >= 1 else np.full(n, np.inf)
+    d2 = d[rows, order[:, 1]] if m >= 2 else np.full(n, np.inf)
+    i1 = np.where(np.isfinite(d1), order[:, 0], -1)
+    i2 = np.where(np.isfinite(d2), order[:, 1], -1)
+    return i1, d1, i2, d2
+
+
+def match_brute_force_numpy(f1, f2, config, maskij=None) -> List[Tuple[int, int]]:
+    i1, d1, i2, d2 = knn2_numpy(f1, f2, maskij)
+    ratio = config["lowes_ratio"]
+    # m.distance (float32 -> Python float) < ratio * n.distance, matching.py:754
+    ok = (i1 >= 0) & (i2 >= 0) & (np.float32(d1).astype(np.float64) < ratio * np.float32(d2).astype(np.float64))
+    return [(int(q), int(i1[q])) for q in np.nonzero(ok)[0]]
+
+
+def match_brute_force_symmetric_numpy(fi, fj, config, maskij=None) -> List[Tuple[int, int]]:
+    mij = set(match_brute_force_numpy(fi, fj, config, maskij))
+    mji = set((b, a) for a, b in match_brute_force_numpy(fj, fi, config, None if maskij is None else maskij.T))
+    return list(mij & mji)

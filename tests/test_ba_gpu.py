@@ -1,0 +1,127 @@
+"""GPU parity of the bundle-adjustment engine against the oracle (restated Ceres path)."""
+import numpy as np
+import pytest
+
+from oracle import ba_lm as oracle
+from opensfm_b200 import ba_problem as bp
+from opensfm_b200 import bundle, synthetic as syn
+from opensfm_b200 import types as T
+
+pytestmark = pytest.mark.gpu
+
+POINT = [1.0, 2.0, 3.0]
+RT = [0.1, 0.2, 0.3, 0.4, 0.5, 0.6]
+OBS = [0.5, 0.5]
+SIGMA = 10.0  # scale 0.1 in the reference test
+# opensfm/src/bundle/test/reprojection_errors_test.cc:114-174
+CAMS = {
+    bp.BROWN: [0.3, 1.0, 0.001, -0.02, 0.1, -0.03, 0.001, -0.005, 0.001],
+    bp.PERSPECTIVE: [0.3, 0.1, -0.03],
+    bp.FISHEYE: [0.3, 0.1, -0.03],
+    bp.FISHEYE_OPENCV: [0.3, 1.0, 0.001, -0.02, 0.1, -0.03, 0.001, -0.005],
+    bp.FISHEYE62: [0.3, 1.0, 0.001, -0.02, 0.1, -0.03, 0.001, -0.005, 0.01, 0.006, 0.02, 0.003],
+    bp.FISHEYE624: [0.3, 1.0, 0.001, -0.02, 0.1, -0.03, 0.001, -0.005, 0.01, 0.006, 0.02, 0.003, 0.001, -0.009,
+                    -0.01, 0.03],
+    bp.DUAL: [0.5, 0.3, 0.1, -0.03],
+    bp.RADIAL: [0.1, -0.03, 0.3, 1.0, 0.001, -0.02],
+    bp.SIMPLE_RADIAL: [0.1, 0.3, 1.0, 0.001, -0.02],
+    bp.SPHERICAL: [0.0],
+}
+
+
+@pytest.mark.parametrize("ptype", sorted(CAMS))
+@pytest.mark.parametrize("use_rc", [True, False])
+def test_device_jacobian_matches_autodiff_on_reference_vectors(ptype, use_rc):
+    """Same inputs and tolerance (1e-14) as the reference's analytic-vs-autodiff tests."""
+    got = bundle.eval_observation(ptype, CAMS[ptype], RT, RT, use_rc, POINT, OBS, SIGMA)
+    ref = oracle.reprojection(ptype, CAMS[ptype], RT, RT, use_rc, POINT, OBS, SIGMA, autodiff=True)
+    for g, r in zip(got, ref):
+        if not use_rc and g.shape == (r.shape[0], 6) and np.all(r == 0):
+            continue
+        assert np.abs(g - r).max() < 1e-14
+
+
+def _compare(pb, tol_cost=1e-6, tol_param=2e-5):
+    ref = oracle.solve(pb)
+    got = bundle.solve(pb)
+    s = got["summary"]
+    assert s["termination"] == "CONVERGENCE", s
+    assert abs(s["initial_cost"] - ref["initial_cost"]) <= 1e-9 * ref["initial_cost"]
+    assert abs(s["final_cost"] - ref["final_cost"]) <= tol_cost * ref["final_cost"], (s, ref["final_cost"])
+    rm_ref = np.sqrt((ref["reprojection_errors"] ** 2).sum(1).mean())
+    rm_got = np.sqrt((got["reprojection_errors"] ** 2).sum(1).mean())
+    assert abs(rm_ref - rm_got) <= 1e-6 * rm_ref
+    assert np.abs(got["points"] - ref["points"]).max() < tol_param
+    assert np.abs(got["inst"] - ref["inst"]).max() < tol_param
+    assert np.abs(got["cam_params"] - ref["cam_params"]).max() < tol_param
+    return ref, got
+
+
+def test_cube_scene_small_matches_oracle():
+    sc = syn.cube_scene(10, 1000, 1.0, with_descriptors=False)
+    _compare(syn.scene_to_problem(sc))
+
+
+def test_cube_scene_shared_intrinsics_and_fixed_cameras():
+    sc = syn.cube_scene(8, 600, 1.0, with_descriptors=False)
+    _compare(syn.scene_to_problem(sc, shared_intrinsics=True))
+    _compare(syn.scene_to_problem(sc, optimize_cameras=False))
+
+
+@pytest.mark.parametrize("loss", ["TrivialLoss", "HuberLoss", "CauchyLoss", "ArctanLoss"])
+def test_losses(loss):
+    sc = syn.cube_scene(6, 300, 2.0, with_descriptors=False)
+    _compare(syn.scene_to_problem(sc, loss_name=loss, loss_threshold=1.0))
+
+
+def test_pose_only_and_point_only():
+    sc = syn.cube_scene(6, 400, 1.0, with_descriptors=False)
+    pb = syn.scene_to_problem(sc, optimize_cameras=False)
+    pb.point_const[:] = 1  # bundle_shot_poses: only poses free (ba_helpers.cc:408-579)
+    _compare(pb)
+    pb2 = syn.scene_to_problem(sc, optimize_cameras=False)
+    pb2.inst_const[:] = 1
+    _compare(pb2)
+
+
+def test_position_prior_and_thinned_visibility():
+    sc = syn.cube_scene(12, 800, 1.0, with_descriptors=False, max_obs_per_point=5)
+    pb = syn.scene_to_problem(sc)
+    pb.inst_has_prior[:] = 1
+    pb.inst_prior_pos = sc.origins + np.random.RandomState(1).normal(0, 0.01, sc.origins.shape)
+    pb.inst_prior_std = np.full((12, 3), 0.05)
+    _compare(pb)
+
+
+def test_bundle_adjuster_api_roundtrip():
+    sc = syn.cube_scene(5, 200, 1.0, with_descriptors=False)
+    pb = syn.scene_to_problem(sc)
+    ba = bundle.BundleAdjuster()
+    for i in range(5):
+        cam = T.Camera.create_perspective(0.9, -0.1, 0.01)
+        ba.add_camera("cam%d" % i, cam, cam, False)
+    ba.add_rig_camera("rc", T.Pose(), T.Pose(), True)
+    for i in range(5):
+        ba.add_rig_instance("inst%d" % i, T.Pose.from_ba_params(pb.inst[i]), {"shot%d" % i: "cam%d" % i},
+                            {"shot%d" % i: "rc"}, False)
+    for p in range(len(pb.points)):
+        ba.add_point("p%d" % p, pb.points[p], False)
+    for k in range(pb.num_observations):
+        ba.add_point_projection_observation("shot%d" % pb.obs_shot[k], "p%d" % pb.obs_point[k], pb.obs_xy[k], 0.004)
+    ba.set_point_projection_loss_function("SoftLOneLoss", 1.0)
+    ba.set_internal_parameters_prior_sd(0.01, 0.01, 0.01, 0.01, 0.01, 0.01, 0.01, 0.01, 0.01)
+    ba.set_max_num_iterations(100)
+    ba.run()
+    ref = oracle.solve(pb)
+    pts = np.array([ba.get_point("p%d" % p).p for p in range(len(pb.points))])
+    assert np.abs(pts - ref["points"]).max() < 2e-5
+    errs = ba.get_point("p0").reprojection_errors
+    assert set(errs) <= {"shot%d" % i for i in range(5)} and all(len(v) == 2 for v in errs.values())
+    assert "Termination" in ba.brief_report()
+    with pytest.raises(RuntimeError):
+        ba.get_camera("nope")
+    with pytest.raises(IndexError):
+        ba.add_point_projection_observation("nope", "p0", [0, 0], 1.0)
+    with pytest.raises(RuntimeError):
+        ba.set_point_projection_loss_function("NopeLoss", 1.0)
+        ba.run()

@@ -1,0 +1,143 @@
+"""GPU parity of the brute-force matcher against the reference's cv2 path (bit-exact indices)."""
+import numpy as np
+import pytest
+
+from oracle import match_oracle as mo
+from opensfm_b200 import matching, synthetic as syn
+
+pytestmark = pytest.mark.gpu
+CFG = {"lowes_ratio": 0.8}
+
+
+def _pairset(x):
+    return sorted((int(a), int(b)) for a, b in x)
+
+
+def _related(n1, n2, seed, lo=0, hi=255):
+    a = syn.hahog_like_descriptors(n1, seed)
+    b = syn.hahog_like_descriptors(n2, seed + 1)
+    k = min(n1, n2) // 2
+    rng = np.random.RandomState(seed + 2)
+    b[:k] = np.clip(a[:k] + rng.randint(-6, 7, (k, 128)), lo, hi).astype(np.float32)
+    perm = rng.permutation(n2)
+    return a, b[perm]
+
+
+@pytest.mark.parametrize("n1,n2", [(1, 2), (2, 1), (5, 3), (64, 64), (65, 129), (300, 1000), (1500, 1700)])
+def test_l2_one_way_matches_cv2(n1, n2):
+    a, b = _related(n1, n2, 10 + n1)
+    assert matching.match_brute_force(a, b, CFG) == mo.match_brute_force(a, b, CFG)
+
+
+def test_l2_ties_lowest_index_first():
+    a, b = _related(200, 400, 3)
+    b[300:310] = b[0:10]  # exact duplicates -> ties
+    for ratio in (0.8, 1.0, 1.5):
+        cfg = {"lowes_ratio": ratio}
+        assert matching.match_brute_force(a, b, cfg) == mo.match_brute_force(a, b, cfg)
+
+
+def test_l2_general_float_descriptors_simt():
+    rng = np.random.RandomState(0)
+    a = rng.rand(500, 128).astype(np.float32)
+    b = rng.rand(700, 128).astype(np.float32)
+    b[:250] = a[:250] + rng.normal(0, 0.02, (250, 128)).astype(np.float32)
+    assert matching.match_brute_force(a, b, CFG) == mo.match_brute_force(a, b, CFG)
+
+
+@pytest.mark.parametrize("dim", [32, 64, 100, 128])
+def test_l2_other_dims(dim):
+    rng = np.random.RandomState(dim)
+    a = rng.randint(0, 256, (333, dim)).astype(np.float32)
+    b = rng.randint(0, 256, (444, dim)).astype(np.float32)
+    b[:100] = np.clip(a[:100] + rng.randint(-3, 4, (100, dim)), 0, 255)
+    assert matching.match_brute_force(a, b, CFG) == mo.match_brute_force(a, b, CFG)
+
+
+def test_l2_mask():
+    a, b = _related(400, 500, 7)
+    rng = np.random.RandomState(1)
+    mask = rng.rand(400, 500) < 0.05
+    mask[:10] = False  # queries with no candidate
+    mask[10, :] = False
+    mask[10, 3] = True  # exactly one candidate -> dropped (matching.py:752)
+    assert matching.match_brute_force(a, b, CFG, mask) == mo.match_brute_force(a, b, CFG, mask)
+    assert _pairset(matching.match_brute_force_symmetric(a, b, CFG, mask)) == _pairset(
+        mo.match_brute_force_symmetric(a, b, CFG, mask))
+
+
+def test_l2_symmetric():
+    a, b = _related(900, 1100, 21)
+    assert _pairset(matching.match_brute_force_symmetric(a, b, CFG)) == _pairset(
+        mo.match_brute_force_symmetric(a, b, CFG))
+
+
+@pytest.mark.parametrize("nbytes", [32, 61, 64])
+def test_hamming(nbytes):
+    u1 = syn.binary_descriptors(700, 1, nbytes)
+    u2 = syn.binary_descriptors(900, 2, nbytes)
+    u2[:300] = u1[:300]
+    u2[:300, :3] ^= 5
+    assert matching.match_brute_force(u1, u2, CFG) == mo.match_brute_force(u1, u2, CFG)
+    assert _pairset(matching.match_brute_force_symmetric(u1, u2, CFG)) == _pairset(
+        mo.match_brute_force_symmetric(u1, u2, CFG))
+
+
+def test_empty_inputs():
+    a = np.zeros((0, 128), np.float32)
+    b = syn.hahog_like_descriptors(10, 1)
+    assert matching.match_brute_force(a, b, CFG) == []
+    assert matching.match_brute_force(b, a, CFG) == []
+
+
+def test_dtype_mismatch_asserts():
+    with pytest.raises(AssertionError):
+        matching.match_brute_force(np.zeros((2, 8), np.float32), np.zeros((2, 8), np.uint8), CFG)
+
+
+@pytest.mark.parametrize("kernel", [1, 2])
+def test_pair_batch_cube_scene_both_kernels(kernel):
+    sc = syn.cube_scene(6, 1500, 1.0)
+    feats = {s: sc.features_of_shot(s)[0] for s in range(6)}
+    pairs = [(i, j) for i in range(6) for j in range(i + 1, 6)]
+    pm = matching.PairMatcher(kernel=kernel)
+    for s, f in feats.items():
+        pm.add(s, f)
+    res = pm.match_pairs(pairs, {"lowes_ratio": 0.8, "symmetric_matching": True})
+    assert pm.last_kernel() == kernel
+    for (i, j) in pairs:
+        ref = _pairset(mo.match_brute_force_symmetric(feats[i], feats[j], CFG))
+        assert _pairset(res[(i, j)]) == ref, (i, j)
+    res1 = pm.match_pairs(pairs, {"lowes_ratio": 0.8}, symmetric=False)
+    for (i, j) in pairs:
+        assert [tuple(x) for x in res1[(i, j)].tolist()] == mo.match_brute_force(feats[i], feats[j], CFG)
+
+
+def test_tc_kernel_large_values_sqrt_collisions():
+    """d^2 near 2^23: distinct d^2 collapse to one float32 sqrt; cv2 ranks on the sqrt."""
+    rng = np.random.RandomState(5)
+    a = rng.randint(200, 256, (600, 128)).astype(np.float32)
+    b = rng.randint(0, 40, (700, 128)).astype(np.float32)
+    for kernel in (1, 2):
+        pm = matching.PairMatcher(kernel=kernel)
+        pm.add("a", a)
+        pm.add("b", b)
+        for ratio in (0.999, 1.0, 1.01):
+            got = pm.match_pairs([("a", "b")], {"lowes_ratio": ratio}, symmetric=False)[("a", "b")]
+            assert [tuple(x) for x in got.tolist()] == mo.match_brute_force(a, b, {"lowes_ratio": ratio})
+
+
+def test_threads_share_nothing():
+    import threading
+
+    a, b = _related(500, 600, 33)
+    ref = mo.match_brute_force(a, b, CFG)
+    out = [None] * 4
+
+    def work(i):
+        out[i] = matching.match_brute_force(a, b, CFG)
+
+    ts = [threading.Thread(target=work, args=(i,)) for i in range(4)]
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    assert all(o == ref for o in out)
