@@ -140,6 +140,13 @@ typedef struct {
   double time_device_ms;      /* CUDA-event time of the LM loop */
   double time_linearize_ms;   /* summed CUDA-event time of the linearise+accumulate kernel */
   int64_t linearize_launches;
+  double time_schur_ms;       /* summed CUDA-event time of the Schur-complement kernel */
+  int64_t schur_launches;
+  double time_pcg_ms;         /* summed CUDA-event time of the PCG solves */
+  double time_backsub_ms;
+  int64_t num_observations_local; /* observations held by this rank */
+  int reduced_dim;            /* dimension of the reduced camera system */
+  int jac_planes;             /* doubles stored per observation: nres * (wc + 3 + 1) */
   int64_t kernel_launches;
   char message[128];
 } osfm_ba_summary;

@@ -23,7 +23,9 @@ class BASummary(ctypes.Structure):
         ("iterations", c_int), ("successful_steps", c_int), ("linear_solves", c_int), ("pcg_iterations", c_int),
         ("termination", c_int), ("initial_cost", c_double), ("final_cost", c_double), ("time_run_s", c_double),
         ("time_device_ms", c_double), ("time_linearize_ms", c_double), ("linearize_launches", c_int64),
-        ("kernel_launches", c_int64), ("message", ctypes.c_char * 128),
+        ("time_schur_ms", c_double), ("schur_launches", c_int64), ("time_pcg_ms", c_double),
+        ("time_backsub_ms", c_double), ("num_observations_local", c_int64), ("reduced_dim", c_int),
+        ("jac_planes", c_int), ("kernel_launches", c_int64), ("message", ctypes.c_char * 128),
     ]
 
 

@@ -745,6 +745,25 @@ __global__ void ba_eval_one(int type, const double* in, int use_rc, double* out,
 // ---------------------------------------------------------------------------
 // Host side
 // ---------------------------------------------------------------------------
+// CUDA-event stopwatch on the launching stream; collect() after a stream synchronize.
+struct EventTimer {
+  cudaEvent_t a = nullptr, b = nullptr;
+  double total_ms = 0.0;
+  long long count = 0;
+  bool pending = false;
+  void init() { OSFM_CUDA(cudaEventCreate(&a)); OSFM_CUDA(cudaEventCreate(&b)); }
+  void destroy() { if (a) cudaEventDestroy(a); if (b) cudaEventDestroy(b); a = b = nullptr; }
+  void start(cudaStream_t st) { collect(); OSFM_CUDA(cudaEventRecord(a, st)); }
+  void stop(cudaStream_t st) { OSFM_CUDA(cudaEventRecord(b, st)); pending = true; }
+  void collect() {
+    if (!pending) return;
+    OSFM_CUDA(cudaEventSynchronize(b));
+    float ms = 0.f;
+    OSFM_CUDA(cudaEventElapsedTime(&ms, a, b));
+    total_ms += ms; ++count; pending = false;
+  }
+};
+
 template <class T>
 static void upload(DevBuf<T>& d, const std::vector<T>& h, cudaStream_t st) {
   d.reserve(std::max<size_t>(h.size(), 1));
@@ -983,11 +1002,10 @@ void BA::run() {
   int cur = 0;  // index of the accepted parameter set
   auto params_of = [&](int b) { return Params{d_cam[b].p, d_inst[b].p, d_rc[b].p, d_pts[b].p}; };
 
-  cudaEvent_t ev0, ev1, evl0, evl1;
+  cudaEvent_t ev0, ev1;
   OSFM_CUDA(cudaEventCreate(&ev0)); OSFM_CUDA(cudaEventCreate(&ev1));
-  OSFM_CUDA(cudaEventCreate(&evl0)); OSFM_CUDA(cudaEventCreate(&evl1));
-  double lin_ms = 0.0;
-  long long lin_launches = 0;
+  EventTimer tm_lin, tm_schur, tm_pcg, tm_back;
+  tm_lin.init(); tm_schur.init(); tm_pcg.init(); tm_back.init();
 
   // cost at parameter set b (sum over ranks)
   auto eval_cost = [&](int b) -> double {
@@ -1009,10 +1027,10 @@ void BA::run() {
     OSFM_CUDA(cudaMemsetAsync(d_colnorm2.p, 0, sizeof(double) * nz, stream));
     OSFM_CUDA(cudaMemsetAsync(d_grad.p, 0, sizeof(double) * nz, stream));
     if (N > 0) {
-      OSFM_CUDA(cudaEventRecord(evl0, stream));
+      tm_lin.start(stream);
       ba_linearize<1><<<grid_for(N, 128), 128, 0, stream>>>(v, params_of(b), d_sc.p, nullptr);
       OSFM_LAUNCH_CHECK();
-      OSFM_CUDA(cudaEventRecord(evl1, stream));
+      tm_lin.stop(stream);
       ba_colnorm_grad<<<grid_for(N, 256), 256, 0, stream>>>(v, d_colnorm2.p, d_grad.p);
       OSFM_LAUNCH_CHECK();
     }
@@ -1031,12 +1049,6 @@ void BA::run() {
       OSFM_LAUNCH_CHECK();
     }
     const Scalars s = read_scalars();
-    if (N > 0) {
-      float ms = 0.f;
-      OSFM_CUDA(cudaEventElapsedTime(&ms, evl0, evl1));
-      lin_ms += ms;
-      lin_launches++;
-    }
     double gm = s.grad_max_bits;
     if (world > 1) {
       // max over ranks of the local point-gradient maxima: sum of one-hot slots
@@ -1106,8 +1118,10 @@ void BA::run() {
     }
     if (P > 0) {
       const size_t smem = (size_t)SCHUR_KC * wc * (2 * 3 * sizeof(double) + 2 * sizeof(int));
+      tm_schur.start(stream);
       ba_schur<<<P, SCHUR_THREADS, smem, stream>>>(v, d_scale.p, d_diag.p, inv_radius, d_S.p, d_rhs.p, d_Vinv.p, d_gp.p);
       OSFM_LAUNCH_CHECK();
+      tm_schur.stop(stream);
     }
     bool ok = true;
     int pcg_it = 0;
@@ -1130,6 +1144,7 @@ void BA::run() {
       ba_finish_system<<<fg, 256, 0, stream>>>(d_S.p, d_diag.p, inv_radius, nc);
       OSFM_LAUNCH_CHECK();
       // --- PCG ---
+      tm_pcg.start(stream);
       pcg_factor_blocks<<<grid_for(nblk, 64), 64, 0, stream>>>(d_S.p, nc, d_blk_off.p, d_blk_sz.p, nblk, d_Minv.p);
       OSFM_LAUNCH_CHECK();
       OSFM_CUDA(cudaMemsetAsync(&d_sc.p->pcg_rz[0], 0, sizeof(double) * 5, stream));
@@ -1161,12 +1176,15 @@ void BA::run() {
       }
       pcg_total += pcg_it;
       OSFM_CUDA(cudaMemcpyAsync(d_y.p, d_px.p, sizeof(double) * nc, cudaMemcpyDeviceToDevice, stream));
+      tm_pcg.stop(stream);
     }
     ++n_solves;
     // --- back-substitution, model cost change ---
     if (P > 0 && npf > 0) {
+      tm_back.start(stream);
       ba_backsub<<<grid_for((long long)P * 32, 256), 256, 0, stream>>>(v, d_scale.p, d_Vinv.p, d_y.p);
       OSFM_LAUNCH_CHECK();
+      tm_back.stop(stream);
     }
     OSFM_CUDA(cudaMemsetAsync(&d_sc.p->model_change, 0, sizeof(double) * 3, stream));  // model_change, step_norm2, x_norm2
     if (N > 0) {
@@ -1254,7 +1272,8 @@ void BA::run() {
   }
   float dev_ms = 0.f;
   OSFM_CUDA(cudaEventElapsedTime(&dev_ms, ev0, ev1));
-  cudaEventDestroy(ev0); cudaEventDestroy(ev1); cudaEventDestroy(evl0); cudaEventDestroy(evl1);
+  cudaEventDestroy(ev0); cudaEventDestroy(ev1);
+  tm_lin.collect(); tm_schur.collect(); tm_pcg.collect(); tm_back.collect();
 
   summary = osfm_ba_summary{};
   summary.iterations = it;
@@ -1265,8 +1284,16 @@ void BA::run() {
   summary.initial_cost = initial_cost;
   summary.final_cost = final_cost;
   summary.time_device_ms = dev_ms;
-  summary.time_linearize_ms = lin_ms;
-  summary.linearize_launches = lin_launches;
+  summary.time_linearize_ms = tm_lin.total_ms;
+  summary.linearize_launches = tm_lin.count;
+  summary.time_schur_ms = tm_schur.total_ms;
+  summary.schur_launches = tm_schur.count;
+  summary.time_pcg_ms = tm_pcg.total_ms;
+  summary.time_backsub_ms = tm_back.total_ms;
+  summary.num_observations_local = N;
+  summary.reduced_dim = nc;
+  summary.jac_planes = nres * (wc + 3 + 1);
+  tm_lin.destroy(); tm_schur.destroy(); tm_pcg.destroy(); tm_back.destroy();
   summary.kernel_launches = g_kernel_launches.load() - launches0;
   snprintf(summary.message, sizeof(summary.message), "%s", message.c_str());
   summary.time_run_s =

@@ -126,12 +126,23 @@ def cube_scene(num_cameras: int, num_points: int, projection_noise: float = 1.0,
     desc = None
     if with_descriptors:
         desc = np.zeros((num_points, 128), dtype=np.float64)
-        # 5 x (randint, random) per point, in this order (synthetic_generator.py:391-397)
-        for p in range(num_points):
-            for _ in range(5):
-                index = rng.randint(0, 128)
-                desc[p, index] = rng.random_sample() * 255
+        if num_points <= 20000:
+            # 5 x (randint, random) per point, in this order (synthetic_generator.py:391-397)
+            for p in range(num_points):
+                for _ in range(5):
+                    index = rng.randint(0, 128)
+                    desc[p, index] = rng.random_sample() * 255
+        else:
+            # same distribution, vectorised draws (the large scenes have no reference sequence to follow)
+            idx = rng.randint(0, 128, (num_points, 5))
+            val = rng.random_sample((num_points, 5)) * 255
+            for k in range(5):
+                desc[np.arange(num_points), idx[:, k]] = val[:, k]
         desc = desc.round().astype(np.float32)
+
+    if max_obs_per_point is not None:
+        return _cube_scene_thinned(rng, R_wc, origins, points, cam_params, desc, projection_noise,
+                                   max_obs_per_point, maximum_depth)
 
     width, height = 800, 600
     perturbation = float(projection_noise) / float(max(width, height))
@@ -166,6 +177,59 @@ def cube_scene(num_cameras: int, num_points: int, projection_noise: float = 1.0,
         o_s, o_p, o_xy = o_s[keep], o_p[keep], o_xy[keep]
         order = np.lexsort((o_p, o_s))  # back to shot-major order
         o_s, o_p, o_xy = o_s[order], o_p[order], o_xy[order]
+    return SyntheticScene(R_wc=R_wc, origins=origins, points=points, cam_params=cam_params, obs_shot=o_s,
+                          obs_point=o_p, obs_xy=o_xy, obs_sigma=np.full(len(o_s), 0.004),
+                          track_descriptors=desc, width=width, height=height)
+
+
+def _cube_scene_thinned(rng, R_wc, origins, points, cam_params, desc, projection_noise, max_obs, maximum_depth,
+                        width=800, height=600, chunk=20000) -> SyntheticScene:
+    """Visibility thinned to the `max_obs` cameras whose view axis is closest to the point
+    direction (largest cosine), chunked over points so the 500 x 200k scene fits in memory.
+    Fixture generation only: uses torch (fp64; on the GPU when one is present) for the
+    S x P visibility sweep."""
+    import torch
+
+    dev = torch.device("cuda" if torch.cuda.is_available() else "cpu")
+    S, P = len(origins), len(points)
+    k1, k2, focal = (float(v) for v in cam_params[0])
+    perturbation = float(projection_noise) / float(max(width, height))
+    R = torch.from_numpy(R_wc).to(dev)
+    O = torch.from_numpy(origins).to(dev)
+    A = R.reshape(S * 3, 3)
+    Ao = torch.einsum("sij,sj->si", R, O).reshape(S * 3, 1)
+    o2 = (O * O).sum(1)[:, None]
+    kk = min(max_obs, S)
+    o_s, o_p, o_xy = [], [], []
+    for c0 in range(0, P, chunk):
+        pts = torch.from_numpy(points[c0:c0 + chunk]).to(dev)
+        n = pts.shape[0]
+        pc = (A @ pts.T - Ao).reshape(S, 3, n)
+        dist = torch.sqrt(torch.clamp((pts * pts).sum(1)[None, :] - 2.0 * (O @ pts.T) + o2, min=0.0))
+        z = pc[:, 2, :]
+        x = pc[:, 0, :] / z
+        y = pc[:, 1, :] / z
+        r2 = x * x + y * y
+        dd = 1.0 + r2 * (k1 + k2 * r2)
+        px, py = focal * x * dd, focal * y * dd
+        ok = (z > 0) & (dist <= maximum_depth) & (px.abs() < 0.5) & (py.abs() < height / (2.0 * width))
+        score = torch.where(ok, z / dist, torch.full_like(z, -float("inf")))
+        # ties broken by camera index (stable sort) so the selection is deterministic
+        order = torch.sort(-score, dim=0, stable=True).indices[:kk]      # kk x n camera ids
+        cols = torch.arange(n, device=dev)[None, :].expand(kk, n)
+        keep = torch.isfinite(score[order, cols])
+        cams = order[keep]
+        pidx = cols[keep]
+        o_s.append(cams.to(torch.int32).cpu().numpy())
+        o_p.append((pidx + c0).to(torch.int32).cpu().numpy())
+        o_xy.append(torch.stack([px[cams, pidx], py[cams, pidx]], dim=1).cpu().numpy())
+    o_s = np.concatenate(o_s)
+    o_p = np.concatenate(o_p)
+    o_xy = np.concatenate(o_xy)
+    order = np.lexsort((o_p, o_s))  # shot-major, like the reference's per-shot loop
+    o_s, o_p, o_xy = o_s[order], o_p[order], o_xy[order]
+    if perturbation > 0:
+        o_xy = o_xy + rng.normal(0.0, perturbation, o_xy.shape)
     return SyntheticScene(R_wc=R_wc, origins=origins, points=points, cam_params=cam_params, obs_shot=o_s,
                           obs_point=o_p, obs_xy=o_xy, obs_sigma=np.full(len(o_s), 0.004),
                           track_descriptors=desc, width=width, height=height)

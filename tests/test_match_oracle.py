@@ -1,0 +1,72 @@
+"""Pins the numpy restatement of cv2.BFMatcher.knnMatch against live cv2 (the real reference)."""
+import numpy as np
+import pytest
+
+from oracle import match_oracle as mo
+from opensfm_b200 import synthetic as syn
+
+cv2 = pytest.importorskip("cv2")
+CFG = {"lowes_ratio": 0.8}
+
+
+def _related(n1, n2, seed):
+    a = syn.hahog_like_descriptors(n1, seed)
+    b = syn.hahog_like_descriptors(n2, seed + 1)
+    k = min(n1, n2) // 2
+    b[:k] = np.clip(a[:k] + np.random.RandomState(seed + 2).randint(-6, 7, (k, 128)), 0, 255).astype(np.float32)
+    return a, b
+
+
+def test_l2_restated_equals_cv2():
+    a, b = _related(700, 900, 1)
+    b[800:805] = b[0:5]
+    for ratio in (0.6, 0.8, 1.0, 1.2):
+        cfg = {"lowes_ratio": ratio}
+        assert mo.match_brute_force_numpy(a, b, cfg) == mo.match_brute_force(a, b, cfg)
+
+
+def test_ties_go_to_lowest_train_index():
+    a = syn.hahog_like_descriptors(50, 3)
+    b = np.concatenate([a, a], axis=0)  # every query has two exact zero-distance candidates
+    m = cv2.DescriptorMatcher_create("BruteForce")
+    m.add([b])
+    res = m.knnMatch(a, k=2)
+    assert all(r[0].trainIdx == i and r[1].trainIdx == i + 50 for i, r in enumerate(res))
+    i1, d1, i2, d2 = mo.knn2_numpy(a, b)
+    assert (i1 == np.arange(50)).all() and (i2 == np.arange(50) + 50).all()
+
+
+def test_mask_and_short_rows():
+    a, b = _related(300, 350, 5)
+    mask = np.random.RandomState(0).rand(300, 350) < 0.03
+    mask[0] = False
+    mask[1] = False
+    mask[1, 7] = True
+    assert mo.match_brute_force_numpy(a, b, CFG, mask) == mo.match_brute_force(a, b, CFG, mask)
+    assert sorted(mo.match_brute_force_symmetric_numpy(a, b, CFG, mask)) == sorted(
+        mo.match_brute_force_symmetric(a, b, CFG, mask))
+
+
+def test_hamming_restated_equals_cv2():
+    u1 = syn.binary_descriptors(400, 1)
+    u2 = syn.binary_descriptors(500, 2)
+    u2[:150] = u1[:150]
+    u2[:150, :2] ^= 3
+    assert mo.match_brute_force_numpy(u1, u2, CFG) == mo.match_brute_force(u1, u2, CFG)
+
+
+def test_distance_is_sqrt_of_float32_sum():
+    a, b = _related(40, 60, 9)
+    m = cv2.DescriptorMatcher_create("BruteForce")
+    m.add([b])
+    res = m.knnMatch(a, k=1)
+    d = mo.distance_matrix(a, b)
+    for i, r in enumerate(res):
+        assert np.float32(r[0].distance) == d[i, r[0].trainIdx]
+
+
+def test_cube_scene_descriptors():
+    sc = syn.cube_scene(3, 800, 1.0)
+    f0, f1 = sc.features_of_shot(0)[0], sc.features_of_shot(1)[0]
+    assert f0.dtype == np.float32 and f0.shape[1] == 128
+    assert mo.match_brute_force_numpy(f0, f1, CFG) == mo.match_brute_force(f0, f1, CFG)
