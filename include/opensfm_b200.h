@@ -146,6 +146,8 @@ typedef struct {
   double time_backsub_ms;
   int64_t num_observations_local; /* observations held by this rank */
   int reduced_dim;            /* dimension of the reduced camera system */
+  int reduced_blocks;         /* stored blocks of the block-sparse reduced system (both triangles) */
+  int64_t reduced_nnz;        /* stored doubles of the reduced system */
   int jac_planes;             /* doubles stored per observation: nres * (wc + 3 + 1) */
   int64_t kernel_launches;
   char message[128];

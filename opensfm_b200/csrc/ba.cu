@@ -57,10 +57,6 @@ struct Scalars {
   double step_norm2;
   double x_norm2;
   double grad_max_bits;  // max |g| via atomicMax on the bit pattern (non-negative doubles)
-  double pcg_rz[2];
-  double pcg_pAp;
-  double pcg_rr;
-  double pcg_bb;
 };
 
 __device__ __forceinline__ double block_reduce_sum(double v) {
@@ -286,329 +282,9 @@ __global__ void ba_grad_max(const double* grad, int n, Scalars* sc) {
   if ((threadIdx.x & 31) == 0 && v > 0.0) atomic_max_nonneg(&sc->grad_max_bits, v);
 }
 
-// ---------------------------------------------------------------------------
-// Schur complement.  One CTA per point.
-//   U   += Jc_s^T Jc_s,  g_c += Jc_s^T r              (every observation)
-//   V    = sum Jp_s^T Jp_s + D_p ; g_p = sum Jp_s^T r   (free points)
-//   S   -= W_a V^-1 W_b^T,  rhs -= W_a V^-1 g_p         (all pairs a <= b, mirrored)
-// Only entries with global column g1 <= g2 are written (upper triangle); the
-// system is finished (all-reduce, priors, damping, mirror) by ba_finish_system.
-// Js = J diag(scale); diag = LM diagonal (already divided by the radius).
-// ---------------------------------------------------------------------------
-constexpr int SCHUR_THREADS = 128;
-constexpr int SCHUR_KC = 16;  // observations staged per chunk
-
-__global__ void __launch_bounds__(SCHUR_THREADS) ba_schur(BAView v, const double* __restrict__ scale,
-                                                          const double* __restrict__ diag, double inv_radius,
-                                                          double* __restrict__ Smat, double* __restrict__ rhs,
-                                                          double* __restrict__ Vinv, double* __restrict__ gpo) {
-  extern __shared__ double sm[];
-  const int wc = v.wc, nres = v.nres, nc = v.nc;
-  // smem: Ya[KC][wc][3], Wb[KC][wc][3], cols a/b [KC][wc] (int), red[...]
-  double* Ya = sm;
-  double* Wb = Ya + SCHUR_KC * wc * 3;
-  int* ca = reinterpret_cast<int*>(Wb + SCHUR_KC * wc * 3);
-  int* cb = ca + SCHUR_KC * wc;
-  __shared__ double sV[9], sVi[9], sg[3], sVig[3];
-
-  const int p = blockIdx.x;
-  const long long b0 = v.pt_start[p], e0 = v.pt_start[p + 1];
-  const int k = (int)(e0 - b0);
-  if (k == 0) return;
-  const int pf = v.pt_poff[p];
-  const size_t N = (size_t)v.N;
-  const int tid = threadIdx.x;
-
-  // ---- U and g_c: (obs, c1, c2 >= c1 in global order) ----
-  for (int idx = tid; idx < k * wc; idx += SCHUR_THREADS) {
-    const int a = idx / wc, c1 = idx % wc;
-    const long long i = b0 + a;
-    const ObsCols oc = obs_cols(v, i);
-    const int g1 = oc.col(c1);
-    if (g1 < 0) continue;
-    const double s1 = scale[g1];
-    double j1[3], rr[3];
-    for (int q = 0; q < nres; ++q) {
-      j1[q] = v.Jc[((size_t)q * wc + c1) * N + i] * s1;
-      rr[q] = v.r[q * N + i];
-    }
-    double g = 0.0;
-    for (int q = 0; q < nres; ++q) g += j1[q] * rr[q];
-    atomicAdd(&rhs[g1], g);
-    for (int c2 = 0; c2 < wc; ++c2) {
-      const int g2 = oc.col(c2);
-      if (g2 < g1) continue;  // also skips -1 / -2
-      const double s2 = scale[g2];
-      double val = 0.0;
-      for (int q = 0; q < nres; ++q) val += j1[q] * v.Jc[((size_t)q * wc + c2) * N + i] * s2;
-      atomicAdd(&Smat[(size_t)g1 * nc + g2], val);
-    }
-  }
-  if (pf < 0) return;
-
-  // ---- V, g_p ----
-  double acc[9];
-#pragma unroll
-  for (int j = 0; j < 9; ++j) acc[j] = 0.0;
-  const double sp0 = scale[nc + 3 * pf], sp1 = scale[nc + 3 * pf + 1], sp2 = scale[nc + 3 * pf + 2];
-  for (int a = tid; a < k; a += SCHUR_THREADS) {
-    const long long i = b0 + a;
-    for (int q = 0; q < nres; ++q) {
-      const double x = v.Jp[((size_t)q * 3 + 0) * N + i] * sp0;
-      const double y = v.Jp[((size_t)q * 3 + 1) * N + i] * sp1;
-      const double z = v.Jp[((size_t)q * 3 + 2) * N + i] * sp2;
-      const double rq = v.r[q * N + i];
-      acc[0] += x * x; acc[1] += x * y; acc[2] += x * z; acc[3] += y * y; acc[4] += y * z; acc[5] += z * z;
-      acc[6] += x * rq; acc[7] += y * rq; acc[8] += z * rq;
-    }
-  }
-  for (int j = 0; j < 9; ++j) {
-    const double t = block_reduce_sum(acc[j]);
-    if (tid == 0) sV[j] = t;
-  }
-  if (tid == 0) {
-    const double a = sV[0] + diag[nc + 3 * pf] * inv_radius, b = sV[1], c = sV[2];
-    const double d = sV[3] + diag[nc + 3 * pf + 1] * inv_radius, e = sV[4];
-    const double f = sV[5] + diag[nc + 3 * pf + 2] * inv_radius;
-    const double A = d * f - e * e, B = c * e - b * f, Cc = b * e - c * d;
-    const double id = 1.0 / (a * A + b * B + c * Cc);
-    sVi[0] = A * id; sVi[1] = B * id; sVi[2] = Cc * id;
-    sVi[3] = B * id; sVi[4] = (a * f - c * c) * id; sVi[5] = (b * c - a * e) * id;
-    sVi[6] = Cc * id; sVi[7] = sVi[5]; sVi[8] = (a * d - b * b) * id;
-    sg[0] = sV[6]; sg[1] = sV[7]; sg[2] = sV[8];
-    for (int j = 0; j < 3; ++j) sVig[j] = sVi[j * 3] * sg[0] + sVi[j * 3 + 1] * sg[1] + sVi[j * 3 + 2] * sg[2];
-    const size_t NP = (size_t)v.npf;
-    Vinv[0 * NP + pf] = sVi[0]; Vinv[1 * NP + pf] = sVi[1]; Vinv[2 * NP + pf] = sVi[2];
-    Vinv[3 * NP + pf] = sVi[4]; Vinv[4 * NP + pf] = sVi[5]; Vinv[5 * NP + pf] = sVi[8];
-    gpo[0 * NP + pf] = sg[0]; gpo[1 * NP + pf] = sg[1]; gpo[2 * NP + pf] = sg[2];
-  }
-  __syncthreads();
-
-  // ---- pairs, tiled KC x KC over (a-chunk <= b-chunk) ----
-  for (int a0 = 0; a0 < k; a0 += SCHUR_KC) {
-    const int na = min(SCHUR_KC, k - a0);
-    __syncthreads();
-    // stage Y_a = W_a V^-1 and the columns of chunk a; also rhs -= W_a V^-1 g_p
-    for (int idx = tid; idx < na * wc; idx += SCHUR_THREADS) {
-      const int a = idx / wc, c1 = idx % wc;
-      const long long i = b0 + a0 + a;
-      const ObsCols oc = obs_cols(v, i);
-      const int g1 = oc.col(c1);
-      ca[a * wc + c1] = g1;
-      double w0 = 0.0, w1 = 0.0, w2 = 0.0;
-      if (g1 >= 0) {
-        const double s1 = scale[g1];
-        for (int q = 0; q < nres; ++q) {
-          const double jc = v.Jc[((size_t)q * wc + c1) * N + i] * s1;
-          w0 += jc * v.Jp[((size_t)q * 3 + 0) * N + i] * sp0;
-          w1 += jc * v.Jp[((size_t)q * 3 + 1) * N + i] * sp1;
-          w2 += jc * v.Jp[((size_t)q * 3 + 2) * N + i] * sp2;
-        }
-        atomicAdd(&rhs[g1], -(w0 * sVig[0] + w1 * sVig[1] + w2 * sVig[2]));
-      }
-      double* y = Ya + (a * wc + c1) * 3;
-      y[0] = w0 * sVi[0] + w1 * sVi[3] + w2 * sVi[6];
-      y[1] = w0 * sVi[1] + w1 * sVi[4] + w2 * sVi[7];
-      y[2] = w0 * sVi[2] + w1 * sVi[5] + w2 * sVi[8];
-    }
-    for (int bb0 = a0; bb0 < k; bb0 += SCHUR_KC) {
-      const int nb = min(SCHUR_KC, k - bb0);
-      __syncthreads();
-      for (int idx = tid; idx < nb * wc; idx += SCHUR_THREADS) {
-        const int b = idx / wc, c2 = idx % wc;
-        const long long i = b0 + bb0 + b;
-        const ObsCols oc = obs_cols(v, i);
-        const int g2 = oc.col(c2);
-        cb[b * wc + c2] = g2;
-        double w0 = 0.0, w1 = 0.0, w2 = 0.0;
-        if (g2 >= 0) {
-          const double s2 = scale[g2];
-          for (int q = 0; q < nres; ++q) {
-            const double jc = v.Jc[((size_t)q * wc + c2) * N + i] * s2;
-            w0 += jc * v.Jp[((size_t)q * 3 + 0) * N + i] * sp0;
-            w1 += jc * v.Jp[((size_t)q * 3 + 1) * N + i] * sp1;
-            w2 += jc * v.Jp[((size_t)q * 3 + 2) * N + i] * sp2;
-          }
-        }
-        double* w = Wb + (b * wc + c2) * 3;
-        w[0] = w0; w[1] = w1; w[2] = w2;
-      }
-      __syncthreads();
-      // all (a, c1, b, c2) of this tile pair with global obs index a <= b
-      const int rowlen = nb * wc;
-      const int total = na * wc * rowlen;
-      for (int idx = tid; idx < total; idx += SCHUR_THREADS) {
-        const int ac = idx / rowlen, bc = idx % rowlen;
-        const int a = ac / wc, b = bc / wc;
-        const int ga = a0 + a, gb = bb0 + b;
-        if (gb < ga) continue;
-        const int g1 = ca[ac], g2 = cb[bc];
-        if (g1 < 0 || g2 < 0) continue;
-        const double* y = Ya + ac * 3;
-        const double* w = Wb + bc * 3;
-        double val = y[0] * w[0] + y[1] * w[1] + y[2] * w[2];
-        if (ga == gb) {
-          if (g2 < g1) continue;  // same observation: each (c1,c2) with g1 <= g2 once
-          atomicAdd(&Smat[(size_t)g1 * nc + g2], -val);
-        } else {
-          if (g1 == g2) val *= 2.0;  // (a,b) and (b,a) both land on the diagonal entry
-          const int lo = min(g1, g2), hi = max(g1, g2);
-          atomicAdd(&Smat[(size_t)lo * nc + hi], -val);
-        }
-      }
-    }
-  }
-}
-
-// After the (optional) all-reduce of the upper triangle: add priors and LM damping
-// to the diagonal, then mirror to the lower triangle.
-__global__ void ba_prior_system(PriorView pv, Params p, const double* scale, double* Smat, double* rhs, int nc) {
-  const int row = blockIdx.x * blockDim.x + threadIdx.x;
-  if (row >= pv.n_cam_rows + pv.n_pos_rows) return;
-  double r, d;
-  int col;
-  prior_row(pv, p, row, &r, &col, &d);
-  const double ds = d * scale[col];
-  atomicAdd(&Smat[(size_t)col * nc + col], ds * ds);
-  atomicAdd(&rhs[col], ds * r);
-}
-__global__ void ba_finish_system(double* Smat, const double* diag, double inv_radius, int nc) {
-  const int j = blockIdx.x * blockDim.x + threadIdx.x;
-  const int i = blockIdx.y;
-  if (j >= nc) return;
-  if (i == j) Smat[(size_t)i * nc + i] += diag[i] * inv_radius;
-  else if (j < i) Smat[(size_t)i * nc + j] = Smat[(size_t)j * nc + i];
-}
-
-// ---------------------------------------------------------------------------
-// PCG on S y = rhs with a block-Jacobi preconditioner (one block per parameter block).
-// ---------------------------------------------------------------------------
-constexpr int MAXB = 16;
-// Cholesky-inverts each diagonal block into Minv[b][MAXB*MAXB] (dense, row-major sz x sz).
-__global__ void pcg_factor_blocks(const double* __restrict__ Smat, int nc, const int* __restrict__ blk_off,
-                                  const int* __restrict__ blk_sz, int nblk, double* __restrict__ Minv) {
-  const int b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= nblk) return;
-  const int o = blk_off[b], n = blk_sz[b];
-  double L[MAXB * MAXB];
-  for (int i = 0; i < n; ++i)
-    for (int j = 0; j <= i; ++j) L[i * MAXB + j] = Smat[(size_t)(o + i) * nc + o + j];
-  // in-place Cholesky (lower)
-  for (int j = 0; j < n; ++j) {
-    double d = L[j * MAXB + j];
-    for (int k = 0; k < j; ++k) d -= L[j * MAXB + k] * L[j * MAXB + k];
-    d = sqrt(fmax(d, 1e-300));
-    L[j * MAXB + j] = d;
-    for (int i = j + 1; i < n; ++i) {
-      double s = L[i * MAXB + j];
-      for (int k = 0; k < j; ++k) s -= L[i * MAXB + k] * L[j * MAXB + k];
-      L[i * MAXB + j] = s / d;
-    }
-  }
-  // inverse: solve L L^T X = I column by column
-  double* out = Minv + (size_t)b * MAXB * MAXB;
-  for (int c = 0; c < n; ++c) {
-    double y[MAXB];
-    for (int i = 0; i < n; ++i) {
-      double s = (i == c) ? 1.0 : 0.0;
-      for (int k = 0; k < i; ++k) s -= L[i * MAXB + k] * y[k];
-      y[i] = s / L[i * MAXB + i];
-    }
-    for (int i = n - 1; i >= 0; --i) {
-      double s = y[i];
-      for (int k = i + 1; k < n; ++k) s -= L[k * MAXB + i] * y[k];
-      y[i] = s / L[i * MAXB + i];
-    }
-    for (int i = 0; i < n; ++i) out[i * MAXB + c] = y[i];
-  }
-}
-
-// z = Minv r for the rows of one block; accumulates r.z into *rz and r.r into *rr
-__device__ __forceinline__ void apply_block(const double* Minv, const int* blk_off, const int* blk_sz, int b,
-                                            const double* r, double* z, double* rz, double* rr) {
-  const int o = blk_off[b], n = blk_sz[b];
-  const double* M = Minv + (size_t)b * MAXB * MAXB;
-  double a_rz = 0.0, a_rr = 0.0;
-  for (int i = 0; i < n; ++i) {
-    double s = 0.0;
-    for (int j = 0; j < n; ++j) s += M[i * MAXB + j] * r[o + j];
-    z[o + i] = s;
-    a_rz += s * r[o + i];
-    a_rr += r[o + i] * r[o + i];
-  }
-  *rz = a_rz;
-  *rr = a_rr;
-}
-
-__global__ void pcg_init(const double* rhs, double* x, double* r, double* z, double* p, int nc,
-                         const double* Minv, const int* blk_off, const int* blk_sz, int nblk, Scalars* sc) {
-  const int b = blockIdx.x * blockDim.x + threadIdx.x;
-  double rz = 0.0, rr = 0.0;
-  if (b < nblk) {
-    const int o = blk_off[b], n = blk_sz[b];
-    for (int i = 0; i < n; ++i) { x[o + i] = 0.0; r[o + i] = rhs[o + i]; }
-    apply_block(Minv, blk_off, blk_sz, b, r, z, &rz, &rr);
-    for (int i = 0; i < n; ++i) p[o + i] = z[o + i];
-  }
-  const double t1 = block_reduce_sum(rz);
-  const double t2 = block_reduce_sum(rr);
-  if (threadIdx.x == 0) {
-    atomicAdd(&sc->pcg_rz[0], t1);
-    atomicAdd(&sc->pcg_bb, t2);
-    atomicAdd(&sc->pcg_rr, t2);
-  }
-}
-
-// Ap = S p (one warp per row), pAp += p.Ap ; zeroes the next rz accumulator
-__global__ void __launch_bounds__(256) pcg_matvec(const double* __restrict__ Smat, const double* __restrict__ p,
-                                                  double* __restrict__ Ap, int nc, Scalars* sc, int it) {
-  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  const int lane = threadIdx.x & 31;
-  if (blockIdx.x == 0 && threadIdx.x == 0) {
-    sc->pcg_rz[(it + 1) & 1] = 0.0;
-    sc->pcg_rr = 0.0;
-  }
-  double s = 0.0;
-  if (row < nc) {
-    const double* Srow = Smat + (size_t)row * nc;
-    for (int j = lane; j < nc; j += 32) s += Srow[j] * p[j];
-#pragma unroll
-    for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    if (lane == 0) Ap[row] = s;
-  }
-  double contrib = (row < nc && lane == 0) ? s * p[row] : 0.0;
-  const double t = block_reduce_sum(contrib);
-  if (threadIdx.x == 0) atomicAdd(&sc->pcg_pAp, t);
-}
-
-// x += alpha p ; r -= alpha Ap ; z = Minv r ; rz_new, rr
-__global__ void pcg_update1(double* x, double* r, double* z, const double* p, const double* Ap,
-                            const double* Minv, const int* blk_off, const int* blk_sz, int nblk, Scalars* sc, int it) {
-  const int b = blockIdx.x * blockDim.x + threadIdx.x;
-  const double alpha = sc->pcg_rz[it & 1] / sc->pcg_pAp;
-  double rz = 0.0, rr = 0.0;
-  if (b < nblk) {
-    const int o = blk_off[b], n = blk_sz[b];
-    for (int i = 0; i < n; ++i) {
-      x[o + i] += alpha * p[o + i];
-      r[o + i] -= alpha * Ap[o + i];
-    }
-    apply_block(Minv, blk_off, blk_sz, b, r, z, &rz, &rr);
-  }
-  const double t1 = block_reduce_sum(rz);
-  const double t2 = block_reduce_sum(rr);
-  if (threadIdx.x == 0) {
-    atomicAdd(&sc->pcg_rz[(it + 1) & 1], t1);
-    atomicAdd(&sc->pcg_rr, t2);
-  }
-}
-// p = z + beta p ; reset pAp
-__global__ void pcg_update2(double* p, const double* z, int nc, Scalars* sc, int it) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  const double beta = sc->pcg_rz[(it + 1) & 1] / sc->pcg_rz[it & 1];
-  if (i < nc) p[i] = z[i] + beta * p[i];
-  if (i == 0) sc->pcg_pAp = 0.0;  // read by pcg_update1 of this iteration (earlier kernel), reset for the next
-}
+}  // namespace osfm
+#include "ba_reduced.cuh"
+namespace osfm {
 
 // ---------------------------------------------------------------------------
 // Back-substitution: y_p = V^-1 (g_p - W^T y_c)  (scaled system), one warp per point.
@@ -807,7 +483,18 @@ struct BA {
   DevBuf<double> d_r, d_Jc, d_Jp, d_S, d_rhs, d_Vinv, d_gp;
   DevBuf<double> d_scale, d_colnorm2, d_grad, d_diag, d_y;
   DevBuf<double> d_px, d_pr, d_pz, d_pp, d_pAp, d_Minv, d_reproj, d_full_pts;
-  DevBuf<int> d_blk_off, d_blk_sz;
+  DevBuf<int> d_blk_off, d_blk_sz, d_cam_blk, d_inst_blk, d_rc_blk;
+  // block-sparse reduced system (ba_reduced.cuh)
+  DevBuf<unsigned long long> d_tkeys, d_skeys, d_skeys2, d_rkeys, d_rkeys2;
+  DevBuf<int> d_tvals, d_area, d_offs, d_row_ptr, d_row_col, d_row_off, d_diag_off, d_prior_diag_off;
+  DevBuf<int> d_pr_blk, d_pr_local, d_g_obs_shot, d_g_obs_point;
+  DevBuf<long long> d_g_pt_start;
+  DevBuf<int4> d_upper;
+  DevBuf<unsigned> d_count;
+  DevBuf<char> d_cub;
+  DevBuf<PcgState> d_pcg;
+  PinnedBuf<PcgState> h_pcg;
+  int num_sms = 148;
   DevBuf<int> d_pr_cam_param, d_pr_cam_col, d_pr_cam_log, d_pr_pos_inst, d_pr_pos_axis, d_pr_pos_col;
   DevBuf<double> d_pr_cam_prior, d_pr_cam_scale, d_pr_pos_prior, d_pr_pos_scale;
   DevBuf<Scalars> d_sc;
@@ -819,6 +506,8 @@ struct BA {
     OSFM_CUDA(cudaStreamCreateWithFlags(&own_stream, cudaStreamNonBlocking));
     stream = own_stream;
     h_sc.reserve(1);
+    h_pcg.reserve(1);
+    OSFM_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, device));
   }
   ~BA() {
     cudaSetDevice(device);
@@ -884,6 +573,14 @@ void BA::run() {
   }
   const int nc = off;
   const int nblk = (int)blk_off.size();
+  // parameter-block id of every camera / rig instance / rig camera (-1 = constant)
+  std::vector<int> cam_blk(std::max(K, 1), -1), inst_blk(std::max(NI, 1), -1), rc_blk(std::max(NR, 1), -1);
+  {
+    int b = 0;
+    for (int k = 0; k < K; ++k) if (!cam_const[k]) cam_blk[k] = b++;
+    for (int i = 0; i < NI; ++i) if (!inst_const[i]) inst_blk[i] = b++;
+    for (int i = 0; i < NR; ++i) if (!rc_const[i]) rc_blk[i] = b++;
+  }
 
   // ---- shard points over ranks (p % world == rank), sort observations by point ----
   std::vector<int> local_of(Pfull, -1), global_of;
@@ -947,6 +644,15 @@ void BA::run() {
   }
   const int npr = (int)(pr_cam_param.size() + pr_pos_inst.size());
   const bool add_priors = rank == 0;
+  std::vector<int> pr_blk, pr_local;  // diagonal entry of every prior row inside its diagonal block
+  for (int k = 0; k < K; ++k) {
+    if (cam_poff[k] < 0) continue;
+    for (int j = 0; j < cam_np[k]; ++j) { pr_blk.push_back(cam_blk[k]); pr_local.push_back(j); }
+  }
+  for (int i = 0; i < NI; ++i) {
+    if (!inst_has_prior[i] || inst_poff[i] < 0) continue;
+    for (int j = 0; j < 3; ++j) { pr_blk.push_back(inst_blk[i]); pr_local.push_back(3 + j); }
+  }
 
   // ---- upload ----
   upload(d_cam_type, cam_type, stream); upload(d_cam_off, cam_off, stream); upload(d_cam_np, cam_np, stream);
@@ -964,6 +670,8 @@ void BA::run() {
     upload(d_pts[b], lpts, stream);
   }
   upload(d_blk_off, blk_off, stream); upload(d_blk_sz, blk_sz, stream);
+  upload(d_cam_blk, cam_blk, stream); upload(d_inst_blk, inst_blk, stream); upload(d_rc_blk, rc_blk, stream);
+  upload(d_pr_blk, pr_blk, stream); upload(d_pr_local, pr_local, stream);
   upload(d_pr_cam_param, pr_cam_param, stream); upload(d_pr_cam_col, pr_cam_col, stream);
   upload(d_pr_cam_log, pr_cam_log, stream); upload(d_pr_cam_prior, pr_cam_prior, stream);
   upload(d_pr_cam_scale, pr_cam_scale, stream); upload(d_pr_pos_inst, pr_pos_inst, stream);
@@ -971,12 +679,13 @@ void BA::run() {
   upload(d_pr_pos_prior, pr_pos_prior, stream); upload(d_pr_pos_scale, pr_pos_scale, stream);
   const size_t Nz = (size_t)std::max<long long>(N, 1);
   d_r.reserve(nres * Nz); d_Jc.reserve((size_t)nres * wc * Nz); d_Jp.reserve((size_t)nres * 3 * Nz);
-  d_S.reserve((size_t)std::max(nc, 1) * std::max(nc, 1)); d_rhs.reserve(std::max(nc, 1));
+  d_rhs.reserve(std::max(nc, 1));
   d_Vinv.reserve(6 * (size_t)std::max(npf, 1)); d_gp.reserve(3 * (size_t)std::max(npf, 1));
   const size_t nz = (size_t)std::max(n, 1);
   d_scale.reserve(nz); d_colnorm2.reserve(nz); d_grad.reserve(nz); d_diag.reserve(nz); d_y.reserve(nz);
   d_px.reserve(std::max(nc, 1)); d_pr.reserve(std::max(nc, 1)); d_pz.reserve(std::max(nc, 1));
   d_pp.reserve(std::max(nc, 1)); d_pAp.reserve(std::max(nc, 1));
+  d_pcg.reserve(1);
   d_Minv.reserve((size_t)std::max(nblk, 1) * MAXB * MAXB);
   d_sc.reserve(1);
 
@@ -1066,6 +775,108 @@ void BA::run() {
     return s.cost;
   };
 
+  // ---- block-sparse structure of the reduced camera system (identical on every rank) ----
+  BlkMaps bm{d_cam_blk.p, d_inst_blk.p, d_rc_blk.p};
+  BsrView bsr{};
+  int n_upper = 0, n_blocks_all = 0;
+  long long s_upper_total = 0, s_total = 0;
+  if (nblk > 0) {
+    // global CSR by point (every rank needs the same structure, not only its shard)
+    const int* g_shot = d_obs_shot.p;
+    const int* g_point = d_obs_point.p;
+    const long long* g_start = d_pt_start.p;
+    long long pair_bound = 0;
+    if (world > 1) {
+      std::vector<long long> gs(Pfull + 1, 0);
+      for (long long i = 0; i < Nfull; ++i) gs[obs_point[i] + 1]++;
+      for (int p = 0; p < Pfull; ++p) gs[p + 1] += gs[p];
+      std::vector<long long> gf(gs.begin(), gs.end() - 1);
+      std::vector<int> gshot(Nfull), gpoint(Nfull);
+      for (long long i = 0; i < Nfull; ++i) { const long long d = gf[obs_point[i]]++; gshot[d] = obs_shot[i]; gpoint[d] = obs_point[i]; }
+      upload(d_g_obs_shot, gshot, stream); upload(d_g_obs_point, gpoint, stream); upload(d_g_pt_start, gs, stream);
+      OSFM_CUDA(cudaStreamSynchronize(stream));  // host vectors go out of scope
+      g_shot = d_g_obs_shot.p; g_point = d_g_obs_point.p; g_start = d_g_pt_start.p;
+      for (int p = 0; p < Pfull; ++p) { const long long k = gs[p + 1] - gs[p]; pair_bound += k * (k + 1) / 2; }
+    } else {
+      for (int p = 0; p < P; ++p) { const long long k = pt_start[p + 1] - pt_start[p]; pair_bound += k * (k + 1) / 2; }
+    }
+    const long long bound = std::min<long long>((long long)nblk * (nblk + 1) / 2, 9 * pair_bound + nblk);
+    unsigned tsize = 1024;
+    while ((long long)tsize < 4 * bound) {
+      if (tsize >= (1u << 28)) throw std::runtime_error("reduced camera system has too many block pairs");
+      tsize <<= 1;
+    }
+    d_tkeys.reserve(tsize); d_tvals.reserve(tsize);
+    OSFM_CUDA(cudaMemsetAsync(d_tkeys.p, 0xff, sizeof(unsigned long long) * tsize, stream));
+    BAView vg = v;  // only the shot tables are used by the enumeration
+    const long long n_enum = world > 1 ? Nfull : N;
+    if (n_enum > 0) {
+      bsr_enum_pairs<<<grid_for(n_enum, 128), 128, 0, stream>>>(vg, bm, g_shot, g_start, g_point, n_enum, d_tkeys.p,
+                                                              tsize - 1, nblk);
+      OSFM_LAUNCH_CHECK();
+    }
+    bsr_insert_diagonal<<<grid_for(nblk, 128), 128, 0, stream>>>(d_tkeys.p, tsize - 1, nblk);
+    OSFM_LAUNCH_CHECK();
+    const size_t cap = (size_t)(2 * bound + 16);
+    d_skeys.reserve(cap); d_skeys2.reserve(cap); d_rkeys.reserve(cap); d_rkeys2.reserve(cap);
+    d_area.reserve(cap); d_offs.reserve(cap); d_count.reserve(4);
+    OSFM_CUDA(cudaMemsetAsync(d_count.p, 0, sizeof(unsigned), stream));
+    bsr_compact<<<grid_for(tsize, 256), 256, 0, stream>>>(d_tkeys.p, tsize, nblk, d_skeys.p, d_count.p);
+    OSFM_LAUNCH_CHECK();
+    unsigned n_all_u = 0;
+    OSFM_CUDA(cudaMemcpyAsync(&n_all_u, d_count.p, sizeof(unsigned), cudaMemcpyDeviceToHost, stream));
+    OSFM_CUDA(cudaStreamSynchronize(stream));
+    const int n_all = (int)n_all_u;
+    n_blocks_all = n_all;
+    n_upper = nblk + (n_all - nblk) / 2;
+    // sort: upper keys (bit 63 clear) first, each group ordered by (bi, bj)
+    size_t tmp1 = 0, tmp2 = 0;
+    cub::DeviceRadixSort::SortKeys(nullptr, tmp1, d_skeys.p, d_skeys2.p, n_all, 0, 64, stream);
+    cub::DeviceScan::ExclusiveSum(nullptr, tmp2, d_area.p, d_offs.p, n_all, stream);
+    d_cub.reserve(std::max(tmp1, tmp2) + 256);
+    size_t tmp = d_cub.cap;
+    OSFM_CUDA(cub::DeviceRadixSort::SortKeys(d_cub.p, tmp, d_skeys.p, d_skeys2.p, n_all, 0, 64, stream));
+    g_kernel_launches.fetch_add(1);
+    bsr_block_areas<<<grid_for(n_all, 256), 256, 0, stream>>>(d_skeys2.p, n_all, nblk, d_blk_sz.p, d_area.p);
+    OSFM_LAUNCH_CHECK();
+    tmp = d_cub.cap;
+    OSFM_CUDA(cub::DeviceScan::ExclusiveSum(d_cub.p, tmp, d_area.p, d_offs.p, n_all, stream));
+    g_kernel_launches.fetch_add(1);
+    int last_off[2] = {0, 0}, last_area = 0, upper_end = 0;
+    OSFM_CUDA(cudaMemcpyAsync(&last_off[0], d_offs.p + n_all - 1, sizeof(int), cudaMemcpyDeviceToHost, stream));
+    OSFM_CUDA(cudaMemcpyAsync(&last_area, d_area.p + n_all - 1, sizeof(int), cudaMemcpyDeviceToHost, stream));
+    if (n_upper < n_all)
+      OSFM_CUDA(cudaMemcpyAsync(&upper_end, d_offs.p + n_upper, sizeof(int), cudaMemcpyDeviceToHost, stream));
+    OSFM_CUDA(cudaStreamSynchronize(stream));
+    s_total = (long long)last_off[0] + last_area;
+    s_upper_total = n_upper < n_all ? upper_end : s_total;
+    // hash table values (inserting the mirrored keys) + plain key list, then block-row lists
+    bsr_fill_table<<<grid_for(n_all, 256), 256, 0, stream>>>(d_skeys2.p, d_offs.p, n_all, d_tkeys.p, d_tvals.p, tsize - 1,
+                                                            d_rkeys.p);
+    OSFM_LAUNCH_CHECK();
+    tmp = d_cub.cap;
+    OSFM_CUDA(cub::DeviceRadixSort::SortKeys(d_cub.p, tmp, d_rkeys.p, d_rkeys2.p, n_all, 0, 64, stream));
+    g_kernel_launches.fetch_add(1);
+    bsr.tkeys = d_tkeys.p; bsr.tvals = d_tvals.p; bsr.tmask = tsize - 1; bsr.nblk = nblk;
+    bsr.blk_off = d_blk_off.p; bsr.blk_sz = d_blk_sz.p;
+    d_row_ptr.reserve(nblk + 2); d_row_col.reserve(n_all + 1); d_row_off.reserve(n_all + 1);
+    bsr_rows<<<grid_for(n_all + 1, 256), 256, 0, stream>>>(d_rkeys2.p, n_all, bsr, d_row_ptr.p, d_row_col.p, d_row_off.p);
+    OSFM_LAUNCH_CHECK();
+    d_upper.reserve(n_upper + 1);
+    bsr_upper_list<<<grid_for(n_upper, 256), 256, 0, stream>>>(d_skeys2.p, d_offs.p, n_upper, bsr, d_upper.p);
+    OSFM_LAUNCH_CHECK();
+    d_diag_off.reserve(nblk + 1);
+    bsr_diag_offsets<<<grid_for(nblk, 128), 128, 0, stream>>>(bsr, d_diag_off.p);
+    OSFM_LAUNCH_CHECK();
+    d_prior_diag_off.reserve(pr_blk.size() + 1);
+    if (!pr_blk.empty()) {
+      bsr_prior_offsets<<<grid_for((long long)pr_blk.size(), 128), 128, 0, stream>>>(
+          d_pr_blk.p, d_pr_local.p, (int)pr_blk.size(), d_diag_off.p, d_blk_sz.p, d_prior_diag_off.p);
+      OSFM_LAUNCH_CHECK();
+    }
+    d_S.reserve((size_t)std::max<long long>(s_total, 1));
+  }
+
   // ---- Levenberg-Marquardt (Ceres trust_region_minimizer / levenberg_marquardt_strategy) ----
   OSFM_CUDA(cudaEventRecord(ev0, stream));
   double radius = 1e4;
@@ -1111,15 +922,17 @@ void BA::run() {
       OSFM_LAUNCH_CHECK();
     }
     const double inv_radius = 1.0 / radius;
-    // --- reduced camera system ---
+    // --- reduced camera system (upper blocks accumulated with L2 atomics) ---
     if (nc > 0) {
-      OSFM_CUDA(cudaMemsetAsync(d_S.p, 0, sizeof(double) * (size_t)nc * nc, stream));
+      OSFM_CUDA(cudaMemsetAsync(d_S.p, 0, sizeof(double) * (size_t)s_upper_total, stream));
       OSFM_CUDA(cudaMemsetAsync(d_rhs.p, 0, sizeof(double) * nc, stream));
     }
     if (P > 0) {
-      const size_t smem = (size_t)SCHUR_KC * wc * (2 * 3 * sizeof(double) + 2 * sizeof(int));
+      const size_t smem = (size_t)SCHUR_KC * wc * (2 * 3 * sizeof(double) + 2 * sizeof(int)) +
+                          (size_t)SCHUR_KC * 8 * sizeof(int) + (size_t)SCHUR_KC * SCHUR_KC * 9 * sizeof(int);
       tm_schur.start(stream);
-      ba_schur<<<P, SCHUR_THREADS, smem, stream>>>(v, d_scale.p, d_diag.p, inv_radius, d_S.p, d_rhs.p, d_Vinv.p, d_gp.p);
+      ba_schur<<<P, SCHUR_THREADS, smem, stream>>>(v, bm, bsr, d_scale.p, d_diag.p, inv_radius, d_S.p, d_rhs.p,
+                                                   d_Vinv.p, d_gp.p);
       OSFM_LAUNCH_CHECK();
       tm_schur.stop(stream);
     }
@@ -1127,7 +940,8 @@ void BA::run() {
     int pcg_it = 0;
     OSFM_CUDA(cudaMemsetAsync(d_y.p, 0, sizeof(double) * nz, stream));
     if (nc > 0) {
-      if (world > 1) { allreduce_dev(d_S.p, (long long)nc * nc); allreduce_dev(d_rhs.p, nc); }
+      // the one exchange step of the LM iteration: sum of the partial reduced systems over ranks
+      if (world > 1) { allreduce_dev(d_S.p, s_upper_total); allreduce_dev(d_rhs.p, nc); }
       {
         // S_g stays a pure partial sum through the all-reduce; every rank then adds the (replicated)
         // prior rows and the damping to its copy of the reduced system.
@@ -1136,46 +950,26 @@ void BA::run() {
         pall.n_pos_rows = (int)pr_pos_inst.size();
         const int nall = pall.n_cam_rows + pall.n_pos_rows;
         if (nall > 0) {
-          ba_prior_system<<<grid_for(nall, 128), 128, 0, stream>>>(pall, params_of(cur), d_scale.p, d_S.p, d_rhs.p, nc);
+          ba_prior_system<<<grid_for(nall, 128), 128, 0, stream>>>(pall, params_of(cur), d_scale.p, d_prior_diag_off.p,
+                                                                  d_S.p, d_rhs.p);
           OSFM_LAUNCH_CHECK();
         }
       }
-      dim3 fg((nc + 255) / 256, nc);
-      ba_finish_system<<<fg, 256, 0, stream>>>(d_S.p, d_diag.p, inv_radius, nc);
+      ba_finish_system<<<grid_for((long long)n_upper * 32, 256), 256, 0, stream>>>(d_upper.p, n_upper, bsr, d_S.p,
+                                                                                 d_diag.p, inv_radius);
       OSFM_LAUNCH_CHECK();
-      // --- PCG ---
+      // --- PCG: one persistent kernel, |r| <= 1e-10 |b| ---
       tm_pcg.start(stream);
-      pcg_factor_blocks<<<grid_for(nblk, 64), 64, 0, stream>>>(d_S.p, nc, d_blk_off.p, d_blk_sz.p, nblk, d_Minv.p);
+      pcg_factor_blocks<<<grid_for(nblk, 64), 64, 0, stream>>>(d_S.p, d_diag_off.p, d_blk_sz.p, nblk, d_Minv.p);
       OSFM_LAUNCH_CHECK();
-      OSFM_CUDA(cudaMemsetAsync(&d_sc.p->pcg_rz[0], 0, sizeof(double) * 5, stream));
-      pcg_init<<<grid_for(nblk, 128), 128, 0, stream>>>(d_rhs.p, d_px.p, d_pr.p, d_pz.p, d_pp.p, nc, d_Minv.p,
-                                                        d_blk_off.p, d_blk_sz.p, nblk, d_sc.p);
-      OSFM_LAUNCH_CHECK();
-      Scalars s0 = read_scalars();
-      const double bb = s0.pcg_bb;
-      const double tol2 = 1e-20 * bb;  // |r| <= 1e-10 |b|
+      OSFM_CUDA(cudaMemsetAsync(d_pcg.p, 0, sizeof(PcgState), stream));
       const int max_pcg = std::min(2 * nc + 100, 5000);
-      const int check_every = 8;
-      if (!(bb > 0.0)) { /* rhs == 0: y_c = 0 */ }
-      else {
-        bool done = false;
-        while (!done && pcg_it < max_pcg) {
-          for (int q = 0; q < check_every; ++q, ++pcg_it) {
-            pcg_matvec<<<grid_for((long long)nc * 32, 256), 256, 0, stream>>>(d_S.p, d_pp.p, d_pAp.p, nc, d_sc.p, pcg_it);
-            OSFM_LAUNCH_CHECK();
-            pcg_update1<<<grid_for(nblk, 128), 128, 0, stream>>>(d_px.p, d_pr.p, d_pz.p, d_pp.p, d_pAp.p, d_Minv.p,
-                                                                d_blk_off.p, d_blk_sz.p, nblk, d_sc.p, pcg_it);
-            OSFM_LAUNCH_CHECK();
-            pcg_update2<<<grid_for(nc, 256), 256, 0, stream>>>(d_pp.p, d_pz.p, nc, d_sc.p, pcg_it);
-            OSFM_LAUNCH_CHECK();
-          }
-          const Scalars s = read_scalars();
-          if (!(s.pcg_rr == s.pcg_rr)) { ok = false; break; }
-          if (s.pcg_rr <= tol2) done = true;
-        }
-      }
-      pcg_total += pcg_it;
+      const int pcg_grid = std::max(1, std::min(num_sms, (nblk + 7) / 8));
+      pcg_persistent<<<pcg_grid, 256, 0, stream>>>(d_S.p, d_row_ptr.p, d_row_col.p, d_row_off.p, bsr, d_Minv.p, d_rhs.p,
+                                                   d_px.p, d_pr.p, d_pz.p, d_pp.p, d_pAp.p, d_pcg.p, max_pcg, 1e-20);
+      OSFM_LAUNCH_CHECK();
       OSFM_CUDA(cudaMemcpyAsync(d_y.p, d_px.p, sizeof(double) * nc, cudaMemcpyDeviceToDevice, stream));
+      OSFM_CUDA(cudaMemcpyAsync(h_pcg.p, d_pcg.p, sizeof(PcgState), cudaMemcpyDeviceToHost, stream));
       tm_pcg.stop(stream);
     }
     ++n_solves;
@@ -1206,6 +1000,12 @@ void BA::run() {
     }
     if (world > 1) allreduce_dev(&d_sc.p->model_change, 3);
     const Scalars sm = read_scalars();
+    if (nc > 0) {
+      pcg_it = h_pcg.p->iterations;
+      pcg_total += pcg_it;
+      const double rr = h_pcg.p->rr[pcg_it & 1];
+      if (!(rr == rr)) ok = false;
+    }
     const double model_change = sm.model_change;
     const double step_norm = std::sqrt(sm.step_norm2);
     if (!ok || !(model_change > 0.0) || !std::isfinite(step_norm)) {
@@ -1292,6 +1092,8 @@ void BA::run() {
   summary.time_backsub_ms = tm_back.total_ms;
   summary.num_observations_local = N;
   summary.reduced_dim = nc;
+  summary.reduced_blocks = n_blocks_all;
+  summary.reduced_nnz = s_total;
   summary.jac_planes = nres * (wc + 3 + 1);
   tm_lin.destroy(); tm_schur.destroy(); tm_pcg.destroy(); tm_back.destroy();
   summary.kernel_launches = g_kernel_launches.load() - launches0;

@@ -148,13 +148,19 @@ __global__ void __launch_bounds__(256) bf_top2_simt(const MatchJob* __restrict__
 // ---------------------------------------------------------------------------
 // Merge chunks + ratio test.  grid = (ceil(max_nq/256), njobs)
 // ---------------------------------------------------------------------------
+// squared != 0: the partials hold squared distances (tcgen05 kernel; only used when float32 sqrt is
+// injective on them, so merging in d^2 is merging in cv2's ranking) and are sqrt'd here.
 __global__ void bf_top2_finalize(const MatchJob* __restrict__ jobs, const Top2* __restrict__ partial,
-                                 int32_t* __restrict__ match_buf, double ratio) {
+                                 int32_t* __restrict__ match_buf, double ratio, int squared) {
   const MatchJob job = jobs[blockIdx.y];
   const int q = blockIdx.x * blockDim.x + threadIdx.x;
   if (q >= job.nq) return;
   Top2 m = top2_empty();
   for (int c = 0; c < job.nchunks; ++c) top2_merge(m, partial[job.partial_off + (size_t)c * job.nq + q]);
+  if (squared) {
+    m.s1 = __fsqrt_rn(m.s1);
+    m.s2 = __fsqrt_rn(m.s2);
+  }
   int out = -1;
   // matching.py:752-755: two candidates and m.distance < ratio * n.distance (double)
   if (m.i1 >= 0 && m.i2 >= 0 && (double)m.s1 < ratio * (double)m.s2) out = m.i1;
@@ -287,7 +293,9 @@ void Matcher::match_pairs_async(int npairs, const int* ids_a, const int* ids_b, 
     if (A.u8 != B.u8 || A.dim != B.dim) throw ArgError("descriptor sets of a pair differ in dtype or dimension");
     any_u8 |= A.u8;
     any_f32 |= !A.u8;
-    all_tc &= (!A.u8 && A.tc_ok && B.tc_ok);
+    // d^2 <= (|a| + |b|)^2 <= 2 (|a|^2 + |b|^2) must stay below 2^22 for the d^2-space ranking of the
+    // tcgen05 kernel to equal cv2's sqrt-space ranking (float32 sqrt injective on integers < 2^22)
+    all_tc &= (!A.u8 && A.tc_ok && B.tc_ok && 2.0f * (A.tc_max_norm + B.tc_max_norm) < 4194304.0f);
     h_out_off[p + 1] = h_out_off[p] + A.n;
     for (int d = 0; d < ndir; ++d) {
       MatchJob& j = h_jobs[p * ndir + d];
@@ -314,7 +322,7 @@ void Matcher::match_pairs_async(int npairs, const int* ids_a, const int* ids_b, 
   // kernel choice
   int use = 1;
   if (kernel_choice == 2) {
-    if (!all_tc || dmask) throw ArgError("tcgen05 kernel forced but descriptors are not bf16-exact or a mask is set");
+    if (!all_tc || dmask) throw ArgError("tcgen05 kernel forced but descriptors are not bf16-exact / norm-bounded, or a mask is set");
     use = 2;
   } else if (kernel_choice == 0 && all_tc && !dmask && any_f32 && tc_available()) {
     use = 2;
@@ -395,7 +403,7 @@ void Matcher::match_pairs_async(int npairs, const int* ids_a, const int* ids_b, 
   OSFM_CUDA(cudaEventRecord(ev[2], stream));
   if (njobs > 0 && max_nq > 0) {
     dim3 grid((max_nq + 255) / 256, njobs);
-    bf_top2_finalize<<<grid, 256, 0, stream>>>(d_jobs.p, d_partial.p, d_match.p, ratio);
+    bf_top2_finalize<<<grid, 256, 0, stream>>>(d_jobs.p, d_partial.p, d_match.p, ratio, use == 2 ? 1 : 0);
     OSFM_LAUNCH_CHECK();
     if (symmetric) {
       dim3 g2((max_nq + 255) / 256, npairs);

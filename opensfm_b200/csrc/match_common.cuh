@@ -72,6 +72,7 @@ struct DescSet {
   const __nv_bfloat16* tc_t = nullptr;
   const float* tc_norm = nullptr;
   bool tc_ok = false;
+  float tc_max_norm = 0.0f;  // max_i |x_i|^2
   int rows_padded = 0;
 };
 

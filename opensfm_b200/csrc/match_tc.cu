@@ -23,10 +23,10 @@
 //   warp 0  bulk-copy producer (Q tile double-buffered per task, T tiles 2 stages)
 //   warp 1  TMEM alloc + single-thread tcgen05.mma issue (M=128, N=256, K=16 x 9)
 //   warps 2-5  epilogue: tcgen05.ld the 128x256 fp32 accumulator (double-buffered
-//           in TMEM, 2 x 256 columns) and keep a running top-2 per query row with
-//           a group-min threshold filter (~1 instruction / element); the exact
-//           cv2 ranking (sqrt'd float32 distance, ties -> lowest index) is applied
-//           only to the rare elements that pass the filter.
+//           in TMEM, 2 x 256 columns, loads software-pipelined) and keep a running
+//           top-2 per query row in d^2 space: branch-free on the first tile of a task,
+//           then a group-of-8 min filter (0.75 instruction / element) with exact
+//           updates only for elements that beat the row's current second best.
 #include <cuda_bf16.h>
 
 #include "common.cuh"
@@ -88,6 +88,15 @@ __global__ void tc_row_norms(const float* __restrict__ src, int n, int dim, int 
 #pragma unroll
   for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
   if (lane == 0) norm[row] = s;
+}
+
+// max_i |x_i|^2 as float bits (non-negative floats order like unsigned integers)
+__global__ void tc_max_norm(const float* __restrict__ norm, int n, unsigned* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  float v = i < n ? norm[i] : 0.0f;
+#pragma unroll
+  for (int o = 16; o; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  if ((threadIdx.x & 31) == 0) atomicMax(out, __float_as_uint(v));
 }
 
 // one thread per (row, 16-byte K chunk): writes both operand roles
@@ -156,9 +165,16 @@ void Matcher::prepare_tc(DescSet& s) {
   float* norm = reinterpret_cast<float*>(reinterpret_cast<char*>(s.tc_data) + 2 * op_bytes);
   tc_row_norms<<<(rows_padded + 7) / 8, 256, 0, stream>>>(src, s.n, s.dim, rows_padded, norm);
   OSFM_LAUNCH_CHECK();
+  OSFM_CUDA(cudaMemsetAsync(d_flags.p + 2, 0, sizeof(int), stream));
+  tc_max_norm<<<(s.n + 255) / 256, 256, 0, stream>>>(norm, s.n, reinterpret_cast<unsigned*>(d_flags.p + 2));
+  OSFM_LAUNCH_CHECK();
+  unsigned max_bits = 0;
+  OSFM_CUDA(cudaMemcpyAsync(&max_bits, d_flags.p + 2, sizeof(unsigned), cudaMemcpyDeviceToHost, stream));
   const size_t items = (size_t)rows_padded * TC_KCH;
   tc_build_operands<<<(unsigned)((items + 255) / 256), 256, 0, stream>>>(src, s.n, s.dim, rows_padded, norm, qa, tb);
   OSFM_LAUNCH_CHECK();
+  OSFM_CUDA(cudaStreamSynchronize(stream));
+  std::memcpy(&s.tc_max_norm, &max_bits, sizeof(float));
   s.tc_q = qa;
   s.tc_t = tb;
   s.tc_norm = norm;
@@ -270,20 +286,62 @@ __device__ __forceinline__ TcTask tc_decode(const MatchJob* jobs, const int* til
   return t;
 }
 
-// Epilogue state of one query row (ranking space of cv2 + the accumulator value of slot 2).
+// Epilogue state of one query row: the two smallest accumulator values (= d^2 - |a|^2, exact
+// integers) with their train indices.  Ranking in d^2 is the ranking cv2 uses (sqrt'd float32
+// distance, ties -> lowest index) as long as float32 sqrt is injective on the integers involved,
+// i.e. d^2 < 2^22; the host only selects this kernel for descriptor sets whose norms guarantee
+// that bound (Matcher::match_pairs_async), everything else goes to the exact SIMT kernel.
 struct RowState {
-  float s1, q1, s2, q2;
+  float q1, q2;
   int i1, i2;
 };
 
-// Exact insertion for an element that passed the threshold filter (rare).
-__device__ __forceinline__ void row_insert(RowState& st, float v, int idx, float na) {
-  const float s = __fsqrt_rn(fmaxf(v + na, 0.0f));
-  if (s < st.s1) {
-    st.s2 = st.s1; st.q2 = st.q1; st.i2 = st.i1;
-    st.s1 = s; st.q1 = v; st.i1 = idx;
-  } else if (s < st.s2) {
-    st.s2 = s; st.q2 = v; st.i2 = idx;
+// Branch-free update (used for the first tile of a task, where most elements are records).
+__device__ __forceinline__ void row_update(RowState& st, float x, int idx) {
+  const bool lt1 = x < st.q1;
+  const bool lt2 = x < st.q2;
+  st.q2 = lt1 ? st.q1 : (lt2 ? x : st.q2);
+  st.i2 = lt1 ? st.i1 : (lt2 ? idx : st.i2);
+  st.q1 = lt1 ? x : st.q1;
+  st.i1 = lt1 ? idx : st.i1;
+}
+
+// 32 accumulator columns of one row: group-min threshold filter, exact update only on hits.
+template <bool FIRST>
+__device__ __forceinline__ void row_consume32(RowState& st, const uint32_t (&v)[32], int col0) {
+  if (FIRST) {
+#pragma unroll
+    for (int e = 0; e < 32; ++e) row_update(st, __uint_as_float(v[e]), col0 + e);
+  } else {
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      // min over 8 as 3 + 3 + 2 so that a triggered group only re-examines the sub-group that hit
+      const float f0 = __uint_as_float(v[g * 8 + 0]), f1 = __uint_as_float(v[g * 8 + 1]);
+      const float f2 = __uint_as_float(v[g * 8 + 2]), f3 = __uint_as_float(v[g * 8 + 3]);
+      const float f4 = __uint_as_float(v[g * 8 + 4]), f5 = __uint_as_float(v[g * 8 + 5]);
+      const float f6 = __uint_as_float(v[g * 8 + 6]), f7 = __uint_as_float(v[g * 8 + 7]);
+      const float ma = fminf(fminf(f0, f1), f2);
+      const float mb = fminf(fminf(f3, f4), f5);
+      const float mc = fminf(f6, f7);
+      const float m = fminf(fminf(ma, mb), mc);
+      if (m < st.q2) {
+        const int c = col0 + g * 8;
+        if (ma < st.q2) {
+          if (f0 < st.q2) row_update(st, f0, c + 0);
+          if (f1 < st.q2) row_update(st, f1, c + 1);
+          if (f2 < st.q2) row_update(st, f2, c + 2);
+        }
+        if (mb < st.q2) {
+          if (f3 < st.q2) row_update(st, f3, c + 3);
+          if (f4 < st.q2) row_update(st, f4, c + 4);
+          if (f5 < st.q2) row_update(st, f5, c + 5);
+        }
+        if (mc < st.q2) {
+          if (f6 < st.q2) row_update(st, f6, c + 6);
+          if (f7 < st.q2) row_update(st, f7, c + 7);
+        }
+      }
+    }
   }
 }
 
@@ -385,7 +443,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
       const int gq = t.q0 + row_in_tile;
       const float na = gq < t.job.nq ? t.job.q_norm[gq] : 0.0f;
       RowState st;
-      st.s1 = st.s2 = st.q1 = st.q2 = __builtin_huge_valf();
+      st.q1 = st.q2 = __builtin_huge_valf();
       st.i1 = st.i2 = -1;
       for (int i = 0; i < t.ntiles; ++i, ++tilecount) {
         const int a = tilecount & 1, aph = (tilecount >> 1) & 1;
@@ -393,32 +451,31 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         tc_fence_after();
         const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)a * TC_N;
         const int col_base = t.t_begin + i * TC_N;
-#pragma unroll 1
-        for (int cb = 0; cb < TC_N / 32; ++cb) {
-          uint32_t v[32];
-          OSFM_TMEM_LD32(taddr + cb * 32, v);
+        // two register buffers: the load of chunk cb+1 is in flight while chunk cb is consumed
+        uint32_t va[32], vb[32];
+        OSFM_TMEM_LD32(taddr, va);
+#pragma unroll
+        for (int cb = 0; cb < TC_N / 32; cb += 2) {
           asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            float m = __uint_as_float(v[g * 8]);
-#pragma unroll
-            for (int e = 1; e < 8; ++e) m = fminf(m, __uint_as_float(v[g * 8 + e]));
-            if (m < st.q2) {
-#pragma unroll
-              for (int e = 0; e < 8; ++e) {
-                const float x = __uint_as_float(v[g * 8 + e]);
-                if (x < st.q2) row_insert(st, x, col_base + cb * 32 + g * 8 + e, na);
-              }
-            }
-          }
+          OSFM_TMEM_LD32(taddr + (cb + 1) * 32, vb);
+          if (i == 0) row_consume32<true>(st, va, col_base + cb * 32);
+          else row_consume32<false>(st, va, col_base + cb * 32);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          if (cb + 2 < TC_N / 32) OSFM_TMEM_LD32(taddr + (cb + 2) * 32, va);
+          if (i == 0) row_consume32<true>(st, vb, col_base + (cb + 1) * 32);
+          else row_consume32<false>(st, vb, col_base + (cb + 1) * 32);
         }
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&bar_accempty[a]);
       }
       if (gq < t.job.nq) {
+        // partial results of this kernel are squared distances (exact integers in fp32)
         Top2 out;
-        out.s1 = st.s1; out.i1 = st.i1; out.s2 = st.s2; out.i2 = st.i2;
+        out.s1 = st.i1 >= 0 ? fmaxf(st.q1 + na, 0.0f) : __builtin_huge_valf();
+        out.i1 = st.i1;
+        out.s2 = st.i2 >= 0 ? fmaxf(st.q2 + na, 0.0f) : __builtin_huge_valf();
+        out.i2 = st.i2;
         partial[t.job.partial_off + (size_t)t.chunk * t.job.nq + gq] = out;
       }
     }

@@ -113,18 +113,25 @@ def test_pair_batch_cube_scene_both_kernels(kernel):
         assert [tuple(x) for x in res1[(i, j)].tolist()] == mo.match_brute_force(feats[i], feats[j], CFG)
 
 
-def test_tc_kernel_large_values_sqrt_collisions():
+def test_large_norms_route_to_exact_kernel():
     """d^2 near 2^23: distinct d^2 collapse to one float32 sqrt; cv2 ranks on the sqrt."""
     rng = np.random.RandomState(5)
     a = rng.randint(200, 256, (600, 128)).astype(np.float32)
     b = rng.randint(0, 40, (700, 128)).astype(np.float32)
-    for kernel in (1, 2):
-        pm = matching.PairMatcher(kernel=kernel)
-        pm.add("a", a)
-        pm.add("b", b)
-        for ratio in (0.999, 1.0, 1.01):
-            got = pm.match_pairs([("a", "b")], {"lowes_ratio": ratio}, symmetric=False)[("a", "b")]
-            assert [tuple(x) for x in got.tolist()] == mo.match_brute_force(a, b, {"lowes_ratio": ratio})
+    # norms this large break the d^2 < 2^22 guarantee: automatic selection must fall to the exact
+    # SIMT kernel, and forcing the tensor-core kernel must be refused
+    pm = matching.PairMatcher(kernel=0)
+    pm.add("a", a)
+    pm.add("b", b)
+    for ratio in (0.999, 1.0, 1.01):
+        got = pm.match_pairs([("a", "b")], {"lowes_ratio": ratio}, symmetric=False)[("a", "b")]
+        assert pm.last_kernel() == 1
+        assert [tuple(x) for x in got.tolist()] == mo.match_brute_force(a, b, {"lowes_ratio": ratio})
+    pm2 = matching.PairMatcher(kernel=2)
+    pm2.add("a", a)
+    pm2.add("b", b)
+    with pytest.raises(ValueError):
+        pm2.match_pairs([("a", "b")], {"lowes_ratio": 0.8}, symmetric=False)
 
 
 def test_threads_share_nothing():
