@@ -493,14 +493,14 @@ __device__ __forceinline__ void grid_barrier(PcgState* st, unsigned nblocks) {
   __syncthreads();
   if (threadIdx.x == 0) {
     __threadfence();
-    const unsigned gen = atomicAdd(&st->bar_gen, 0u);
+    const unsigned gen = *reinterpret_cast<volatile unsigned*>(&st->bar_gen);
     if (atomicAdd(&st->bar_count, 1u) == nblocks - 1) {
       atomicExch(&st->bar_count, 0u);
       __threadfence();
       atomicAdd(&st->bar_gen, 1u);
     } else {
       const long long t0 = clock64();
-      while (atomicAdd(&st->bar_gen, 0u) == gen) {
+      while (*reinterpret_cast<volatile unsigned*>(&st->bar_gen) == gen) {
         if (clock64() - t0 > 8000000000LL) __trap();  // a protocol bug must not hang the GPU
       }
     }
@@ -511,7 +511,7 @@ __device__ __forceinline__ void grid_barrier(PcgState* st, unsigned nblocks) {
 __device__ __forceinline__ double ldcg_d(const double* p) { return __ldcg(p); }
 
 // One warp per block row.  Vectors written by other CTAs are read with ld.global.cg (L2).
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 1)
     pcg_persistent(const double* __restrict__ Sval, const int* __restrict__ row_ptr, const int* __restrict__ row_col,
                    const int* __restrict__ row_off, BsrView h, const double* __restrict__ Minv,
                    const double* __restrict__ rhs, double* x, double* r, double* z, double* p0, double* p1,
@@ -562,25 +562,39 @@ __global__ void __launch_bounds__(256)
       double a_pAp = 0.0;
       for (int b = gw; b < nblk; b += nw) {
         const int o = h.blk_off[b], n = h.blk_sz[b];
-        // lanes: row = lane % n ... use (row, column-split) so that up to 32 lanes work on one block row
-        const int rows = n;
-        int split = 1;                           // lanes per row: largest power of two <= 32 / rows
-        while (split * 2 * rows <= 32) split *= 2;
-        const int myrow = lane / split, part = lane % split;
-        double s = 0.0;
-        if (myrow < rows) {
-          for (int e = row_ptr[b]; e < row_ptr[b + 1]; ++e) {
-            const int cb = row_col[e];
-            const int m = h.blk_sz[cb], co = h.blk_off[cb];
-            const double* B = Sval + row_off[e] + myrow * m;
-            for (int j = part; j < m; j += split) s += B[j] * ldcg_d(&p[co + j]);
+        // every lane takes one stored block of this block row (32 independent load chains in flight)
+        double acc[MAXB];
+#pragma unroll
+        for (int r = 0; r < MAXB; ++r) acc[r] = 0.0;
+        for (int e = row_ptr[b] + lane; e < row_ptr[b + 1]; e += 32) {
+          const int cb = row_col[e];
+          const int m = h.blk_sz[cb], co = h.blk_off[cb];
+          const double* B = Sval + row_off[e];
+          double pv[MAXB];
+#pragma unroll
+          for (int j = 0; j < MAXB; ++j) pv[j] = j < m ? ldcg_d(&p[co + j]) : 0.0;
+#pragma unroll
+          for (int r = 0; r < MAXB; ++r) {
+            if (r < n) {
+              double t = 0.0;
+#pragma unroll
+              for (int j = 0; j < MAXB; ++j)
+                if (j < m) t += B[r * m + j] * pv[j];
+              acc[r] += t;
+            }
           }
         }
-        // reduce the `split` partial sums of each row
-        for (int d = 1; d < split; d <<= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
-        if (myrow < rows && part == 0) {
-          Ap[o + myrow] = s;
-          a_pAp += s * ldcg_d(&p[o + myrow]);
+#pragma unroll
+        for (int r = 0; r < MAXB; ++r) {
+          if (r < n) {  // n is warp-uniform
+            double t = acc[r];
+#pragma unroll
+            for (int d = 16; d; d >>= 1) t += __shfl_xor_sync(0xffffffffu, t, d);
+            if (lane == r) {
+              Ap[o + r] = t;
+              a_pAp += t * ldcg_d(&p[o + r]);
+            }
+          }
         }
       }
 #pragma unroll
