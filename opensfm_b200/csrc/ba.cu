@@ -964,9 +964,37 @@ void BA::run() {
       OSFM_LAUNCH_CHECK();
       OSFM_CUDA(cudaMemsetAsync(d_pcg.p, 0, sizeof(PcgState), stream));
       const int max_pcg = std::min(2 * nc + 100, 5000);
-      const int pcg_grid = std::max(1, std::min(num_sms, (nblk + 7) / 8));
-      pcg_persistent<<<pcg_grid, 256, 0, stream>>>(d_S.p, d_row_ptr.p, d_row_col.p, d_row_off.p, bsr, d_Minv.p, d_rhs.p,
-                                                   d_px.p, d_pr.p, d_pz.p, d_pp.p, d_pAp.p, d_pcg.p, max_pcg, 1e-20);
+      // one cluster: the smallest power of two of CTAs (<= 16) that gives every block row its own warp
+      int pcg_grid = 1;
+      while (pcg_grid < 16 && pcg_grid * (PCG_THREADS / 32) < nblk) pcg_grid *= 2;
+      {
+        static bool attr_set = false;
+        if (!attr_set) {
+          OSFM_CUDA(cudaFuncSetAttribute(pcg_persistent, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+          attr_set = true;
+        }
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3(pcg_grid);
+        cfg.blockDim = dim3(PCG_THREADS);
+        cfg.dynamicSmemBytes = 0;
+        cfg.stream = stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = pcg_grid;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        const double* c_S = d_S.p;
+        const int *c_rp = d_row_ptr.p, *c_rc = d_row_col.p, *c_ro = d_row_off.p;
+        const double *c_M = d_Minv.p, *c_rhs = d_rhs.p;
+        double *c_x = d_px.p, *c_r = d_pr.p, *c_z = d_pz.p, *c_p0 = d_pp.p, *c_p1 = d_pAp.p;
+        PcgState* c_st = d_pcg.p;
+        int c_max = max_pcg;
+        double c_tol = 1e-20;
+        OSFM_CUDA(cudaLaunchKernelEx(&cfg, pcg_persistent, c_S, c_rp, c_rc, c_ro, bsr, c_M, c_rhs, c_x, c_r, c_z, c_p0,
+                                     c_p1, c_st, c_max, c_tol));
+      }
       OSFM_LAUNCH_CHECK();
       OSFM_CUDA(cudaMemcpyAsync(d_y.p, d_px.p, sizeof(double) * nc, cudaMemcpyDeviceToDevice, stream));
       OSFM_CUDA(cudaMemcpyAsync(h_pcg.p, d_pcg.p, sizeof(PcgState), cudaMemcpyDeviceToHost, stream));

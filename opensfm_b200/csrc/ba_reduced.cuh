@@ -200,12 +200,12 @@ __global__ void __launch_bounds__(SCHUR_THREADS)
   const int wc = v.wc, nres = v.nres, nc = v.nc;
   double* Ya = sm;                                   // [KC][wc][3]
   double* Wb = Ya + SCHUR_KC * wc * 3;               // [KC][wc][3]
-  int* ga_col = reinterpret_cast<int*>(Wb + SCHUR_KC * wc * 3);  // [KC][wc] global column or -1
+  int* ga_col = reinterpret_cast<int*>(Wb + SCHUR_KC * wc * 3);  // [KC][wc] packed (blk, slot, size, row) or -1
   int* gb_col = ga_col + SCHUR_KC * wc;
   int* oba = gb_col + SCHUR_KC * wc;                 // [KC][4]: blk0, blk1, blk2, C
   int* obb = oba + SCHUR_KC * 4;
   int* offt = obb + SCHUR_KC * 4;                    // [KC][KC][9] value offsets of (min blk, max blk)
-  __shared__ double sV[9], sVi[9], sg[3], sVig[3];
+  __shared__ double sVi[9], sg[3], sVig[3];
 
   const int p = blockIdx.x;
   const long long b0 = v.pt_start[p], e0 = v.pt_start[p + 1];
@@ -252,41 +252,44 @@ __global__ void __launch_bounds__(SCHUR_THREADS)
   }
   if (pf < 0) return;
 
-  // ---- V, g_p ----
-  double acc[9];
-#pragma unroll
-  for (int j = 0; j < 9; ++j) acc[j] = 0.0;
+  // ---- V, g_p: warp 0 (a point has few observations), shuffle reduction ----
   const double sp0 = scale[nc + 3 * pf], sp1 = scale[nc + 3 * pf + 1], sp2 = scale[nc + 3 * pf + 2];
-  for (int a = tid; a < k; a += SCHUR_THREADS) {
-    const long long i = b0 + a;
-    for (int q = 0; q < nres; ++q) {
-      const double x = v.Jp[((size_t)q * 3 + 0) * N + i] * sp0;
-      const double y = v.Jp[((size_t)q * 3 + 1) * N + i] * sp1;
-      const double z = v.Jp[((size_t)q * 3 + 2) * N + i] * sp2;
-      const double rq = v.r[q * N + i];
-      acc[0] += x * x; acc[1] += x * y; acc[2] += x * z; acc[3] += y * y; acc[4] += y * z; acc[5] += z * z;
-      acc[6] += x * rq; acc[7] += y * rq; acc[8] += z * rq;
+  if (tid < 32) {
+    double acc[9];
+#pragma unroll
+    for (int j = 0; j < 9; ++j) acc[j] = 0.0;
+    for (int a = tid; a < k; a += 32) {
+      const long long i = b0 + a;
+      for (int q = 0; q < nres; ++q) {
+        const double x = v.Jp[((size_t)q * 3 + 0) * N + i] * sp0;
+        const double y = v.Jp[((size_t)q * 3 + 1) * N + i] * sp1;
+        const double z = v.Jp[((size_t)q * 3 + 2) * N + i] * sp2;
+        const double rq = v.r[q * N + i];
+        acc[0] += x * x; acc[1] += x * y; acc[2] += x * z; acc[3] += y * y; acc[4] += y * z; acc[5] += z * z;
+        acc[6] += x * rq; acc[7] += y * rq; acc[8] += z * rq;
+      }
     }
-  }
-  for (int j = 0; j < 9; ++j) {
-    const double t = block_reduce_sum(acc[j]);
-    if (tid == 0) sV[j] = t;
-  }
-  if (tid == 0) {
-    const double a = sV[0] + diag[nc + 3 * pf] * inv_radius, b = sV[1], c = sV[2];
-    const double d = sV[3] + diag[nc + 3 * pf + 1] * inv_radius, e = sV[4];
-    const double f = sV[5] + diag[nc + 3 * pf + 2] * inv_radius;
-    const double A = d * f - e * e, B = c * e - b * f, Cc = b * e - c * d;
-    const double id = 1.0 / (a * A + b * B + c * Cc);
-    sVi[0] = A * id; sVi[1] = B * id; sVi[2] = Cc * id;
-    sVi[3] = B * id; sVi[4] = (a * f - c * c) * id; sVi[5] = (b * c - a * e) * id;
-    sVi[6] = Cc * id; sVi[7] = sVi[5]; sVi[8] = (a * d - b * b) * id;
-    sg[0] = sV[6]; sg[1] = sV[7]; sg[2] = sV[8];
-    for (int j = 0; j < 3; ++j) sVig[j] = sVi[j * 3] * sg[0] + sVi[j * 3 + 1] * sg[1] + sVi[j * 3 + 2] * sg[2];
-    const size_t NP = (size_t)v.npf;
-    Vinv[0 * NP + pf] = sVi[0]; Vinv[1 * NP + pf] = sVi[1]; Vinv[2 * NP + pf] = sVi[2];
-    Vinv[3 * NP + pf] = sVi[4]; Vinv[4 * NP + pf] = sVi[5]; Vinv[5 * NP + pf] = sVi[8];
-    gpo[0 * NP + pf] = sg[0]; gpo[1 * NP + pf] = sg[1]; gpo[2 * NP + pf] = sg[2];
+#pragma unroll
+    for (int j = 0; j < 9; ++j) {
+#pragma unroll
+      for (int o = 16; o; o >>= 1) acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], o);
+    }
+    if (tid == 0) {
+      const double a = acc[0] + diag[nc + 3 * pf] * inv_radius, b = acc[1], c = acc[2];
+      const double d = acc[3] + diag[nc + 3 * pf + 1] * inv_radius, e = acc[4];
+      const double f = acc[5] + diag[nc + 3 * pf + 2] * inv_radius;
+      const double A = d * f - e * e, B = c * e - b * f, Cc = b * e - c * d;
+      const double id = 1.0 / (a * A + b * B + c * Cc);
+      sVi[0] = A * id; sVi[1] = B * id; sVi[2] = Cc * id;
+      sVi[3] = B * id; sVi[4] = (a * f - c * c) * id; sVi[5] = (b * c - a * e) * id;
+      sVi[6] = Cc * id; sVi[7] = sVi[5]; sVi[8] = (a * d - b * b) * id;
+      sg[0] = acc[6]; sg[1] = acc[7]; sg[2] = acc[8];
+      for (int j = 0; j < 3; ++j) sVig[j] = sVi[j * 3] * sg[0] + sVi[j * 3 + 1] * sg[1] + sVi[j * 3 + 2] * sg[2];
+      const size_t NP = (size_t)v.npf;
+      Vinv[0 * NP + pf] = sVi[0]; Vinv[1 * NP + pf] = sVi[1]; Vinv[2 * NP + pf] = sVi[2];
+      Vinv[3 * NP + pf] = sVi[4]; Vinv[4 * NP + pf] = sVi[5]; Vinv[5 * NP + pf] = sVi[8];
+      gpo[0 * NP + pf] = sg[0]; gpo[1 * NP + pf] = sg[1]; gpo[2 * NP + pf] = sg[2];
+    }
   }
   __syncthreads();
 
@@ -299,12 +302,16 @@ __global__ void __launch_bounds__(SCHUR_THREADS)
       const long long i = b0 + a0 + a;
       const ObsBlk ob = obs_blocks(v, bm, v.obs_shot[i]);
       if (c1 == 0) { oba[a * 4] = ob.blk[0]; oba[a * 4 + 1] = ob.blk[1]; oba[a * 4 + 2] = ob.blk[2]; oba[a * 4 + 3] = ob.C; }
-      int g1 = -1;
+      int g1 = -1, m1 = -1;
       if (c1 < ob.C + 12) {
         const int s1 = ob.slot_of(c1);
-        if (ob.blk[s1] >= 0) g1 = h.blk_off[ob.blk[s1]] + c1 - ob.lstart(s1);
+        if (ob.blk[s1] >= 0) {
+          const int r1 = c1 - ob.lstart(s1);
+          g1 = h.blk_off[ob.blk[s1]] + r1;
+          m1 = (ob.blk[s1] << 12) | (s1 << 10) | (ob.size(s1) << 5) | r1;
+        }
       }
-      ga_col[a * wc + c1] = g1;
+      ga_col[a * wc + c1] = m1;
       double w0 = 0.0, w1 = 0.0, w2 = 0.0;
       if (g1 >= 0) {
         const double s1 = scale[g1];
@@ -329,12 +336,16 @@ __global__ void __launch_bounds__(SCHUR_THREADS)
         const long long i = b0 + bb0 + b;
         const ObsBlk ob = obs_blocks(v, bm, v.obs_shot[i]);
         if (c2 == 0) { obb[b * 4] = ob.blk[0]; obb[b * 4 + 1] = ob.blk[1]; obb[b * 4 + 2] = ob.blk[2]; obb[b * 4 + 3] = ob.C; }
-        int g2 = -1;
+        int g2 = -1, m2 = -1;
         if (c2 < ob.C + 12) {
           const int s2 = ob.slot_of(c2);
-          if (ob.blk[s2] >= 0) g2 = h.blk_off[ob.blk[s2]] + c2 - ob.lstart(s2);
+          if (ob.blk[s2] >= 0) {
+            const int r2 = c2 - ob.lstart(s2);
+            g2 = h.blk_off[ob.blk[s2]] + r2;
+            m2 = (ob.blk[s2] << 12) | (s2 << 10) | (ob.size(s2) << 5) | r2;
+          }
         }
-        gb_col[b * wc + c2] = g2;
+        gb_col[b * wc + c2] = m2;
         double w0 = 0.0, w1 = 0.0, w2 = 0.0;
         if (g2 >= 0) {
           const double s2 = scale[g2];
@@ -357,41 +368,45 @@ __global__ void __launch_bounds__(SCHUR_THREADS)
         offt[(a * SCHUR_KC + b) * 9 + ss] = (B1 < 0 || B2 < 0) ? -1 : bsr_lookup(h, min(B1, B2), max(B1, B2));
       }
       __syncthreads();
-      const int rowlen = nb * wc;
-      const int total = na * wc * rowlen;
-      for (int idx = tid; idx < total; idx += SCHUR_THREADS) {
-        const int ac = idx / rowlen, bc = idx % rowlen;
-        const int a = ac / wc, b = bc / wc;
-        const int ga = a0 + a, gb = bb0 + b;
-        if (gb < ga) continue;
-        if (ga_col[ac] < 0 || gb_col[bc] < 0) continue;
-        const int c1 = ac - a * wc, c2 = bc - b * wc;
-        const int Ca = oba[a * 4 + 3], Cb = obb[b * 4 + 3];
-        const int s1 = c1 < Ca ? 0 : (c1 < Ca + 6 ? 1 : 2), s2 = c2 < Cb ? 0 : (c2 < Cb + 6 ? 1 : 2);
-        const int B1 = oba[a * 4 + s1], B2 = obb[b * 4 + s2];
-        const int r1 = c1 - (s1 == 0 ? 0 : (s1 == 1 ? Ca : Ca + 6));
-        const int r2 = c2 - (s2 == 0 ? 0 : (s2 == 1 ? Cb : Cb + 6));
-        const int sz1 = s1 == 0 ? Ca : 6, sz2 = s2 == 0 ? Cb : 6;
-        const double* y = Ya + ac * 3;
-        const double* w = Wb + bc * 3;
-        double val = y[0] * w[0] + y[1] * w[1] + y[2] * w[2];
-        const int off = offt[(a * SCHUR_KC + b) * 9 + s1 * 3 + s2];
-        int pos;
-        if (B1 < B2) {
-          pos = r1 * sz2 + r2;
-        } else if (B1 > B2) {
-          if (ga == gb) continue;  // same observation: produced by the mirrored (c2, c1) visit
-          pos = r2 * sz1 + r1;
-        } else {
-          if (ga == gb) {
-            if (r2 < r1) continue;
-            pos = r1 * sz1 + r2;
-          } else {
-            if (r1 == r2) val *= 2.0;  // (a,b) and (b,a) land on the same diagonal entry
-            pos = min(r1, r2) * sz1 + max(r1, r2);
+      // thread <-> one (b, c2) column of the staged b-chunk (its W row lives in registers); it walks
+      // all (a <= b, c1): Y_a[c1] is a warp-uniform shared-memory broadcast and consecutive threads
+      // hit consecutive addresses of S (coalesced L2 atomics).
+      for (int item = tid; item < nb * wc; item += SCHUR_THREADS) {
+        const int m2 = gb_col[item];
+        if (m2 < 0) continue;
+        const int b = item / wc;
+        const int B2 = m2 >> 12, s2 = (m2 >> 10) & 3, sz2 = (m2 >> 5) & 31, r2 = m2 & 31;
+        const double w0 = Wb[item * 3], w1 = Wb[item * 3 + 1], w2 = Wb[item * 3 + 2];
+        const int gb = bb0 + b;
+        for (int a = 0; a < na; ++a) {
+          const int ga = a0 + a;
+          if (ga > gb) break;
+          const int* offrow = offt + (a * SCHUR_KC + b) * 9 + s2;
+          const int* ma = ga_col + a * wc;
+          const double* ya = Ya + a * wc * 3;
+          for (int c1 = 0; c1 < wc; ++c1) {
+            const int m1 = ma[c1];
+            if (m1 < 0) continue;
+            const int B1 = m1 >> 12, s1 = (m1 >> 10) & 3, sz1 = (m1 >> 5) & 31, r1 = m1 & 31;
+            double val = ya[c1 * 3] * w0 + ya[c1 * 3 + 1] * w1 + ya[c1 * 3 + 2] * w2;
+            int pos;
+            if (B1 < B2) {
+              pos = r1 * sz2 + r2;
+            } else if (B1 > B2) {
+              if (ga == gb) continue;  // same observation: produced by the mirrored (c2, c1) visit
+              pos = r2 * sz1 + r1;
+            } else {
+              if (ga == gb) {
+                if (r2 < r1) continue;
+                pos = r1 * sz1 + r2;
+              } else {
+                if (r1 == r2) val *= 2.0;  // (a,b) and (b,a) land on the same diagonal entry
+                pos = min(r1, r2) * sz1 + max(r1, r2);
+              }
+            }
+            atomicAdd(&Sval[offrow[s1 * 3] + pos], -val);
           }
         }
-        atomicAdd(&Sval[off + pos], -val);
       }
     }
   }
@@ -436,9 +451,10 @@ __global__ void __launch_bounds__(256)
 }
 
 // ---------------------------------------------------------------------------
-// PCG on S y = rhs: block-Jacobi preconditioner, one persistent kernel, grid-wide barriers.
+// PCG on S y = rhs: block-Jacobi preconditioner, one persistent kernel = one thread-block cluster.
 // ---------------------------------------------------------------------------
 constexpr int MAXB = 16;
+constexpr int PCG_THREADS = 512;
 
 // Cholesky-inverts each diagonal block into Minv[b][MAXB*MAXB].
 __global__ void pcg_factor_blocks(const double* __restrict__ Sval, const int* __restrict__ diag_off,
@@ -479,7 +495,6 @@ __global__ void pcg_factor_blocks(const double* __restrict__ Sval, const int* __
 }
 
 struct PcgState {
-  unsigned bar_count, bar_gen;
   int iterations;
   int pad;
   double rz[2];
@@ -488,30 +503,16 @@ struct PcgState {
   double bb;
 };
 
-// Sense-reversing barrier over a grid that is fully resident (grid <= #SMs, 1 CTA / SM).
-__device__ __forceinline__ void grid_barrier(PcgState* st, unsigned nblocks) {
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    __threadfence();
-    const unsigned gen = *reinterpret_cast<volatile unsigned*>(&st->bar_gen);
-    if (atomicAdd(&st->bar_count, 1u) == nblocks - 1) {
-      atomicExch(&st->bar_count, 0u);
-      __threadfence();
-      atomicAdd(&st->bar_gen, 1u);
-    } else {
-      const long long t0 = clock64();
-      while (*reinterpret_cast<volatile unsigned*>(&st->bar_gen) == gen) {
-        if (clock64() - t0 > 8000000000LL) __trap();  // a protocol bug must not hang the GPU
-      }
-    }
-    __threadfence();
-  }
-  __syncthreads();
+// The PCG kernel runs as ONE thread-block cluster (<= 16 CTAs, co-scheduled by hardware), so the
+// three synchronisation points of a CG iteration are hardware cluster barriers (~0.2 us) instead of
+// a software grid barrier through L2 (measured ~4 us each, profiles/r01_ncu_ba_v1.txt).
+__device__ __forceinline__ void cluster_barrier() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 __device__ __forceinline__ double ldcg_d(const double* p) { return __ldcg(p); }
 
 // One warp per block row.  Vectors written by other CTAs are read with ld.global.cg (L2).
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(PCG_THREADS, 1)
     pcg_persistent(const double* __restrict__ Sval, const int* __restrict__ row_ptr, const int* __restrict__ row_col,
                    const int* __restrict__ row_off, BsrView h, const double* __restrict__ Minv,
                    const double* __restrict__ rhs, double* x, double* r, double* z, double* p0, double* p1,
@@ -548,7 +549,7 @@ __global__ void __launch_bounds__(256, 1)
       atomicAdd(&st->bb, a_rr);
     }
   }
-  grid_barrier(st, gridDim.x);
+  cluster_barrier();
   const double bb = ldcg_d(&st->bb);
   const double tol2 = tol2_rel * bb;
   int it = 0;
@@ -601,7 +602,7 @@ __global__ void __launch_bounds__(256, 1)
       for (int o = 16; o; o >>= 1) a_pAp += __shfl_xor_sync(0xffffffffu, a_pAp, o);
       if (lane == 0 && a_pAp != 0.0) atomicAdd(&st->pAp[cur], a_pAp);
       if (gw == 0 && lane == 0) { st->rz[nxt] = 0.0; st->rr[nxt] = 0.0; st->pAp[nxt] = 0.0; }
-      grid_barrier(st, gridDim.x);
+      cluster_barrier();
       // ---- phase B: x += alpha p ; r -= alpha Ap ; z = M^-1 r ; rz_new, rr ----
       const double alpha = ldcg_d(&st->rz[cur]) / ldcg_d(&st->pAp[cur]);
       double a_rz = 0.0, a_rr = 0.0;
@@ -634,7 +635,7 @@ __global__ void __launch_bounds__(256, 1)
         if (a_rz != 0.0) atomicAdd(&st->rz[nxt], a_rz);
         if (a_rr != 0.0) atomicAdd(&st->rr[nxt], a_rr);
       }
-      grid_barrier(st, gridDim.x);
+      cluster_barrier();
       // ---- phase C: p_next = z + beta p (into pbuf[nxt], which held Ap) ----
       const double rr = ldcg_d(&st->rr[nxt]);
       if (!(rr == rr)) { ++it; break; }  // NaN: give up (step will be rejected)
@@ -644,7 +645,7 @@ __global__ void __launch_bounds__(256, 1)
         const int o = h.blk_off[b], n = h.blk_sz[b];
         if (lane < n) pbuf[nxt][o + lane] = z[o + lane] + beta * ldcg_d(&p[o + lane]);
       }
-      grid_barrier(st, gridDim.x);
+      cluster_barrier();
     }
   }
   if (gw == 0 && lane == 0) st->iterations = it;

@@ -24,9 +24,9 @@
 //   warp 1  TMEM alloc + single-thread tcgen05.mma issue (M=128, N=256, K=16 x 9)
 //   warps 2-5  epilogue: tcgen05.ld the 128x256 fp32 accumulator (double-buffered
 //           in TMEM, 2 x 256 columns, loads software-pipelined) and keep a running
-//           top-2 per query row in d^2 space: branch-free on the first tile of a task,
-//           then a group-of-8 min filter (0.75 instruction / element) with exact
-//           updates only for elements that beat the row's current second best.
+//           top-2 per query row in d^2 space: group-of-8 min filter (0.75 instruction /
+//           element) with exact updates only for elements that beat the row's current
+//           second best; the loop body is kept small enough for the instruction cache.
 #include <cuda_bf16.h>
 
 #include "common.cuh"
@@ -250,17 +250,14 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
 constexpr uint32_t TC_IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TC_N >> 3) << 17) |
                               ((uint32_t)(TC_M >> 4) << 24);
 
-#define OSFM_TMEM_LD32(taddr, v)                                                                           \
-  asm volatile(                                                                                            \
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "                                                            \
-      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26," \
-      "%27,%28,%29,%30,%31}, [%32];"                                                                       \
-      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),    \
-        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]),           \
-        "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]),         \
-        "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]),         \
-        "=r"(v[29]), "=r"(v[30]), "=r"(v[31])                                                              \
-      : "r"(taddr)                                                                                         \
+#define OSFM_TMEM_LD16(taddr, v)                                                                          \
+  asm volatile(                                                                                           \
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "                                                           \
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"                                    \
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),   \
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]),          \
+        "=r"(v[15])                                                                                       \
+      : "r"(taddr)                                                                                        \
       : "memory")
 
 struct TcTask {
@@ -306,40 +303,22 @@ __device__ __forceinline__ void row_update(RowState& st, float x, int idx) {
   st.i1 = lt1 ? idx : st.i1;
 }
 
-// 32 accumulator columns of one row: group-min threshold filter, exact update only on hits.
-template <bool FIRST>
-__device__ __forceinline__ void row_consume32(RowState& st, const uint32_t (&v)[32], int col0) {
-  if (FIRST) {
+// 16 accumulator columns of one row: two groups of 8, min filter against the row's current second
+// best, exact (predicated) updates only inside a group that beats it.  Deliberately small: the whole
+// epilogue loop body must stay resident in the instruction cache (an earlier fully unrolled version was
+// 89 KB of SASS and spent most of its time in instruction-fetch stalls, profiles/r01_*).
+__device__ __forceinline__ void row_consume16(RowState& st, const uint32_t (&v)[16], int col0) {
 #pragma unroll
-    for (int e = 0; e < 32; ++e) row_update(st, __uint_as_float(v[e]), col0 + e);
-  } else {
+  for (int g = 0; g < 2; ++g) {
+    float m = fminf(fminf(__uint_as_float(v[g * 8]), __uint_as_float(v[g * 8 + 1])), __uint_as_float(v[g * 8 + 2]));
+    m = fminf(fminf(m, __uint_as_float(v[g * 8 + 3])), __uint_as_float(v[g * 8 + 4]));
+    m = fminf(fminf(m, __uint_as_float(v[g * 8 + 5])), __uint_as_float(v[g * 8 + 6]));
+    m = fminf(m, __uint_as_float(v[g * 8 + 7]));
+    if (m < st.q2) {
 #pragma unroll
-    for (int g = 0; g < 4; ++g) {
-      // min over 8 as 3 + 3 + 2 so that a triggered group only re-examines the sub-group that hit
-      const float f0 = __uint_as_float(v[g * 8 + 0]), f1 = __uint_as_float(v[g * 8 + 1]);
-      const float f2 = __uint_as_float(v[g * 8 + 2]), f3 = __uint_as_float(v[g * 8 + 3]);
-      const float f4 = __uint_as_float(v[g * 8 + 4]), f5 = __uint_as_float(v[g * 8 + 5]);
-      const float f6 = __uint_as_float(v[g * 8 + 6]), f7 = __uint_as_float(v[g * 8 + 7]);
-      const float ma = fminf(fminf(f0, f1), f2);
-      const float mb = fminf(fminf(f3, f4), f5);
-      const float mc = fminf(f6, f7);
-      const float m = fminf(fminf(ma, mb), mc);
-      if (m < st.q2) {
-        const int c = col0 + g * 8;
-        if (ma < st.q2) {
-          if (f0 < st.q2) row_update(st, f0, c + 0);
-          if (f1 < st.q2) row_update(st, f1, c + 1);
-          if (f2 < st.q2) row_update(st, f2, c + 2);
-        }
-        if (mb < st.q2) {
-          if (f3 < st.q2) row_update(st, f3, c + 3);
-          if (f4 < st.q2) row_update(st, f4, c + 4);
-          if (f5 < st.q2) row_update(st, f5, c + 5);
-        }
-        if (mc < st.q2) {
-          if (f6 < st.q2) row_update(st, f6, c + 6);
-          if (f7 < st.q2) row_update(st, f7, c + 7);
-        }
+      for (int e = 0; e < 8; ++e) {
+        const float x = __uint_as_float(v[g * 8 + e]);
+        if (x < st.q2) row_update(st, x, col0 + g * 8 + e);
       }
     }
   }
@@ -451,19 +430,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         tc_fence_after();
         const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)a * TC_N;
         const int col_base = t.t_begin + i * TC_N;
-        // two register buffers: the load of chunk cb+1 is in flight while chunk cb is consumed
-        uint32_t va[32], vb[32];
-        OSFM_TMEM_LD32(taddr, va);
-#pragma unroll
-        for (int cb = 0; cb < TC_N / 32; cb += 2) {
+        // two 16-column register buffers: the load of the next chunk is in flight while one is consumed
+        uint32_t va[16], vb[16];
+        OSFM_TMEM_LD16(taddr, va);
+#pragma unroll 1
+        for (int cb = 0; cb < TC_N / 16; cb += 2) {
           asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-          OSFM_TMEM_LD32(taddr + (cb + 1) * 32, vb);
-          if (i == 0) row_consume32<true>(st, va, col_base + cb * 32);
-          else row_consume32<false>(st, va, col_base + cb * 32);
+          OSFM_TMEM_LD16(taddr + (cb + 1) * 16, vb);
+          row_consume16(st, va, col_base + cb * 16);
           asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-          if (cb + 2 < TC_N / 32) OSFM_TMEM_LD32(taddr + (cb + 2) * 32, va);
-          if (i == 0) row_consume32<true>(st, vb, col_base + (cb + 1) * 32);
-          else row_consume32<false>(st, vb, col_base + (cb + 1) * 32);
+          if (cb + 2 < TC_N / 16) OSFM_TMEM_LD16(taddr + (cb + 2) * 16, va);
+          row_consume16(st, vb, col_base + (cb + 1) * 16);
         }
         tc_fence_before();
         __syncwarp();
