@@ -493,6 +493,9 @@ struct BA {
   DevBuf<unsigned> d_count;
   DevBuf<char> d_cub;
   DevBuf<PcgState> d_pcg;
+  DevBuf<int> d_row_M, d_qoff, d_blk_row, d_cbase, d_colidx, d_row_of, d_grp_b1, d_grp_b2;
+  DevBuf<long long> d_rowbase;
+  DevBuf<double> d_Spcg, d_Ap;
   PinnedBuf<PcgState> h_pcg;
   int num_sms = 148;
   DevBuf<int> d_pr_cam_param, d_pr_cam_col, d_pr_cam_log, d_pr_pos_inst, d_pr_pos_axis, d_pr_pos_col;
@@ -581,6 +584,33 @@ void BA::run() {
     for (int i = 0; i < NI; ++i) if (!inst_const[i]) inst_blk[i] = b++;
     for (int i = 0; i < NR; ++i) if (!rc_const[i]) rc_blk[i] = b++;
   }
+
+  // preconditioner groups: a camera and the rig instance that is its only user (and vice versa) are
+  // merged into one diagonal block when they fit (C + 6 <= 16); everything else stays on its own
+  std::vector<int> grp_b1, grp_b2;
+  {
+    std::vector<int> cam_user(std::max(K, 1), -1), inst_cam(std::max(NI, 1), -1);  // -1 none, -2 several
+    for (int s2 = 0; s2 < S; ++s2) {
+      const int k = shot_cam[s2], i = shot_inst[s2];
+      cam_user[k] = cam_user[k] == -1 || cam_user[k] == i ? i : -2;
+      inst_cam[i] = inst_cam[i] == -1 || inst_cam[i] == k ? k : -2;
+    }
+    std::vector<char> inst_done(std::max(NI, 1), 0);
+    for (int k = 0; k < K; ++k) {
+      if (cam_blk[k] < 0) continue;
+      const int i = cam_user[k];
+      if (i >= 0 && inst_blk[i] >= 0 && inst_cam[i] == k && cam_np[k] + 6 <= 16) {
+        grp_b1.push_back(cam_blk[k]); grp_b2.push_back(inst_blk[i]); inst_done[i] = 1;
+      } else {
+        grp_b1.push_back(cam_blk[k]); grp_b2.push_back(-1);
+      }
+    }
+    for (int i = 0; i < NI; ++i)
+      if (inst_blk[i] >= 0 && !inst_done[i]) { grp_b1.push_back(inst_blk[i]); grp_b2.push_back(-1); }
+    for (int i = 0; i < NR; ++i)
+      if (rc_blk[i] >= 0) { grp_b1.push_back(rc_blk[i]); grp_b2.push_back(-1); }
+  }
+  const int ngroups = (int)grp_b1.size();
 
   // ---- shard points over ranks (p % world == rank), sort observations by point ----
   std::vector<int> local_of(Pfull, -1), global_of;
@@ -672,6 +702,7 @@ void BA::run() {
   upload(d_blk_off, blk_off, stream); upload(d_blk_sz, blk_sz, stream);
   upload(d_cam_blk, cam_blk, stream); upload(d_inst_blk, inst_blk, stream); upload(d_rc_blk, rc_blk, stream);
   upload(d_pr_blk, pr_blk, stream); upload(d_pr_local, pr_local, stream);
+  upload(d_grp_b1, grp_b1, stream); upload(d_grp_b2, grp_b2, stream);
   upload(d_pr_cam_param, pr_cam_param, stream); upload(d_pr_cam_col, pr_cam_col, stream);
   upload(d_pr_cam_log, pr_cam_log, stream); upload(d_pr_cam_prior, pr_cam_prior, stream);
   upload(d_pr_cam_scale, pr_cam_scale, stream); upload(d_pr_pos_inst, pr_pos_inst, stream);
@@ -686,7 +717,8 @@ void BA::run() {
   d_px.reserve(std::max(nc, 1)); d_pr.reserve(std::max(nc, 1)); d_pz.reserve(std::max(nc, 1));
   d_pp.reserve(std::max(nc, 1)); d_pAp.reserve(std::max(nc, 1));
   d_pcg.reserve(1);
-  d_Minv.reserve((size_t)std::max(nblk, 1) * MAXB * MAXB);
+  d_Minv.reserve((size_t)std::max(ngroups, 1) * MAXB * MAXB);
+  d_Ap.reserve(std::max(nc, 1));
   d_sc.reserve(1);
 
   BAView v{};
@@ -875,7 +907,31 @@ void BA::run() {
       OSFM_LAUNCH_CHECK();
     }
     d_S.reserve((size_t)std::max<long long>(s_total, 1));
+    // block-row ELL layout of the PCG mat-vec
+    d_row_M.reserve(nblk + 1); d_qoff.reserve(n_all + 1); d_blk_row.reserve(n_all + 1);
+    pcg_row_sizes<<<grid_for(nblk, 128), 128, 0, stream>>>(d_row_ptr.p, d_row_col.p, bsr, d_row_M.p, d_qoff.p, d_blk_row.p);
+    OSFM_LAUNCH_CHECK();
+    std::vector<int> row_M(nblk);
+    OSFM_CUDA(cudaMemcpyAsync(row_M.data(), d_row_M.p, sizeof(int) * nblk, cudaMemcpyDeviceToHost, stream));
+    OSFM_CUDA(cudaStreamSynchronize(stream));
+    std::vector<long long> rowbase(nblk);
+    std::vector<int> cbase(nblk);
+    long long vb = 0, cbt = 0;
+    for (int b = 0; b < nblk; ++b) {
+      rowbase[b] = vb; cbase[b] = (int)cbt;
+      vb += (long long)blk_sz[b] * row_M[b];
+      cbt += row_M[b];
+    }
+    upload(d_rowbase, rowbase, stream); upload(d_cbase, cbase, stream);
+    d_colidx.reserve((size_t)cbt + 1); d_row_of.reserve(nc + 1); d_Spcg.reserve((size_t)vb + 1);
+    pcg_fill_colidx<<<grid_for(n_all, 128), 128, 0, stream>>>(d_row_col.p, d_qoff.p, d_blk_row.p, n_all, bsr, d_cbase.p,
+                                                             d_colidx.p, d_row_of.p);
+    OSFM_LAUNCH_CHECK();
+    OSFM_CUDA(cudaStreamSynchronize(stream));  // rowbase / cbase host vectors go out of scope
   }
+  PcgLayout lay{};
+  lay.row_of = d_row_of.p; lay.row_M = d_row_M.p; lay.rowbase = d_rowbase.p; lay.cbase = d_cbase.p;
+  lay.colidx = d_colidx.p; lay.ngroups = ngroups; lay.grp_b1 = d_grp_b1.p; lay.grp_b2 = d_grp_b2.p;
 
   // ---- Levenberg-Marquardt (Ceres trust_region_minimizer / levenberg_marquardt_strategy) ----
   OSFM_CUDA(cudaEventRecord(ev0, stream));
@@ -960,41 +1016,18 @@ void BA::run() {
       OSFM_LAUNCH_CHECK();
       // --- PCG: one persistent kernel, |r| <= 1e-10 |b| ---
       tm_pcg.start(stream);
-      pcg_factor_blocks<<<grid_for(nblk, 64), 64, 0, stream>>>(d_S.p, d_diag_off.p, d_blk_sz.p, nblk, d_Minv.p);
+      pcg_convert<<<grid_for((long long)n_blocks_all * 32, 256), 256, 0, stream>>>(
+          d_S.p, d_row_col.p, d_row_off.p, d_qoff.p, d_blk_row.p, n_blocks_all, bsr, d_row_M.p, d_rowbase.p, d_Spcg.p);
+      OSFM_LAUNCH_CHECK();
+      pcg_factor_groups<<<grid_for(ngroups, 64), 64, 0, stream>>>(d_S.p, bsr, d_diag_off.p, d_grp_b1.p, d_grp_b2.p,
+                                                                 ngroups, d_Minv.p);
       OSFM_LAUNCH_CHECK();
       OSFM_CUDA(cudaMemsetAsync(d_pcg.p, 0, sizeof(PcgState), stream));
       const int max_pcg = std::min(2 * nc + 100, 5000);
-      // one cluster: the smallest power of two of CTAs (<= 16) that gives every block row its own warp
-      int pcg_grid = 1;
-      while (pcg_grid < 16 && pcg_grid * (PCG_THREADS / 32) < nblk) pcg_grid *= 2;
-      {
-        static bool attr_set = false;
-        if (!attr_set) {
-          OSFM_CUDA(cudaFuncSetAttribute(pcg_persistent, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
-          attr_set = true;
-        }
-        cudaLaunchConfig_t cfg{};
-        cfg.gridDim = dim3(pcg_grid);
-        cfg.blockDim = dim3(PCG_THREADS);
-        cfg.dynamicSmemBytes = 0;
-        cfg.stream = stream;
-        cudaLaunchAttribute attr[1];
-        attr[0].id = cudaLaunchAttributeClusterDimension;
-        attr[0].val.clusterDim.x = pcg_grid;
-        attr[0].val.clusterDim.y = 1;
-        attr[0].val.clusterDim.z = 1;
-        cfg.attrs = attr;
-        cfg.numAttrs = 1;
-        const double* c_S = d_S.p;
-        const int *c_rp = d_row_ptr.p, *c_rc = d_row_col.p, *c_ro = d_row_off.p;
-        const double *c_M = d_Minv.p, *c_rhs = d_rhs.p;
-        double *c_x = d_px.p, *c_r = d_pr.p, *c_z = d_pz.p, *c_p0 = d_pp.p, *c_p1 = d_pAp.p;
-        PcgState* c_st = d_pcg.p;
-        int c_max = max_pcg;
-        double c_tol = 1e-20;
-        OSFM_CUDA(cudaLaunchKernelEx(&cfg, pcg_persistent, c_S, c_rp, c_rc, c_ro, bsr, c_M, c_rhs, c_x, c_r, c_z, c_p0,
-                                     c_p1, c_st, c_max, c_tol));
-      }
+      // persistent grid: every CTA must be resident (1 CTA / SM) for the grid barrier
+      const int pcg_grid = std::max(1, std::min(num_sms, (nc + PCG_THREADS / 32 - 1) / (PCG_THREADS / 32)));
+      pcg_persistent<<<pcg_grid, PCG_THREADS, 0, stream>>>(d_Spcg.p, lay, bsr, d_Minv.p, d_rhs.p, d_px.p, d_pr.p, d_pz.p,
+                                                           d_pp.p, d_pAp.p, d_Ap.p, d_pcg.p, nc, max_pcg, 1e-20);
       OSFM_LAUNCH_CHECK();
       OSFM_CUDA(cudaMemcpyAsync(d_y.p, d_px.p, sizeof(double) * nc, cudaMemcpyDeviceToDevice, stream));
       OSFM_CUDA(cudaMemcpyAsync(h_pcg.p, d_pcg.p, sizeof(PcgState), cudaMemcpyDeviceToHost, stream));

@@ -451,21 +451,99 @@ __global__ void __launch_bounds__(256)
 }
 
 // ---------------------------------------------------------------------------
-// PCG on S y = rhs: block-Jacobi preconditioner, one persistent kernel = one thread-block cluster.
+// PCG on S y = rhs.  Block-Jacobi preconditioner over *groups* of parameter blocks (a camera and the
+// rig instance that is its only user form one group: intrinsics and pose of a shot are strongly
+// coupled), one persistent kernel over all SMs, two grid barriers per iteration.
+//
+// Mat-vec layout ("block-row ELL", rebuilt from the block values every LM iteration by
+// pcg_convert): for block row b with n scalar rows and M = sum of its blocks' column counts,
+// Spcg[rowbase[b] + r*M + q] is entry (r, q) and colidx[cbase[b] + q] its global column, so a warp
+// streams one scalar row with fully coalesced loads.
 // ---------------------------------------------------------------------------
 constexpr int MAXB = 16;
 constexpr int PCG_THREADS = 512;
 
-// Cholesky-inverts each diagonal block into Minv[b][MAXB*MAXB].
-__global__ void pcg_factor_blocks(const double* __restrict__ Sval, const int* __restrict__ diag_off,
-                                  const int* __restrict__ blk_sz, int nblk, double* __restrict__ Minv) {
+struct PcgLayout {
+  const int* row_of;     // [nc] block row of every scalar row
+  const int* row_M;      // [nblk]
+  const long long* rowbase;  // [nblk] offset into Spcg
+  const int* cbase;      // [nblk] offset into colidx
+  const int* colidx;
+  int ngroups;
+  const int* grp_b1;     // [ngroups] first block of the group
+  const int* grp_b2;     // [ngroups] second block or -1
+};
+
+// M of every block row and the in-row column offset of every stored block
+__global__ void pcg_row_sizes(const int* __restrict__ row_ptr, const int* __restrict__ row_col, BsrView h, int* row_M,
+                              int* qoff, int* blk_row) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= nblk) return;
-  const int n = blk_sz[b];
-  const double* D = Sval + diag_off[b];
+  if (b >= h.nblk) return;
+  int acc = 0;
+  for (int e = row_ptr[b]; e < row_ptr[b + 1]; ++e) {
+    qoff[e] = acc;
+    blk_row[e] = b;
+    acc += h.blk_sz[row_col[e]];
+  }
+  row_M[b] = acc;
+}
+__global__ void pcg_fill_colidx(const int* __restrict__ row_col, const int* __restrict__ qoff,
+                                const int* __restrict__ blk_row, int n_all, BsrView h, const int* __restrict__ cbase,
+                                int* colidx, int* row_of) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n_all) return;
+  const int b = blk_row[e], cb = row_col[e];
+  const int m = h.blk_sz[cb], co = h.blk_off[cb];
+  for (int j = 0; j < m; ++j) colidx[cbase[b] + qoff[e] + j] = co + j;
+  if (cb == b) {
+    const int n = h.blk_sz[b], o = h.blk_off[b];
+    for (int r = 0; r < n; ++r) row_of[o + r] = b;
+  }
+}
+// one warp per stored block: scatter its values into the block-row ELL layout
+__global__ void __launch_bounds__(256)
+    pcg_convert(const double* __restrict__ Sval, const int* __restrict__ row_col, const int* __restrict__ row_off,
+                const int* __restrict__ qoff, const int* __restrict__ blk_row, int n_all, BsrView h,
+                const int* __restrict__ row_M, const long long* __restrict__ rowbase, double* __restrict__ Spcg) {
+  const int e = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (e >= n_all) return;
+  const int b = blk_row[e];
+  const int n = h.blk_sz[b], m = h.blk_sz[row_col[e]], M = row_M[b];
+  const double* src = Sval + row_off[e];
+  double* dst = Spcg + rowbase[b] + qoff[e];
+  for (int t = lane; t < n * m; t += 32) {
+    const int r = t / m, j = t - r * m;
+    dst[(size_t)r * M + j] = src[t];
+  }
+}
+
+// Cholesky-inverts the diagonal matrix of every preconditioner group into Minv[g][MAXB*MAXB].
+__global__ void pcg_factor_groups(const double* __restrict__ Sval, BsrView h, const int* __restrict__ diag_off,
+                                  const int* __restrict__ grp_b1, const int* __restrict__ grp_b2, int ngroups,
+                                  double* __restrict__ Minv) {
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= ngroups) return;
+  const int b1 = grp_b1[g], b2 = grp_b2[g];
+  const int n1 = h.blk_sz[b1], n2 = b2 >= 0 ? h.blk_sz[b2] : 0;
+  const int n = n1 + n2;
   double L[MAXB * MAXB];
-  for (int i = 0; i < n; ++i)
-    for (int j = 0; j <= i; ++j) L[i * MAXB + j] = D[i * n + j];
+  const double* D1 = Sval + diag_off[b1];
+  for (int i = 0; i < n1; ++i)
+    for (int j = 0; j <= i; ++j) L[i * MAXB + j] = D1[i * n1 + j];
+  if (b2 >= 0) {
+    const double* D2 = Sval + diag_off[b2];
+    for (int i = 0; i < n2; ++i)
+      for (int j = 0; j <= i; ++j) L[(n1 + i) * MAXB + n1 + j] = D2[i * n2 + j];
+    const int o12 = bsr_lookup(h, min(b1, b2), max(b1, b2));
+    for (int i = 0; i < n2; ++i)
+      for (int j = 0; j < n1; ++j) {
+        // lower-left part = block (b2 rows, b1 cols); the stored upper block is (min, max)
+        double v = 0.0;
+        if (o12 >= 0) v = b1 < b2 ? Sval[o12 + j * n2 + i] : Sval[o12 + i * n1 + j];
+        L[(n1 + i) * MAXB + j] = v;
+      }
+  }
   for (int j = 0; j < n; ++j) {
     double d = L[j * MAXB + j];
     for (int k = 0; k < j; ++k) d -= L[j * MAXB + k] * L[j * MAXB + k];
@@ -477,7 +555,7 @@ __global__ void pcg_factor_blocks(const double* __restrict__ Sval, const int* __
       L[i * MAXB + j] = s / d;
     }
   }
-  double* out = Minv + (size_t)b * MAXB * MAXB;
+  double* out = Minv + (size_t)g * MAXB * MAXB;
   for (int c = 0; c < n; ++c) {
     double y[MAXB];
     for (int i = 0; i < n; ++i) {
@@ -495,6 +573,7 @@ __global__ void pcg_factor_blocks(const double* __restrict__ Sval, const int* __
 }
 
 struct PcgState {
+  unsigned bar_count, bar_gen;
   int iterations;
   int pad;
   double rz[2];
@@ -503,41 +582,71 @@ struct PcgState {
   double bb;
 };
 
-// The PCG kernel runs as ONE thread-block cluster (<= 16 CTAs, co-scheduled by hardware), so the
-// three synchronisation points of a CG iteration are hardware cluster barriers (~0.2 us) instead of
-// a software grid barrier through L2 (measured ~4 us each, profiles/r01_ncu_ba_v1.txt).
-__device__ __forceinline__ void cluster_barrier() {
-  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+// Grid barrier for a fully resident grid (grid <= #SMs, 1 CTA / SM): one acq_rel atomic to arrive,
+// acquire loads to wait, no separate fences.
+__device__ __forceinline__ void grid_barrier(PcgState* st, unsigned nblocks) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned gen, prev;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(gen) : "l"(&st->bar_gen) : "memory");
+    asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], 1;" : "=r"(prev) : "l"(&st->bar_count) : "memory");
+    if (prev == nblocks - 1) {
+      asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(&st->bar_count), "r"(0u) : "memory");
+      asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(&st->bar_gen), "r"(gen + 1) : "memory");
+    } else {
+      const long long t0 = clock64();
+      unsigned cur;
+      do {
+        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(cur) : "l"(&st->bar_gen) : "memory");
+        if (clock64() - t0 > 8000000000LL) __trap();  // a protocol bug must not hang the GPU
+      } while (cur == gen);
+    }
+  }
+  __syncthreads();
 }
 __device__ __forceinline__ double ldcg_d(const double* p) { return __ldcg(p); }
 
-// One warp per block row.  Vectors written by other CTAs are read with ld.global.cg (L2).
+// z_G = Minv_G r_G for one group (one warp); returns this lane's contributions to r.z and r.r
+__device__ __forceinline__ void pcg_apply_group(const BsrView& h, const PcgLayout& L, const double* Minv, int g, int lane,
+                                                double rn, double* z, double* a_rz, double* a_rr, int n, int o_lane) {
+  const double* M = Minv + (size_t)g * MAXB * MAXB;
+  double s = 0.0;
+  for (int j = 0; j < n; ++j) {
+    const double rj = __shfl_sync(0xffffffffu, rn, j);
+    if (lane < n) s += M[lane * MAXB + j] * rj;
+  }
+  if (lane < n) {
+    z[o_lane] = s;
+    *a_rz += s * rn;
+    *a_rr += rn * rn;
+  }
+}
+
 __global__ void __launch_bounds__(PCG_THREADS, 1)
-    pcg_persistent(const double* __restrict__ Sval, const int* __restrict__ row_ptr, const int* __restrict__ row_col,
-                   const int* __restrict__ row_off, BsrView h, const double* __restrict__ Minv,
-                   const double* __restrict__ rhs, double* x, double* r, double* z, double* p0, double* p1,
-                   PcgState* st, int max_iter, double tol2_rel) {
-  const int nblk = h.nblk;
+    pcg_persistent(const double* __restrict__ Spcg, PcgLayout L, BsrView h, const double* __restrict__ Minv,
+                   const double* __restrict__ rhs, double* x, double* r, double* z, double* p0, double* p1, double* Ap,
+                   PcgState* st, int nc, int max_iter, double tol2_rel) {
   const int warps_per_cta = blockDim.x >> 5;
   const int gw = blockIdx.x * warps_per_cta + (threadIdx.x >> 5);
   const int nw = gridDim.x * warps_per_cta;
   const int lane = threadIdx.x & 31;
   double* pbuf[2] = {p0, p1};
 
-  // ---- init: x = 0, r = rhs, z = M^-1 r, p = z, rz, bb ----
+  // ---- init: x = 0, r = rhs, z = M^-1 r, p_old = z, rz, bb ----
   {
     double a_rz = 0.0, a_rr = 0.0;
-    for (int b = gw; b < nblk; b += nw) {
-      const int o = h.blk_off[b], n = h.blk_sz[b];
-      const double* M = Minv + (size_t)b * MAXB * MAXB;
+    for (int g = gw; g < L.ngroups; g += nw) {
+      const int b1 = L.grp_b1[g], b2 = L.grp_b2[g];
+      const int n1 = h.blk_sz[b1], n2 = b2 >= 0 ? h.blk_sz[b2] : 0, n = n1 + n2;
+      const int o = lane < n1 ? h.blk_off[b1] + lane : (lane < n ? h.blk_off[b2] + lane - n1 : 0);
+      double rn = 0.0;
       if (lane < n) {
-        double s = 0.0;
-        for (int j = 0; j < n; ++j) s += M[lane * MAXB + j] * rhs[o + j];
-        const double ri = rhs[o + lane];
-        x[o + lane] = 0.0; r[o + lane] = ri; z[o + lane] = s; p0[o + lane] = s;
-        a_rz += s * ri;
-        a_rr += ri * ri;
+        rn = rhs[o];
+        x[o] = 0.0;
+        r[o] = rn;
       }
+      pcg_apply_group(h, L, Minv, g, lane, rn, z, &a_rz, &a_rr, n, o);
+      if (lane < n) p0[o] = 0.0;
     }
 #pragma unroll
     for (int o = 16; o; o >>= 1) {
@@ -549,82 +658,55 @@ __global__ void __launch_bounds__(PCG_THREADS, 1)
       atomicAdd(&st->bb, a_rr);
     }
   }
-  cluster_barrier();
+  grid_barrier(st, gridDim.x);
   const double bb = ldcg_d(&st->bb);
   const double tol2 = tol2_rel * bb;
   int it = 0;
   if (bb > 0.0) {
+    double beta = 0.0;  // p_1 = z_0
     for (; it < max_iter; ++it) {
       const int cur = it & 1, nxt = cur ^ 1;
-      const double* p = pbuf[cur];
-      // ---- phase A: Ap (kept in z's slot? no: separate) ; pAp ----
-      // each warp computes the rows of its blocks; Ap is stored in pbuf[nxt] temporarily
-      double* Ap = pbuf[nxt];
+      const double* pold = pbuf[cur];
+      double* pnew = pbuf[nxt];
+      // ---- phase A: p = z + beta p_old (on the fly), Ap = S p, pAp ----
       double a_pAp = 0.0;
-      for (int b = gw; b < nblk; b += nw) {
-        const int o = h.blk_off[b], n = h.blk_sz[b];
-        // every lane takes one stored block of this block row (32 independent load chains in flight)
-        double acc[MAXB];
-#pragma unroll
-        for (int r = 0; r < MAXB; ++r) acc[r] = 0.0;
-        for (int e = row_ptr[b] + lane; e < row_ptr[b + 1]; e += 32) {
-          const int cb = row_col[e];
-          const int m = h.blk_sz[cb], co = h.blk_off[cb];
-          const double* B = Sval + row_off[e];
-          double pv[MAXB];
-#pragma unroll
-          for (int j = 0; j < MAXB; ++j) pv[j] = j < m ? ldcg_d(&p[co + j]) : 0.0;
-#pragma unroll
-          for (int r = 0; r < MAXB; ++r) {
-            if (r < n) {
-              double t = 0.0;
-#pragma unroll
-              for (int j = 0; j < MAXB; ++j)
-                if (j < m) t += B[r * m + j] * pv[j];
-              acc[r] += t;
-            }
-          }
+      for (int i = gw; i < nc; i += nw) {
+        const int b = L.row_of[i];
+        const int rr_ = i - h.blk_off[b];
+        const int M = L.row_M[b];
+        const double* vals = Spcg + L.rowbase[b] + (size_t)rr_ * M;
+        const int* cols = L.colidx + L.cbase[b];
+        double s = 0.0;
+        for (int q = lane; q < M; q += 32) {
+          const int c = cols[q];
+          s += vals[q] * (ldcg_d(&z[c]) + beta * ldcg_d(&pold[c]));
         }
 #pragma unroll
-        for (int r = 0; r < MAXB; ++r) {
-          if (r < n) {  // n is warp-uniform
-            double t = acc[r];
-#pragma unroll
-            for (int d = 16; d; d >>= 1) t += __shfl_xor_sync(0xffffffffu, t, d);
-            if (lane == r) {
-              Ap[o + r] = t;
-              a_pAp += t * ldcg_d(&p[o + r]);
-            }
-          }
+        for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (lane == 0) {
+          const double pi = ldcg_d(&z[i]) + beta * ldcg_d(&pold[i]);
+          pnew[i] = pi;
+          Ap[i] = s;
+          a_pAp += s * pi;
         }
       }
-#pragma unroll
-      for (int o = 16; o; o >>= 1) a_pAp += __shfl_xor_sync(0xffffffffu, a_pAp, o);
       if (lane == 0 && a_pAp != 0.0) atomicAdd(&st->pAp[cur], a_pAp);
       if (gw == 0 && lane == 0) { st->rz[nxt] = 0.0; st->rr[nxt] = 0.0; st->pAp[nxt] = 0.0; }
-      cluster_barrier();
+      grid_barrier(st, gridDim.x);
       // ---- phase B: x += alpha p ; r -= alpha Ap ; z = M^-1 r ; rz_new, rr ----
       const double alpha = ldcg_d(&st->rz[cur]) / ldcg_d(&st->pAp[cur]);
       double a_rz = 0.0, a_rr = 0.0;
-      for (int b = gw; b < nblk; b += nw) {
-        const int o = h.blk_off[b], n = h.blk_sz[b];
-        const double* M = Minv + (size_t)b * MAXB * MAXB;
+      for (int g = gw; g < L.ngroups; g += nw) {
+        const int b1 = L.grp_b1[g], b2 = L.grp_b2[g];
+        const int n1 = h.blk_sz[b1], n2 = b2 >= 0 ? h.blk_sz[b2] : 0, n = n1 + n2;
+        const int o = lane < n1 ? h.blk_off[b1] + lane : (lane < n ? h.blk_off[b2] + lane - n1 : 0);
         double rn = 0.0;
         if (lane < n) {
-          x[o + lane] += alpha * ldcg_d(&p[o + lane]);
-          rn = r[o + lane] - alpha * ldcg_d(&Ap[o + lane]);
-          r[o + lane] = rn;
+          x[o] += alpha * ldcg_d(&pnew[o]);
+          rn = r[o] - alpha * ldcg_d(&Ap[o]);
+          r[o] = rn;
         }
-        double s = 0.0;
-        for (int j = 0; j < n; ++j) {
-          const double rj = __shfl_sync(0xffffffffu, rn, j);
-          if (lane < n) s += M[lane * MAXB + j] * rj;
-        }
-        if (lane < n) {
-          z[o + lane] = s;
-          a_rz += s * rn;
-          a_rr += rn * rn;
-        }
+        pcg_apply_group(h, L, Minv, g, lane, rn, z, &a_rz, &a_rr, n, o);
       }
 #pragma unroll
       for (int o = 16; o; o >>= 1) {
@@ -635,17 +717,10 @@ __global__ void __launch_bounds__(PCG_THREADS, 1)
         if (a_rz != 0.0) atomicAdd(&st->rz[nxt], a_rz);
         if (a_rr != 0.0) atomicAdd(&st->rr[nxt], a_rr);
       }
-      cluster_barrier();
-      // ---- phase C: p_next = z + beta p (into pbuf[nxt], which held Ap) ----
+      grid_barrier(st, gridDim.x);
       const double rr = ldcg_d(&st->rr[nxt]);
-      if (!(rr == rr)) { ++it; break; }  // NaN: give up (step will be rejected)
-      if (rr <= tol2) { ++it; break; }
-      const double beta = ldcg_d(&st->rz[nxt]) / ldcg_d(&st->rz[cur]);
-      for (int b = gw; b < nblk; b += nw) {
-        const int o = h.blk_off[b], n = h.blk_sz[b];
-        if (lane < n) pbuf[nxt][o + lane] = z[o + lane] + beta * ldcg_d(&p[o + lane]);
-      }
-      cluster_barrier();
+      if (!(rr == rr) || rr <= tol2) { ++it; break; }  // NaN (step will be rejected) or converged
+      beta = ldcg_d(&st->rz[nxt]) / ldcg_d(&st->rz[cur]);
     }
   }
   if (gw == 0 && lane == 0) st->iterations = it;

@@ -45,7 +45,8 @@ constexpr int TC_T_BYTES = TC_N * TC_ROW_BYTES;  // 73728
 constexpr int TC_SBO = TC_KCH * 128;     // bytes between 8-row groups
 constexpr int TC_LBO = 128;              // bytes between K-adjacent core matrices
 constexpr int TC_STAGES = 2;
-constexpr int TC_THREADS = 192;
+constexpr int TC_EPI_WARPS = 8;            // two per TMEM lane quarter, interleaved over 16-column chunks
+constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;
 constexpr int TC_SMEM = 2 * TC_Q_BYTES + TC_STAGES * TC_T_BYTES;  // 221184
 
 int tc_tile_m() { return TC_M; }
@@ -308,17 +309,24 @@ __device__ __forceinline__ void row_update(RowState& st, float x, int idx) {
 // epilogue loop body must stay resident in the instruction cache (an earlier fully unrolled version was
 // 89 KB of SASS and spent most of its time in instruction-fetch stalls, profiles/r01_*).
 __device__ __forceinline__ void row_consume16(RowState& st, const uint32_t (&v)[16], int col0) {
+  // both group minima first (two independent dependency chains), one test for the common case
+  float m[2];
 #pragma unroll
   for (int g = 0; g < 2; ++g) {
-    float m = fminf(fminf(__uint_as_float(v[g * 8]), __uint_as_float(v[g * 8 + 1])), __uint_as_float(v[g * 8 + 2]));
-    m = fminf(fminf(m, __uint_as_float(v[g * 8 + 3])), __uint_as_float(v[g * 8 + 4]));
-    m = fminf(fminf(m, __uint_as_float(v[g * 8 + 5])), __uint_as_float(v[g * 8 + 6]));
-    m = fminf(m, __uint_as_float(v[g * 8 + 7]));
-    if (m < st.q2) {
+    float t = fminf(fminf(__uint_as_float(v[g * 8]), __uint_as_float(v[g * 8 + 1])), __uint_as_float(v[g * 8 + 2]));
+    t = fminf(fminf(t, __uint_as_float(v[g * 8 + 3])), __uint_as_float(v[g * 8 + 4]));
+    t = fminf(fminf(t, __uint_as_float(v[g * 8 + 5])), __uint_as_float(v[g * 8 + 6]));
+    m[g] = fminf(t, __uint_as_float(v[g * 8 + 7]));
+  }
+  if (fminf(m[0], m[1]) < st.q2) {
 #pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        const float x = __uint_as_float(v[g * 8 + e]);
-        if (x < st.q2) row_update(st, x, col0 + g * 8 + e);
+    for (int g = 0; g < 2; ++g) {
+      if (m[g] < st.q2) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const float x = __uint_as_float(v[g * 8 + e]);
+          if (x < st.q2) row_update(st, x, col0 + g * 8 + e);
+        }
       }
     }
   }
@@ -331,6 +339,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
   __shared__ __align__(8) uint64_t bar_qfull[2], bar_qempty[2], bar_full[TC_STAGES], bar_empty[TC_STAGES],
       bar_accfull[2], bar_accempty[2];
   __shared__ uint32_t tmem_base_smem;
+  __shared__ float4 merge_buf[TC_M];
 
   uint8_t* q_smem[2] = {smem, smem + TC_Q_BYTES};
   uint8_t* t_smem[TC_STAGES];
@@ -344,7 +353,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
       mbar_init(&bar_qfull[i], 1);
       mbar_init(&bar_qempty[i], 1);
       mbar_init(&bar_accfull[i], 1);
-      mbar_init(&bar_accempty[i], 4);  // one arrival per epilogue warp
+      mbar_init(&bar_accempty[i], TC_EPI_WARPS);  // one arrival per epilogue warp
     }
     for (int i = 0; i < TC_STAGES; ++i) {
       mbar_init(&bar_full[i], 1);
@@ -413,8 +422,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
       }
     }
   } else {
-    // ===== epilogue: warps 2..5 own TMEM lane quarters (warp % 4) =====
+    // ===== epilogue: warps 2..9; a warp may only touch TMEM lanes 32*(warp%4)..+31.  The two warps
+    // of a quarter take alternating pairs of 16-column chunks, so each SM sub-partition always has two
+    // independent instruction streams (the single-warp version was latency-bound, profiles/r01_ncu_tc_v2) =====
     const int quarter = warp & 3;
+    const int half = (warp - 2) >> 2;
     const int row_in_tile = quarter * 32 + lane;
     int tilecount = 0;
     for (int task = blockIdx.x; task < ntasks; task += gridDim.x) {
@@ -432,21 +444,37 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         const int col_base = t.t_begin + i * TC_N;
         // two 16-column register buffers: the load of the next chunk is in flight while one is consumed
         uint32_t va[16], vb[16];
-        OSFM_TMEM_LD16(taddr, va);
+        constexpr int kStep = 2 * (TC_EPI_WARPS / 4);  // chunks between two visits of this warp
+        OSFM_TMEM_LD16(taddr + (2 * half) * 16, va);
 #pragma unroll 1
-        for (int cb = 0; cb < TC_N / 16; cb += 2) {
+        for (int cb = 2 * half; cb < TC_N / 16; cb += kStep) {
           asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
           OSFM_TMEM_LD16(taddr + (cb + 1) * 16, vb);
           row_consume16(st, va, col_base + cb * 16);
           asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-          if (cb + 2 < TC_N / 16) OSFM_TMEM_LD16(taddr + (cb + 2) * 16, va);
+          if (cb + kStep < TC_N / 16) OSFM_TMEM_LD16(taddr + (cb + kStep) * 16, va);
           row_consume16(st, vb, col_base + (cb + 1) * 16);
         }
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&bar_accempty[a]);
       }
-      if (gq < t.job.nq) {
+      // merge the two column halves of a row (lexicographic (d^2, index), like cv2's insertion order)
+      if (half == 1) {
+        merge_buf[row_in_tile] = make_float4(st.q1, __int_as_float(st.i1), st.q2, __int_as_float(st.i2));
+      }
+      asm volatile("bar.sync 1, %0;" ::"r"(32 * TC_EPI_WARPS) : "memory");
+      if (half == 0) {
+        const float4 o = merge_buf[row_in_tile];
+        Top2 a2;
+        a2.s1 = st.q1; a2.i1 = st.i1; a2.s2 = st.q2; a2.i2 = st.i2;
+        Top2 b2;
+        b2.s1 = o.x; b2.i1 = __float_as_int(o.y); b2.s2 = o.z; b2.i2 = __float_as_int(o.w);
+        top2_merge(a2, b2);
+        st.q1 = a2.s1; st.i1 = a2.i1; st.q2 = a2.s2; st.i2 = a2.i2;
+      }
+      asm volatile("bar.sync 1, %0;" ::"r"(32 * TC_EPI_WARPS) : "memory");
+      if (half == 0 && gq < t.job.nq) {
         // partial results of this kernel are squared distances (exact integers in fp32)
         Top2 out;
         out.s1 = st.i1 >= 0 ? fmaxf(st.q1 + na, 0.0f) : __builtin_huge_valf();
