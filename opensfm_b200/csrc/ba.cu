@@ -17,6 +17,7 @@
 // Kernels: ba_linearize (per observation), ba_colnorm_grad, ba_schur (CTA per point:
 // U, g_c, V^-1 and W V^-1 W^T scattered to S with fp64 atomics), ba_finish_system,
 // PCG kernels (block-Jacobi), ba_backsub (warp per point), ba_model_change, ba_update.
+#include <algorithm>
 #include <chrono>
 #include <cmath>
 #include <string>
@@ -493,6 +494,7 @@ struct BA {
   DevBuf<unsigned> d_count;
   DevBuf<char> d_cub;
   DevBuf<PcgState> d_pcg;
+  DevBuf<int> d_seg_start;
   DevBuf<int> d_row_M, d_qoff, d_blk_row, d_cbase, d_colidx, d_row_of, d_grp_b1, d_grp_b2;
   DevBuf<long long> d_rowbase;
   DevBuf<double> d_Spcg, d_Ap;
@@ -612,29 +614,90 @@ void BA::run() {
   }
   const int ngroups = (int)grp_b1.size();
 
-  // ---- shard points over ranks (p % world == rank), sort observations by point ----
-  std::vector<int> local_of(Pfull, -1), global_of;
-  for (int p = 0; p < Pfull; ++p)
-    if (p % world == rank) { local_of[p] = (int)global_of.size(); global_of.push_back(p); }
-  const int P = (int)global_of.size();
-  std::vector<long long> pt_start(P + 1, 0);
-  for (long long i = 0; i < Nfull; ++i) {
-    const int lp = local_of[obs_point[i]];
-    if (lp >= 0) pt_start[lp + 1]++;
+  int wc = 0, nres = 2;
+  for (int s = 0; s < S; ++s) {
+    wc = std::max(wc, cam_np[shot_cam[s]] + 6 + (shot_use_rc[s] ? 6 : 0));
+    if (cam_type[shot_cam[s]] == PT_SPHERICAL) nres = 3;
   }
-  for (int p = 0; p < P; ++p) pt_start[p + 1] += pt_start[p];
-  const long long N = pt_start[P];
-  std::vector<long long> fill(pt_start.begin(), pt_start.end() - 1), obs_orig(N);
+  wc = std::max(wc, 1);
+
+  // ---- shard points over ranks (p % world == rank); order the local points so that points seen by
+  //      exactly the same shots are contiguous (segments of the fast Schur kernel); sort the
+  //      observations by (point, shot) ----
+  std::vector<int> old_of(Pfull, -1), old_global;
+  for (int p = 0; p < Pfull; ++p)
+    if (p % world == rank) { old_of[p] = (int)old_global.size(); old_global.push_back(p); }
+  const int P = (int)old_global.size();
+  std::vector<long long> ostart(P + 1, 0);
+  for (long long i = 0; i < Nfull; ++i) {
+    const int lp = old_of[obs_point[i]];
+    if (lp >= 0) ostart[lp + 1]++;
+  }
+  for (int p = 0; p < P; ++p) ostart[p + 1] += ostart[p];
+  const long long N = ostart[P];
+  std::vector<long long> olist(N);
+  {
+    std::vector<long long> fill(ostart.begin(), ostart.end() - 1);
+    for (long long i = 0; i < Nfull; ++i) {
+      const int lp = old_of[obs_point[i]];
+      if (lp >= 0) olist[fill[lp]++] = i;
+    }
+  }
+  std::vector<unsigned long long> sig(P);
+  std::vector<char> eligible(P);
+  for (int p = 0; p < P; ++p) {
+    long long* lo = olist.data() + ostart[p];
+    long long* hi = olist.data() + ostart[p + 1];
+    std::sort(lo, hi, [&](long long x, long long y) { return obs_shot[x] != obs_shot[y] ? obs_shot[x] < obs_shot[y] : x < y; });
+    const long long k = hi - lo;
+    unsigned long long hsh = 1469598103934665603ULL ^ (unsigned long long)(pt_const[old_global[p]] ? 1 : 0);
+    for (long long* q = lo; q < hi; ++q) { hsh ^= (unsigned long long)obs_shot[*q] + 0x9e3779b97f4a7c15ULL; hsh *= 1099511628211ULL; }
+    sig[p] = hsh;
+    eligible[p] = (k >= 1 && k <= SEG_KMAX && k * wc <= SEG_NA && wc <= SEG_WCMAX) ? 1 : 0;
+  }
+  std::vector<int> order(P);
+  for (int p = 0; p < P; ++p) order[p] = p;
+  std::sort(order.begin(), order.end(), [&](int x, int y) {
+    if (eligible[x] != eligible[y]) return eligible[x] > eligible[y];
+    if (sig[x] != sig[y]) return sig[x] < sig[y];
+    return x < y;
+  });
+  std::vector<int> global_of(P);
+  std::vector<long long> pt_start(P + 1, 0), obs_orig(N);
   std::vector<int> s_shot(N), s_point(N);
   std::vector<double> s_x(N), s_y(N), s_isig(N);
-  for (long long i = 0; i < Nfull; ++i) {
-    const int lp = local_of[obs_point[i]];
-    if (lp < 0) continue;
-    const long long d = fill[lp]++;
-    obs_orig[d] = i; s_shot[d] = obs_shot[i]; s_point[d] = lp;
-    s_x[d] = obs_xy[2 * i]; s_y[d] = obs_xy[2 * i + 1];
-    s_isig[d] = 1.0 / obs_sigma[i];  // projection_errors.h:21
+  std::vector<int> seg_start;  // point ranges of the fast path; the last entry is P_fast
+  int P_fast = 0;
+  {
+    constexpr int kSegMaxPoints = 64;
+    long long d = 0;
+    int prev = -1;
+    for (int np = 0; np < P; ++np) {
+      const int op = order[np];
+      global_of[np] = old_global[op];
+      pt_start[np] = d;
+      const long long kk = ostart[op + 1] - ostart[op];
+      for (long long t = 0; t < kk; ++t, ++d) {
+        const long long i = olist[ostart[op] + t];
+        obs_orig[d] = i; s_shot[d] = obs_shot[i]; s_point[d] = np;
+        s_x[d] = obs_xy[2 * i]; s_y[d] = obs_xy[2 * i + 1];
+        s_isig[d] = 1.0 / obs_sigma[i];  // projection_errors.h:21
+      }
+      if (eligible[op]) {
+        bool same = prev >= 0 && sig[prev] == sig[op] && (ostart[prev + 1] - ostart[prev]) == kk &&
+                    (np - seg_start.back()) < kSegMaxPoints && pt_const[old_global[prev]] == pt_const[old_global[op]];
+        if (same)
+          for (long long t = 0; t < kk && same; ++t)
+            same = obs_shot[olist[ostart[prev] + t]] == obs_shot[olist[ostart[op] + t]];
+        if (!same) seg_start.push_back(np);
+        prev = op;
+        P_fast = np + 1;
+      }
+    }
+    pt_start[P] = d;
+    seg_start.push_back(P_fast);
   }
+  const int nseg = (int)seg_start.size() - 1;
   std::vector<int> pt_poff(std::max(P, 1), -1);
   std::vector<double> lpts(3 * (size_t)std::max(P, 1), 0.0);
   int npf = 0;
@@ -643,12 +706,6 @@ void BA::run() {
     for (int j = 0; j < 3; ++j) lpts[3 * (size_t)p + j] = pts[3 * (size_t)global_of[p] + j];
   }
   const int n = nc + 3 * npf;
-  int wc = 0, nres = 2;
-  for (int s = 0; s < S; ++s) {
-    wc = std::max(wc, cam_np[shot_cam[s]] + 6 + (shot_use_rc[s] ? 6 : 0));
-    if (cam_type[shot_cam[s]] == PT_SPHERICAL) nres = 3;
-  }
-  wc = std::max(wc, 1);
 
   // ---- prior rows (rank 0 adds them; Ceres drops residuals of constant blocks) ----
   std::vector<int> pr_cam_param, pr_cam_col, pr_cam_log, pr_pos_inst, pr_pos_axis, pr_pos_col;
@@ -693,6 +750,7 @@ void BA::run() {
   upload(d_obs_shot, s_shot, stream); upload(d_obs_point, s_point, stream);
   upload(d_obs_x, s_x, stream); upload(d_obs_y, s_y, stream); upload(d_obs_isig, s_isig, stream);
   upload(d_obs_orig, obs_orig, stream); upload(d_pt_start, pt_start, stream);
+  upload(d_seg_start, seg_start, stream);
   std::vector<double> rc_h = rc;
   if (rc_h.empty()) rc_h.assign(6, 0.0);
   for (int b = 0; b < 2; ++b) {
@@ -987,9 +1045,16 @@ void BA::run() {
       const size_t smem = (size_t)SCHUR_KC * wc * (2 * 3 * sizeof(double) + 2 * sizeof(int)) +
                           (size_t)SCHUR_KC * 8 * sizeof(int) + (size_t)SCHUR_KC * SCHUR_KC * 9 * sizeof(int);
       tm_schur.start(stream);
-      ba_schur<<<P, SCHUR_THREADS, smem, stream>>>(v, bm, bsr, d_scale.p, d_diag.p, inv_radius, d_S.p, d_rhs.p,
-                                                   d_Vinv.p, d_gp.p);
-      OSFM_LAUNCH_CHECK();
+      if (nseg > 0) {
+        ba_schur_seg<<<nseg, SEG_THREADS, 0, stream>>>(v, bm, bsr, d_seg_start.p, d_scale.p, d_diag.p, inv_radius, d_S.p,
+                                                      d_rhs.p, d_Vinv.p, d_gp.p);
+        OSFM_LAUNCH_CHECK();
+      }
+      if (P > P_fast) {
+        ba_schur<<<P - P_fast, SCHUR_THREADS, smem, stream>>>(v, bm, bsr, d_scale.p, d_diag.p, inv_radius, d_S.p,
+                                                             d_rhs.p, d_Vinv.p, d_gp.p, P_fast);
+        OSFM_LAUNCH_CHECK();
+      }
       tm_schur.stop(stream);
     }
     bool ok = true;
@@ -1014,7 +1079,7 @@ void BA::run() {
       ba_finish_system<<<grid_for((long long)n_upper * 32, 256), 256, 0, stream>>>(d_upper.p, n_upper, bsr, d_S.p,
                                                                                  d_diag.p, inv_radius);
       OSFM_LAUNCH_CHECK();
-      // --- PCG: one persistent kernel, |r| <= 1e-10 |b| ---
+      // --- PCG: one persistent kernel, |r| <= 1e-8 |b| ---
       tm_pcg.start(stream);
       pcg_convert<<<grid_for((long long)n_blocks_all * 32, 256), 256, 0, stream>>>(
           d_S.p, d_row_col.p, d_row_off.p, d_qoff.p, d_blk_row.p, n_blocks_all, bsr, d_row_M.p, d_rowbase.p, d_Spcg.p);
@@ -1025,9 +1090,9 @@ void BA::run() {
       OSFM_CUDA(cudaMemsetAsync(d_pcg.p, 0, sizeof(PcgState), stream));
       const int max_pcg = std::min(2 * nc + 100, 5000);
       // persistent grid: every CTA must be resident (1 CTA / SM) for the grid barrier
-      const int pcg_grid = std::max(1, std::min(num_sms, (nc + PCG_THREADS / 32 - 1) / (PCG_THREADS / 32)));
+      const int pcg_grid = std::max(1, std::min(std::min(num_sms, PCG_MAX_CTAS), (nc + PCG_THREADS / 32 - 1) / (PCG_THREADS / 32)));
       pcg_persistent<<<pcg_grid, PCG_THREADS, 0, stream>>>(d_Spcg.p, lay, bsr, d_Minv.p, d_rhs.p, d_px.p, d_pr.p, d_pz.p,
-                                                           d_pp.p, d_pAp.p, d_Ap.p, d_pcg.p, nc, max_pcg, 1e-20);
+                                                           d_pp.p, d_pAp.p, d_Ap.p, d_pcg.p, nc, max_pcg, 1e-16);
       OSFM_LAUNCH_CHECK();
       OSFM_CUDA(cudaMemcpyAsync(d_y.p, d_px.p, sizeof(double) * nc, cudaMemcpyDeviceToDevice, stream));
       OSFM_CUDA(cudaMemcpyAsync(h_pcg.p, d_pcg.p, sizeof(PcgState), cudaMemcpyDeviceToHost, stream));
