@@ -15,6 +15,7 @@ No CPU fallback: every `run()` goes to the GPU library.
 from __future__ import annotations
 
 import ctypes
+import threading
 from typing import Any, Dict, List, Optional, Sequence
 
 import numpy as np
@@ -24,6 +25,32 @@ from . import ba_problem as bp
 from . import types as T
 
 _TERMINATION = {0: "CONVERGENCE", 1: "NO_CONVERGENCE", 2: "FAILURE"}
+
+# One engine handle per (thread, device): its HBM workspaces (Jacobian planes, reduced system, ...)
+# are kept between solves, so repeated bundle() calls do not pay cudaMalloc/cudaFree every time.
+_tls = threading.local()
+
+
+class _Handle:
+    def __init__(self, device: int):
+        self.L = _lib.load()
+        self.h = ctypes.c_void_p()
+        _lib.check(self.L.osfm_ba_create(int(device), ctypes.byref(self.h)))
+
+    def __del__(self):
+        try:
+            self.L.osfm_ba_destroy(self.h)
+        except Exception:
+            pass
+
+
+def _handle(device: int) -> "_Handle":
+    cache = getattr(_tls, "handles", None)
+    if cache is None:
+        cache = _tls.handles = {}
+    if device not in cache:
+        cache[device] = _Handle(device)
+    return cache[device]
 
 
 def _p(a: np.ndarray):
@@ -39,9 +66,8 @@ def solve(pb: bp.BAProblem, device: int = 0, rank: int = 0, world: int = 1, allr
     that sums `count` float64 at device pointer `ptr` across ranks (see opensfm_b200.dist)."""
     pb.validate()
     L = _lib.load()
-    h = ctypes.c_void_p()
-    _lib.check(L.osfm_ba_create(int(device), ctypes.byref(h)))
-    try:
+    h = _handle(int(device)).h
+    if True:
         i32 = lambda a: np.ascontiguousarray(a, dtype=np.int32)
         f64 = lambda a: np.ascontiguousarray(a, dtype=np.float64)
         K, NI, NR = len(pb.cam_type), len(pb.inst), len(pb.rigcam)
@@ -81,8 +107,10 @@ def solve(pb: bp.BAProblem, device: int = 0, rank: int = 0, world: int = 1, allr
 
             cb = _lib.ALLREDUCE_FN(_cb)
             _lib.check(L.osfm_ba_set_distributed(h, int(rank), int(world), cb, None))
-        if stream is not None:
-            _lib.check(L.osfm_ba_set_stream(h, ctypes.c_void_p(stream)))
+        else:
+            # the handle is reused between calls: reset whatever a previous distributed solve left
+            _lib.check(L.osfm_ba_set_distributed(h, 0, 1, ctypes.cast(None, _lib.ALLREDUCE_FN), None))
+        _lib.check(L.osfm_ba_set_stream(h, ctypes.c_void_p(stream) if stream is not None else None))
         _lib.check(L.osfm_ba_run(h))
         cam = np.zeros_like(keep[1])
         inst = np.zeros((NI, 6))
@@ -102,8 +130,6 @@ def solve(pb: bp.BAProblem, device: int = 0, rank: int = 0, world: int = 1, allr
         summary["termination"] = _TERMINATION[s.termination]
         return {"cam_params": cam, "inst": inst, "rigcam": rc, "points": pts, "reprojection_errors": rep,
                 "summary": summary}
-    finally:
-        L.osfm_ba_destroy(h)
 
 
 def eval_observation(projection_type: int, camera, rig_instance, rig_camera, use_rig_camera: bool, point, observed,

@@ -309,23 +309,22 @@ __device__ __forceinline__ void row_update(RowState& st, float x, int idx) {
 // epilogue loop body must stay resident in the instruction cache (an earlier fully unrolled version was
 // 89 KB of SASS and spent most of its time in instruction-fetch stalls, profiles/r01_*).
 __device__ __forceinline__ void row_consume16(RowState& st, const uint32_t (&v)[16], int col0) {
-  // both group minima first (two independent dependency chains), one test for the common case
-  float m[2];
+  // minima of four groups of 4 (independent chains), one test for the common case; a triggered chunk
+  // re-examines only the group(s) of 4 that beat the threshold (their updates are predicated by ptxas,
+  // 7 instructions per element, so small groups matter)
+  float m[4];
 #pragma unroll
-  for (int g = 0; g < 2; ++g) {
-    float t = fminf(fminf(__uint_as_float(v[g * 8]), __uint_as_float(v[g * 8 + 1])), __uint_as_float(v[g * 8 + 2]));
-    t = fminf(fminf(t, __uint_as_float(v[g * 8 + 3])), __uint_as_float(v[g * 8 + 4]));
-    t = fminf(fminf(t, __uint_as_float(v[g * 8 + 5])), __uint_as_float(v[g * 8 + 6]));
-    m[g] = fminf(t, __uint_as_float(v[g * 8 + 7]));
-  }
-  if (fminf(m[0], m[1]) < st.q2) {
+  for (int g = 0; g < 4; ++g)
+    m[g] = fminf(fminf(fminf(__uint_as_float(v[g * 4]), __uint_as_float(v[g * 4 + 1])), __uint_as_float(v[g * 4 + 2])),
+                 __uint_as_float(v[g * 4 + 3]));
+  if (fminf(fminf(fminf(m[0], m[1]), m[2]), m[3]) < st.q2) {
 #pragma unroll
-    for (int g = 0; g < 2; ++g) {
+    for (int g = 0; g < 4; ++g) {
       if (m[g] < st.q2) {
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          const float x = __uint_as_float(v[g * 8 + e]);
-          if (x < st.q2) row_update(st, x, col0 + g * 8 + e);
+        for (int e = 0; e < 4; ++e) {
+          const float x = __uint_as_float(v[g * 4 + e]);
+          if (x < st.q2) row_update(st, x, col0 + g * 4 + e);
         }
       }
     }
