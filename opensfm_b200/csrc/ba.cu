@@ -1046,7 +1046,12 @@ void BA::run() {
                           (size_t)SCHUR_KC * 8 * sizeof(int) + (size_t)SCHUR_KC * SCHUR_KC * 9 * sizeof(int);
       tm_schur.start(stream);
       if (nseg > 0) {
-        ba_schur_seg<<<nseg, SEG_THREADS, 0, stream>>>(v, bm, bsr, d_seg_start.p, d_scale.p, d_diag.p, inv_radius, d_S.p,
+        static bool seg_attr = false;
+        if (!seg_attr) {
+          OSFM_CUDA(cudaFuncSetAttribute(ba_schur_seg, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SegSmem)));
+          seg_attr = true;
+        }
+        ba_schur_seg<<<nseg, SEG_THREADS, sizeof(SegSmem), stream>>>(v, bm, bsr, d_seg_start.p, d_scale.p, d_diag.p, inv_radius, d_S.p,
                                                       d_rhs.p, d_Vinv.p, d_gp.p);
         OSFM_LAUNCH_CHECK();
       }

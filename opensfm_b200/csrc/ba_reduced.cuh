@@ -415,31 +415,40 @@ __global__ void __launch_bounds__(SCHUR_THREADS)
 // ---------------------------------------------------------------------------
 // Segmented Schur complement (fast path).  Points are ordered on the host so that points observed
 // by exactly the same shots are contiguous ("segment"); one CTA owns a segment.  Because every point
-// of the segment scatters into the same entries of S, the CTA keeps those entries in REGISTERS
-// (thread = one column (b, c2) of the segment's k*wc camera-side columns x half of the rows (a, c1)),
-// adds U_a - Y_a W_b^T for point after point with pure DFMA + shared-memory broadcasts, and issues
-// the L2 atomics once per segment instead of once per point (9.5x fewer on the 500-camera scene,
-// and no address arithmetic in the inner loop).
-// Eligible: k * wc <= NA and wc <= 16; everything else goes through ba_schur.
+// of the segment scatters into the same entries of S, the segment's update is a small dense product
+//   S_seg += sum_p ( U_p - Y_p W_p^T ),   Y_p, W_p: (k*wc) x 3,
+// accumulated in REGISTERS (thread = one column (b, c2) x half of the rows (a, c1)) and flushed
+// with one L2 atomic per entry per segment instead of per point (9.5x fewer on the 500-camera scene;
+// no address arithmetic in the inner loop).  Points are processed in chunks of SEG_PCHUNK at once:
+// all their loads are in flight together and there are three CTA barriers per chunk, not per point
+// (a first version that walked the points one by one was latency-bound, profiles/r01_ncu_ba_v4.txt).
+// Eligible: k <= 16, k * wc <= SEG_NA, wc <= 16; everything else goes through ba_schur.
 // ---------------------------------------------------------------------------
 constexpr int SEG_NA = 96;                 // max camera-side columns of a segment (k * wc)
 constexpr int SEG_THREADS = 2 * SEG_NA;    // two row-halves per column
 constexpr int SEG_KMAX = 16;
 constexpr int SEG_WCMAX = 16;
+constexpr int SEG_PCHUNK = 8;              // points staged per chunk
+
+struct SegSmem {
+  double Ys[SEG_PCHUNK][SEG_NA][3];
+  double Ws[SEG_PCHUNK][SEG_NA][3];
+  double Js[SEG_PCHUNK][3][SEG_NA];         // scaled camera-side Jacobian rows [p][q][item]
+  double Jps[SEG_PCHUNK][SEG_KMAX][3][4];   // scaled point Jacobian + residual [p][b][q][x,y,z,r]
+  double Vi[SEG_PCHUNK][9];
+  double Vig[SEG_PCHUNK][3];
+  int meta[SEG_NA];
+  int gcol[SEG_NA];
+  int oblk[SEG_KMAX][4];
+  int offt[SEG_KMAX * SEG_KMAX * 9];
+};
 
 __global__ void __launch_bounds__(SEG_THREADS, 2)
     ba_schur_seg(BAView v, BlkMaps bm, BsrView h, const int* __restrict__ seg_start, const double* __restrict__ scale,
                  const double* __restrict__ diag, double inv_radius, double* __restrict__ Sval,
                  double* __restrict__ rhs, double* __restrict__ Vinv, double* __restrict__ gpo) {
-  __shared__ double Ys[SEG_NA][3];
-  __shared__ double Ws[SEG_NA][3];
-  __shared__ double Js[3][SEG_NA];          // scaled camera-side Jacobian rows [q][item]
-  __shared__ double Jps[SEG_KMAX][3][4];    // scaled point Jacobian + residual per observation [b][q][x,y,z,r]
-  __shared__ double sVi[9], sVig[3];
-  __shared__ int meta[SEG_NA];              // packed (blk, slot, size, row) or -1
-  __shared__ int gcol[SEG_NA];              // global reduced column or -1
-  __shared__ int oblk[SEG_KMAX][4];
-  __shared__ int offt[SEG_KMAX * SEG_KMAX * 9];
+  extern __shared__ __align__(16) unsigned char seg_raw[];
+  SegSmem& sm = *reinterpret_cast<SegSmem*>(seg_raw);
 
   const int wc = v.wc, nres = v.nres, nc = v.nc;
   const int p_begin = seg_start[blockIdx.x], p_end = seg_start[blockIdx.x + 1];
@@ -457,7 +466,7 @@ __global__ void __launch_bounds__(SEG_THREADS, 2)
   // ---- structure of the segment (from its first point) ----
   if (half == 0 && active) {
     const ObsBlk ob = obs_blocks(v, bm, v.obs_shot[o0 + b]);
-    if (c2 == 0) { oblk[b][0] = ob.blk[0]; oblk[b][1] = ob.blk[1]; oblk[b][2] = ob.blk[2]; oblk[b][3] = ob.C; }
+    if (c2 == 0) { sm.oblk[b][0] = ob.blk[0]; sm.oblk[b][1] = ob.blk[1]; sm.oblk[b][2] = ob.blk[2]; sm.oblk[b][3] = ob.C; }
     int g = -1, m = -1;
     if (c2 < ob.C + 12) {
       const int s2 = ob.slot_of(c2);
@@ -467,20 +476,19 @@ __global__ void __launch_bounds__(SEG_THREADS, 2)
         m = (ob.blk[s2] << 12) | (s2 << 10) | (ob.size(s2) << 5) | r2;
       }
     }
-    gcol[item] = g;
-    meta[item] = m;
+    sm.gcol[item] = g;
+    sm.meta[item] = m;
   }
   __syncthreads();
   for (int idx = tid; idx < k * k * 9; idx += SEG_THREADS) {
     const int ab = idx / 9, ss = idx - ab * 9;
     const int a = ab / k, bb = ab - a * k;
-    const int B1 = oblk[a][ss / 3], B2 = oblk[bb][ss % 3];
-    offt[(a * SEG_KMAX + bb) * 9 + ss] = (B1 < 0 || B2 < 0) ? -1 : bsr_lookup(h, min(B1, B2), max(B1, B2));
+    const int B1 = sm.oblk[a][ss / 3], B2 = sm.oblk[bb][ss % 3];
+    sm.offt[(a * SEG_KMAX + bb) * 9 + ss] = (B1 < 0 || B2 < 0) ? -1 : bsr_lookup(h, min(B1, B2), max(B1, B2));
   }
-  const int mycol = active ? gcol[item] : -1;
+  const int mycol = active ? sm.gcol[item] : -1;
   const double myscale = mycol >= 0 ? scale[mycol] : 0.0;
 
-  // ---- accumulate over the points of the segment ----
   constexpr int ROWS = SEG_NA / 2;
   double acc[ROWS];
 #pragma unroll
@@ -491,89 +499,109 @@ __global__ void __launch_bounds__(SEG_THREADS, 2)
   double rhs_acc = 0.0;
   const int row0 = half * ROWS;
 
-  for (int p = p_begin; p < p_end; ++p) {
-    const long long ob0 = v.pt_start[p];
-    const int pf = v.pt_poff[p];
-    __syncthreads();  // previous point's shared data fully consumed
-    double js[3] = {0.0, 0.0, 0.0};
-    if (half == 0 && active) {
-      const long long i = ob0 + b;
-      double w0 = 0.0, w1 = 0.0, w2 = 0.0, gr = 0.0;
+  for (int pc0 = p_begin; pc0 < p_end; pc0 += SEG_PCHUNK) {
+    const int np = min(SEG_PCHUNK, p_end - pc0);
+    __syncthreads();  // previous chunk fully consumed
+    // ---- phase 1: every (point, column) of the chunk: scaled Jacobian row, W row, g_c ----
+    for (int idx = tid; idx < np * ncols; idx += SEG_THREADS) {
+      const int lp = idx / ncols, it2 = idx - lp * ncols;
+      const int bb = it2 / wc, cc = it2 - bb * wc;
+      const int p = pc0 + lp;
+      const long long i = v.pt_start[p] + bb;
+      const int g = sm.gcol[it2];
+      const double sc = g >= 0 ? scale[g] : 0.0;
+      const int pf = v.pt_poff[p];
       double sp0 = 0.0, sp1 = 0.0, sp2 = 0.0;
       if (pfree) { sp0 = scale[nc + 3 * pf]; sp1 = scale[nc + 3 * pf + 1]; sp2 = scale[nc + 3 * pf + 2]; }
+      double w0 = 0.0, w1 = 0.0, w2 = 0.0;
       for (int q = 0; q < nres; ++q) {
-        const double jc = mycol >= 0 ? v.Jc[((size_t)q * wc + c2) * N + i] * myscale : 0.0;
-        const double rq = v.r[q * N + i];
-        js[q] = jc;
-        Js[q][item] = jc;
-        gr += jc * rq;
+        const double jc = g >= 0 ? v.Jc[((size_t)q * wc + cc) * N + i] * sc : 0.0;
+        sm.Js[lp][q][it2] = jc;
         if (pfree) {
           const double x = v.Jp[((size_t)q * 3 + 0) * N + i] * sp0;
           const double y = v.Jp[((size_t)q * 3 + 1) * N + i] * sp1;
           const double z = v.Jp[((size_t)q * 3 + 2) * N + i] * sp2;
           w0 += jc * x; w1 += jc * y; w2 += jc * z;
-          if (c2 == 0) { Jps[b][q][0] = x; Jps[b][q][1] = y; Jps[b][q][2] = z; Jps[b][q][3] = rq; }
+          if (cc == 0) {
+            sm.Jps[lp][bb][q][0] = x; sm.Jps[lp][bb][q][1] = y; sm.Jps[lp][bb][q][2] = z;
+            sm.Jps[lp][bb][q][3] = v.r[q * N + i];
+          }
         }
       }
-      rhs_acc += gr;
-      Ws[item][0] = w0; Ws[item][1] = w1; Ws[item][2] = w2;
+      sm.Ws[lp][it2][0] = w0; sm.Ws[lp][it2][1] = w1; sm.Ws[lp][it2][2] = w2;
+    }
+    // g_c of my column over the chunk (half 0 only; reads the residual planes directly)
+    if (half == 0 && mycol >= 0) {
+      for (int lp = 0; lp < np; ++lp) {
+        const long long i = v.pt_start[pc0 + lp] + b;
+        for (int q = 0; q < nres; ++q) rhs_acc += v.Jc[((size_t)q * wc + c2) * N + i] * myscale * v.r[q * N + i];
+      }
     }
     __syncthreads();
     if (pfree) {
-      if (tid < 32) {
-        // V, g_p over the k observations: lanes 0..8 own one accumulator each
-        double a9 = 0.0;
-        if (tid < 9) {
-          const int i0 = tid < 6 ? (tid < 3 ? 0 : (tid < 5 ? 1 : 2)) : tid - 6;          // row index
-          const int j0 = tid < 6 ? (tid < 3 ? tid : (tid < 5 ? tid - 2 : 2)) : 3;        // column (3 = residual)
-          for (int bb = 0; bb < k; ++bb)
-            for (int q = 0; q < nres; ++q) a9 += Jps[bb][q][i0] * Jps[bb][q][j0];
-        }
+      // ---- V^-1 and V^-1 g_p: one thread per point of the chunk ----
+      if (tid < np) {
+        const int pf = v.pt_poff[pc0 + tid];
         double V[9];
 #pragma unroll
-        for (int j = 0; j < 9; ++j) V[j] = __shfl_sync(0xffffffffu, a9, j);
-        if (tid == 0) {
-          // order: xx xy xz yy yz zz | gx gy gz
-          const double a = V[0] + diag[nc + 3 * pf] * inv_radius, bq = V[1], c = V[2];
-          const double d = V[3] + diag[nc + 3 * pf + 1] * inv_radius, e = V[4];
-          const double f = V[5] + diag[nc + 3 * pf + 2] * inv_radius;
-          const double A = d * f - e * e, B = c * e - bq * f, Cc = bq * e - c * d;
-          const double id = 1.0 / (a * A + bq * B + c * Cc);
-          sVi[0] = A * id; sVi[1] = B * id; sVi[2] = Cc * id;
-          sVi[3] = B * id; sVi[4] = (a * f - c * c) * id; sVi[5] = (bq * c - a * e) * id;
-          sVi[6] = Cc * id; sVi[7] = sVi[5]; sVi[8] = (a * d - bq * bq) * id;
-          for (int j = 0; j < 3; ++j) sVig[j] = sVi[j * 3] * V[6] + sVi[j * 3 + 1] * V[7] + sVi[j * 3 + 2] * V[8];
-          const size_t NP = (size_t)v.npf;
-          Vinv[0 * NP + pf] = sVi[0]; Vinv[1 * NP + pf] = sVi[1]; Vinv[2 * NP + pf] = sVi[2];
-          Vinv[3 * NP + pf] = sVi[4]; Vinv[4 * NP + pf] = sVi[5]; Vinv[5 * NP + pf] = sVi[8];
-          gpo[0 * NP + pf] = V[6]; gpo[1 * NP + pf] = V[7]; gpo[2 * NP + pf] = V[8];
-        }
+        for (int j = 0; j < 9; ++j) V[j] = 0.0;
+        for (int bb = 0; bb < k; ++bb)
+          for (int q = 0; q < nres; ++q) {
+            const double x = sm.Jps[tid][bb][q][0], y = sm.Jps[tid][bb][q][1], z = sm.Jps[tid][bb][q][2];
+            const double rq = sm.Jps[tid][bb][q][3];
+            V[0] += x * x; V[1] += x * y; V[2] += x * z; V[3] += y * y; V[4] += y * z; V[5] += z * z;
+            V[6] += x * rq; V[7] += y * rq; V[8] += z * rq;
+          }
+        const double a = V[0] + diag[nc + 3 * pf] * inv_radius, bq = V[1], c = V[2];
+        const double d = V[3] + diag[nc + 3 * pf + 1] * inv_radius, e = V[4];
+        const double f = V[5] + diag[nc + 3 * pf + 2] * inv_radius;
+        const double A = d * f - e * e, B = c * e - bq * f, Cc = bq * e - c * d;
+        const double id = 1.0 / (a * A + bq * B + c * Cc);
+        double* Vi = sm.Vi[tid];
+        Vi[0] = A * id; Vi[1] = B * id; Vi[2] = Cc * id;
+        Vi[3] = B * id; Vi[4] = (a * f - c * c) * id; Vi[5] = (bq * c - a * e) * id;
+        Vi[6] = Cc * id; Vi[7] = Vi[5]; Vi[8] = (a * d - bq * bq) * id;
+        for (int j = 0; j < 3; ++j) sm.Vig[tid][j] = Vi[j * 3] * V[6] + Vi[j * 3 + 1] * V[7] + Vi[j * 3 + 2] * V[8];
+        const size_t NP = (size_t)v.npf;
+        Vinv[0 * NP + pf] = Vi[0]; Vinv[1 * NP + pf] = Vi[1]; Vinv[2 * NP + pf] = Vi[2];
+        Vinv[3 * NP + pf] = Vi[4]; Vinv[4 * NP + pf] = Vi[5]; Vinv[5 * NP + pf] = Vi[8];
+        gpo[0 * NP + pf] = V[6]; gpo[1 * NP + pf] = V[7]; gpo[2 * NP + pf] = V[8];
       }
       __syncthreads();
-      if (half == 0 && active) {
-        const double w0 = Ws[item][0], w1 = Ws[item][1], w2 = Ws[item][2];
-        Ys[item][0] = w0 * sVi[0] + w1 * sVi[3] + w2 * sVi[6];
-        Ys[item][1] = w0 * sVi[1] + w1 * sVi[4] + w2 * sVi[7];
-        Ys[item][2] = w0 * sVi[2] + w1 * sVi[5] + w2 * sVi[8];
-        rhs_acc -= w0 * sVig[0] + w1 * sVig[1] + w2 * sVig[2];
+      // ---- Y = W V^-1 for every (point, column); rhs -= W V^-1 g_p ----
+      for (int idx = tid; idx < np * ncols; idx += SEG_THREADS) {
+        const int lp = idx / ncols, it2 = idx - lp * ncols;
+        const double w0 = sm.Ws[lp][it2][0], w1 = sm.Ws[lp][it2][1], w2 = sm.Ws[lp][it2][2];
+        const double* Vi = sm.Vi[lp];
+        sm.Ys[lp][it2][0] = w0 * Vi[0] + w1 * Vi[3] + w2 * Vi[6];
+        sm.Ys[lp][it2][1] = w0 * Vi[1] + w1 * Vi[4] + w2 * Vi[7];
+        sm.Ys[lp][it2][2] = w0 * Vi[2] + w1 * Vi[5] + w2 * Vi[8];
       }
+      if (half == 0 && mycol >= 0)
+        for (int lp = 0; lp < np; ++lp)
+          rhs_acc -= sm.Ws[lp][item][0] * sm.Vig[lp][0] + sm.Ws[lp][item][1] * sm.Vig[lp][1] +
+                     sm.Ws[lp][item][2] * sm.Vig[lp][2];
       __syncthreads();
+      // ---- the dense product: my column against my half of the rows, all points of the chunk ----
       if (active) {
-        const double w0 = Ws[item][0], w1 = Ws[item][1], w2 = Ws[item][2];
+        for (int lp = 0; lp < np; ++lp) {
+          const double w0 = sm.Ws[lp][item][0], w1 = sm.Ws[lp][item][1], w2 = sm.Ws[lp][item][2];
 #pragma unroll
-        for (int e = 0; e < ROWS; ++e) {
-          if (row0 + e < ncols) acc[e] -= Ys[row0 + e][0] * w0 + Ys[row0 + e][1] * w1 + Ys[row0 + e][2] * w2;
+          for (int e = 0; e < ROWS; ++e)
+            acc[e] -= sm.Ys[lp][row0 + e][0] * w0 + sm.Ys[lp][row0 + e][1] * w1 + sm.Ys[lp][row0 + e][2] * w2;
         }
       }
     }
     // U_b = Js_b^T Js_b: column (b, c2) against the wc rows of the same observation
     if (half == 0 && active) {
+      for (int lp = 0; lp < np; ++lp) {
 #pragma unroll
-      for (int c1 = 0; c1 < SEG_WCMAX; ++c1) {
-        if (c1 < wc) {
-          double u = 0.0;
-          for (int q = 0; q < nres; ++q) u += Js[q][b * wc + c1] * js[q];
-          uacc[c1] += u;
+        for (int c1 = 0; c1 < SEG_WCMAX; ++c1) {
+          if (c1 < wc) {
+            double u = 0.0;
+            for (int q = 0; q < nres; ++q) u += sm.Js[lp][q][b * wc + c1] * sm.Js[lp][q][item];
+            uacc[c1] += u;
+          }
         }
       }
     }
@@ -581,19 +609,18 @@ __global__ void __launch_bounds__(SEG_THREADS, 2)
 
   // ---- flush: one atomic per owned entry of the segment ----
   if (!active || mycol < 0) return;
-  const int m2 = meta[item];
+  const int m2 = sm.meta[item];
   const int B2 = m2 >> 12, s2 = (m2 >> 10) & 3, sz2 = (m2 >> 5) & 31, r2 = m2 & 31;
   if (half == 0) {
     atomicAdd(&rhs[mycol], rhs_acc);
-    // U: entries (c1, c2) of the same observation, upper part only
 #pragma unroll
     for (int c1 = 0; c1 < SEG_WCMAX; ++c1) {
       if (c1 < wc) {
-        const int m1 = meta[b * wc + c1];
+        const int m1 = sm.meta[b * wc + c1];
         if (m1 >= 0) {
           const int B1 = m1 >> 12, s1 = (m1 >> 10) & 3, r1 = m1 & 31;
           const bool keep = B1 < B2 || (B1 == B2 && r1 <= r2);
-          if (keep) atomicAdd(&Sval[offt[(b * SEG_KMAX + b) * 9 + s1 * 3 + s2] + r1 * sz2 + r2], uacc[c1]);
+          if (keep) atomicAdd(&Sval[sm.offt[(b * SEG_KMAX + b) * 9 + s1 * 3 + s2] + r1 * sz2 + r2], uacc[c1]);
         }
       }
     }
@@ -603,7 +630,7 @@ __global__ void __launch_bounds__(SEG_THREADS, 2)
   for (int e = 0; e < ROWS; ++e) {
     const int row = row0 + e;
     if (row >= ncols) continue;
-    const int m1 = meta[row];
+    const int m1 = sm.meta[row];
     if (m1 < 0) continue;
     const int a = row / wc;
     if (a > b) continue;
@@ -624,7 +651,7 @@ __global__ void __launch_bounds__(SEG_THREADS, 2)
         pos = min(r1, r2) * sz1 + max(r1, r2);
       }
     }
-    atomicAdd(&Sval[offt[(a * SEG_KMAX + b) * 9 + s1 * 3 + s2] + pos], val);
+    atomicAdd(&Sval[sm.offt[(a * SEG_KMAX + b) * 9 + s1 * 3 + s2] + pos], val);
   }
 }
 

@@ -130,3 +130,102 @@ def test_bundle_adjuster_api_roundtrip():
     with pytest.raises(RuntimeError):
         ba.set_point_projection_loss_function("NopeLoss", 1.0)
         ba.run()
+
+
+def _mixed_problem(seed=0, rig=False, free_rig=False):
+    """6 instances looking at a point cloud through different camera models (and, optionally, a
+    two-camera rig so that the two-pose path of projection_errors.h:95-149 runs)."""
+    from scipy.spatial.transform import Rotation
+
+    rng = np.random.RandomState(seed)
+    types = [bp.PERSPECTIVE, bp.BROWN, bp.FISHEYE, bp.FISHEYE_OPENCV, bp.RADIAL, bp.SPHERICAL, bp.DUAL,
+             bp.SIMPLE_RADIAL, bp.FISHEYE62, bp.FISHEYE624]
+    params = {
+        bp.PERSPECTIVE: [-0.05, 0.01, 0.8], bp.BROWN: [-0.05, 0.01, 0.001, 0.001, -0.001, 0.8, 1.0, 0.01, -0.01],
+        bp.FISHEYE: [-0.02, 0.005, 0.7], bp.FISHEYE_OPENCV: [-0.02, 0.005, 0.001, 0.0, 0.7, 1.0, 0.0, 0.01],
+        bp.RADIAL: [-0.05, 0.01, 0.8, 1.0, 0.0, 0.0], bp.SPHERICAL: [0.0], bp.DUAL: [0.4, -0.03, 0.005, 0.75],
+        bp.SIMPLE_RADIAL: [-0.04, 0.8, 1.0, 0.0, 0.0],
+        bp.FISHEYE62: [-0.02, 0.005, 0.0, 0.0, 0.0, 0.0, 0.001, -0.001, 0.7, 1.0, 0.0, 0.0],
+        bp.FISHEYE624: [-0.02, 0.005, 0.0, 0.0, 0.0, 0.0, 0.001, -0.001, 0.001, 0.0, -0.001, 0.0, 0.7, 1.0, 0.0, 0.0],
+    }
+    K = len(types)
+    NI = K
+    pts = rng.uniform(-0.5, 0.5, (300, 3))
+    inst = np.zeros((NI, 6))
+    for i in range(NI):
+        ang = 2 * np.pi * i / NI
+        origin = 2.5 * np.array([np.cos(ang), np.sin(ang), 0.2 * np.sin(3 * ang)])
+        ez = -origin / np.linalg.norm(origin)
+        ex = np.cross(ez, [0, 0, 1.0]); ex /= np.linalg.norm(ex)
+        ey = np.cross(ez, ex)
+        R_wc = np.array([ex, ey, ez])
+        inst[i] = np.concatenate([Rotation.from_matrix(R_wc.T).as_rotvec(), origin])
+    if rig:
+        rigcam = np.array([[0.0, 0.0, 0.0, 0.0, 0.0, 0.0], [0.02, -0.03, 0.01, 0.1, 0.0, 0.02]])
+        shot_inst = np.repeat(np.arange(NI), 2)
+        shot_cam = np.repeat(np.arange(K), 2)
+        shot_rc = np.tile([0, 1], NI)
+        shot_use = np.tile([0, 1], NI)  # rig camera 0 is the identity: not "useful" (bundle_adjuster.cc:17-20)
+    else:
+        rigcam = np.zeros((1, 6))
+        shot_inst = np.arange(NI); shot_cam = np.arange(K); shot_rc = np.zeros(NI, int); shot_use = np.zeros(NI, int)
+    S = len(shot_inst)
+    obs_shot, obs_point, obs_xy = [], [], []
+    for s in range(S):
+        i, k = shot_inst[s], shot_cam[s]
+        for p in range(len(pts)):
+            xc = Rotation.from_rotvec(-inst[i, :3]).apply(pts[p] - inst[i, 3:])
+            if shot_use[s]:
+                rc = rigcam[shot_rc[s]]
+                xc = Rotation.from_rotvec(-rc[:3]).apply(xc - rc[3:])
+            if types[k] != bp.SPHERICAL and xc[2] < 0.5:
+                continue
+            if types[k] == bp.SPHERICAL:
+                lon, lat = np.arctan2(xc[0], xc[2]), np.arctan2(-xc[1], np.hypot(xc[0], xc[2]))
+                px = np.array([lon / (2 * np.pi), -lat / (2 * np.pi)])
+            else:
+                px = oracle.project(types[k], params[types[k]], xc)
+            obs_shot.append(s); obs_point.append(p); obs_xy.append(px + rng.normal(0, 5e-4, 2))
+    pb = bp.make_problem(types, [params[t] for t in types], inst, pts + rng.normal(0, 0.01, pts.shape), obs_shot,
+                         obs_point, np.array(obs_xy), np.full(len(obs_shot), 0.004), shot_inst=shot_inst,
+                         shot_cam=shot_cam, rigcam=rigcam, shot_rc=shot_rc, shot_use_rc=shot_use,
+                         rigcam_const=[1, 0 if free_rig else 1],
+                         prior_sd=dict(focal_sd=0.01, aspect_ratio_sd=0.01, c_sd=0.01, k1_sd=0.01, k2_sd=0.01,
+                                       p1_sd=0.01, p2_sd=0.01, k3_sd=0.01, k4_sd=0.01),
+                         loss_name="SoftLOneLoss", loss_threshold=1.0, max_iterations=50)
+    pb.inst[:, 3:] += rng.normal(0, 0.01, (NI, 3))
+    return pb
+
+
+def test_all_camera_models_in_one_problem():
+    _compare(_mixed_problem(0), tol_param=5e-5)
+
+
+def test_rig_cameras_two_pose_path():
+    _compare(_mixed_problem(1, rig=True), tol_param=5e-5)
+    _compare(_mixed_problem(2, rig=True, free_rig=True), tol_param=5e-5)
+
+
+def test_degenerate_inputs():
+    sc = syn.cube_scene(4, 60, 1.0, with_descriptors=False)
+    pb = syn.scene_to_problem(sc)
+    # everything constant: nothing to optimise, reprojection errors still produced
+    pb.cam_const[:] = 1; pb.inst_const[:] = 1; pb.point_const[:] = 1
+    got = bundle.solve(pb)
+    assert got["summary"]["termination"] == "CONVERGENCE" and got["summary"]["iterations"] == 0
+    assert np.allclose(got["points"], pb.points)
+    ref_cost, ref_rep = oracle.OracleBA(pb).cost(want_reproj=True)
+    assert abs(got["summary"]["final_cost"] - ref_cost) <= 1e-9 * ref_cost
+    assert np.abs(got["reprojection_errors"] - ref_rep).max() < 1e-12
+    # no observations at all
+    pb2 = syn.scene_to_problem(sc)
+    pb2.obs_shot = pb2.obs_shot[:0]; pb2.obs_point = pb2.obs_point[:0]
+    pb2.obs_xy = pb2.obs_xy[:0]; pb2.obs_sigma = pb2.obs_sigma[:0]
+    got2 = bundle.solve(pb2)
+    assert got2["reprojection_errors"].shape == (0, 3)
+    assert np.allclose(got2["points"], pb2.points)
+    # dangling index -> error, like std::map::at / "doesn't exist" in the reference
+    pb3 = syn.scene_to_problem(sc)
+    pb3.obs_point = pb3.obs_point.copy(); pb3.obs_point[0] = 10 ** 6
+    with pytest.raises((AssertionError, ValueError, RuntimeError)):
+        bundle.solve(pb3)
