@@ -229,3 +229,28 @@ def test_degenerate_inputs():
     pb3.obs_point = pb3.obs_point.copy(); pb3.obs_point[0] = 10 ** 6
     with pytest.raises((AssertionError, ValueError, RuntimeError)):
         bundle.solve(pb3)
+
+
+def test_segmented_schur_kernel_opt_in():
+    """ba_schur_seg (register-accumulated segments) must give the same solve as the default kernel."""
+    import os
+    import subprocess
+    import sys
+
+    code = (
+        "import sys; sys.path.insert(0, %r)\n"
+        "import numpy as np\n"
+        "from opensfm_b200 import bundle, synthetic as syn\n"
+        "sc = syn.cube_scene(30, 4000, 1.0, with_descriptors=False, max_obs_per_point=8)\n"
+        "r = bundle.solve(syn.scene_to_problem(sc))\n"
+        "np.save(sys.argv[1], np.concatenate([[r['summary']['final_cost'], r['summary']['iterations']], r['points'].ravel()]))\n"
+    ) % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = {}
+    for flag in ("0", "1"):
+        path = "/tmp/osfm_seg_%s.npy" % flag
+        env = dict(os.environ, OSFM_BA_SEGMENT_SCHUR=flag)
+        subprocess.run([sys.executable, "-c", code, path], check=True, env=env, timeout=600)
+        out[flag] = np.load(path)
+    assert out["0"][1] == out["1"][1]
+    assert abs(out["0"][0] - out["1"][0]) <= 1e-9 * out["0"][0]
+    assert np.abs(out["0"][2:] - out["1"][2:]).max() < 1e-8
