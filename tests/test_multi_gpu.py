@@ -23,5 +23,12 @@ def test_two_gpu_ba_and_pair_sharding():
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr",
            "127.0.0.1", "--master-port", "29633", os.path.join(HERE, "mgpu_worker.py")]
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
-    assert out.returncode == 0, (out.stdout[-3000:], out.stderr[-3000:])
+    log = os.path.join(HERE, "..", "gpurun_out")
+    if os.path.isdir(log):
+        with open(os.path.join(log, "mgpu_worker.log"), "w") as f:
+            f.write(out.stdout + "\n=====STDERR=====\n" + out.stderr)
+    if out.returncode != 0:
+        print(out.stdout[-4000:])
+        print(out.stderr[-6000:])
+    assert out.returncode == 0
     assert "MGPU_OK" in out.stdout
