@@ -482,7 +482,7 @@ struct BA {
   DevBuf<double> d_obs_x, d_obs_y, d_obs_isig;
   DevBuf<long long> d_obs_orig, d_pt_start;
   DevBuf<double> d_cam[2], d_inst[2], d_rc[2], d_pts[2];
-  DevBuf<double> d_r, d_Jc, d_Jp, d_S, d_rhs, d_Vinv, d_gp;
+  DevBuf<double> d_r, d_Jc, d_Jp, d_Sbuf, d_Vinv, d_gp, d_slots;
   DevBuf<double> d_scale, d_colnorm2, d_grad, d_diag, d_y;
   DevBuf<double> d_px, d_pr, d_pz, d_pp, d_pAp, d_Minv, d_reproj, d_full_pts;
   DevBuf<int> d_blk_off, d_blk_sz, d_cam_blk, d_inst_blk, d_rc_blk;
@@ -580,6 +580,7 @@ void BA::run() {
   }
   const int nc = off;
   const int nblk = (int)blk_off.size();
+  const int nc_pad = (nc + 15) / 16 * 16;  // rhs sits in front of the reduced system in one buffer
   // parameter-block id of every camera / rig instance / rig camera (-1 = constant)
   std::vector<int> cam_blk(std::max(K, 1), -1), inst_blk(std::max(NI, 1), -1), rc_blk(std::max(NR, 1), -1);
   {
@@ -774,7 +775,6 @@ void BA::run() {
   upload(d_pr_pos_prior, pr_pos_prior, stream); upload(d_pr_pos_scale, pr_pos_scale, stream);
   const size_t Nz = (size_t)std::max<long long>(N, 1);
   d_r.reserve(nres * Nz); d_Jc.reserve((size_t)nres * wc * Nz); d_Jp.reserve((size_t)nres * 3 * Nz);
-  d_rhs.reserve(std::max(nc, 1));
   d_Vinv.reserve(6 * (size_t)std::max(npf, 1)); d_gp.reserve(3 * (size_t)std::max(npf, 1));
   const size_t nz = (size_t)std::max(n, 1);
   d_scale.reserve(nz); d_colnorm2.reserve(nz); d_grad.reserve(nz); d_diag.reserve(nz); d_y.reserve(nz);
@@ -859,11 +859,10 @@ void BA::run() {
       // max over ranks of the local point-gradient maxima: sum of one-hot slots
       std::vector<double> slots(world, 0.0);
       slots[rank] = gm;
-      DevBuf<double> tmp;
-      tmp.reserve(world);
-      OSFM_CUDA(cudaMemcpyAsync(tmp.p, slots.data(), sizeof(double) * world, cudaMemcpyHostToDevice, stream));
-      allreduce_dev(tmp.p, world);
-      OSFM_CUDA(cudaMemcpyAsync(slots.data(), tmp.p, sizeof(double) * world, cudaMemcpyDeviceToHost, stream));
+      d_slots.reserve(world);
+      OSFM_CUDA(cudaMemcpyAsync(d_slots.p, slots.data(), sizeof(double) * world, cudaMemcpyHostToDevice, stream));
+      allreduce_dev(d_slots.p, world);
+      OSFM_CUDA(cudaMemcpyAsync(slots.data(), d_slots.p, sizeof(double) * world, cudaMemcpyDeviceToHost, stream));
       OSFM_CUDA(cudaStreamSynchronize(stream));
       for (double x : slots) gm = std::max(gm, x);
     }
@@ -970,7 +969,7 @@ void BA::run() {
           d_pr_blk.p, d_pr_local.p, (int)pr_blk.size(), d_diag_off.p, d_blk_sz.p, d_prior_diag_off.p);
       OSFM_LAUNCH_CHECK();
     }
-    d_S.reserve((size_t)std::max<long long>(s_total, 1));
+    d_Sbuf.reserve((size_t)std::max<long long>(s_total, 1) + nc_pad);
     // block-row ELL layout of the PCG mat-vec
     d_row_M.reserve(nblk + 1); d_qoff.reserve(n_all + 1); d_blk_row.reserve(n_all + 1);
     pcg_row_sizes<<<grid_for(nblk, 128), 128, 0, stream>>>(d_row_ptr.p, d_row_col.p, bsr, d_row_M.p, d_qoff.p, d_blk_row.p);
@@ -993,6 +992,9 @@ void BA::run() {
     OSFM_LAUNCH_CHECK();
     OSFM_CUDA(cudaStreamSynchronize(stream));  // rowbase / cbase host vectors go out of scope
   }
+  if (nblk == 0) d_Sbuf.reserve(nc_pad + 16);
+  double* const d_rhs_p = d_Sbuf.p;          // [nc] right-hand side
+  double* const d_S_p = d_Sbuf.p + nc_pad;   // block values: upper blocks first
   PcgLayout lay{};
   lay.row_of = d_row_of.p; lay.row_M = d_row_M.p; lay.rowbase = d_rowbase.p; lay.cbase = d_cbase.p;
   lay.colidx = d_colidx.p; lay.ngroups = ngroups; lay.grp_b1 = d_grp_b1.p; lay.grp_b2 = d_grp_b2.p;
@@ -1044,8 +1046,7 @@ void BA::run() {
     const double inv_radius = 1.0 / radius;
     // --- reduced camera system (upper blocks accumulated with L2 atomics) ---
     if (nc > 0) {
-      OSFM_CUDA(cudaMemsetAsync(d_S.p, 0, sizeof(double) * (size_t)s_upper_total, stream));
-      OSFM_CUDA(cudaMemsetAsync(d_rhs.p, 0, sizeof(double) * nc, stream));
+      OSFM_CUDA(cudaMemsetAsync(d_Sbuf.p, 0, sizeof(double) * ((size_t)nc_pad + (size_t)s_upper_total), stream));
     }
     if (P > 0) {
       const size_t smem = (size_t)SCHUR_KC * wc * (2 * 3 * sizeof(double) + 2 * sizeof(int)) +
@@ -1054,7 +1055,8 @@ void BA::run() {
       if (nseg > 0) {
         static bool seg_attr = false;
         if (!seg_attr) {
-          OSFM_CUDA(cudaFuncSetAttribute(ba_schur_seg, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SegSmem)));
+          OSFM_CUDA(cudaFuncSetAttribute(ba_schur_seg<9>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SegSmem)));
+          OSFM_CUDA(cudaFuncSetAttribute(ba_schur_seg<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SegSmem)));
           seg_attr = true;
         }
         const long long n_fast = pt_start[P_fast];
@@ -1064,15 +1066,19 @@ void BA::run() {
                                                                  d_gp.p, d_Vig.p);
         OSFM_LAUNCH_CHECK();
         ba_obs_rows<<<grid_for(n_fast * wc, 256), 256, 0, stream>>>(v, bm, bsr, n_fast, d_scale.p, d_Vinv.p, d_Vig.p,
-                                                                  d_rowsJ.p, d_rowsW.p, d_rowsY.p, d_rhs.p);
+                                                                  d_rowsJ.p, d_rowsW.p, d_rowsY.p, d_rhs_p);
         OSFM_LAUNCH_CHECK();
-        ba_schur_seg<<<nseg, SEG_THREADS, sizeof(SegSmem), stream>>>(v, bm, bsr, d_seg_start.p, d_rowsJ.p, d_rowsW.p,
-                                                                    d_rowsY.p, d_S.p);
+        if (wc == 9)
+          ba_schur_seg<9><<<nseg, SEG_THREADS, sizeof(SegSmem), stream>>>(v, bm, bsr, d_seg_start.p, n_fast, d_rowsJ.p,
+                                                                         d_rowsW.p, d_rowsY.p, d_S_p);
+        else
+          ba_schur_seg<0><<<nseg, SEG_THREADS, sizeof(SegSmem), stream>>>(v, bm, bsr, d_seg_start.p, n_fast, d_rowsJ.p,
+                                                                         d_rowsW.p, d_rowsY.p, d_S_p);
         OSFM_LAUNCH_CHECK();
       }
       if (P > P_fast) {
-        ba_schur<<<P - P_fast, SCHUR_THREADS, smem, stream>>>(v, bm, bsr, d_scale.p, d_diag.p, inv_radius, d_S.p,
-                                                             d_rhs.p, d_Vinv.p, d_gp.p, P_fast);
+        ba_schur<<<P - P_fast, SCHUR_THREADS, smem, stream>>>(v, bm, bsr, d_scale.p, d_diag.p, inv_radius, d_S_p,
+                                                             d_rhs_p, d_Vinv.p, d_gp.p, P_fast);
         OSFM_LAUNCH_CHECK();
       }
       tm_schur.stop(stream);
@@ -1082,7 +1088,7 @@ void BA::run() {
     OSFM_CUDA(cudaMemsetAsync(d_y.p, 0, sizeof(double) * nz, stream));
     if (nc > 0) {
       // the one exchange step of the LM iteration: sum of the partial reduced systems over ranks
-      if (world > 1) { allreduce_dev(d_S.p, s_upper_total); allreduce_dev(d_rhs.p, nc); }
+      if (world > 1) allreduce_dev(d_Sbuf.p, (long long)nc_pad + s_upper_total);  // rhs + upper blocks, one call
       {
         // S_g stays a pure partial sum through the all-reduce; every rank then adds the (replicated)
         // prior rows and the damping to its copy of the reduced system.
@@ -1092,26 +1098,26 @@ void BA::run() {
         const int nall = pall.n_cam_rows + pall.n_pos_rows;
         if (nall > 0) {
           ba_prior_system<<<grid_for(nall, 128), 128, 0, stream>>>(pall, params_of(cur), d_scale.p, d_prior_diag_off.p,
-                                                                  d_S.p, d_rhs.p);
+                                                                  d_S_p, d_rhs_p);
           OSFM_LAUNCH_CHECK();
         }
       }
-      ba_finish_system<<<grid_for((long long)n_upper * 32, 256), 256, 0, stream>>>(d_upper.p, n_upper, bsr, d_S.p,
+      ba_finish_system<<<grid_for((long long)n_upper * 32, 256), 256, 0, stream>>>(d_upper.p, n_upper, bsr, d_S_p,
                                                                                  d_diag.p, inv_radius);
       OSFM_LAUNCH_CHECK();
       // --- PCG: one persistent kernel, |r| <= 1e-8 |b| ---
       tm_pcg.start(stream);
       pcg_convert<<<grid_for((long long)n_blocks_all * 32, 256), 256, 0, stream>>>(
-          d_S.p, d_row_col.p, d_row_off.p, d_qoff.p, d_blk_row.p, n_blocks_all, bsr, d_row_M.p, d_rowbase.p, d_Spcg.p);
+          d_S_p, d_row_col.p, d_row_off.p, d_qoff.p, d_blk_row.p, n_blocks_all, bsr, d_row_M.p, d_rowbase.p, d_Spcg.p);
       OSFM_LAUNCH_CHECK();
-      pcg_factor_groups<<<grid_for(ngroups, 64), 64, 0, stream>>>(d_S.p, bsr, d_diag_off.p, d_grp_b1.p, d_grp_b2.p,
+      pcg_factor_groups<<<grid_for(ngroups, 64), 64, 0, stream>>>(d_S_p, bsr, d_diag_off.p, d_grp_b1.p, d_grp_b2.p,
                                                                  ngroups, d_Minv.p);
       OSFM_LAUNCH_CHECK();
       OSFM_CUDA(cudaMemsetAsync(d_pcg.p, 0, sizeof(PcgState), stream));
       const int max_pcg = std::min(2 * nc + 100, 5000);
       // persistent grid: every CTA must be resident (1 CTA / SM) for the grid barrier
       const int pcg_grid = std::max(1, std::min(std::min(num_sms, PCG_MAX_CTAS), (nc + PCG_THREADS / 32 - 1) / (PCG_THREADS / 32)));
-      pcg_persistent<<<pcg_grid, PCG_THREADS, 0, stream>>>(d_Spcg.p, lay, bsr, d_Minv.p, d_rhs.p, d_px.p, d_pr.p, d_pz.p,
+      pcg_persistent<<<pcg_grid, PCG_THREADS, 0, stream>>>(d_Spcg.p, lay, bsr, d_Minv.p, d_rhs_p, d_px.p, d_pr.p, d_pz.p,
                                                            d_pp.p, d_pAp.p, d_Ap.p, d_pcg.p, nc, max_pcg, 1e-16);
       OSFM_LAUNCH_CHECK();
       OSFM_CUDA(cudaMemcpyAsync(d_y.p, d_px.p, sizeof(double) * nc, cudaMemcpyDeviceToDevice, stream));

@@ -430,7 +430,8 @@ __global__ void __launch_bounds__(SCHUR_THREADS)
 // Eligible: k <= 16, k * wc <= SEG_NA, wc <= 16; everything else goes through ba_schur.
 // ---------------------------------------------------------------------------
 constexpr int SEG_NA = 96;                 // max camera-side columns of a segment (k * wc)
-constexpr int SEG_THREADS = 2 * SEG_NA;    // two row-halves per column
+constexpr int SEG_SPLIT = 4;                // row quarters per column
+constexpr int SEG_THREADS = SEG_SPLIT * SEG_NA;
 constexpr int SEG_KMAX = 16;
 constexpr int SEG_WCMAX = 16;
 constexpr int SEG_PCHUNK = 8;              // points staged per chunk
@@ -474,8 +475,9 @@ __global__ void __launch_bounds__(128)
   Vig[2 * NP + pf] = i02 * V[6] + i12 * V[7] + i22 * V[8];
 }
 
-// A1: rows of every (observation i < n_obs, local column c2): rowsJ[(i*wc+c2)*3 + q] scaled Jacobian,
-// rowsW / rowsY [(i*wc+c2)*3 + j]; rhs += Js^T r - W V^-1 g_p.  Thread index: i fastest (coalesced planes).
+// A1: rows of every (observation i < n_obs, local column c2) in plane layout rows[(c2*3 + j) * n_obs + i]
+// (coalesced for this kernel, 640-byte runs for a segment in kernel B): rowsJ scaled Jacobian,
+// rowsW = Js^T Jp, rowsY = W V^-1; rhs += Js^T r - W V^-1 g_p.  Thread index: i fastest.
 __global__ void __launch_bounds__(256)
     ba_obs_rows(BAView v, BlkMaps bm, BsrView h, long long n_obs, const double* __restrict__ scale,
                 const double* __restrict__ Vinv, const double* __restrict__ Vig, double* __restrict__ rowsJ,
@@ -492,7 +494,6 @@ __global__ void __launch_bounds__(256)
     const int s2 = ob.slot_of(c2);
     if (ob.blk[s2] >= 0) g = h.blk_off[ob.blk[s2]] + c2 - ob.lstart(s2);
   }
-  const size_t o = ((size_t)i * wc + c2) * 3;
   double js[3] = {0.0, 0.0, 0.0}, w[3] = {0.0, 0.0, 0.0}, y[3] = {0.0, 0.0, 0.0};
   if (g >= 0) {
     const double sc = scale[g];
@@ -522,7 +523,10 @@ __global__ void __launch_bounds__(256)
     atomicAdd(&rhs[g], gr);
   }
 #pragma unroll
-  for (int j = 0; j < 3; ++j) { rowsJ[o + j] = js[j]; rowsW[o + j] = w[j]; rowsY[o + j] = y[j]; }
+  for (int j = 0; j < 3; ++j) {
+    const size_t o = ((size_t)c2 * 3 + j) * (size_t)n_obs + (size_t)i;
+    rowsJ[o] = js[j]; rowsW[o] = w[j]; rowsY[o] = y[j];
+  }
 }
 
 struct SegSmem {
@@ -534,29 +538,35 @@ struct SegSmem {
   int oblk[SEG_KMAX][4];
   int offt[SEG_KMAX * SEG_KMAX * 9];
 };
+// the chunk buffers are dead when the accumulators are flushed: a (SEG_NA/2) x SEG_NA tile aliases them
+static_assert(sizeof(double) * (SEG_NA / 2) * SEG_NA <= sizeof(double) * 3 * SEG_PCHUNK * SEG_NA * 3, "tile must fit");
 
-// B: one CTA per segment.
-__global__ void __launch_bounds__(SEG_THREADS, 3)
-    ba_schur_seg(BAView v, BlkMaps bm, BsrView h, const int* __restrict__ seg_start,
+// B: one CTA per segment.  WC = compile-time camera-side width (0 = runtime, up to SEG_WCMAX).
+template <int WC>
+__global__ void __launch_bounds__(SEG_THREADS, 2)
+    ba_schur_seg(BAView v, BlkMaps bm, BsrView h, const int* __restrict__ seg_start, long long n_obs,
                  const double* __restrict__ rowsJ, const double* __restrict__ rowsW,
                  const double* __restrict__ rowsY, double* __restrict__ Sval) {
   extern __shared__ __align__(16) unsigned char seg_raw[];
   SegSmem& sm = *reinterpret_cast<SegSmem*>(seg_raw);
+  double* tile = reinterpret_cast<double*>(seg_raw);  // [SEG_NA][SEG_NA], valid after the last chunk
 
-  const int wc = v.wc, nres = v.nres;
+  const int wc = WC ? WC : v.wc;
   const int p_begin = seg_start[blockIdx.x], p_end = seg_start[blockIdx.x + 1];
   const long long o0 = v.pt_start[p_begin];
   const int k = (int)(v.pt_start[p_begin + 1] - o0);
   const int ncols = k * wc;
   const int tid = threadIdx.x;
-  const int item = tid < SEG_NA ? tid : tid - SEG_NA;   // my column (b, c2)
-  const int half = tid < SEG_NA ? 0 : 1;
+  const int split = tid / SEG_NA;          // which quarter of the rows
+  const int item = tid - split * SEG_NA;   // my column (b, c2)
+  const int half = split;                  // (split 0 also owns the structure setup and U)
   const bool active = item < ncols;
-  const int b = active ? item / wc : 0, c2 = active ? item - b * wc : 0;
+  const int b = active ? item / wc : 0;
   const bool pfree = v.pt_poff[p_begin] >= 0;   // same for the whole segment (part of the signature)
 
   // ---- structure of the segment (from its first point) ----
   if (half == 0 && active) {
+    const int c2 = item - b * wc;
     const ObsBlk ob = obs_blocks(v, bm, v.obs_shot[o0 + b]);
     if (c2 == 0) { sm.oblk[b][0] = ob.blk[0]; sm.oblk[b][1] = ob.blk[1]; sm.oblk[b][2] = ob.blk[2]; sm.oblk[b][3] = ob.C; }
     int g = -1, m = -1;
@@ -578,30 +588,34 @@ __global__ void __launch_bounds__(SEG_THREADS, 3)
     const int B1 = sm.oblk[a][ss / 3], B2 = sm.oblk[bb][ss % 3];
     sm.offt[(a * SEG_KMAX + bb) * 9 + ss] = (B1 < 0 || B2 < 0) ? -1 : bsr_lookup(h, min(B1, B2), max(B1, B2));
   }
-  const int mycol = active ? sm.gcol[item] : -1;
 
-  constexpr int ROWS = SEG_NA / 2;
+  constexpr int ROWS = SEG_NA / SEG_SPLIT;
+  constexpr int PASS_ROWS = SEG_NA / 2;
+  constexpr int WCU = WC ? WC : SEG_WCMAX;
   double acc[ROWS];
 #pragma unroll
   for (int e = 0; e < ROWS; ++e) acc[e] = 0.0;
-  double uacc[SEG_WCMAX];
+  double uacc[WCU];
 #pragma unroll
-  for (int e = 0; e < SEG_WCMAX; ++e) uacc[e] = 0.0;
-  const int row0 = half * ROWS;
+  for (int e = 0; e < WCU; ++e) uacc[e] = 0.0;
+  const int row0 = split * ROWS;
 
   for (int pc0 = p_begin; pc0 < p_end; pc0 += SEG_PCHUNK) {
     const int np = min(SEG_PCHUNK, p_end - pc0);
     __syncthreads();  // previous chunk fully consumed
-    // the rows of the chunk's points are contiguous in HBM: stream them in (coalesced)
+    // rows of the chunk: for every plane (c2, j) a run of np*k consecutive observations
     {
-      const size_t base = (size_t)v.pt_start[pc0] * wc * 3;
-      const int per_point = ncols * 3;
-      for (int t = tid; t < np * per_point; t += SEG_THREADS) {
-        const int lp = t / per_point, rem = t - lp * per_point;
-        (&sm.Js[lp][0][0])[rem] = rowsJ[base + t];
+      const long long ibase = v.pt_start[pc0];
+      const int run = np * k;
+      for (int t = tid; t < wc * 3 * run; t += SEG_THREADS) {
+        const int plane = t / run, off = t - plane * run;   // off = lp * k + b
+        const int c2 = plane / 3, j = plane - c2 * 3;
+        const int lp = off / k, bb = off - lp * k;
+        const size_t src = (size_t)plane * (size_t)n_obs + (size_t)(ibase + off);
+        sm.Js[lp][bb * wc + c2][j] = rowsJ[src];
         if (pfree) {
-          (&sm.Ws[lp][0][0])[rem] = rowsW[base + t];
-          (&sm.Ys[lp][0][0])[rem] = rowsY[base + t];
+          sm.Ws[lp][bb * wc + c2][j] = rowsW[src];
+          sm.Ys[lp][bb * wc + c2][j] = rowsY[src];
         }
       }
     }
@@ -617,9 +631,9 @@ __global__ void __launch_bounds__(SEG_THREADS, 3)
     // U_b = Js_b^T Js_b: column (b, c2) against the wc rows of the same observation
     if (half == 0 && active) {
       for (int lp = 0; lp < np; ++lp) {
-        const double j0 = sm.Js[lp][item][0], j1 = sm.Js[lp][item][1], j2 = nres == 3 ? sm.Js[lp][item][2] : 0.0;
+        const double j0 = sm.Js[lp][item][0], j1 = sm.Js[lp][item][1], j2 = sm.Js[lp][item][2];
 #pragma unroll
-        for (int c1 = 0; c1 < SEG_WCMAX; ++c1) {
+        for (int c1 = 0; c1 < WCU; ++c1) {
           if (c1 < wc) {
             const double* jr = sm.Js[lp][b * wc + c1];
             uacc[c1] += jr[0] * j0 + jr[1] * j1 + jr[2] * j2;
@@ -629,50 +643,52 @@ __global__ void __launch_bounds__(SEG_THREADS, 3)
     }
   }
 
-  // ---- flush: one atomic per owned entry of the segment ----
-  if (!active || mycol < 0) return;
-  const int m2 = sm.meta[item];
-  const int B2 = m2 >> 12, s2 = (m2 >> 10) & 3, sz2 = (m2 >> 5) & 31, r2 = m2 & 31;
-  if (half == 0) {
+  // ---- accumulators -> shared tile [row - h*ROWS][column], one row-half at a time; U is added on the
+  //      same-observation rows; then a rolled flush loop (small code) issues the atomics ----
+  for (int hpass = 0; hpass < 2; ++hpass) {
+    __syncthreads();  // chunk buffers / previous pass no longer needed: the tile aliases them
+    if (active && row0 / PASS_ROWS == hpass) {
 #pragma unroll
-    for (int c1 = 0; c1 < SEG_WCMAX; ++c1) {
-      if (c1 < wc) {
-        const int m1 = sm.meta[b * wc + c1];
-        if (m1 >= 0) {
-          const int B1 = m1 >> 12, s1 = (m1 >> 10) & 3, r1 = m1 & 31;
-          const bool keep = B1 < B2 || (B1 == B2 && r1 <= r2);
-          if (keep) atomicAdd(&Sval[sm.offt[(b * SEG_KMAX + b) * 9 + s1 * 3 + s2] + r1 * sz2 + r2], uacc[c1]);
+      for (int e = 0; e < ROWS; ++e) tile[(row0 - hpass * PASS_ROWS + e) * SEG_NA + item] = pfree ? acc[e] : 0.0;
+    }
+    __syncthreads();
+    if (half == 0 && active) {
+#pragma unroll
+      for (int c1 = 0; c1 < WCU; ++c1) {
+        const int row = b * wc + c1;
+        if (c1 < wc && row >= hpass * PASS_ROWS && row < (hpass + 1) * PASS_ROWS)
+          tile[(row - hpass * PASS_ROWS) * SEG_NA + item] += uacc[c1];
+      }
+    }
+    __syncthreads();
+    const int rbeg = hpass * PASS_ROWS, rend = min(ncols, (hpass + 1) * PASS_ROWS);
+    for (int t = tid; t < (rend - rbeg) * ncols; t += SEG_THREADS) {
+      const int lr = t / ncols, col = t - lr * ncols;
+      const int row = rbeg + lr;
+      const int m1 = sm.meta[row], m2 = sm.meta[col];
+      if (m1 < 0 || m2 < 0) continue;
+      const int a = row / wc, bb = col / wc;
+      if (a > bb) continue;
+      const int B1 = m1 >> 12, s1 = (m1 >> 10) & 3, sz1 = (m1 >> 5) & 31, r1 = m1 & 31;
+      const int B2 = m2 >> 12, s2 = (m2 >> 10) & 3, sz2 = (m2 >> 5) & 31, r2 = m2 & 31;
+      double val = tile[lr * SEG_NA + col];
+      int pos;
+      if (B1 < B2) {
+        pos = r1 * sz2 + r2;
+      } else if (B1 > B2) {
+        if (a == bb) continue;
+        pos = r2 * sz1 + r1;
+      } else {
+        if (a == bb) {
+          if (r2 < r1) continue;
+          pos = r1 * sz1 + r2;
+        } else {
+          if (r1 == r2) val *= 2.0;
+          pos = min(r1, r2) * sz1 + max(r1, r2);
         }
       }
+      atomicAdd(&Sval[sm.offt[(a * SEG_KMAX + bb) * 9 + s1 * 3 + s2] + pos], val);
     }
-  }
-  if (!pfree) return;
-#pragma unroll
-  for (int e = 0; e < ROWS; ++e) {
-    const int row = row0 + e;
-    if (row >= ncols) continue;
-    const int m1 = sm.meta[row];
-    if (m1 < 0) continue;
-    const int a = row / wc;
-    if (a > b) continue;
-    const int B1 = m1 >> 12, s1 = (m1 >> 10) & 3, sz1 = (m1 >> 5) & 31, r1 = m1 & 31;
-    double val = acc[e];
-    int pos;
-    if (B1 < B2) {
-      pos = r1 * sz2 + r2;
-    } else if (B1 > B2) {
-      if (a == b) continue;
-      pos = r2 * sz1 + r1;
-    } else {
-      if (a == b) {
-        if (r2 < r1) continue;
-        pos = r1 * sz1 + r2;
-      } else {
-        if (r1 == r2) val *= 2.0;
-        pos = min(r1, r2) * sz1 + max(r1, r2);
-      }
-    }
-    atomicAdd(&Sval[sm.offt[(a * SEG_KMAX + b) * 9 + s1 * 3 + s2] + pos], val);
   }
 }
 

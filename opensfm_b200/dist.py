@@ -51,12 +51,21 @@ def make_allreduce(group=None, device: Optional[int] = None) -> Callable[[int, i
     import torch.distributed as dist
 
     backend = dist.get_backend(group)
+    views: Dict[Tuple[int, int], Any] = {}    # (ptr, count) -> tensor view (the library reuses its buffers)
+    streams: Dict[int, Any] = {}
 
     def allreduce(ptr: int, count: int, stream: int) -> None:
         if backend == "nccl":
             dev = torch.cuda.current_device() if device is None else device
-            t = torch.as_tensor(_CudaPtr(ptr, count), device="cuda:%d" % dev)
-            ext = torch.cuda.ExternalStream(stream, device=dev) if stream else torch.cuda.current_stream(dev)
+            t = views.get((ptr, count))
+            if t is None:
+                if len(views) > 256:
+                    views.clear()
+                t = views[(ptr, count)] = torch.as_tensor(_CudaPtr(ptr, count), device="cuda:%d" % dev)
+            ext = streams.get(stream)
+            if ext is None:
+                ext = streams[stream] = (torch.cuda.ExternalStream(stream, device=dev) if stream
+                                         else torch.cuda.current_stream(dev))
             with torch.cuda.stream(ext):
                 dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
         else:  # gloo: host memory
