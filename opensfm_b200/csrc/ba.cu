@@ -540,6 +540,15 @@ static int grid_for(long long n, int threads) { return (int)std::max<long long>(
 void BA::run() {
   OSFM_CUDA(cudaSetDevice(device));
   const auto t_start = std::chrono::high_resolution_clock::now();
+  // OSFM_BA_TRACE=1: host wall-clock per phase of run() on stderr (diagnostics only)
+  static const bool trace_on = []() { const char* e = getenv("OSFM_BA_TRACE"); return e && e[0] == '1'; }();
+  auto t_prev = t_start;
+  auto trace = [&](const char* what) {
+    if (!trace_on) return;
+    const auto now = std::chrono::high_resolution_clock::now();
+    fprintf(stderr, "[osfm_ba] %-12s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(now - t_prev).count());
+    t_prev = now;
+  };
   const int K = (int)cam_type.size(), NI = (int)inst_const.size(), NR = (int)rc_const.size();
   const int S = (int)shot_inst.size(), Pfull = (int)pt_const.size();
   const long long Nfull = (long long)obs_shot.size();
@@ -558,6 +567,7 @@ void BA::run() {
     if (obs_point[i] < 0 || obs_point[i] >= Pfull) throw ArgError("observation references a point that doesn't exist");
   }
 
+  trace("validate");
   // ---- layout of the reduced vector: [free cameras | free instances | free rig cameras] ----
   std::vector<int> cam_off(K + 1, 0), cam_np(K), cam_poff(K), inst_poff(NI), rc_poff(std::max(NR, 1), -1);
   std::vector<int> blk_off, blk_sz;
@@ -624,6 +634,7 @@ void BA::run() {
   }
   wc = std::max(wc, 1);
 
+  trace("layout");
   // ---- shard points over ranks (p % world == rank); order the local points so that points seen by
   //      exactly the same shots are contiguous (segments of the fast Schur kernel); sort the
   //      observations by (point, shot) ----
@@ -646,10 +657,10 @@ void BA::run() {
       if (lp >= 0) olist[fill[lp]++] = i;
     }
   }
-  // The segmented Schur kernel (ba_schur_seg) is correct (tests run it) but, as measured on B200
-  // (profiles/README.md), still slower than the per-point kernel on the 2M-observation scene because a
-  // segment's CTA is latency-bound at 2 CTAs/SM; it stays opt-in until that is fixed.
-  static const bool use_seg = []() { const char* e = getenv("OSFM_BA_SEGMENT_SCHUR"); return e && e[0] == '1'; }();
+  // The segmented Schur path (ba_point_blocks + ba_obs_rows + ba_schur_seg) is the default: 3.6 ms vs 5.3 ms
+  // per launch for the per-point kernel on the 2M-observation scene (profiles/README.md).
+  // OSFM_BA_SEGMENT_SCHUR=0 forces every point through ba_schur (kept for A/B runs and tests).
+  static const bool use_seg = []() { const char* e = getenv("OSFM_BA_SEGMENT_SCHUR"); return !(e && e[0] == '0'); }();
   std::vector<unsigned long long> sig(P);
   std::vector<char> eligible(P);
   for (int p = 0; p < P; ++p) {
@@ -714,6 +725,7 @@ void BA::run() {
   }
   const int n = nc + 3 * npf;
 
+  trace("sort");
   // ---- prior rows (rank 0 adds them; Ceres drops residuals of constant blocks) ----
   std::vector<int> pr_cam_param, pr_cam_col, pr_cam_log, pr_pos_inst, pr_pos_axis, pr_pos_col;
   std::vector<double> pr_cam_prior, pr_cam_scale, pr_pos_prior, pr_pos_scale;
@@ -748,6 +760,7 @@ void BA::run() {
     for (int j = 0; j < 3; ++j) { pr_blk.push_back(inst_blk[i]); pr_local.push_back(3 + j); }
   }
 
+  trace("priors");
   // ---- upload ----
   upload(d_cam_type, cam_type, stream); upload(d_cam_off, cam_off, stream); upload(d_cam_np, cam_np, stream);
   upload(d_cam_poff, cam_poff, stream); upload(d_inst_poff, inst_poff, stream); upload(d_rc_poff, rc_poff, stream);
@@ -809,6 +822,7 @@ void BA::run() {
 
   cudaEvent_t ev0, ev1;
   OSFM_CUDA(cudaEventCreate(&ev0)); OSFM_CUDA(cudaEventCreate(&ev1));
+  trace("upload");
   EventTimer tm_lin, tm_schur, tm_pcg, tm_back;
   tm_lin.init(); tm_schur.init(); tm_pcg.init(); tm_back.init();
 
@@ -870,6 +884,7 @@ void BA::run() {
     return s.cost;
   };
 
+  trace("pre-struct");
   // ---- block-sparse structure of the reduced camera system (identical on every rank) ----
   BlkMaps bm{d_cam_blk.p, d_inst_blk.p, d_rc_blk.p};
   BsrView bsr{};
@@ -999,6 +1014,7 @@ void BA::run() {
   lay.row_of = d_row_of.p; lay.row_M = d_row_M.p; lay.rowbase = d_rowbase.p; lay.cbase = d_cbase.p;
   lay.colidx = d_colidx.p; lay.ngroups = ngroups; lay.grp_b1 = d_grp_b1.p; lay.grp_b2 = d_grp_b2.p;
 
+  trace("structure");
   // ---- Levenberg-Marquardt (Ceres trust_region_minimizer / levenberg_marquardt_strategy) ----
   OSFM_CUDA(cudaEventRecord(ev0, stream));
   double radius = 1e4;
@@ -1190,6 +1206,7 @@ void BA::run() {
   OSFM_CUDA(cudaEventRecord(ev1, stream));
   const double final_cost = eval_cost(cur);
 
+  trace("lm");
   // ---- results back to the host ----
   OSFM_CUDA(cudaMemcpyAsync(cam_params.data(), d_cam[cur].p, sizeof(double) * cam_params.size(), cudaMemcpyDeviceToHost, stream));
   OSFM_CUDA(cudaMemcpyAsync(inst.data(), d_inst[cur].p, sizeof(double) * inst.size(), cudaMemcpyDeviceToHost, stream));
@@ -1222,6 +1239,7 @@ void BA::run() {
     for (int p = 0; p < P; ++p)
       for (int j = 0; j < 3; ++j) pts[3 * (size_t)global_of[p] + j] = lp[3 * (size_t)p + j];
   }
+  trace("results");
   float dev_ms = 0.f;
   OSFM_CUDA(cudaEventElapsedTime(&dev_ms, ev0, ev1));
   cudaEventDestroy(ev0); cudaEventDestroy(ev1);
