@@ -116,7 +116,7 @@ def solve(pb: bp.BAProblem, device: int = 0, rank: int = 0, world: int = 1, allr
         inst = np.zeros((NI, 6))
         rc = np.zeros((NR, 6))
         pts = np.zeros((P, 3))
-        rep = np.zeros((N, 3))
+        rep = np.empty((N, 3)) if compute_reprojection_errors else np.zeros((N, 3))
         _lib.check(L.osfm_ba_get_cameras(h, _p(cam)))
         _lib.check(L.osfm_ba_get_rig_instances(h, _p(inst)))
         _lib.check(L.osfm_ba_get_rig_cameras(h, _p(rc)))

@@ -286,6 +286,7 @@ __global__ void ba_grad_max(const double* grad, int n, Scalars* sc) {
 
 }  // namespace osfm
 #include "ba_reduced.cuh"
+#include "ba_order.cuh"
 namespace osfm {
 
 // ---------------------------------------------------------------------------
@@ -461,8 +462,7 @@ struct BA {
   std::vector<int> shot_inst, shot_cam, shot_rc, shot_use_rc;
   std::vector<double> pts;
   std::vector<int> pt_const;
-  std::vector<int> obs_shot, obs_point;
-  std::vector<double> obs_xy, obs_sigma;
+  long long n_obs_full = 0;  // observations live on the device only (d_raw_*)
   // options (defaults of bundle::BundleAdjuster(), bundle_adjuster.cc:24-44)
   int loss = OSFM_LOSS_CAUCHY;
   double loss_a = 1.0;
@@ -472,7 +472,7 @@ struct BA {
   osfm_allreduce_fn allreduce = nullptr;
   void* allreduce_user = nullptr;
   // results
-  std::vector<double> reproj;
+  bool reproj_valid = false;
   osfm_ba_summary summary{};
   bool has_run = false;
 
@@ -496,6 +496,15 @@ struct BA {
   DevBuf<char> d_cub;
   DevBuf<PcgState> d_pcg;
   DevBuf<int> d_seg_start;
+  // raw observations as the caller gave them + scratch of the device-side ordering (ba_order.cuh)
+  DevBuf<int> d_raw_shot, d_raw_point, d_ptc_full;
+  DevBuf<double> d_raw_xy, d_raw_sigma, d_pts_in;
+  DevBuf<unsigned long long> d_okeys, d_okeys2, d_pkey, d_pkey2;
+  DevBuf<int> d_ovals, d_ovals2, d_pval, d_order, d_inv_order, d_global_of, d_free_flag, d_free_scan, d_head, d_run_head, d_nsel;
+  DevBuf<long long> d_kk;
+  DevBuf<char> d_seg_flags;
+  DevBuf<OrderCounts> d_oc;
+  PinnedBuf<OrderCounts> h_oc;
   DevBuf<double> d_rowsJ, d_rowsW, d_rowsY, d_Vig;
   DevBuf<int> d_row_M, d_qoff, d_blk_row, d_cbase, d_colidx, d_row_of, d_grp_b1, d_grp_b2;
   DevBuf<long long> d_rowbase;
@@ -551,7 +560,7 @@ void BA::run() {
   };
   const int K = (int)cam_type.size(), NI = (int)inst_const.size(), NR = (int)rc_const.size();
   const int S = (int)shot_inst.size(), Pfull = (int)pt_const.size();
-  const long long Nfull = (long long)obs_shot.size();
+  const long long Nfull = n_obs_full;
   if (K == 0 && Nfull > 0) throw ArgError("observations but no cameras");
   int64_t launches0 = g_kernel_launches.load();
 
@@ -562,10 +571,7 @@ void BA::run() {
     if (shot_use_rc[s] && (shot_rc[s] < 0 || shot_rc[s] >= NR))
       throw ArgError("shot references a rig camera that doesn't exist");
   }
-  for (long long i = 0; i < Nfull; ++i) {
-    if (obs_shot[i] < 0 || obs_shot[i] >= S) throw ArgError("observation references a shot that doesn't exist");
-    if (obs_point[i] < 0 || obs_point[i] >= Pfull) throw ArgError("observation references a point that doesn't exist");
-  }
+  // (observation indices are checked on the device, ord_make_keys)
 
   trace("validate");
   // ---- layout of the reduced vector: [free cameras | free instances | free rig cameras] ----
@@ -635,95 +641,101 @@ void BA::run() {
   wc = std::max(wc, 1);
 
   trace("layout");
-  // ---- shard points over ranks (p % world == rank); order the local points so that points seen by
-  //      exactly the same shots are contiguous (segments of the fast Schur kernel); sort the
-  //      observations by (point, shot) ----
-  std::vector<int> old_of(Pfull, -1), old_global;
-  for (int p = 0; p < Pfull; ++p)
-    if (p % world == rank) { old_of[p] = (int)old_global.size(); old_global.push_back(p); }
-  const int P = (int)old_global.size();
-  std::vector<long long> ostart(P + 1, 0);
-  for (long long i = 0; i < Nfull; ++i) {
-    const int lp = old_of[obs_point[i]];
-    if (lp >= 0) ostart[lp + 1]++;
-  }
-  for (int p = 0; p < P; ++p) ostart[p + 1] += ostart[p];
-  const long long N = ostart[P];
-  std::vector<long long> olist(N);
-  {
-    std::vector<long long> fill(ostart.begin(), ostart.end() - 1);
-    for (long long i = 0; i < Nfull; ++i) {
-      const int lp = old_of[obs_point[i]];
-      if (lp >= 0) olist[fill[lp]++] = i;
-    }
-  }
+  // ---- order the observations on the device (ba_order.cuh): shard points over ranks
+  //      (p % world == rank), sort by (point, shot), put points seen by exactly the same shots next to
+  //      each other (segments of the fast Schur path) ----
   // The segmented Schur path (ba_point_blocks + ba_obs_rows + ba_schur_seg) is the default: 3.6 ms vs 5.3 ms
   // per launch for the per-point kernel on the 2M-observation scene (profiles/README.md).
   // OSFM_BA_SEGMENT_SCHUR=0 forces every point through ba_schur (kept for A/B runs and tests).
   static const bool use_seg = []() { const char* e = getenv("OSFM_BA_SEGMENT_SCHUR"); return !(e && e[0] == '0'); }();
-  std::vector<unsigned long long> sig(P);
-  std::vector<char> eligible(P);
-  for (int p = 0; p < P; ++p) {
-    long long* lo = olist.data() + ostart[p];
-    long long* hi = olist.data() + ostart[p + 1];
-    std::sort(lo, hi, [&](long long x, long long y) { return obs_shot[x] != obs_shot[y] ? obs_shot[x] < obs_shot[y] : x < y; });
-    const long long k = hi - lo;
-    unsigned long long hsh = 1469598103934665603ULL ^ (unsigned long long)(pt_const[old_global[p]] ? 1 : 0);
-    for (long long* q = lo; q < hi; ++q) { hsh ^= (unsigned long long)obs_shot[*q] + 0x9e3779b97f4a7c15ULL; hsh *= 1099511628211ULL; }
-    sig[p] = hsh;
-    eligible[p] = (use_seg && k >= 1 && k <= SEG_KMAX && k * wc <= SEG_NA && wc <= SEG_WCMAX) ? 1 : 0;
-  }
-  std::vector<int> order(P);
-  for (int p = 0; p < P; ++p) order[p] = p;
-  if (use_seg) std::sort(order.begin(), order.end(), [&](int x, int y) {
-    if (eligible[x] != eligible[y]) return eligible[x] > eligible[y];
-    if (sig[x] != sig[y]) return sig[x] < sig[y];
-    return x < y;
-  });
-  std::vector<int> global_of(P);
-  std::vector<long long> pt_start(P + 1, 0), obs_orig(N);
-  std::vector<int> s_shot(N), s_point(N);
-  std::vector<double> s_x(N), s_y(N), s_isig(N);
-  std::vector<int> seg_start;  // point ranges of the fast path; the last entry is P_fast
-  int P_fast = 0;
+  if (Nfull >= (1LL << 31)) throw ArgError("too many observations");
+  const int P = Pfull > rank ? (Pfull - rank + world - 1) / world : 0;
+  const size_t Nfz = (size_t)std::max<long long>(Nfull, 1), Pz = (size_t)std::max(P, 1);
+  upload(d_ptc_full, pt_const, stream);
+  upload(d_pts_in, pts, stream);
+  d_okeys.reserve(Nfz); d_okeys2.reserve(Nfz); d_ovals.reserve(Nfz); d_ovals2.reserve(Nfz);
+  d_g_pt_start.reserve((size_t)Pfull + 1);
+  d_pkey.reserve(Pz); d_pkey2.reserve(Pz); d_pval.reserve(Pz); d_order.reserve(Pz); d_inv_order.reserve(Pz);
+  d_global_of.reserve(Pz); d_free_flag.reserve(Pz + 1); d_free_scan.reserve(Pz + 1); d_kk.reserve(Pz + 1);
+  d_pt_start.reserve(Pz + 1); d_pt_poff.reserve(Pz); d_head.reserve(Pz); d_run_head.reserve(Pz);
+  d_seg_flags.reserve(Pz); d_seg_start.reserve(Pz + 1); d_nsel.reserve(1); d_oc.reserve(1); h_oc.reserve(1);
+  d_pts[0].reserve(3 * Pz); d_pts[1].reserve(3 * Pz);
+  int pbits = 1;
+  while ((1LL << pbits) <= (long long)Pfull) ++pbits;
   {
-    constexpr int kSegMaxPoints = 64;
-    long long d = 0;
-    int prev = -1;
-    for (int np = 0; np < P; ++np) {
-      const int op = order[np];
-      global_of[np] = old_global[op];
-      pt_start[np] = d;
-      const long long kk = ostart[op + 1] - ostart[op];
-      for (long long t = 0; t < kk; ++t, ++d) {
-        const long long i = olist[ostart[op] + t];
-        obs_orig[d] = i; s_shot[d] = obs_shot[i]; s_point[d] = np;
-        s_x[d] = obs_xy[2 * i]; s_y[d] = obs_xy[2 * i + 1];
-        s_isig[d] = 1.0 / obs_sigma[i];  // projection_errors.h:21
-      }
-      if (eligible[op]) {
-        bool same = prev >= 0 && sig[prev] == sig[op] && (ostart[prev + 1] - ostart[prev]) == kk &&
-                    (np - seg_start.back()) < kSegMaxPoints && pt_const[old_global[prev]] == pt_const[old_global[op]];
-        if (same)
-          for (long long t = 0; t < kk && same; ++t)
-            same = obs_shot[olist[ostart[prev] + t]] == obs_shot[olist[ostart[op] + t]];
-        if (!same) seg_start.push_back(np);
-        prev = op;
-        P_fast = np + 1;
-      }
-    }
-    pt_start[P] = d;
-    seg_start.push_back(P_fast);
+    size_t t1 = 0, t2 = 0, t3 = 0, t4 = 0, t5 = 0, t6 = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, t1, d_okeys.p, d_okeys2.p, d_ovals.p, d_ovals2.p, (int)Nfull, 0, 32 + pbits, stream);
+    cub::DeviceRadixSort::SortPairs(nullptr, t2, d_pkey.p, d_pkey2.p, d_pval.p, d_order.p, P, 0, 64, stream);
+    cub::DeviceScan::ExclusiveSum(nullptr, t3, d_kk.p, d_pt_start.p, P + 1, stream);
+    cub::DeviceScan::ExclusiveSum(nullptr, t4, d_free_flag.p, d_free_scan.p, P + 1, stream);
+    cub::DeviceScan::InclusiveScan(nullptr, t5, d_head.p, d_run_head.p, OrdMax(), P, stream);
+    cub::DeviceSelect::Flagged(nullptr, t6, thrust::counting_iterator<int>(0), d_seg_flags.p, d_seg_start.p, d_nsel.p, P, stream);
+    d_cub.reserve(std::max({t1, t2, t3, t4, t5, t6}) + 256);
   }
-  const int nseg = (int)seg_start.size() - 1;
-  std::vector<int> pt_poff(std::max(P, 1), -1);
-  std::vector<double> lpts(3 * (size_t)std::max(P, 1), 0.0);
-  int npf = 0;
-  for (int p = 0; p < P; ++p) {
-    pt_poff[p] = pt_const[global_of[p]] ? -1 : npf++;
-    for (int j = 0; j < 3; ++j) lpts[3 * (size_t)p + j] = pts[3 * (size_t)global_of[p] + j];
-  }
+  OSFM_CUDA(cudaMemsetAsync(d_oc.p, 0, sizeof(OrderCounts), stream));
+  ord_make_keys<<<grid_for(Nfull, 256), 256, 0, stream>>>(Nfull, d_raw_shot.p, d_raw_point.p, S, Pfull, d_okeys.p, d_ovals.p, d_oc.p);
+  OSFM_LAUNCH_CHECK();
+  size_t tmpb = d_cub.cap;
+  OSFM_CUDA(cub::DeviceRadixSort::SortPairs(d_cub.p, tmpb, d_okeys.p, d_okeys2.p, d_ovals.p, d_ovals2.p, (int)Nfull, 0, 32 + pbits, stream));
+  const unsigned long long* okeys = d_okeys2.p;  // sorted keys / positions in the caller's list
+  const int* ovals = d_ovals2.p;
+  ord_point_starts<<<grid_for(Pfull + 1, 256), 256, 0, stream>>>(okeys, Nfull, Pfull, d_g_pt_start.p);
+  OSFM_LAUNCH_CHECK();
+  ord_pair_bound<<<grid_for(Pfull, 256), 256, 0, stream>>>(d_g_pt_start.p, Pfull, d_oc.p);
+  OSFM_LAUNCH_CHECK();
+  ord_signatures<<<grid_for(P, 256), 256, 0, stream>>>(okeys, d_g_pt_start.p, d_ptc_full.p, P, world, rank, wc, use_seg ? 1 : 0,
+                                                       SEG_KMAX, SEG_NA, SEG_WCMAX, d_pkey.p, d_pval.p);
+  OSFM_LAUNCH_CHECK();
+  tmpb = d_cub.cap;
+  OSFM_CUDA(cub::DeviceRadixSort::SortPairs(d_cub.p, tmpb, d_pkey.p, d_pkey2.p, d_pval.p, d_order.p, P, 0, 64, stream));
+  ord_counts<<<grid_for(P + 1, 256), 256, 0, stream>>>(d_order.p, d_g_pt_start.p, d_ptc_full.p, P, world, rank, d_kk.p,
+                                                       d_free_flag.p, d_inv_order.p, d_global_of.p);
+  OSFM_LAUNCH_CHECK();
+  tmpb = d_cub.cap;
+  OSFM_CUDA(cub::DeviceScan::ExclusiveSum(d_cub.p, tmpb, d_kk.p, d_pt_start.p, P + 1, stream));
+  tmpb = d_cub.cap;
+  OSFM_CUDA(cub::DeviceScan::ExclusiveSum(d_cub.p, tmpb, d_free_flag.p, d_free_scan.p, P + 1, stream));
+  ord_finish_points<<<grid_for(P + 1, 256), 256, 0, stream>>>(P, d_free_flag.p, d_free_scan.p, d_pt_start.p, d_global_of.p,
+                                                              d_pts_in.p, d_pt_poff.p, d_pts[0].p, d_pts[1].p, d_oc.p);
+  OSFM_LAUNCH_CHECK();
+  OSFM_CUDA(cudaMemcpyAsync(h_oc.p, d_oc.p, sizeof(OrderCounts), cudaMemcpyDeviceToHost, stream));
+  OSFM_CUDA(cudaStreamSynchronize(stream));
+  if (h_oc.p->err & 1) throw ArgError("observation references a shot that doesn't exist");
+  if (h_oc.p->err & 2) throw ArgError("observation references a point that doesn't exist");
+  const long long N = h_oc.p->n_local;
+  const int npf = h_oc.p->npf;
   const int n = nc + 3 * npf;
+  {
+    const size_t Nz0 = (size_t)std::max<long long>(N, 1);
+    d_obs_orig.reserve(Nz0); d_obs_shot.reserve(Nz0); d_obs_point.reserve(Nz0);
+    d_obs_x.reserve(Nz0); d_obs_y.reserve(Nz0); d_obs_isig.reserve(Nz0);
+  }
+  ord_gather_obs<<<grid_for(Nfull, 256), 256, 0, stream>>>(okeys, ovals, Nfull, d_g_pt_start.p, d_inv_order.p, d_pt_start.p, world,
+                                                           rank, d_raw_xy.p, d_raw_sigma.p, d_obs_orig.p, d_obs_shot.p,
+                                                           d_obs_point.p, d_obs_x.p, d_obs_y.p, d_obs_isig.p);
+  OSFM_LAUNCH_CHECK();
+  ord_seg_heads<<<grid_for(P, 256), 256, 0, stream>>>(P, d_pkey2.p, d_order.p, d_g_pt_start.p, okeys, d_ptc_full.p, world, rank,
+                                                      d_head.p);
+  OSFM_LAUNCH_CHECK();
+  tmpb = d_cub.cap;
+  OSFM_CUDA(cub::DeviceScan::InclusiveScan(d_cub.p, tmpb, d_head.p, d_run_head.p, OrdMax(), P, stream));
+  ord_seg_flags<<<grid_for(P, 256), 256, 0, stream>>>(P, d_pkey2.p, d_run_head.p, d_seg_flags.p);
+  OSFM_LAUNCH_CHECK();
+  tmpb = d_cub.cap;
+  OSFM_CUDA(cub::DeviceSelect::Flagged(d_cub.p, tmpb, thrust::counting_iterator<int>(0), d_seg_flags.p, d_seg_start.p, d_nsel.p, P,
+                                       stream));
+  ord_seg_finish<<<1, 32, 0, stream>>>(P, d_pkey2.p, d_pt_start.p, d_seg_start.p, d_nsel.p, d_oc.p);
+  OSFM_LAUNCH_CHECK();
+  if (world > 1) {  // the structure of the reduced system needs every point's shots on every rank
+    d_g_obs_shot.reserve(Nfz); d_g_obs_point.reserve(Nfz);
+    ord_split_keys<<<grid_for(Nfull, 256), 256, 0, stream>>>(okeys, Nfull, d_g_obs_shot.p, d_g_obs_point.p);
+    OSFM_LAUNCH_CHECK();
+  }
+  OSFM_CUDA(cudaMemcpyAsync(h_oc.p, d_oc.p, sizeof(OrderCounts), cudaMemcpyDeviceToHost, stream));
+  OSFM_CUDA(cudaStreamSynchronize(stream));
+  const int nseg = h_oc.p->nseg, P_fast = h_oc.p->p_fast;
+  const long long n_fast_obs = h_oc.p->n_fast;
+  const long long pair_bound_all = (long long)h_oc.p->pair_bound;
 
   trace("sort");
   // ---- prior rows (rank 0 adds them; Ceres drops residuals of constant blocks) ----
@@ -764,18 +776,12 @@ void BA::run() {
   // ---- upload ----
   upload(d_cam_type, cam_type, stream); upload(d_cam_off, cam_off, stream); upload(d_cam_np, cam_np, stream);
   upload(d_cam_poff, cam_poff, stream); upload(d_inst_poff, inst_poff, stream); upload(d_rc_poff, rc_poff, stream);
-  upload(d_pt_poff, pt_poff, stream);
   upload(d_shot_inst, shot_inst, stream); upload(d_shot_cam, shot_cam, stream); upload(d_shot_rc, shot_rc, stream);
   upload(d_shot_use_rc, shot_use_rc, stream);
-  upload(d_obs_shot, s_shot, stream); upload(d_obs_point, s_point, stream);
-  upload(d_obs_x, s_x, stream); upload(d_obs_y, s_y, stream); upload(d_obs_isig, s_isig, stream);
-  upload(d_obs_orig, obs_orig, stream); upload(d_pt_start, pt_start, stream);
-  upload(d_seg_start, seg_start, stream);
   std::vector<double> rc_h = rc;
   if (rc_h.empty()) rc_h.assign(6, 0.0);
   for (int b = 0; b < 2; ++b) {
     upload(d_cam[b], cam_params, stream); upload(d_inst[b], inst, stream); upload(d_rc[b], rc_h, stream);
-    upload(d_pts[b], lpts, stream);
   }
   upload(d_blk_off, blk_off, stream); upload(d_blk_sz, blk_sz, stream);
   upload(d_cam_blk, cam_blk, stream); upload(d_inst_blk, inst_blk, stream); upload(d_rc_blk, rc_blk, stream);
@@ -895,21 +901,8 @@ void BA::run() {
     const int* g_shot = d_obs_shot.p;
     const int* g_point = d_obs_point.p;
     const long long* g_start = d_pt_start.p;
-    long long pair_bound = 0;
-    if (world > 1) {
-      std::vector<long long> gs(Pfull + 1, 0);
-      for (long long i = 0; i < Nfull; ++i) gs[obs_point[i] + 1]++;
-      for (int p = 0; p < Pfull; ++p) gs[p + 1] += gs[p];
-      std::vector<long long> gf(gs.begin(), gs.end() - 1);
-      std::vector<int> gshot(Nfull), gpoint(Nfull);
-      for (long long i = 0; i < Nfull; ++i) { const long long d = gf[obs_point[i]]++; gshot[d] = obs_shot[i]; gpoint[d] = obs_point[i]; }
-      upload(d_g_obs_shot, gshot, stream); upload(d_g_obs_point, gpoint, stream); upload(d_g_pt_start, gs, stream);
-      OSFM_CUDA(cudaStreamSynchronize(stream));  // host vectors go out of scope
-      g_shot = d_g_obs_shot.p; g_point = d_g_obs_point.p; g_start = d_g_pt_start.p;
-      for (int p = 0; p < Pfull; ++p) { const long long k = gs[p + 1] - gs[p]; pair_bound += k * (k + 1) / 2; }
-    } else {
-      for (int p = 0; p < P; ++p) { const long long k = pt_start[p + 1] - pt_start[p]; pair_bound += k * (k + 1) / 2; }
-    }
+    const long long pair_bound = pair_bound_all;
+    if (world > 1) { g_shot = d_g_obs_shot.p; g_point = d_g_obs_point.p; g_start = d_g_pt_start.p; }
     const long long bound = std::min<long long>((long long)nblk * (nblk + 1) / 2, 9 * pair_bound + nblk);
     unsigned tsize = 1024;
     while ((long long)tsize < 4 * bound) {
@@ -1075,7 +1068,7 @@ void BA::run() {
           OSFM_CUDA(cudaFuncSetAttribute(ba_schur_seg<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SegSmem)));
           seg_attr = true;
         }
-        const long long n_fast = pt_start[P_fast];
+        const long long n_fast = n_fast_obs;
         d_rowsJ.reserve((size_t)n_fast * wc * 3 + 8); d_rowsW.reserve((size_t)n_fast * wc * 3 + 8);
         d_rowsY.reserve((size_t)n_fast * wc * 3 + 8); d_Vig.reserve(3 * (size_t)std::max(npf, 1));
         ba_point_blocks<<<grid_for(P_fast, 128), 128, 0, stream>>>(v, P_fast, d_scale.p, d_diag.p, inv_radius, d_Vinv.p,
@@ -1212,9 +1205,16 @@ void BA::run() {
   OSFM_CUDA(cudaMemcpyAsync(inst.data(), d_inst[cur].p, sizeof(double) * inst.size(), cudaMemcpyDeviceToHost, stream));
   if (!rc.empty())
     OSFM_CUDA(cudaMemcpyAsync(rc.data(), d_rc[cur].p, sizeof(double) * rc.size(), cudaMemcpyDeviceToHost, stream));
-  std::vector<double> lp(3 * (size_t)std::max(P, 1));
-  OSFM_CUDA(cudaMemcpyAsync(lp.data(), d_pts[cur].p, sizeof(double) * 3 * (size_t)P, cudaMemcpyDeviceToHost, stream));
-  reproj.assign(3 * (size_t)Nfull, 0.0);
+  d_full_pts.reserve(3 * (size_t)std::max(Pfull, 1));
+  if (world > 1) OSFM_CUDA(cudaMemsetAsync(d_full_pts.p, 0, sizeof(double) * 3 * (size_t)Pfull, stream));
+  if (P > 0) {
+    ord_scatter_points<<<grid_for(P, 256), 256, 0, stream>>>(P, d_pts[cur].p, d_global_of.p, d_full_pts.p);
+    OSFM_LAUNCH_CHECK();
+  }
+  allreduce_dev(d_full_pts.p, 3 * (long long)Pfull);
+  OSFM_CUDA(cudaMemcpyAsync(pts.data(), d_full_pts.p, sizeof(double) * 3 * (size_t)Pfull, cudaMemcpyDeviceToHost, stream));
+  // the reprojection errors stay on the device until osfm_ba_get_reprojection_errors fetches them
+  reproj_valid = false;
   if (compute_reproj && Nfull > 0) {
     d_reproj.reserve(3 * (size_t)Nfull);
     OSFM_CUDA(cudaMemsetAsync(d_reproj.p, 0, sizeof(double) * 3 * (size_t)Nfull, stream));
@@ -1223,22 +1223,9 @@ void BA::run() {
       OSFM_LAUNCH_CHECK();
     }
     allreduce_dev(d_reproj.p, 3 * Nfull);
-    OSFM_CUDA(cudaMemcpyAsync(reproj.data(), d_reproj.p, sizeof(double) * 3 * (size_t)Nfull, cudaMemcpyDeviceToHost, stream));
+    reproj_valid = true;
   }
   OSFM_CUDA(cudaStreamSynchronize(stream));
-  if (world > 1) {
-    std::vector<double> full(3 * (size_t)Pfull, 0.0);
-    for (int p = 0; p < P; ++p)
-      for (int j = 0; j < 3; ++j) full[3 * (size_t)global_of[p] + j] = lp[3 * (size_t)p + j];
-    d_full_pts.reserve(full.size());
-    OSFM_CUDA(cudaMemcpyAsync(d_full_pts.p, full.data(), sizeof(double) * full.size(), cudaMemcpyHostToDevice, stream));
-    allreduce_dev(d_full_pts.p, (long long)full.size());
-    OSFM_CUDA(cudaMemcpyAsync(pts.data(), d_full_pts.p, sizeof(double) * full.size(), cudaMemcpyDeviceToHost, stream));
-    OSFM_CUDA(cudaStreamSynchronize(stream));
-  } else {
-    for (int p = 0; p < P; ++p)
-      for (int j = 0; j < 3; ++j) pts[3 * (size_t)global_of[p] + j] = lp[3 * (size_t)p + j];
-  }
   trace("results");
   float dev_ms = 0.f;
   OSFM_CUDA(cudaEventElapsedTime(&dev_ms, ev0, ev1));
@@ -1379,10 +1366,20 @@ int osfm_ba_set_observations(osfm_ba* ba, int64_t n, const int32_t* shot, const 
   OSFM_API_BEGIN
   OSFM_BA_CHECK
   if (n < 0 || (n > 0 && (!shot || !point || !xy || !std_deviation))) throw ArgError("bad observation arrays");
-  ba->impl.obs_shot.assign(shot, shot + n);
-  ba->impl.obs_point.assign(point, point + n);
-  ba->impl.obs_xy.assign(xy, xy + 2 * n);
-  ba->impl.obs_sigma.assign(std_deviation, std_deviation + n);
+  // straight to the device: the ordering, the index checks and the 1/sigma happen there (ba_order.cuh)
+  auto& b = ba->impl;
+  OSFM_CUDA(cudaSetDevice(b.device));
+  const size_t nz = (size_t)std::max<int64_t>(n, 1);
+  b.d_raw_shot.reserve(nz); b.d_raw_point.reserve(nz); b.d_raw_xy.reserve(2 * nz); b.d_raw_sigma.reserve(nz);
+  if (n > 0) {
+    OSFM_CUDA(cudaMemcpyAsync(b.d_raw_shot.p, shot, sizeof(int32_t) * n, cudaMemcpyHostToDevice, b.own_stream));
+    OSFM_CUDA(cudaMemcpyAsync(b.d_raw_point.p, point, sizeof(int32_t) * n, cudaMemcpyHostToDevice, b.own_stream));
+    OSFM_CUDA(cudaMemcpyAsync(b.d_raw_xy.p, xy, sizeof(double) * 2 * n, cudaMemcpyHostToDevice, b.own_stream));
+    OSFM_CUDA(cudaMemcpyAsync(b.d_raw_sigma.p, std_deviation, sizeof(double) * n, cudaMemcpyHostToDevice, b.own_stream));
+    OSFM_CUDA(cudaStreamSynchronize(b.own_stream));
+  }
+  b.n_obs_full = n;
+  b.has_run = false;
   OSFM_API_END
 }
 int osfm_ba_set_options(osfm_ba* ba, int loss, double loss_threshold, int max_iterations, const char* linear_solver,
@@ -1460,7 +1457,14 @@ int osfm_ba_get_reprojection_errors(osfm_ba* ba, double* out_n_by_3) {
   OSFM_API_BEGIN
   OSFM_BA_CHECK
   if (!ba->impl.has_run) throw std::runtime_error("run() has not been called");
-  std::copy(ba->impl.reproj.begin(), ba->impl.reproj.end(), out_n_by_3);
+  auto& b = ba->impl;
+  OSFM_CUDA(cudaSetDevice(b.device));
+  if (b.n_obs_full > 0) {
+    if (b.reproj_valid)
+      OSFM_CUDA(cudaMemcpy(out_n_by_3, b.d_reproj.p, sizeof(double) * 3 * (size_t)b.n_obs_full, cudaMemcpyDeviceToHost));
+    else
+      std::fill(out_n_by_3, out_n_by_3 + 3 * (size_t)b.n_obs_full, 0.0);
+  }
   OSFM_API_END
 }
 
