@@ -510,6 +510,10 @@ struct BA {
   DevBuf<long long> d_rowbase;
   DevBuf<double> d_Spcg, d_Ap;
   PinnedBuf<PcgState> h_pcg;
+  DevBuf<int> d_pcg_rowlo;
+  PcgResident pcg_res{};
+  bool pcg_resident = false;
+  int pcg_smem = 0;
   int num_sms = 148;
   DevBuf<int> d_pr_cam_param, d_pr_cam_col, d_pr_cam_log, d_pr_pos_inst, d_pr_pos_axis, d_pr_pos_col;
   DevBuf<double> d_pr_cam_prior, d_pr_cam_scale, d_pr_pos_prior, d_pr_pos_scale;
@@ -890,6 +894,8 @@ void BA::run() {
     return s.cost;
   };
 
+  // persistent PCG grid: every CTA must be resident (1 CTA / SM) for the grid barrier
+  const int pcg_grid = std::max(1, std::min(std::min(num_sms, PCG_MAX_CTAS), (nc + PCG_THREADS / 32 - 1) / (PCG_THREADS / 32)));
   trace("pre-struct");
   // ---- block-sparse structure of the reduced camera system (identical on every rank) ----
   BlkMaps bm{d_cam_blk.p, d_inst_blk.p, d_rc_blk.p};
@@ -998,6 +1004,54 @@ void BA::run() {
     pcg_fill_colidx<<<grid_for(n_all, 128), 128, 0, stream>>>(d_row_col.p, d_qoff.p, d_blk_row.p, n_all, bsr, d_cbase.p,
                                                              d_colidx.p, d_row_of.p);
     OSFM_LAUNCH_CHECK();
+    // resident PCG: contiguous scalar-row ranges per CTA, balanced by stored entries; usable when every CTA's
+    // slice of S + its column indices (uint16) + p fit in shared memory
+    {
+      std::vector<long long> off(nc + 1, 0);
+      std::vector<int> row_blk(nc, 0);
+      bool monotone = true;
+      for (int b = 0; b < nblk; ++b) {
+        for (int r = 0; r < blk_sz[b]; ++r) {
+          off[blk_off[b] + r] = rowbase[b] + (long long)r * row_M[b];
+          row_blk[blk_off[b] + r] = b;
+        }
+        if (b > 0 && blk_off[b] != blk_off[b - 1] + blk_sz[b - 1]) monotone = false;
+      }
+      off[nc] = vb;
+      const int G = pcg_grid;
+      std::vector<int> row_lo(G + 1, nc);
+      row_lo[0] = 0;
+      for (int c = 1, i = 0; c < G; ++c) {
+        const long long want = vb * c / G;
+        while (i < nc && off[i] < want) ++i;
+        row_lo[c] = i;
+      }
+      long long ent_max = 0, col_max = 0;
+      int rows_max = 0;
+      for (int c = 0; c < G; ++c) {
+        const int lo = row_lo[c], hi = row_lo[c + 1];
+        if (hi <= lo) continue;
+        ent_max = std::max(ent_max, off[hi] - off[lo]);
+        const int b_lo = row_blk[lo], b_hi = row_blk[hi - 1];
+        col_max = std::max<long long>(col_max, (long long)cbase[b_hi] + row_M[b_hi] - cbase[b_lo]);
+        rows_max = std::max(rows_max, hi - lo);
+      }
+      auto up16 = [](long long x) { return (x + 15) / 16 * 16; };
+      const long long off_S = up16(8LL * nc), off_cols = off_S + up16(8 * ent_max), off_rows = off_cols + up16(2 * col_max);
+      const long long total = off_rows + 12LL * rows_max;
+      static const bool allow_res = []() { const char* e = getenv("OSFM_BA_PCG_RESIDENT"); return !(e && e[0] == '0'); }();
+      int max_smem = 0;
+      OSFM_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
+      pcg_resident = allow_res && monotone && nc <= 65535 && total + 1024 <= max_smem;
+      pcg_smem = pcg_resident ? (int)total : 0;
+      pcg_res = PcgResident{};
+      if (pcg_resident) {
+        upload(d_pcg_rowlo, row_lo, stream);
+        pcg_res.row_lo = d_pcg_rowlo.p; pcg_res.off_S = (int)off_S; pcg_res.off_cols = (int)off_cols;
+        pcg_res.off_rows = (int)off_rows; pcg_res.max_rows = rows_max;
+        OSFM_CUDA(cudaFuncSetAttribute(pcg_persistent<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, pcg_smem));
+      }
+    }
     OSFM_CUDA(cudaStreamSynchronize(stream));  // rowbase / cbase host vectors go out of scope
   }
   if (nblk == 0) d_Sbuf.reserve(nc_pad + 16);
@@ -1124,10 +1178,14 @@ void BA::run() {
       OSFM_LAUNCH_CHECK();
       OSFM_CUDA(cudaMemsetAsync(d_pcg.p, 0, sizeof(PcgState), stream));
       const int max_pcg = std::min(2 * nc + 100, 5000);
-      // persistent grid: every CTA must be resident (1 CTA / SM) for the grid barrier
-      const int pcg_grid = std::max(1, std::min(std::min(num_sms, PCG_MAX_CTAS), (nc + PCG_THREADS / 32 - 1) / (PCG_THREADS / 32)));
-      pcg_persistent<<<pcg_grid, PCG_THREADS, 0, stream>>>(d_Spcg.p, lay, bsr, d_Minv.p, d_rhs_p, d_px.p, d_pr.p, d_pz.p,
-                                                           d_pp.p, d_pAp.p, d_Ap.p, d_pcg.p, nc, max_pcg, 1e-16);
+      if (pcg_resident)
+        pcg_persistent<true><<<pcg_grid, PCG_THREADS, pcg_smem, stream>>>(d_Spcg.p, lay, bsr, d_Minv.p, d_rhs_p, d_px.p, d_pr.p,
+                                                                          d_pz.p, d_pp.p, d_pAp.p, d_Ap.p, d_pcg.p, nc,
+                                                                          max_pcg, 1e-16, pcg_res);
+      else
+        pcg_persistent<false><<<pcg_grid, PCG_THREADS, 0, stream>>>(d_Spcg.p, lay, bsr, d_Minv.p, d_rhs_p, d_px.p, d_pr.p,
+                                                                    d_pz.p, d_pp.p, d_pAp.p, d_Ap.p, d_pcg.p, nc, max_pcg,
+                                                                    1e-16, pcg_res);
       OSFM_LAUNCH_CHECK();
       OSFM_CUDA(cudaMemcpyAsync(d_y.p, d_px.p, sizeof(double) * nc, cudaMemcpyDeviceToDevice, stream));
       OSFM_CUDA(cudaMemcpyAsync(h_pcg.p, d_pcg.p, sizeof(PcgState), cudaMemcpyDeviceToHost, stream));
@@ -1164,7 +1222,7 @@ void BA::run() {
     if (nc > 0) {
       pcg_it = h_pcg.p->iterations;
       pcg_total += pcg_it;
-      const double rr = h_pcg.p->rr[pcg_it & 1];
+      const double rr = h_pcg.p->rr_final;
       if (!(rr == rr)) ok = false;
     }
     const double model_change = sm.model_change;

@@ -854,47 +854,68 @@ __global__ void pcg_factor_groups(const double* __restrict__ Sval, BsrView h, co
 
 constexpr int PCG_MAX_CTAS = 256;
 struct PcgState {
-  unsigned flags[PCG_MAX_CTAS];  // per-CTA arrival generation
-  unsigned release;              // generation published by CTA 0
+  unsigned flags[PCG_MAX_CTAS];        // per-CTA arrival generation
+  double slot[2][PCG_MAX_CTAS][2];     // per-CTA partial sums of the reduction riding on the barrier
   int iterations;
-  double rz[2];
-  double pAp[2];
-  double rr[2];
-  double bb;
+  double rr_final;                     // |r|^2 at exit (NaN -> the step is rejected)
 };
 
-// Grid barrier for a fully resident grid (grid <= #SMs, 1 CTA / SM).  Arrivals are independent
-// release-stores to per-CTA flags (no serialised same-address atomics); the threads of CTA 0 poll one
-// flag each and publish the new generation; everyone else polls that single word.
-__device__ __forceinline__ void grid_barrier(PcgState* st, unsigned nblocks, unsigned& gen) {
-  ++gen;
-  __syncthreads();
-  if (blockIdx.x == 0) {
-    if (threadIdx.x > 0 && threadIdx.x < nblocks) {
-      const long long t0 = clock64();
-      unsigned cur;
-      do {
-        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(cur) : "l"(&st->flags[threadIdx.x]) : "memory");
-        if (clock64() - t0 > 8000000000LL) __trap();  // a protocol bug must not hang the GPU
-      } while (cur != gen);
-    }
-    __syncthreads();
-    if (threadIdx.x == 0)
-      asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(&st->release), "r"(gen) : "memory");
-  } else {
-    if (threadIdx.x == 0) {
-      asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(&st->flags[blockIdx.x]), "r"(gen) : "memory");
-      const long long t0 = clock64();
-      unsigned cur;
-      do {
-        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(cur) : "l"(&st->release) : "memory");
-        if (clock64() - t0 > 8000000000LL) __trap();
-      } while (cur != gen);
-    }
-    __syncthreads();
-  }
-}
+// Where the resident variant keeps things in shared memory (byte offsets; host-computed, uniform).
+struct PcgResident {
+  const int* row_lo;   // [grid + 1] scalar-row range of every CTA (balanced by stored entries)
+  int off_S, off_cols, off_rows;  // p at 0
+  int max_rows;
+};
+
 __device__ __forceinline__ double ldcg_d(const double* p) { return __ldcg(p); }
+
+// Grid barrier + all-reduce of two doubles for a fully resident grid (grid <= #SMs, 1 CTA / SM).
+// Every CTA publishes its partial sums in its own slot (double-buffered by generation parity) and
+// release-stores its flag; every CTA then polls all flags (thread t polls CTA t) and sums the slots
+// in a fixed order, so all CTAs get bit-identical totals and the result does not depend on timing.
+__device__ __forceinline__ void grid_reduce2(PcgState* st, unsigned nblocks, unsigned& gen, double a, double b,
+                                             double& A, double& B, double (*red)[2]) {
+  ++gen;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+#pragma unroll
+  for (int o = 16; o; o >>= 1) {
+    a += __shfl_xor_sync(0xffffffffu, a, o);
+    b += __shfl_xor_sync(0xffffffffu, b, o);
+  }
+  if (lane == 0) { red[warp][0] = a; red[warp][1] = b; }
+  __syncthreads();  // also: every global write of this CTA happens-before thread 0's release below
+  if (threadIdx.x == 0) {
+    double sa = 0.0, sb = 0.0;
+    for (int w = 0; w < nwarps; ++w) { sa += red[w][0]; sb += red[w][1]; }
+    __stcg(&st->slot[gen & 1][blockIdx.x][0], sa);
+    __stcg(&st->slot[gen & 1][blockIdx.x][1], sb);
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(&st->flags[blockIdx.x]), "r"(gen) : "memory");
+  }
+  double va = 0.0, vb = 0.0;
+  if (threadIdx.x < nblocks) {
+    const long long t0 = clock64();
+    unsigned cur;
+    do {
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(cur) : "l"(&st->flags[threadIdx.x]) : "memory");
+      if (clock64() - t0 > 8000000000LL) __trap();  // a protocol bug must not hang the GPU
+    } while (cur != gen);
+    va = ldcg_d(&st->slot[gen & 1][threadIdx.x][0]);
+    vb = ldcg_d(&st->slot[gen & 1][threadIdx.x][1]);
+  }
+  __syncthreads();  // red[] is free again; the acquires above order every thread's later loads
+#pragma unroll
+  for (int o = 16; o; o >>= 1) {
+    va += __shfl_xor_sync(0xffffffffu, va, o);
+    vb += __shfl_xor_sync(0xffffffffu, vb, o);
+  }
+  if (lane == 0) { red[warp][0] = va; red[warp][1] = vb; }
+  __syncthreads();
+  double sa = 0.0, sb = 0.0;
+  const int wmax = (int)((nblocks + 31) >> 5);
+  for (int w = 0; w < wmax; ++w) { sa += red[w][0]; sb += red[w][1]; }
+  A = sa; B = sb;
+  __syncthreads();
+}
 
 // z_G = Minv_G r_G for one group (one warp); returns this lane's contributions to r.z and r.r
 __device__ __forceinline__ void pcg_apply_group(const BsrView& h, const PcgLayout& L, const double* Minv, int g, int lane,
@@ -912,18 +933,52 @@ __device__ __forceinline__ void pcg_apply_group(const BsrView& h, const PcgLayou
   }
 }
 
+// RES = true: the CTA's slice of S (contiguous scalar rows, balanced by entries), its column indices
+// (uint16) and the search direction p live in shared memory for the whole solve; an iteration then
+// moves only the vectors through L2 (2 * nc doubles per CTA).  RES = false streams S from L2 / HBM.
+template <bool RES>
 __global__ void __launch_bounds__(PCG_THREADS, 1)
     pcg_persistent(const double* __restrict__ Spcg, PcgLayout L, BsrView h, const double* __restrict__ Minv,
                    const double* __restrict__ rhs, double* x, double* r, double* z, double* p0, double* p1, double* Ap,
-                   PcgState* st, int nc, int max_iter, double tol2_rel) {
+                   PcgState* st, int nc, int max_iter, double tol2_rel, PcgResident R) {
+  extern __shared__ __align__(16) unsigned char pcg_smem[];
+  __shared__ double red[PCG_THREADS / 32][2];
   const int warps_per_cta = blockDim.x >> 5;
-  const int gw = blockIdx.x * warps_per_cta + (threadIdx.x >> 5);
+  const int warp = threadIdx.x >> 5;
+  const int gw = blockIdx.x * warps_per_cta + warp;
   const int nw = gridDim.x * warps_per_cta;
   const int lane = threadIdx.x & 31;
   double* pbuf[2] = {p0, p1};
   unsigned bar_gen = 0;
 
-  // ---- init: x = 0, r = rhs, z = M^-1 r, p_old = z, rz, bb ----
+  double* p_s = reinterpret_cast<double*>(pcg_smem);
+  double* S_s = reinterpret_cast<double*>(pcg_smem + R.off_S);
+  unsigned short* cols_s = reinterpret_cast<unsigned short*>(pcg_smem + R.off_cols);
+  int* row_soff = reinterpret_cast<int*>(pcg_smem + R.off_rows);
+  int* row_coff = row_soff + R.max_rows;
+  int* row_len = row_coff + R.max_rows;
+  int lo = 0, hi = 0;
+  if (RES) {
+    lo = R.row_lo[blockIdx.x];
+    hi = R.row_lo[blockIdx.x + 1];
+    if (hi > lo) {
+      const int b_lo = L.row_of[lo], b_hi = L.row_of[hi - 1];
+      const long long s_base = L.rowbase[b_lo] + (long long)(lo - h.blk_off[b_lo]) * L.row_M[b_lo];
+      const long long s_end = L.rowbase[b_hi] + (long long)(hi - h.blk_off[b_hi]) * L.row_M[b_hi];
+      const int c_base = L.cbase[b_lo], c_end = L.cbase[b_hi] + L.row_M[b_hi];
+      for (int t = threadIdx.x; t < (int)(s_end - s_base); t += blockDim.x) S_s[t] = __ldcs(Spcg + s_base + t);
+      for (int t = threadIdx.x; t < c_end - c_base; t += blockDim.x) cols_s[t] = (unsigned short)L.colidx[c_base + t];
+      for (int t = threadIdx.x; t < hi - lo; t += blockDim.x) {
+        const int i = lo + t, b = L.row_of[i], M = L.row_M[b];
+        row_soff[t] = (int)(L.rowbase[b] + (long long)(i - h.blk_off[b]) * M - s_base);
+        row_coff[t] = L.cbase[b] - c_base;
+        row_len[t] = M;
+      }
+    }
+  }
+
+  // ---- init: x = 0, r = rhs, z = M^-1 r, p_old = 0, rz, bb ----
+  double rz_cur, bb;
   {
     double a_rz = 0.0, a_rr = 0.0;
     for (int g = gw; g < L.ngroups; g += nw) {
@@ -939,19 +994,10 @@ __global__ void __launch_bounds__(PCG_THREADS, 1)
       pcg_apply_group(h, L, Minv, g, lane, rn, z, &a_rz, &a_rr, n, o);
       if (lane < n) p0[o] = 0.0;
     }
-#pragma unroll
-    for (int o = 16; o; o >>= 1) {
-      a_rz += __shfl_xor_sync(0xffffffffu, a_rz, o);
-      a_rr += __shfl_xor_sync(0xffffffffu, a_rr, o);
-    }
-    if (lane == 0 && (a_rz != 0.0 || a_rr != 0.0)) {
-      atomicAdd(&st->rz[0], a_rz);
-      atomicAdd(&st->bb, a_rr);
-    }
+    grid_reduce2(st, gridDim.x, bar_gen, a_rz, a_rr, rz_cur, bb, red);
   }
-  grid_barrier(st, gridDim.x, bar_gen);
-  const double bb = ldcg_d(&st->bb);
   const double tol2 = tol2_rel * bb;
+  double rr = bb;
   int it = 0;
   if (bb > 0.0) {
     double beta = 0.0;  // p_1 = z_0
@@ -961,31 +1007,57 @@ __global__ void __launch_bounds__(PCG_THREADS, 1)
       double* pnew = pbuf[nxt];
       // ---- phase A: p = z + beta p_old (on the fly), Ap = S p, pAp ----
       double a_pAp = 0.0;
-      for (int i = gw; i < nc; i += nw) {
-        const int b = L.row_of[i];
-        const int rr_ = i - h.blk_off[b];
-        const int M = L.row_M[b];
-        const double* vals = Spcg + L.rowbase[b] + (size_t)rr_ * M;
-        const int* cols = L.colidx + L.cbase[b];
-        double s = 0.0;
-        for (int q = lane; q < M; q += 32) {
-          const int c = cols[q];
-          s += vals[q] * (ldcg_d(&z[c]) + beta * ldcg_d(&pold[c]));
-        }
+      if (RES) {
+        for (int c = threadIdx.x; c < nc; c += blockDim.x) p_s[c] = ldcg_d(&z[c]) + beta * ldcg_d(&pold[c]);
+        __syncthreads();
+        for (int t = warp; t < hi - lo; t += warps_per_cta) {
+          const double* vals = S_s + row_soff[t];
+          const unsigned short* cols = cols_s + row_coff[t];
+          const int M = row_len[t];
+          double s0 = 0.0, s1 = 0.0;
+          int q = lane;
+          for (; q + 32 < M; q += 64) {
+            s0 += vals[q] * p_s[cols[q]];
+            s1 += vals[q + 32] * p_s[cols[q + 32]];
+          }
+          if (q < M) s0 += vals[q] * p_s[cols[q]];
+          double s = s0 + s1;
 #pragma unroll
-        for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-        if (lane == 0) {
-          const double pi = ldcg_d(&z[i]) + beta * ldcg_d(&pold[i]);
-          pnew[i] = pi;
-          Ap[i] = s;
-          a_pAp += s * pi;
+          for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+          if (lane == 0) {
+            const int i = lo + t;
+            const double pi = p_s[i];
+            pnew[i] = pi;
+            Ap[i] = s;
+            a_pAp += s * pi;
+          }
+        }
+      } else {
+        for (int i = gw; i < nc; i += nw) {
+          const int b = L.row_of[i];
+          const int rr_ = i - h.blk_off[b];
+          const int M = L.row_M[b];
+          const double* vals = Spcg + L.rowbase[b] + (size_t)rr_ * M;
+          const int* cols = L.colidx + L.cbase[b];
+          double s = 0.0;
+          for (int q = lane; q < M; q += 32) {
+            const int c = cols[q];
+            s += vals[q] * (ldcg_d(&z[c]) + beta * ldcg_d(&pold[c]));
+          }
+#pragma unroll
+          for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+          if (lane == 0) {
+            const double pi = ldcg_d(&z[i]) + beta * ldcg_d(&pold[i]);
+            pnew[i] = pi;
+            Ap[i] = s;
+            a_pAp += s * pi;
+          }
         }
       }
-      if (lane == 0 && a_pAp != 0.0) atomicAdd(&st->pAp[cur], a_pAp);
-      if (gw == 0 && lane == 0) { st->rz[nxt] = 0.0; st->rr[nxt] = 0.0; st->pAp[nxt] = 0.0; }
-      grid_barrier(st, gridDim.x, bar_gen);
+      double pAp, unused;
+      grid_reduce2(st, gridDim.x, bar_gen, a_pAp, 0.0, pAp, unused, red);
       // ---- phase B: x += alpha p ; r -= alpha Ap ; z = M^-1 r ; rz_new, rr ----
-      const double alpha = ldcg_d(&st->rz[cur]) / ldcg_d(&st->pAp[cur]);
+      const double alpha = rz_cur / pAp;
       double a_rz = 0.0, a_rr = 0.0;
       for (int g = gw; g < L.ngroups; g += nw) {
         const int b1 = L.grp_b1[g], b2 = L.grp_b2[g];
@@ -999,22 +1071,14 @@ __global__ void __launch_bounds__(PCG_THREADS, 1)
         }
         pcg_apply_group(h, L, Minv, g, lane, rn, z, &a_rz, &a_rr, n, o);
       }
-#pragma unroll
-      for (int o = 16; o; o >>= 1) {
-        a_rz += __shfl_xor_sync(0xffffffffu, a_rz, o);
-        a_rr += __shfl_xor_sync(0xffffffffu, a_rr, o);
-      }
-      if (lane == 0) {
-        if (a_rz != 0.0) atomicAdd(&st->rz[nxt], a_rz);
-        if (a_rr != 0.0) atomicAdd(&st->rr[nxt], a_rr);
-      }
-      grid_barrier(st, gridDim.x, bar_gen);
-      const double rr = ldcg_d(&st->rr[nxt]);
+      double rz_new;
+      grid_reduce2(st, gridDim.x, bar_gen, a_rz, a_rr, rz_new, rr, red);
       if (!(rr == rr) || rr <= tol2) { ++it; break; }  // NaN (step will be rejected) or converged
-      beta = ldcg_d(&st->rz[nxt]) / ldcg_d(&st->rz[cur]);
+      beta = rz_new / rz_cur;
+      rz_cur = rz_new;
     }
   }
-  if (gw == 0 && lane == 0) st->iterations = it;
+  if (blockIdx.x == 0 && threadIdx.x == 0) { st->iterations = it; st->rr_final = rr; }
 }
 
 }  // namespace osfm

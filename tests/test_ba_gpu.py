@@ -231,8 +231,9 @@ def test_degenerate_inputs():
         bundle.solve(pb3)
 
 
-def test_segmented_schur_kernel_opt_in():
-    """ba_schur_seg (register-accumulated segments) must give the same solve as the default kernel."""
+def test_kernel_variants_agree():
+    """The default path (segmented Schur, S resident in shared memory during the PCG) and the generic
+    kernels it replaces (per-point ba_schur, PCG streaming S from L2) must give the same solve."""
     import os
     import subprocess
     import sys
@@ -246,11 +247,13 @@ def test_segmented_schur_kernel_opt_in():
         "np.save(sys.argv[1], np.concatenate([[r['summary']['final_cost'], r['summary']['iterations']], r['points'].ravel()]))\n"
     ) % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     out = {}
-    for flag in ("0", "1"):
-        path = "/tmp/osfm_seg_%s.npy" % flag
-        env = dict(os.environ, OSFM_BA_SEGMENT_SCHUR=flag)
+    variants = {"default": {}, "generic_schur": {"OSFM_BA_SEGMENT_SCHUR": "0"}, "streamed_pcg": {"OSFM_BA_PCG_RESIDENT": "0"}}
+    for name, extra in variants.items():
+        path = "/tmp/osfm_variant_%s.npy" % name
+        env = dict(os.environ, **extra)
         subprocess.run([sys.executable, "-c", code, path], check=True, env=env, timeout=600)
-        out[flag] = np.load(path)
-    assert out["0"][1] == out["1"][1]
-    assert abs(out["0"][0] - out["1"][0]) <= 1e-9 * out["0"][0]
-    assert np.abs(out["0"][2:] - out["1"][2:]).max() < 1e-8
+        out[name] = np.load(path)
+    for name in ("generic_schur", "streamed_pcg"):
+        assert out["default"][1] == out[name][1]
+        assert abs(out["default"][0] - out[name][0]) <= 1e-9 * out["default"][0]
+        assert np.abs(out["default"][2:] - out[name][2:]).max() < 1e-8
