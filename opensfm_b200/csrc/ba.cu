@@ -514,6 +514,10 @@ struct BA {
   PcgResident pcg_res{};
   bool pcg_resident = false;
   int pcg_smem = 0;
+  DevBuf<int> d_pcg_grplo;
+  PcgPipe pcg_pipe{};
+  bool pcg_pipe_ok = false;
+  int pcg_pipe_smem = 0, pcg_pipe_its = 0, pcg_fallbacks = 0;
   int num_sms = 148;
   DevBuf<int> d_pr_cam_param, d_pr_cam_col, d_pr_cam_log, d_pr_pos_inst, d_pr_pos_axis, d_pr_pos_col;
   DevBuf<double> d_pr_cam_prior, d_pr_cam_scale, d_pr_pos_prior, d_pr_pos_scale;
@@ -1052,6 +1056,59 @@ void BA::run() {
         OSFM_CUDA(cudaFuncSetAttribute(pcg_persistent<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, pcg_smem));
       }
     }
+    // pipelined PCG: whole preconditioner groups per CTA, balanced by stored entries
+    {
+      const int G = pcg_grid;
+      std::vector<long long> wsum(ngroups + 1, 0);
+      auto gw_of = [&](int g, long long* cols, int* rows) {
+        long long w = 0;
+        for (int k = 0; k < 2; ++k) {
+          const int b = k ? grp_b2[g] : grp_b1[g];
+          if (b < 0) continue;
+          w += (long long)blk_sz[b] * row_M[b];
+          if (cols) *cols += row_M[b];
+          if (rows) *rows += blk_sz[b];
+        }
+        return w;
+      };
+      for (int g = 0; g < ngroups; ++g) wsum[g + 1] = wsum[g] + gw_of(g, nullptr, nullptr);
+      std::vector<int> grp_lo(G + 1, ngroups);
+      grp_lo[0] = 0;
+      for (int c = 1, g = 0; c < G; ++c) {
+        const long long want = wsum[ngroups] * c / G;
+        while (g < ngroups && wsum[g] < want) ++g;
+        grp_lo[c] = g;
+      }
+      long long ent_max = 0, col_max = 0;
+      int rows_max = 0, grp_max = 0;
+      for (int c = 0; c < G; ++c) {
+        long long cols = 0;
+        int rows = 0;
+        for (int g = grp_lo[c]; g < grp_lo[c + 1]; ++g) gw_of(g, &cols, &rows);
+        ent_max = std::max(ent_max, wsum[grp_lo[c + 1]] - wsum[grp_lo[c]]);
+        col_max = std::max(col_max, cols);
+        rows_max = std::max(rows_max, rows);
+        grp_max = std::max(grp_max, grp_lo[c + 1] - grp_lo[c]);
+      }
+      auto up16 = [](long long x) { return (x + 15) / 16 * 16; };
+      const long long off_S = up16(8LL * nc), off_Minv = off_S + up16(8 * ent_max);
+      const long long off_vec = off_Minv + 8LL * grp_max * MAXB * MAXB, off_cols = off_vec + up16(16LL * rows_max);
+      const long long off_rows = off_cols + up16(2 * col_max);
+      const long long total = off_rows + 16LL * rows_max + 4LL * (grp_max + 1);
+      static const bool allow_pipe = []() { const char* e = getenv("OSFM_BA_PCG_PIPELINED"); return !(e && e[0] == '0'); }();
+      int max_smem = 0;
+      OSFM_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
+      pcg_pipe_ok = allow_pipe && nc <= 65535 && rows_max <= PCG_THREADS && ent_max < (1LL << 30) && total + 1024 <= max_smem;
+      pcg_pipe_smem = pcg_pipe_ok ? (int)total : 0;
+      pcg_pipe = PcgPipe{};
+      if (pcg_pipe_ok) {
+        upload(d_pcg_grplo, grp_lo, stream);
+        pcg_pipe.grp_lo = d_pcg_grplo.p; pcg_pipe.off_S = (int)off_S; pcg_pipe.off_Minv = (int)off_Minv;
+        pcg_pipe.off_vec = (int)off_vec; pcg_pipe.off_cols = (int)off_cols; pcg_pipe.off_rows = (int)off_rows;
+        pcg_pipe.max_rows = rows_max; pcg_pipe.max_groups = grp_max;
+        OSFM_CUDA(cudaFuncSetAttribute(pcg_pipelined, cudaFuncAttributeMaxDynamicSharedMemorySize, pcg_pipe_smem));
+      }
+    }
     OSFM_CUDA(cudaStreamSynchronize(stream));  // rowbase / cbase host vectors go out of scope
   }
   if (nblk == 0) d_Sbuf.reserve(nc_pad + 16);
@@ -1070,6 +1127,7 @@ void BA::run() {
   double decrease_factor = 2.0;
   bool reuse_diagonal = false;
   int n_invalid = 0, it = 0, n_success = 0, n_solves = 0, pcg_total = 0;
+  pcg_fallbacks = 0;
   int termination = 1;
   std::string message = "Maximum number of iterations reached.";
 
@@ -1178,17 +1236,39 @@ void BA::run() {
       OSFM_LAUNCH_CHECK();
       OSFM_CUDA(cudaMemsetAsync(d_pcg.p, 0, sizeof(PcgState), stream));
       const int max_pcg = std::min(2 * nc + 100, 5000);
-      if (pcg_resident)
-        pcg_persistent<true><<<pcg_grid, PCG_THREADS, pcg_smem, stream>>>(d_Spcg.p, lay, bsr, d_Minv.p, d_rhs_p, d_px.p, d_pr.p,
-                                                                          d_pz.p, d_pp.p, d_pAp.p, d_Ap.p, d_pcg.p, nc,
-                                                                          max_pcg, 1e-16, pcg_res);
-      else
-        pcg_persistent<false><<<pcg_grid, PCG_THREADS, 0, stream>>>(d_Spcg.p, lay, bsr, d_Minv.p, d_rhs_p, d_px.p, d_pr.p,
-                                                                    d_pz.p, d_pp.p, d_pAp.p, d_Ap.p, d_pcg.p, nc, max_pcg,
-                                                                    1e-16, pcg_res);
-      OSFM_LAUNCH_CHECK();
+      bool solved = false;
+      if (pcg_pipe_ok) {
+        pcg_pipelined<<<pcg_grid, PCG_THREADS, pcg_pipe_smem, stream>>>(d_Spcg.p, lay, bsr, d_Minv.p, d_rhs_p, d_px.p, d_pz.p,
+                                                                        d_pp.p, d_pcg.p, nc, max_pcg, 1e-16, pcg_pipe);
+        OSFM_LAUNCH_CHECK();
+        OSFM_CUDA(cudaMemcpyAsync(h_pcg.p, d_pcg.p, PCG_STATE_HEADER, cudaMemcpyDeviceToHost, stream));
+        OSFM_CUDA(cudaStreamSynchronize(stream));
+        solved = h_pcg.p->converged != 0;
+        pcg_pipe_its = h_pcg.p->iterations;
+        if (trace_on)
+          fprintf(stderr, "[osfm_ba] pipelined pcg %d its converged %d, CTA0 clocks/it: stage %lld matvec %lld reduce %lld update %lld\n",
+                  h_pcg.p->iterations, h_pcg.p->converged, h_pcg.p->prof[0] / std::max(pcg_pipe_its, 1),
+                  h_pcg.p->prof[1] / std::max(pcg_pipe_its, 1), h_pcg.p->prof[2] / std::max(pcg_pipe_its, 1),
+                  h_pcg.p->prof[3] / std::max(pcg_pipe_its, 1));
+        if (!solved) {  // stagnation / breakdown of the pipelined recurrences: classic PCG from scratch
+          pcg_total += pcg_pipe_its;
+          ++pcg_fallbacks;
+          OSFM_CUDA(cudaMemsetAsync(d_pcg.p, 0, sizeof(PcgState), stream));
+        }
+      }
+      if (!solved) {
+        if (pcg_resident)
+          pcg_persistent<true><<<pcg_grid, PCG_THREADS, pcg_smem, stream>>>(d_Spcg.p, lay, bsr, d_Minv.p, d_rhs_p, d_px.p,
+                                                                            d_pr.p, d_pz.p, d_pp.p, d_pAp.p, d_Ap.p, d_pcg.p,
+                                                                            nc, max_pcg, 1e-16, pcg_res);
+        else
+          pcg_persistent<false><<<pcg_grid, PCG_THREADS, 0, stream>>>(d_Spcg.p, lay, bsr, d_Minv.p, d_rhs_p, d_px.p, d_pr.p,
+                                                                      d_pz.p, d_pp.p, d_pAp.p, d_Ap.p, d_pcg.p, nc, max_pcg,
+                                                                      1e-16, pcg_res);
+        OSFM_LAUNCH_CHECK();
+      }
       OSFM_CUDA(cudaMemcpyAsync(d_y.p, d_px.p, sizeof(double) * nc, cudaMemcpyDeviceToDevice, stream));
-      OSFM_CUDA(cudaMemcpyAsync(h_pcg.p, d_pcg.p, sizeof(PcgState), cudaMemcpyDeviceToHost, stream));
+      OSFM_CUDA(cudaMemcpyAsync(h_pcg.p, d_pcg.p, PCG_STATE_HEADER, cudaMemcpyDeviceToHost, stream));
       tm_pcg.stop(stream);
     }
     ++n_solves;
@@ -1223,6 +1303,11 @@ void BA::run() {
       pcg_it = h_pcg.p->iterations;
       pcg_total += pcg_it;
       const double rr = h_pcg.p->rr_final;
+      if (trace_on)
+        fprintf(stderr, "[osfm_ba] pcg %d its, CTA0 clocks/it: stage %lld matvec %lld reduce1 %lld phaseB %lld reduce2 %lld (resident %d)\n",
+                pcg_it, h_pcg.p->prof[0] / std::max(pcg_it, 1), h_pcg.p->prof[1] / std::max(pcg_it, 1),
+                h_pcg.p->prof[2] / std::max(pcg_it, 1), h_pcg.p->prof[3] / std::max(pcg_it, 1),
+                h_pcg.p->prof[4] / std::max(pcg_it, 1), (int)pcg_resident);
       if (!(rr == rr)) ok = false;
     }
     const double model_change = sm.model_change;

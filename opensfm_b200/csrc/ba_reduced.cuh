@@ -853,12 +853,20 @@ __global__ void pcg_factor_groups(const double* __restrict__ Sval, BsrView h, co
 }
 
 constexpr int PCG_MAX_CTAS = 256;
+constexpr int PCG_FLAG_STRIDE = 32;
 struct PcgState {
-  unsigned flags[PCG_MAX_CTAS];        // per-CTA arrival generation
-  double slot[2][PCG_MAX_CTAS][2];     // per-CTA partial sums of the reduction riding on the barrier
+  // header: what the host reads back after a solve
   int iterations;
+  int converged;
   double rr_final;                     // |r|^2 at exit (NaN -> the step is rejected)
+  long long prof[8];                   // CTA 0 / thread 0 clock64 totals per phase (OSFM_BA_TRACE)
+  // per-CTA partial sums of the reduction riding on the barrier (double-buffered by generation parity)
+  double slot[2][PCG_MAX_CTAS][4];
+  // per-CTA arrival generation, one 128-byte line each (packed flags cost 9.3k clk per barrier,
+  // strided ones 4.4k: scripts/bench_barrier.cu)
+  unsigned flags[PCG_MAX_CTAS * PCG_FLAG_STRIDE];
 };
+constexpr size_t PCG_STATE_HEADER = offsetof(PcgState, slot);
 
 // Where the resident variant keeps things in shared memory (byte offsets; host-computed, uniform).
 struct PcgResident {
@@ -889,14 +897,14 @@ __device__ __forceinline__ void grid_reduce2(PcgState* st, unsigned nblocks, uns
     for (int w = 0; w < nwarps; ++w) { sa += red[w][0]; sb += red[w][1]; }
     __stcg(&st->slot[gen & 1][blockIdx.x][0], sa);
     __stcg(&st->slot[gen & 1][blockIdx.x][1], sb);
-    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(&st->flags[blockIdx.x]), "r"(gen) : "memory");
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(&st->flags[blockIdx.x * PCG_FLAG_STRIDE]), "r"(gen) : "memory");
   }
   double va = 0.0, vb = 0.0;
   if (threadIdx.x < nblocks) {
     const long long t0 = clock64();
     unsigned cur;
     do {
-      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(cur) : "l"(&st->flags[threadIdx.x]) : "memory");
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(cur) : "l"(&st->flags[threadIdx.x * PCG_FLAG_STRIDE]) : "memory");
       if (clock64() - t0 > 8000000000LL) __trap();  // a protocol bug must not hang the GPU
     } while (cur != gen);
     va = ldcg_d(&st->slot[gen & 1][threadIdx.x][0]);
@@ -1007,9 +1015,12 @@ __global__ void __launch_bounds__(PCG_THREADS, 1)
       double* pnew = pbuf[nxt];
       // ---- phase A: p = z + beta p_old (on the fly), Ap = S p, pAp ----
       double a_pAp = 0.0;
+      const long long tk0 = clock64();
+      long long tk1 = tk0;
       if (RES) {
         for (int c = threadIdx.x; c < nc; c += blockDim.x) p_s[c] = ldcg_d(&z[c]) + beta * ldcg_d(&pold[c]);
         __syncthreads();
+        tk1 = clock64();
         for (int t = warp; t < hi - lo; t += warps_per_cta) {
           const double* vals = S_s + row_soff[t];
           const unsigned short* cols = cols_s + row_coff[t];
@@ -1055,7 +1066,9 @@ __global__ void __launch_bounds__(PCG_THREADS, 1)
         }
       }
       double pAp, unused;
+      const long long tk2 = clock64();
       grid_reduce2(st, gridDim.x, bar_gen, a_pAp, 0.0, pAp, unused, red);
+      const long long tk3 = clock64();
       // ---- phase B: x += alpha p ; r -= alpha Ap ; z = M^-1 r ; rz_new, rr ----
       const double alpha = rz_cur / pAp;
       double a_rz = 0.0, a_rr = 0.0;
@@ -1072,13 +1085,257 @@ __global__ void __launch_bounds__(PCG_THREADS, 1)
         pcg_apply_group(h, L, Minv, g, lane, rn, z, &a_rz, &a_rr, n, o);
       }
       double rz_new;
+      const long long tk4 = clock64();
       grid_reduce2(st, gridDim.x, bar_gen, a_rz, a_rr, rz_new, rr, red);
+      if (blockIdx.x == 0 && threadIdx.x == 0) {
+        const long long tk5 = clock64();
+        st->prof[0] += tk1 - tk0; st->prof[1] += tk2 - tk1; st->prof[2] += tk3 - tk2; st->prof[3] += tk4 - tk3;
+        st->prof[4] += tk5 - tk4;
+      }
       if (!(rr == rr) || rr <= tol2) { ++it; break; }  // NaN (step will be rejected) or converged
       beta = rz_new / rz_cur;
       rz_cur = rz_new;
     }
   }
-  if (blockIdx.x == 0 && threadIdx.x == 0) { st->iterations = it; st->rr_final = rr; }
+  if (blockIdx.x == 0 && threadIdx.x == 0) { st->iterations = it; st->rr_final = rr; st->converged = (rr <= tol2) ? 1 : 0; }
+}
+
+
+// ---------------------------------------------------------------------------
+// Pipelined PCG (Ghysels & Vanroose 2014, preconditioned pipelined CG): the reduction of an
+// iteration's dot products and the exchange of the vector the next mat-vec needs ride on the SAME
+// grid barrier, so an iteration costs one barrier instead of two.  Every CTA owns whole
+// preconditioner groups: their rows of S, the groups' inverse blocks and all eight recurrence
+// vectors of those rows stay in shared memory / registers for the whole solve; the only vector that
+// moves through L2 is m = M^-1 w (nc doubles, double-buffered by iteration parity).
+// The recurrences drift from the true residual earlier than classic CG; the kernel reports
+// converged = 0 on stagnation / breakdown and the host re-solves with pcg_persistent.
+// ---------------------------------------------------------------------------
+struct PcgPipe {
+  const int* grp_lo;  // [grid + 1] group range of every CTA (balanced by stored entries)
+  int off_S, off_Minv, off_vec, off_cols, off_rows;  // byte offsets into dynamic shared memory; m at 0
+  int max_rows, max_groups;
+};
+
+__device__ __forceinline__ void grid_reduce3(PcgState* st, unsigned nblocks, unsigned& gen, double a, double b, double c,
+                                             double& A, double& B, double& C, double (*red)[3]) {
+  ++gen;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+#pragma unroll
+  for (int o = 16; o; o >>= 1) {
+    a += __shfl_xor_sync(0xffffffffu, a, o);
+    b += __shfl_xor_sync(0xffffffffu, b, o);
+    c += __shfl_xor_sync(0xffffffffu, c, o);
+  }
+  if (lane == 0) { red[warp][0] = a; red[warp][1] = b; red[warp][2] = c; }
+  __syncthreads();  // also: every global write of this CTA happens-before thread 0's release below
+  if (threadIdx.x == 0) {
+    double sa = 0.0, sb = 0.0, sc = 0.0;
+    for (int w = 0; w < nwarps; ++w) { sa += red[w][0]; sb += red[w][1]; sc += red[w][2]; }
+    double* sl = st->slot[gen & 1][blockIdx.x];
+    __stcg(reinterpret_cast<double2*>(sl), make_double2(sa, sb));
+    __stcg(sl + 2, sc);
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(&st->flags[blockIdx.x * PCG_FLAG_STRIDE]), "r"(gen) : "memory");
+  }
+  double va = 0.0, vb = 0.0, vc = 0.0;
+  if (threadIdx.x < nblocks) {
+    const long long t0 = clock64();
+    unsigned cur;
+    do {
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(cur) : "l"(&st->flags[threadIdx.x * PCG_FLAG_STRIDE]) : "memory");
+      if (clock64() - t0 > 8000000000LL) __trap();  // a protocol bug must not hang the GPU
+    } while (cur != gen);
+    const double* sl = st->slot[gen & 1][threadIdx.x];
+    const double2 ab = __ldcg(reinterpret_cast<const double2*>(sl));
+    va = ab.x; vb = ab.y;
+    vc = __ldcg(sl + 2);
+  }
+  __syncthreads();
+#pragma unroll
+  for (int o = 16; o; o >>= 1) {
+    va += __shfl_xor_sync(0xffffffffu, va, o);
+    vb += __shfl_xor_sync(0xffffffffu, vb, o);
+    vc += __shfl_xor_sync(0xffffffffu, vc, o);
+  }
+  if (lane == 0) { red[warp][0] = va; red[warp][1] = vb; red[warp][2] = vc; }
+  __syncthreads();
+  double sa = 0.0, sb = 0.0, sc = 0.0;
+  const int wmax = (int)((nblocks + 31) >> 5);
+  for (int w = 0; w < wmax; ++w) { sa += red[w][0]; sb += red[w][1]; sc += red[w][2]; }
+  A = sa; B = sb; C = sc;
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(PCG_THREADS, 1)
+    pcg_pipelined(const double* __restrict__ Spcg, PcgLayout L, BsrView h, const double* __restrict__ Minv,
+                  const double* __restrict__ rhs, double* __restrict__ x_out, double* mbuf0, double* mbuf1, PcgState* st,
+                  int nc, int max_iter, double tol2_rel, PcgPipe R) {
+  extern __shared__ __align__(16) unsigned char pcg_smem[];
+  __shared__ double red[PCG_THREADS / 32][3];
+  __shared__ int s_nrows;
+  const int nwarps = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31, tid = threadIdx.x;
+  double* m_s = reinterpret_cast<double*>(pcg_smem);
+  double* S_s = reinterpret_cast<double*>(pcg_smem + R.off_S);
+  double* Minv_s = reinterpret_cast<double*>(pcg_smem + R.off_Minv);
+  double* w_s = reinterpret_cast<double*>(pcg_smem + R.off_vec);  // input of the group solves
+  double* n_s = w_s + R.max_rows;                                  // mat-vec output / group-solve output
+  unsigned short* cols_s = reinterpret_cast<unsigned short*>(pcg_smem + R.off_cols);
+  int* row_soff = reinterpret_cast<int*>(pcg_smem + R.off_rows);
+  int* row_coff = row_soff + R.max_rows;
+  int* row_len = row_coff + R.max_rows;
+  int* row_gidx = row_len + R.max_rows;
+  int* grp_row0 = row_gidx + R.max_rows;  // [max_groups + 1]
+  double* mbuf[2] = {mbuf0, mbuf1};
+  unsigned bar_gen = 0;
+
+  const int g_lo = R.grp_lo[blockIdx.x], g_hi = R.grp_lo[blockIdx.x + 1], ng = g_hi - g_lo;
+  if (tid == 0) {
+    int lr = 0, s_off = 0, c_off = 0;
+    for (int g = g_lo; g < g_hi; ++g) {
+      grp_row0[g - g_lo] = lr;
+      for (int k = 0; k < 2; ++k) {
+        const int b = k ? L.grp_b2[g] : L.grp_b1[g];
+        if (b < 0) continue;
+        const int n = h.blk_sz[b], M = L.row_M[b];
+        for (int r = 0; r < n; ++r, ++lr) {
+          row_soff[lr] = s_off + r * M;
+          row_coff[lr] = c_off;
+          row_len[lr] = M;
+          row_gidx[lr] = h.blk_off[b] + r;
+        }
+        s_off += n * M;
+        c_off += M;
+      }
+    }
+    grp_row0[ng] = lr;
+    s_nrows = lr;
+  }
+  __syncthreads();
+  const int nrows = s_nrows;
+  for (int lr = warp; lr < nrows; lr += nwarps) {
+    const int i = row_gidx[lr], b = L.row_of[i], M = row_len[lr];
+    const double* src = Spcg + L.rowbase[b] + (long long)(i - h.blk_off[b]) * M;
+    for (int q = lane; q < M; q += 32) S_s[row_soff[lr] + q] = __ldcs(src + q);
+    if (i == h.blk_off[b]) {
+      const int* csrc = L.colidx + L.cbase[b];
+      for (int q = lane; q < M; q += 32) cols_s[row_coff[lr] + q] = (unsigned short)csrc[q];
+    }
+  }
+  for (int t = tid; t < ng * MAXB * MAXB; t += blockDim.x) Minv_s[t] = Minv[(size_t)g_lo * MAXB * MAXB + t];
+
+  // group solve: n_s[rows of g] = Minv_g * w_s[rows of g]; optionally published to a global vector
+  auto group_solve = [&](double* publish) {
+    for (int gl = warp; gl < ng; gl += nwarps) {
+      const int r0 = grp_row0[gl], n = grp_row0[gl + 1] - r0;
+      const double* M = Minv_s + gl * MAXB * MAXB;
+      double sv = 0.0;
+      if (lane < n)
+        for (int j = 0; j < n; ++j) sv += M[lane * MAXB + j] * w_s[r0 + j];
+      if (lane < n) {
+        n_s[r0 + lane] = sv;
+        if (publish) publish[row_gidx[r0 + lane]] = sv;
+      }
+    }
+  };
+  // n_s[lr] = (S m_s)[row lr]
+  auto matvec = [&]() {
+    for (int lr = warp; lr < nrows; lr += nwarps) {
+      const double* vals = S_s + row_soff[lr];
+      const unsigned short* cols = cols_s + row_coff[lr];
+      const int M = row_len[lr];
+      double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+      int q = lane;
+      for (; q + 96 < M; q += 128) {
+        const int c0 = cols[q], c1 = cols[q + 32], c2 = cols[q + 64], c3 = cols[q + 96];
+        const double v0 = vals[q], v1 = vals[q + 32], v2 = vals[q + 64], v3 = vals[q + 96];
+        s0 += v0 * m_s[c0]; s1 += v1 * m_s[c1]; s2 += v2 * m_s[c2]; s3 += v3 * m_s[c3];
+      }
+      for (; q < M; q += 32) s0 += vals[q] * m_s[cols[q]];
+      double sv = (s0 + s1) + (s2 + s3);
+#pragma unroll
+      for (int o = 16; o; o >>= 1) sv += __shfl_xor_sync(0xffffffffu, sv, o);
+      if (lane == 0) n_s[lr] = sv;
+    }
+  };
+  auto stage = [&](const double* src) {
+    int c = tid;
+    for (; c + 3 * (int)blockDim.x < nc; c += 4 * blockDim.x) {
+      const double a0 = ldcg_d(src + c), a1 = ldcg_d(src + c + blockDim.x), a2 = ldcg_d(src + c + 2 * blockDim.x),
+                   a3 = ldcg_d(src + c + 3 * blockDim.x);
+      m_s[c] = a0; m_s[c + blockDim.x] = a1; m_s[c + 2 * blockDim.x] = a2; m_s[c + 3 * blockDim.x] = a3;
+    }
+    for (; c < nc; c += blockDim.x) m_s[c] = ldcg_d(src + c);
+  };
+
+  // ---- init: x = 0, r = b, u = M^-1 r, w = S u, m = M^-1 w ----
+  const bool mine = tid < nrows;
+  const int gi = mine ? row_gidx[tid] : 0;
+  double xr = 0.0, rr_ = mine ? rhs[gi] : 0.0, u = 0.0, w = 0.0, z = 0.0, q = 0.0, sv_ = 0.0, p = 0.0;
+  if (mine) w_s[tid] = rr_;
+  __syncthreads();
+  group_solve(mbuf[0]);
+  double d0, d1, d2;
+  grid_reduce3(st, gridDim.x, bar_gen, 0.0, 0.0, mine ? rr_ * rr_ : 0.0, d0, d1, d2, red);
+  const double bb = d2;
+  const double tol2 = tol2_rel * bb;
+  double rr = bb;
+  int it = 0, converged = 0;
+  if (bb > 0.0) {
+    if (mine) u = n_s[tid];
+    stage(mbuf[0]);
+    __syncthreads();
+    matvec();
+    __syncthreads();
+    if (mine) { w = n_s[tid]; w_s[tid] = w; }
+    __syncthreads();
+    group_solve(mbuf[1]);
+    double gamma_prev = 1.0, alpha_prev = 1.0, best = bb;
+    int since_best = 0;
+    for (;; ++it) {
+      const long long tk0 = clock64();
+      double gamma, delta;
+      grid_reduce3(st, gridDim.x, bar_gen, mine ? rr_ * u : 0.0, mine ? w * u : 0.0, mine ? rr_ * rr_ : 0.0, gamma, delta, rr,
+                   red);
+      const long long tk1 = clock64();
+      if (!(rr == rr)) break;
+      if (rr <= tol2) { converged = 1; break; }
+      if (rr < best) { best = rr; since_best = 0; } else if (++since_best > 150) break;  // stagnation
+      if (it >= max_iter) break;
+      const double* mcur = mbuf[(it + 1) & 1];
+      stage(mcur);
+      __syncthreads();
+      const long long tk2 = clock64();
+      matvec();
+      __syncthreads();
+      const long long tk3 = clock64();
+      const double beta = it > 0 ? gamma / gamma_prev : 0.0;
+      const double alpha = it > 0 ? gamma / (delta - beta * gamma / alpha_prev) : gamma / delta;
+      if (mine) {
+        const double mo = m_s[gi], nn = n_s[tid];
+        z = nn + beta * z;
+        q = mo + beta * q;
+        sv_ = w + beta * sv_;
+        p = u + beta * p;
+        xr += alpha * p;
+        rr_ -= alpha * sv_;
+        u -= alpha * q;
+        w -= alpha * z;
+        w_s[tid] = w;
+      }
+      __syncthreads();
+      group_solve(mbuf[it & 1]);
+      gamma_prev = gamma;
+      alpha_prev = alpha;
+      if (blockIdx.x == 0 && tid == 0) {
+        const long long tk4 = clock64();
+        st->prof[0] += tk2 - tk1; st->prof[1] += tk3 - tk2; st->prof[2] += tk1 - tk0; st->prof[3] += tk4 - tk3;
+      }
+    }
+  } else {
+    converged = 1;
+  }
+  if (mine) x_out[gi] = xr;
+  if (blockIdx.x == 0 && tid == 0) { st->iterations = it; st->rr_final = rr; st->converged = converged; }
 }
 
 }  // namespace osfm
