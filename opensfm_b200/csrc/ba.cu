@@ -221,8 +221,9 @@ __global__ void ba_prior_cost(PriorView pv, Params p, Scalars* sc) {
 }
 
 // Squared column norms and gradient of the (unscaled, robustified) Jacobian.
-__global__ void __launch_bounds__(256) ba_colnorm_grad(BAView v, double* colnorm2, double* grad) {
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+// (camera-side columns of the observations i >= i0: the ones no segment covers)
+__global__ void __launch_bounds__(256) ba_colnorm_grad(BAView v, long long i0, double* colnorm2, double* grad) {
+  const long long i = i0 + (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= v.N) return;
   const size_t N = (size_t)v.N;
   const ObsCols oc = obs_cols(v, i);
@@ -240,18 +241,118 @@ __global__ void __launch_bounds__(256) ba_colnorm_grad(BAView v, double* colnorm
     atomicAdd(&colnorm2[g], n2);
     atomicAdd(&grad[g], gr);
   }
-  const int pf = v.pt_poff[v.obs_point[i]];
-  if (pf >= 0) {
+}
+
+// Segmented sum over lanes holding consecutive observations of the same point (observations are
+// sorted by point): after the call the LAST lane of every run holds the run's total.
+template <int NV>
+__device__ __forceinline__ void seg_scan_by_point(int pt, double (&val)[NV]) {
+  const int lane = threadIdx.x & 31;
 #pragma unroll
-    for (int j = 0; j < 3; ++j) {
-      double n2 = 0.0, gr = 0.0;
-      for (int k = 0; k < v.nres; ++k) {
+  for (int o = 1; o < 32; o <<= 1) {
+    const int other = __shfl_up_sync(0xffffffffu, pt, o);
+    const bool take = lane >= o && other == pt;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      const double up = __shfl_up_sync(0xffffffffu, val[k], o);
+      if (take) val[k] += up;
+    }
+  }
+}
+
+// Point-side columns: one thread per observation (coalesced plane reads), run totals by shuffles,
+// one atomic per (run, column) -- a run is cut only at warp boundaries.
+__global__ void __launch_bounds__(256) ba_colnorm_grad_points(BAView v, double* colnorm2, double* grad) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t N = (size_t)v.N;
+  const bool in = i < v.N;
+  const int pt = in ? v.obs_point[i] : -1;
+  double val[6] = {0, 0, 0, 0, 0, 0};
+  if (in) {
+    for (int k = 0; k < v.nres; ++k) {
+      const double rk = v.r[k * N + i];
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
         const double a = v.Jp[((size_t)k * 3 + j) * N + i];
-        n2 += a * a;
-        gr += a * r[k];
+        val[j] += a * a;
+        val[3 + j] += a * rk;
       }
-      atomicAdd(&colnorm2[v.nc + 3 * pf + j], n2);
-      atomicAdd(&grad[v.nc + 3 * pf + j], gr);
+    }
+  }
+  seg_scan_by_point<6>(pt, val);
+  const int next = __shfl_down_sync(0xffffffffu, pt, 1);
+  const bool tail = (threadIdx.x & 31) == 31 || next != pt;
+  if (in && tail) {
+    const int pf = v.pt_poff[pt];
+    if (pf >= 0) {
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        atomicAdd(&colnorm2[v.nc + 3 * pf + j], val[j]);
+        atomicAdd(&grad[v.nc + 3 * pf + j], val[3 + j]);
+      }
+    }
+  }
+}
+
+// Camera-side columns of the segments (points seen by exactly the same k shots, ba_order.cuh): one
+// warp per segment, lane = (point slot g, shot c) so that a lane always works on the same shot; the
+// running sums stay in registers and a segment issues k * wc atomics instead of points * k * wc.
+template <int WCT>
+__global__ void __launch_bounds__(256) ba_colnorm_grad_seg(BAView v, const int* __restrict__ seg_start, int nseg,
+                                                           double* colnorm2, double* grad) {
+  const int s = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (s >= nseg) return;
+  const int lane = threadIdx.x & 31;
+  const int p0 = seg_start[s], np = seg_start[s + 1] - p0;
+  const long long base = v.pt_start[p0];
+  const int k = (int)(v.pt_start[p0 + 1] - base);
+  const int G = 32 / k;
+  const int g = lane / k, c = lane - g * k;
+  const bool active = g < G;
+  const size_t N = (size_t)v.N;
+  const int wc = WCT ? WCT : v.wc;
+  constexpr int WCU = WCT ? WCT : 16;
+  double n2[WCU], gr[WCU];
+#pragma unroll
+  for (int j = 0; j < WCU; ++j) { n2[j] = 0.0; gr[j] = 0.0; }
+  if (active) {
+    for (int pi = g; pi < np; pi += G) {
+      const size_t i = (size_t)(base + (long long)pi * k + c);
+      for (int q = 0; q < v.nres; ++q) {
+        const double rq = v.r[q * N + i];
+#pragma unroll
+        for (int j = 0; j < WCU; ++j) {
+          if (j < wc) {
+            const double a = v.Jc[((size_t)q * wc + j) * N + i];
+            n2[j] += a * a;
+            gr[j] += a * rq;
+          }
+        }
+      }
+    }
+  }
+  // lanes c, c + k, c + 2k, ... hold partial sums of the same shot
+  for (int gg = 1; gg < G; ++gg) {
+#pragma unroll
+    for (int j = 0; j < WCU; ++j) {
+      if (j < wc) {
+        const double a = __shfl_down_sync(0xffffffffu, n2[j], gg * k);
+        const double b = __shfl_down_sync(0xffffffffu, gr[j], gg * k);
+        if (lane < k) { n2[j] += a; gr[j] += b; }
+      }
+    }
+  }
+  if (lane < k) {
+    const ObsCols oc = obs_cols(v, base + c);
+#pragma unroll
+    for (int j = 0; j < WCU; ++j) {
+      if (j < wc) {
+        const int col = oc.col(j);
+        if (col >= 0) {
+          atomicAdd(&colnorm2[col], n2[j]);
+          atomicAdd(&grad[col], gr[j]);
+        }
+      }
     }
   }
 }
@@ -290,20 +391,21 @@ __global__ void ba_grad_max(const double* grad, int n, Scalars* sc) {
 namespace osfm {
 
 // ---------------------------------------------------------------------------
-// Back-substitution: y_p = V^-1 (g_p - W^T y_c)  (scaled system), one warp per point.
+// Back-substitution: y_p = V^-1 (g_p - W^T y_c)  (scaled system).
+// ba_backsub_rows: one thread per observation (coalesced plane reads) computes its share of
+// g_p - W^T y_c, run totals by shuffles, one atomic per (run, coordinate) into t[3][npf];
+// ba_backsub_points: one thread per point applies V^-1.
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) ba_backsub(BAView v, const double* __restrict__ scale,
-                                                  const double* __restrict__ Vinv, double* __restrict__ y) {
-  const int p = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  const int lane = threadIdx.x & 31;
-  if (p >= v.P) return;
-  const int pf = v.pt_poff[p];
-  if (pf < 0) return;
+__global__ void __launch_bounds__(256) ba_backsub_rows(BAView v, const double* __restrict__ scale,
+                                                       const double* __restrict__ y, double* __restrict__ t) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const size_t N = (size_t)v.N;
-  const int nc = v.nc, wc = v.wc;
-  const double sp0 = scale[nc + 3 * pf], sp1 = scale[nc + 3 * pf + 1], sp2 = scale[nc + 3 * pf + 2];
-  double t0 = 0.0, t1 = 0.0, t2 = 0.0;
-  for (long long i = v.pt_start[p] + lane; i < v.pt_start[p + 1]; i += 32) {
+  const bool in = i < v.N;
+  const int pt = in ? v.obs_point[i] : -1;
+  const int pf = in ? v.pt_poff[pt] : -1;
+  double val[3] = {0.0, 0.0, 0.0};
+  if (pf >= 0) {
+    const int wc = v.wc;
     const ObsCols oc = obs_cols(v, i);
     for (int q = 0; q < v.nres; ++q) {
       double e = v.r[q * N + i];
@@ -311,25 +413,33 @@ __global__ void __launch_bounds__(256) ba_backsub(BAView v, const double* __rest
         const int g = oc.col(j);
         if (g >= 0) e -= v.Jc[((size_t)q * wc + j) * N + i] * scale[g] * y[g];
       }
-      t0 += v.Jp[((size_t)q * 3 + 0) * N + i] * sp0 * e;
-      t1 += v.Jp[((size_t)q * 3 + 1) * N + i] * sp1 * e;
-      t2 += v.Jp[((size_t)q * 3 + 2) * N + i] * sp2 * e;
+#pragma unroll
+      for (int j = 0; j < 3; ++j) val[j] += v.Jp[((size_t)q * 3 + j) * N + i] * e;
     }
   }
-#pragma unroll
-  for (int o = 16; o; o >>= 1) {
-    t0 += __shfl_xor_sync(0xffffffffu, t0, o);
-    t1 += __shfl_xor_sync(0xffffffffu, t1, o);
-    t2 += __shfl_xor_sync(0xffffffffu, t2, o);
-  }
-  if (lane == 0) {
+  seg_scan_by_point<3>(pt, val);
+  const int next = __shfl_down_sync(0xffffffffu, pt, 1);
+  const bool tail = (threadIdx.x & 31) == 31 || next != pt;
+  if (pf >= 0 && tail) {
     const size_t NP = (size_t)v.npf;
-    const double a = Vinv[0 * NP + pf], b = Vinv[1 * NP + pf], c = Vinv[2 * NP + pf];
-    const double d = Vinv[3 * NP + pf], e = Vinv[4 * NP + pf], f = Vinv[5 * NP + pf];
-    y[nc + 3 * pf + 0] = a * t0 + b * t1 + c * t2;
-    y[nc + 3 * pf + 1] = b * t0 + d * t1 + e * t2;
-    y[nc + 3 * pf + 2] = c * t0 + e * t1 + f * t2;
+#pragma unroll
+    for (int j = 0; j < 3; ++j) atomicAdd(&t[j * NP + pf], val[j]);
   }
+}
+__global__ void __launch_bounds__(256) ba_backsub_points(BAView v, const double* __restrict__ scale,
+                                                         const double* __restrict__ Vinv, const double* __restrict__ t,
+                                                         double* __restrict__ y) {
+  const int pf = blockIdx.x * blockDim.x + threadIdx.x;
+  if (pf >= v.npf) return;
+  const size_t NP = (size_t)v.npf;
+  const int nc = v.nc;
+  const double t0 = t[pf] * scale[nc + 3 * pf], t1 = t[NP + pf] * scale[nc + 3 * pf + 1],
+               t2 = t[2 * NP + pf] * scale[nc + 3 * pf + 2];
+  const double a = Vinv[0 * NP + pf], b = Vinv[1 * NP + pf], c = Vinv[2 * NP + pf];
+  const double d = Vinv[3 * NP + pf], e = Vinv[4 * NP + pf], f = Vinv[5 * NP + pf];
+  y[nc + 3 * pf + 0] = a * t0 + b * t1 + c * t2;
+  y[nc + 3 * pf + 1] = b * t0 + d * t1 + e * t2;
+  y[nc + 3 * pf + 2] = c * t0 + e * t1 + f * t2;
 }
 
 // Ceres: model_cost_change = -sum m (r + m/2), m = Js step ; step = -y
@@ -483,7 +593,7 @@ struct BA {
   DevBuf<long long> d_obs_orig, d_pt_start;
   DevBuf<double> d_cam[2], d_inst[2], d_rc[2], d_pts[2];
   DevBuf<double> d_r, d_Jc, d_Jp, d_Sbuf, d_Vinv, d_gp, d_slots;
-  DevBuf<double> d_scale, d_colnorm2, d_grad, d_diag, d_y;
+  DevBuf<double> d_scale, d_colnorm2, d_grad, d_diag, d_y, d_bs_t;
   DevBuf<double> d_px, d_pr, d_pz, d_pp, d_pAp, d_Minv, d_reproj, d_full_pts;
   DevBuf<int> d_blk_off, d_blk_sz, d_cam_blk, d_inst_blk, d_rc_blk;
   // block-sparse reduced system (ba_reduced.cuh)
@@ -744,6 +854,9 @@ void BA::run() {
   const int nseg = h_oc.p->nseg, P_fast = h_oc.p->p_fast;
   const long long n_fast_obs = h_oc.p->n_fast;
   const long long pair_bound_all = (long long)h_oc.p->pair_bound;
+  if (trace_on)
+    fprintf(stderr, "[osfm_ba] points %d (fast path %d in %d segments), observations %lld (fast path %lld), free points %d\n", P,
+            P_fast, nseg, N, n_fast_obs, npf);
 
   trace("sort");
   // ---- prior rows (rank 0 adds them; Ceres drops residuals of constant blocks) ----
@@ -864,8 +977,19 @@ void BA::run() {
       ba_linearize<1><<<grid_for(N, 128), 128, 0, stream>>>(v, params_of(b), d_sc.p, nullptr);
       OSFM_LAUNCH_CHECK();
       tm_lin.stop(stream);
-      ba_colnorm_grad<<<grid_for(N, 256), 256, 0, stream>>>(v, d_colnorm2.p, d_grad.p);
+      ba_colnorm_grad_points<<<grid_for(N, 256), 256, 0, stream>>>(v, d_colnorm2.p, d_grad.p);
       OSFM_LAUNCH_CHECK();
+      if (nseg > 0) {
+        if (wc == 9)
+          ba_colnorm_grad_seg<9><<<grid_for((long long)nseg * 32, 256), 256, 0, stream>>>(v, d_seg_start.p, nseg, d_colnorm2.p, d_grad.p);
+        else
+          ba_colnorm_grad_seg<0><<<grid_for((long long)nseg * 32, 256), 256, 0, stream>>>(v, d_seg_start.p, nseg, d_colnorm2.p, d_grad.p);
+        OSFM_LAUNCH_CHECK();
+      }
+      if (N > n_fast_obs) {
+        ba_colnorm_grad<<<grid_for(N - n_fast_obs, 256), 256, 0, stream>>>(v, n_fast_obs, d_colnorm2.p, d_grad.p);
+        OSFM_LAUNCH_CHECK();
+      }
     }
     if (npr_local > 0) {
       ba_prior_cost<<<grid_for(npr_local, 128), 128, 0, stream>>>(pv, params_of(b), d_sc.p);
@@ -1275,7 +1399,11 @@ void BA::run() {
     // --- back-substitution, model cost change ---
     if (P > 0 && npf > 0) {
       tm_back.start(stream);
-      ba_backsub<<<grid_for((long long)P * 32, 256), 256, 0, stream>>>(v, d_scale.p, d_Vinv.p, d_y.p);
+      d_bs_t.reserve(3 * (size_t)npf);
+      OSFM_CUDA(cudaMemsetAsync(d_bs_t.p, 0, sizeof(double) * 3 * (size_t)npf, stream));
+      ba_backsub_rows<<<grid_for(N, 256), 256, 0, stream>>>(v, d_scale.p, d_y.p, d_bs_t.p);
+      OSFM_LAUNCH_CHECK();
+      ba_backsub_points<<<grid_for(npf, 256), 256, 0, stream>>>(v, d_scale.p, d_Vinv.p, d_bs_t.p, d_y.p);
       OSFM_LAUNCH_CHECK();
       tm_back.stop(stream);
     }
