@@ -63,6 +63,11 @@ int osfm_bf_match_u8(osfm_matcher* m, const uint8_t* f1, int n1, const uint8_t* 
  * uploaded once; a pair list is matched in one submission. */
 int osfm_matcher_add_f32(osfm_matcher* m, const float* desc, int n, int dim, int* out_id);
 int osfm_matcher_add_u8(osfm_matcher* m, const uint8_t* desc, int n, int nbytes, int* out_id);
+/* Upload `count` descriptor matrices (desc[i] is n[i] x dim) with one host synchronisation at the end:
+ * the per-image loop of matching.match_images_with_pairs loading features (matching.py:70-82). */
+int osfm_matcher_add_batch_f32(osfm_matcher* m, int count, const float* const* desc, const int* n, int dim, int* out_ids);
+int osfm_matcher_add_batch_u8(osfm_matcher* m, int count, const uint8_t* const* desc, const int* n, int nbytes,
+                              int* out_ids);
 int osfm_matcher_remove(osfm_matcher* m, int id);
 int osfm_matcher_clear(osfm_matcher* m);
 /* Enqueue matching of npairs pairs (ids_a[p], ids_b[p]).  Results stay on the

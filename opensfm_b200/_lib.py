@@ -42,6 +42,8 @@ SIGNATURES = {
     "osfm_bf_match_u8": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_double, c_void_p, c_int, c_void_p]),
     "osfm_matcher_add_f32": (c_int, [c_void_p, c_void_p, c_int, c_int, POINTER(c_int)]),
     "osfm_matcher_add_u8": (c_int, [c_void_p, c_void_p, c_int, c_int, POINTER(c_int)]),
+    "osfm_matcher_add_batch_f32": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p]),
+    "osfm_matcher_add_batch_u8": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p]),
     "osfm_matcher_remove": (c_int, [c_void_p, c_int]),
     "osfm_matcher_clear": (c_int, [c_void_p]),
     "osfm_matcher_match_pairs_async": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_double, c_int]),

@@ -58,12 +58,16 @@ def _p(a: np.ndarray):
 
 
 def solve(pb: bp.BAProblem, device: int = 0, rank: int = 0, world: int = 1, allreduce=None,
-          stream: Optional[int] = None, compute_reprojection_errors: bool = True) -> Dict[str, Any]:
+          stream: Optional[int] = None, compute_reprojection_errors: bool = True,
+          out: Optional[Dict[str, np.ndarray]] = None) -> Dict[str, Any]:
     """Run the GPU bundle adjustment on a BAProblem.  Returns updated parameter arrays,
     unscaled reprojection errors (bundle_adjuster.cc:1196-1208) and the run summary.
 
     Multi-GPU: pass rank/world and `allreduce(ptr:int, count:int, stream:int) -> None`
-    that sums `count` float64 at device pointer `ptr` across ranks (see opensfm_b200.dist)."""
+    that sums `count` float64 at device pointer `ptr` across ranks (see opensfm_b200.dist).
+
+    `out` may hold preallocated C-contiguous float64 arrays "points" (P, 3) and "reprojection_errors"
+    (N, 3) to receive the results (page-locked buffers make the device->host copy a plain DMA)."""
     pb.validate()
     L = _lib.load()
     h = _handle(int(device)).h
@@ -115,8 +119,18 @@ def solve(pb: bp.BAProblem, device: int = 0, rank: int = 0, world: int = 1, allr
         cam = np.zeros_like(keep[1])
         inst = np.zeros((NI, 6))
         rc = np.zeros((NR, 6))
-        pts = np.zeros((P, 3))
-        rep = np.empty((N, 3)) if compute_reprojection_errors else np.zeros((N, 3))
+        def _out(name, shape):
+            a = out.get(name) if out else None
+            if a is None:
+                return np.empty(shape)
+            if a.shape != shape or a.dtype != np.float64 or not a.flags.c_contiguous:
+                raise ValueError("out[%r] must be a C-contiguous float64 array of shape %r" % (name, shape))
+            return a
+
+        pts = _out("points", (P, 3))
+        rep = _out("reprojection_errors", (N, 3))
+        if not compute_reprojection_errors:
+            rep[:] = 0.0
         _lib.check(L.osfm_ba_get_cameras(h, _p(cam)))
         _lib.check(L.osfm_ba_get_rig_instances(h, _p(inst)))
         _lib.check(L.osfm_ba_get_rig_cameras(h, _p(rc)))

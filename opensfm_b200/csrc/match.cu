@@ -207,20 +207,75 @@ Matcher::Matcher(int dev) : device(dev) {
 
 Matcher::~Matcher() {
   cudaSetDevice(device);
-  for (auto& kv : sets) free_set(kv.second);
+  cudaStreamSynchronize(stream);
+  for (auto& sl : slabs) cudaFree(sl.base);
   for (auto& e : ev) cudaEventDestroy(e);
   cudaStreamDestroy(stream);
 }
 
+void* Matcher::slab_alloc(size_t bytes, int* slab_idx) {
+  bytes = (bytes + 255) / 256 * 256;
+  for (size_t i = 0; i < slabs.size(); ++i) {
+    Slab& sl = slabs[i];
+    if (sl.cap - sl.used >= bytes) {
+      void* p = sl.base + sl.used;
+      sl.used += bytes;
+      ++sl.live;
+      *slab_idx = (int)i;
+      return p;
+    }
+  }
+  // 16 MB first, doubling up to 512 MB: one-shot matchers stay small, resident image sets need few cudaMallocs
+  size_t cap = (size_t)16 << 20;
+  for (size_t i = 0; i < slabs.size() && cap < ((size_t)512 << 20); ++i) cap *= 2;
+  cap = std::max(cap, bytes);
+  Slab sl;
+  OSFM_CUDA(cudaMalloc(&sl.base, cap));
+  sl.cap = cap;
+  sl.used = bytes;
+  sl.live = 1;
+  slabs.push_back(sl);
+  *slab_idx = (int)slabs.size() - 1;
+  return sl.base;
+}
+
+void Matcher::slab_release(int idx) {
+  if (idx < 0) return;
+  Slab& sl = slabs[idx];
+  if (--sl.live == 0) sl.used = 0;  // callers synchronise the stream before releasing
+}
+
+// exactness flags / max norms of the sets added since the last call (one D2H copy for all of them)
+void Matcher::refresh_info() {
+  if (pending.empty()) return;
+  h_info.resize(2 * (size_t)next_slot);
+  OSFM_CUDA(cudaMemcpyAsync(h_info.data(), d_info.p, sizeof(int) * 2 * (size_t)next_slot, cudaMemcpyDeviceToHost, stream));
+  OSFM_CUDA(cudaStreamSynchronize(stream));
+  for (int id : pending) {
+    auto it = sets.find(id);
+    if (it == sets.end() || !it->second.info_pending) continue;
+    DescSet& s = it->second;
+    s.tc_ok = h_info[2 * s.slot] == 0;
+    std::memcpy(&s.tc_max_norm, &h_info[2 * s.slot + 1], sizeof(float));
+    s.info_pending = false;
+  }
+  pending.clear();
+}
+
 void Matcher::free_set(DescSet& s) {
-  if (s.data) cudaFree(s.data);
-  if (s.tc_data) cudaFree(s.tc_data);
+  slab_release(s.slab);
+  if (s.slot >= 0) {
+    cudaMemsetAsync(d_info.p + 2 * s.slot, 0, 2 * sizeof(int), stream);
+    free_slots.push_back(s.slot);
+  }
   s.data = nullptr;
   s.tc_data = nullptr;
   s.tc_ok = false;
+  s.slab = -1;
+  s.slot = -1;
 }
 
-int Matcher::add(const void* host, int n, int dim, bool u8) {
+int Matcher::add_async(const void* host, int n, int dim, bool u8) {
   if (n < 0 || dim <= 0) throw ArgError("descriptor matrix must be n x dim with dim > 0");
   if (!host && n > 0) throw ArgError("null descriptor pointer");
   OSFM_CUDA(cudaSetDevice(device));
@@ -231,27 +286,57 @@ int Matcher::add(const void* host, int n, int dim, bool u8) {
   const size_t esz = u8 ? 1 : 4;
   // padded row length in bytes: multiple of DK elements (64 B for both types)
   const int row_bytes = (int)(((size_t)dim * esz + 63) / 64 * 64);
-  s.dim_padded = row_bytes / (u8 ? 4 : 4);  // in 4-byte elements
+  s.dim_padded = row_bytes / 4;  // in 4-byte elements
   s.row_bytes = row_bytes;
-  const size_t bytes = (size_t)std::max(n, 1) * row_bytes;
-  OSFM_CUDA(cudaMalloc(&s.data, bytes));
+  const bool tc = tc_capable(dim, u8, n);
+  const size_t data_bytes = ((size_t)std::max(n, 1) * row_bytes + 255) / 256 * 256;
+  s.rows_padded = tc ? tc_rows_padded(n) : 0;
+  const size_t tc_bytes = tc ? tc_operand_bytes(s.rows_padded) : 0;
+  char* chunk = static_cast<char*>(slab_alloc(data_bytes + tc_bytes, &s.slab));
+  s.data = chunk;
+  s.tc_data = tc ? chunk + data_bytes : nullptr;
+  if (tc) {
+    if (d_info.p == nullptr) {
+      d_info.reserve(2 * (size_t)MAX_SLOTS);
+      OSFM_CUDA(cudaMemsetAsync(d_info.p, 0, sizeof(int) * 2 * (size_t)MAX_SLOTS, stream));
+    }
+    if (!free_slots.empty()) { s.slot = free_slots.back(); free_slots.pop_back(); }
+    else if (next_slot < MAX_SLOTS) s.slot = next_slot++;
+    else { slab_release(s.slab); throw std::runtime_error("too many resident descriptor sets"); }
+  }
   if (n > 0) {
-    staging.reserve((size_t)n * dim * esz);
-    OSFM_CUDA(cudaMemcpyAsync(staging.p, host, (size_t)n * dim * esz, cudaMemcpyHostToDevice, stream));
-    const size_t total = (size_t)n * row_bytes / esz;
-    const int threads = 256;
-    const unsigned blocks = (unsigned)((total + threads - 1) / threads);
-    if (u8)
-      pad_rows_kernel<uint8_t><<<blocks, threads, 0, stream>>>(staging.p, n, dim, (uint8_t*)s.data, row_bytes);
-    else
-      pad_rows_kernel<float><<<blocks, threads, 0, stream>>>((const float*)staging.p, n, dim, (float*)s.data,
-                                                             row_bytes / 4);
-    OSFM_LAUNCH_CHECK();
-    if (!u8) prepare_tc(s);  // bf16 operand copy + exactness flag (match_tc.cu)
-    OSFM_CUDA(cudaStreamSynchronize(stream));
+    const bool dense = (size_t)dim * esz == (size_t)row_bytes;  // the upload already is the padded copy
+    const void* src = s.data;
+    if (dense) {
+      OSFM_CUDA(cudaMemcpyAsync(s.data, host, (size_t)n * row_bytes, cudaMemcpyHostToDevice, stream));
+    } else {
+      staging.reserve(std::max<size_t>((size_t)n * dim * esz, (size_t)4 << 20));
+      OSFM_CUDA(cudaMemcpyAsync(staging.p, host, (size_t)n * dim * esz, cudaMemcpyHostToDevice, stream));
+      src = staging.p;
+    }
+    if (tc) {
+      // one fused pass: padded copy (if needed) + exactness + norms + bf16 operands (match_tc.cu)
+      prepare_tc(s, static_cast<const float*>(src), dense ? nullptr : static_cast<float*>(s.data));
+    } else if (!dense) {
+      const size_t total = (size_t)n * row_bytes / esz;
+      const int threads = 256;
+      const unsigned blocks = (unsigned)((total + threads - 1) / threads);
+      if (u8)
+        pad_rows_kernel<uint8_t><<<blocks, threads, 0, stream>>>(staging.p, n, dim, (uint8_t*)s.data, row_bytes);
+      else
+        pad_rows_kernel<float><<<blocks, threads, 0, stream>>>((const float*)staging.p, n, dim, (float*)s.data, row_bytes / 4);
+      OSFM_LAUNCH_CHECK();
+    }
   }
   const int id = next_id++;
   sets[id] = s;
+  if (s.info_pending) pending.push_back(id);
+  return id;
+}
+
+int Matcher::add(const void* host, int n, int dim, bool u8) {
+  const int id = add_async(host, n, dim, u8);
+  OSFM_CUDA(cudaStreamSynchronize(stream));  // the caller may reuse its buffer
   return id;
 }
 
@@ -274,6 +359,7 @@ void Matcher::clear() {
 void Matcher::match_pairs_async(int npairs, const int* ids_a, const int* ids_b, double ratio, bool symmetric,
                                 const uint8_t* dmask) {
   OSFM_CUDA(cudaSetDevice(device));
+  refresh_info();
   if (npairs < 0) throw ArgError("npairs < 0");
   if (npairs > 30000) throw ArgError("at most 30000 pairs per submission");
   const int ndir = symmetric ? 2 : 1;
@@ -527,6 +613,29 @@ int osfm_matcher_add_u8(osfm_matcher* m, const uint8_t* desc, int n, int nbytes,
   if (!out_id) throw osfm::ArgError("null out_id");
   *out_id = m->impl.add(desc, n, nbytes, true);
   OSFM_API_END
+}
+
+static int add_batch(osfm_matcher* m, int count, const void* const* desc, const int* n, int dim, bool u8, int* out_ids) {
+  OSFM_API_BEGIN
+  OSFM_M_LOCK
+  if (count < 0 || (count > 0 && (!desc || !n || !out_ids))) throw osfm::ArgError("bad batch arguments");
+  int done = 0;
+  try {
+    for (; done < count; ++done) out_ids[done] = m->impl.add_async(desc[done], n[done], dim, u8);
+    OSFM_CUDA(cudaStreamSynchronize(m->impl.stream));
+  } catch (...) {
+    cudaStreamSynchronize(m->impl.stream);
+    for (int i = 0; i < done; ++i) m->impl.remove(out_ids[i]);
+    throw;
+  }
+  OSFM_API_END
+}
+int osfm_matcher_add_batch_f32(osfm_matcher* m, int count, const float* const* desc, const int* n, int dim, int* out_ids) {
+  return add_batch(m, count, reinterpret_cast<const void* const*>(desc), n, dim, false, out_ids);
+}
+int osfm_matcher_add_batch_u8(osfm_matcher* m, int count, const uint8_t* const* desc, const int* n, int nbytes,
+                              int* out_ids) {
+  return add_batch(m, count, reinterpret_cast<const void* const*>(desc), n, nbytes, true, out_ids);
 }
 
 int osfm_matcher_remove(osfm_matcher* m, int id) {

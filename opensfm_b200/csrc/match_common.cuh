@@ -74,6 +74,16 @@ struct DescSet {
   bool tc_ok = false;
   float tc_max_norm = 0.0f;  // max_i |x_i|^2
   int rows_padded = 0;
+  // device memory comes from the matcher's slabs; the exactness flag / max norm of a freshly added set
+  // live in d_info[slot] until refresh_info() reads them back (no host sync per add)
+  int slab = -1, slot = -1;
+  bool info_pending = false;
+};
+
+struct Slab {
+  char* base = nullptr;
+  size_t cap = 0, used = 0;
+  int live = 0;
 };
 
 struct Matcher {
@@ -107,6 +117,16 @@ struct Matcher {
   Matcher(const Matcher&) = delete;
   Matcher& operator=(const Matcher&) = delete;
 
+  std::vector<Slab> slabs;
+  DevBuf<int> d_info;                 // [MAX_SLOTS][2]: not-exact flag, max |x|^2 (float bits)
+  std::vector<int> h_info;
+  std::vector<int> free_slots, pending;
+  int next_slot = 0;
+  static constexpr int MAX_SLOTS = 1 << 16;
+  void* slab_alloc(size_t bytes, int* slab_idx);
+  void slab_release(int idx);
+  void refresh_info();
+  int add_async(const void* host, int n, int dim, bool u8);  // no host sync; the host buffer must stay valid
   int add(const void* host, int n, int dim, bool u8);
   void remove(int id);
   void clear();
@@ -119,7 +139,7 @@ struct Matcher {
   void one_shot(const void* f1, int n1, const void* f2, int n2, int dim, bool u8, double ratio,
                 const uint8_t* mask, bool symmetric, int32_t* out);
   // match_tc.cu
-  void prepare_tc(DescSet& s);
+  void prepare_tc(DescSet& s, const float* src, float* padded_dst);
 };
 
 // match_tc.cu
@@ -127,5 +147,8 @@ bool tc_available();
 int tc_tile_m();
 int tc_tile_n();
 void launch_tc(Matcher& m, int njobs, int ntiles);
+int tc_rows_padded(int n);
+size_t tc_operand_bytes(int rows_padded);
+bool tc_capable(int dim, bool u8, int n);
 
 }  // namespace osfm

@@ -63,124 +63,106 @@ bool tc_available() {
 // ---------------------------------------------------------------------------
 // Operand preparation
 // ---------------------------------------------------------------------------
-// flags[0] |= 1 if any value is not an integer in [0,255]
-__global__ void tc_check_exact(const float* __restrict__ src, size_t count, int* __restrict__ flags) {
-  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  bool bad = false;
-  if (i < count) {
-    const float v = src[i];
-    bad = !(v >= 0.0f && v <= 255.0f && v == floorf(v));
-  }
-  if (__syncthreads_or(bad) && threadIdx.x == 0) atomicOr(flags, 1);
-}
-
-// one warp per row: |x|^2 (exact integer in fp32 for the accepted inputs)
-__global__ void tc_row_norms(const float* __restrict__ src, int n, int dim, int rows_padded,
-                             float* __restrict__ norm) {
+// One warp per padded row, one pass over the uploaded float32 matrix: exactness check (integers in
+// [0,255]), |x|^2, max |x|^2, the zero-padded float32 row of the SIMT kernel (when it is not the
+// upload itself) and both bf16 operand roles in the UMMA core-matrix order.
+// info[0] |= 1 if any value is not bf16-exact; info[1] = max |x|^2 as float bits.
+__global__ void __launch_bounds__(256)
+    tc_prepare_set(const float* __restrict__ src, int n, int dim, int rows_padded, float* __restrict__ padded, int dim_padded,
+                   float* __restrict__ norm, __nv_bfloat16* __restrict__ qa, __nv_bfloat16* __restrict__ tb,
+                   int* __restrict__ info) {
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= rows_padded) return;
-  float s = 0.0f;
-  if (row < n)
-    for (int k = lane; k < dim; k += 32) {
-      const float v = src[(size_t)row * dim + k];
-      s = fmaf(v, v, s);
-    }
+  float v[4] = {0.f, 0.f, 0.f, 0.f};
+  bool bad = false;
+  if (row < n) {
 #pragma unroll
-  for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-  if (lane == 0) norm[row] = s;
-}
-
-// max_i |x_i|^2 as float bits (non-negative floats order like unsigned integers)
-__global__ void tc_max_norm(const float* __restrict__ norm, int n, unsigned* __restrict__ out) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  float v = i < n ? norm[i] : 0.0f;
-#pragma unroll
-  for (int o = 16; o; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
-  if ((threadIdx.x & 31) == 0) atomicMax(out, __float_as_uint(v));
-}
-
-// one thread per (row, 16-byte K chunk): writes both operand roles
-__global__ void tc_build_operands(const float* __restrict__ src, int n, int dim, int rows_padded,
-                                  const float* __restrict__ norm, __nv_bfloat16* __restrict__ qa,
-                                  __nv_bfloat16* __restrict__ tb) {
-  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= (size_t)rows_padded * TC_KCH) return;
-  const int row = idx / TC_KCH, c = idx % TC_KCH;
-  const size_t off = ((size_t)(row >> 3) * TC_KCH + c) * 64 + (row & 7) * 8;
-  __align__(16) __nv_bfloat16 a[8], b[8];
-#pragma unroll
-  for (int e = 0; e < 8; ++e) {
-    a[e] = __float2bfloat16(0.0f);
-    b[e] = __float2bfloat16(0.0f);
-  }
-  if (c < TC_KD / 8) {
-    if (row < n) {
-#pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        const int k = c * 8 + e;
-        const float v = k < dim ? src[(size_t)row * dim + k] : 0.0f;
-        a[e] = __float2bfloat16(v);
-        b[e] = __float2bfloat16(-2.0f * v);
+    for (int e = 0; e < 4; ++e) {
+      const int k = lane * 4 + e;
+      if (k < dim) {
+        v[e] = src[(size_t)row * dim + k];
+        bad |= !(v[e] >= 0.0f && v[e] <= 255.0f && v[e] == floorf(v[e]));
       }
     }
-  } else if (c == TC_KD / 8) {
-    if (row < n) {
-      a[0] = a[1] = a[2] = __float2bfloat16(1.0f);
-      const float nb = norm[row];
-      const __nv_bfloat16 hi = __float2bfloat16(nb);
-      const float r1 = nb - __bfloat162float(hi);
-      const __nv_bfloat16 mid = __float2bfloat16(r1);
-      const float r2 = r1 - __bfloat162float(mid);
-      b[0] = hi; b[1] = mid; b[2] = __float2bfloat16(r2);
-    } else {
-      // padding trains can never be selected: accumulator = +inf for real queries
-      a[0] = a[1] = a[2] = __float2bfloat16(0.0f);
-      b[0] = __float2bfloat16(__builtin_huge_valf());
+    if (padded) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int k = lane * 4 + e;
+        if (k < dim_padded) padded[(size_t)row * dim_padded + k] = v[e];
+      }
     }
   }
-  *reinterpret_cast<uint4*>(qa + off) = *reinterpret_cast<const uint4*>(a);
-  *reinterpret_cast<uint4*>(tb + off) = *reinterpret_cast<const uint4*>(b);
+  float s = fmaf(v[0], v[0], fmaf(v[1], v[1], fmaf(v[2], v[2], v[3] * v[3])));
+#pragma unroll
+  for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  bad = __any_sync(0xffffffffu, bad);
+  if (lane == 0) {
+    norm[row] = s;
+    if (bad) atomicOr(&info[0], 1);
+    if (row < n) atomicMax(reinterpret_cast<unsigned*>(&info[1]), __float_as_uint(s));
+  }
+  // data chunks: lanes 2c and 2c+1 hold the two halves of 16-byte chunk c
+  {
+    const int c = lane >> 1;
+    const size_t off = ((size_t)(row >> 3) * TC_KCH + c) * 64 + (row & 7) * 8 + (lane & 1) * 4;
+    __align__(8) __nv_bfloat16 a[4], b[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      a[e] = __float2bfloat16(v[e]);
+      b[e] = __float2bfloat16(-2.0f * v[e]);
+    }
+    *reinterpret_cast<uint2*>(qa + off) = *reinterpret_cast<const uint2*>(a);
+    *reinterpret_cast<uint2*>(tb + off) = *reinterpret_cast<const uint2*>(b);
+  }
+  // augmentation chunk (lane 0) and the zero chunk that pads K to 144 (lane 1)
+  if (lane < TC_KCH - TC_KD / 8) {
+    const int c = TC_KD / 8 + lane;
+    const size_t off = ((size_t)(row >> 3) * TC_KCH + c) * 64 + (row & 7) * 8;
+    __align__(16) __nv_bfloat16 a[8], b[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      a[e] = __float2bfloat16(0.0f);
+      b[e] = __float2bfloat16(0.0f);
+    }
+    if (lane == 0) {
+      if (row < n) {
+        a[0] = a[1] = a[2] = __float2bfloat16(1.0f);
+        const __nv_bfloat16 hi = __float2bfloat16(s);
+        const float r1 = s - __bfloat162float(hi);
+        const __nv_bfloat16 mid = __float2bfloat16(r1);
+        const float r2 = r1 - __bfloat162float(mid);
+        b[0] = hi; b[1] = mid; b[2] = __float2bfloat16(r2);
+      } else {
+        // padding trains can never be selected: accumulator = +inf for real queries
+        b[0] = __float2bfloat16(__builtin_huge_valf());
+      }
+    }
+    *reinterpret_cast<uint4*>(qa + off) = *reinterpret_cast<const uint4*>(a);
+    *reinterpret_cast<uint4*>(tb + off) = *reinterpret_cast<const uint4*>(b);
+  }
 }
 
-void Matcher::prepare_tc(DescSet& s) {
-  s.tc_ok = false;
-  if (s.u8 || s.dim > TC_KD || s.n == 0 || !tc_available()) return;
-  // staging.p still holds the dense float32 upload (n x dim) on this stream
-  const float* src = reinterpret_cast<const float*>(staging.p);
-  d_flags.reserve(4);
-  OSFM_CUDA(cudaMemsetAsync(d_flags.p, 0, sizeof(int), stream));
-  const size_t count = (size_t)s.n * s.dim;
-  tc_check_exact<<<(unsigned)((count + 255) / 256), 256, 0, stream>>>(src, count, d_flags.p);
-  OSFM_LAUNCH_CHECK();
-  int flag = 0;
-  OSFM_CUDA(cudaMemcpyAsync(&flag, d_flags.p, sizeof(int), cudaMemcpyDeviceToHost, stream));
-  OSFM_CUDA(cudaStreamSynchronize(stream));
-  if (flag) return;  // not bf16-exact: the exact SIMT kernel serves this set
-  const int rows_padded = (s.n + TC_N - 1) / TC_N * TC_N;
-  s.rows_padded = rows_padded;
+// src: the dense n x dim float32 upload on this stream; padded_dst: the SIMT kernel's zero-padded copy
+// to fill as well, or null when the upload already is that copy.  Asynchronous: s.tc_ok is decided by
+// Matcher::refresh_info() from d_info[s.slot].
+void Matcher::prepare_tc(DescSet& s, const float* src, float* padded_dst) {
+  const int rows_padded = s.rows_padded;
   const size_t op_bytes = (size_t)rows_padded * TC_ROW_BYTES;
-  OSFM_CUDA(cudaMalloc(&s.tc_data, 2 * op_bytes + (size_t)rows_padded * sizeof(float)));
   __nv_bfloat16* qa = reinterpret_cast<__nv_bfloat16*>(s.tc_data);
   __nv_bfloat16* tb = reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<char*>(s.tc_data) + op_bytes);
   float* norm = reinterpret_cast<float*>(reinterpret_cast<char*>(s.tc_data) + 2 * op_bytes);
-  tc_row_norms<<<(rows_padded + 7) / 8, 256, 0, stream>>>(src, s.n, s.dim, rows_padded, norm);
+  tc_prepare_set<<<(rows_padded + 7) / 8, 256, 0, stream>>>(src, s.n, s.dim, rows_padded, padded_dst, s.dim_padded, norm, qa, tb,
+                                                           d_info.p + 2 * s.slot);
   OSFM_LAUNCH_CHECK();
-  OSFM_CUDA(cudaMemsetAsync(d_flags.p + 2, 0, sizeof(int), stream));
-  tc_max_norm<<<(s.n + 255) / 256, 256, 0, stream>>>(norm, s.n, reinterpret_cast<unsigned*>(d_flags.p + 2));
-  OSFM_LAUNCH_CHECK();
-  unsigned max_bits = 0;
-  OSFM_CUDA(cudaMemcpyAsync(&max_bits, d_flags.p + 2, sizeof(unsigned), cudaMemcpyDeviceToHost, stream));
-  const size_t items = (size_t)rows_padded * TC_KCH;
-  tc_build_operands<<<(unsigned)((items + 255) / 256), 256, 0, stream>>>(src, s.n, s.dim, rows_padded, norm, qa, tb);
-  OSFM_LAUNCH_CHECK();
-  OSFM_CUDA(cudaStreamSynchronize(stream));
-  std::memcpy(&s.tc_max_norm, &max_bits, sizeof(float));
   s.tc_q = qa;
   s.tc_t = tb;
   s.tc_norm = norm;
-  s.tc_ok = true;
+  s.info_pending = true;
 }
+int tc_rows_padded(int n) { return (n + TC_N - 1) / TC_N * TC_N; }
+size_t tc_operand_bytes(int rows_padded) { return 2 * (size_t)rows_padded * TC_ROW_BYTES + (size_t)rows_padded * sizeof(float); }
+bool tc_capable(int dim, bool u8, int n) { return !u8 && dim <= TC_KD && n > 0 && tc_available(); }
 
 // ---------------------------------------------------------------------------
 // PTX wrappers

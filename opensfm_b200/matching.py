@@ -126,6 +126,30 @@ class PairMatcher:
         self._ids[key] = out.value
         self._n[key] = d.shape[0]
 
+    def add_many(self, items: Sequence[Tuple[Any, np.ndarray]]) -> None:
+        """Upload many images' descriptors with a single host synchronisation (same dtype and
+        descriptor length for all; anything else goes through `add`)."""
+        prepped = [(k, _prep(d)) for k, d in items]
+        if not prepped:
+            return
+        d0 = prepped[0][1]
+        if any(d.dtype != d0.dtype or d.shape[1] != d0.shape[1] for _, d in prepped):
+            for k, d in prepped:
+                self.add(k, d)
+            return
+        cnt = len(prepped)
+        ptrs = (ctypes.c_void_p * cnt)(*[d.ctypes.data for _, d in prepped])
+        ns = np.array([d.shape[0] for _, d in prepped], dtype=np.int32)
+        ids = np.empty(cnt, dtype=np.int32)
+        fn = self._m.L.osfm_matcher_add_batch_u8 if d0.dtype == np.uint8 else self._m.L.osfm_matcher_add_batch_f32
+        _lib.check(fn(self._m.h, cnt, ctypes.cast(ptrs, ctypes.c_void_p), ns.ctypes.data_as(ctypes.c_void_p), d0.shape[1],
+                      ids.ctypes.data_as(ctypes.c_void_p)))
+        for (k, d), i in zip(prepped, ids):
+            if k in self._ids:
+                _lib.check(self._m.L.osfm_matcher_remove(self._m.h, self._ids[k]))
+            self._ids[k] = int(i)
+            self._n[k] = d.shape[0]
+
     def submit(self, pairs: Sequence[Tuple[Any, Any]], lowes_ratio: float, symmetric: bool = True) -> None:
         ia = np.array([self._ids[a] for a, _ in pairs], dtype=np.int32)
         ib = np.array([self._ids[b] for _, b in pairs], dtype=np.int32)
