@@ -150,6 +150,12 @@ class PairMatcher:
             self._ids[k] = int(i)
             self._n[k] = d.shape[0]
 
+    def clear(self) -> None:
+        """Drop every resident descriptor set (device memory stays with the matcher for reuse)."""
+        _lib.check(self._m.L.osfm_matcher_clear(self._m.h))
+        self._ids.clear()
+        self._n.clear()
+
     def submit(self, pairs: Sequence[Tuple[Any, Any]], lowes_ratio: float, symmetric: bool = True) -> None:
         ia = np.array([self._ids[a] for a, _ in pairs], dtype=np.int32)
         ib = np.array([self._ids[b] for _, b in pairs], dtype=np.int32)
@@ -181,15 +187,17 @@ class PairMatcher:
             symmetric = bool(config.get("symmetric_matching", True))  # config.py:101
         self.submit(pairs, config["lowes_ratio"], symmetric)
         raw = self.fetch_raw()
-        res: Dict[Tuple[Any, Any], np.ndarray] = {}
-        off = 0
-        for a, b in self._pairs:
-            n = self._n[a]
-            idx = raw[off:off + n]
-            off += n
-            q = np.nonzero(idx >= 0)[0]
-            res[(a, b)] = np.stack([q, idx[q]], axis=1).astype(np.int64) if len(q) else np.zeros((0, 2), dtype=np.int64)
-        return res
+        # one vectorised pass over all pairs' match lists instead of a numpy call per pair
+        counts = np.array([self._n[a] for a, _ in self._pairs], dtype=np.int64)
+        starts = np.concatenate([[0], np.cumsum(counts)])
+        hit = np.flatnonzero(raw >= 0)
+        pair_of = np.searchsorted(starts, hit, side="right") - 1
+        both = np.empty((len(hit), 2), dtype=np.int64)
+        both[:, 0] = hit - starts[pair_of]
+        both[:, 1] = raw[hit]
+        cuts = np.searchsorted(pair_of, np.arange(1, len(self._pairs)))
+        parts = np.split(both, cuts) if len(self._pairs) else []
+        return dict(zip(self._pairs, parts))
 
 
 def shard_pairs(pairs: Sequence[Tuple[Any, Any]], sizes: Dict[Any, int], world: int) -> List[List[Tuple[Any, Any]]]:
