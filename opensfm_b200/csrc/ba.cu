@@ -1215,8 +1215,8 @@ void BA::run() {
         grp_max = std::max(grp_max, grp_lo[c + 1] - grp_lo[c]);
       }
       auto up16 = [](long long x) { return (x + 15) / 16 * 16; };
-      const long long off_S = up16(8LL * nc), off_Minv = off_S + up16(8 * ent_max);
-      const long long off_vec = off_Minv + 8LL * grp_max * MAXB * MAXB, off_cols = off_vec + up16(16LL * rows_max);
+      const long long off_S = up16(8 * col_max), off_Minv = off_S + up16(8 * ent_max);
+      const long long off_vec = off_Minv + 8LL * grp_max * MAXB * MAXB, off_cols = off_vec + up16(24LL * rows_max);
       const long long off_rows = off_cols + up16(2 * col_max);
       const long long total = off_rows + 16LL * rows_max + 4LL * (grp_max + 1);
       static const bool allow_pipe = []() { const char* e = getenv("OSFM_BA_PCG_PIPELINED"); return !(e && e[0] == '0'); }();
@@ -1229,7 +1229,7 @@ void BA::run() {
         upload(d_pcg_grplo, grp_lo, stream);
         pcg_pipe.grp_lo = d_pcg_grplo.p; pcg_pipe.off_S = (int)off_S; pcg_pipe.off_Minv = (int)off_Minv;
         pcg_pipe.off_vec = (int)off_vec; pcg_pipe.off_cols = (int)off_cols; pcg_pipe.off_rows = (int)off_rows;
-        pcg_pipe.max_rows = rows_max; pcg_pipe.max_groups = grp_max;
+        pcg_pipe.max_rows = rows_max; pcg_pipe.max_groups = grp_max; pcg_pipe.max_cols = (int)col_max;
         OSFM_CUDA(cudaFuncSetAttribute(pcg_pipelined, cudaFuncAttributeMaxDynamicSharedMemorySize, pcg_pipe_smem));
       }
     }

@@ -1107,13 +1107,16 @@ __global__ void __launch_bounds__(PCG_THREADS, 1)
 // grid barrier, so an iteration costs one barrier instead of two.  Every CTA owns whole
 // preconditioner groups: their rows of S, the groups' inverse blocks and all eight recurrence
 // vectors of those rows stay in shared memory / registers for the whole solve; the only vector that
-// moves through L2 is m = M^-1 w (nc doubles, double-buffered by iteration parity).
+// moves through L2 is m = M^-1 w (nc doubles, double-buffered by iteration parity): after the barrier a
+// CTA gathers, per owned block row, the entries of m its columns need into a packed copy (mp), so the
+// rows then stream S and mp from shared memory without bank conflicts.
 // The recurrences drift from the true residual earlier than classic CG; the kernel reports
 // converged = 0 on stagnation / breakdown and the host re-solves with pcg_persistent.
 // ---------------------------------------------------------------------------
 struct PcgPipe {
   const int* grp_lo;  // [grid + 1] group range of every CTA (balanced by stored entries)
-  int off_S, off_Minv, off_vec, off_cols, off_rows;  // byte offsets into dynamic shared memory; m at 0
+  int off_S, off_Minv, off_vec, off_cols, off_rows;  // byte offsets into dynamic shared memory; mp at 0
+  int max_cols;
   int max_rows, max_groups;
 };
 
@@ -1172,13 +1175,14 @@ __global__ void __launch_bounds__(PCG_THREADS, 1)
                   int nc, int max_iter, double tol2_rel, PcgPipe R) {
   extern __shared__ __align__(16) unsigned char pcg_smem[];
   __shared__ double red[PCG_THREADS / 32][3];
-  __shared__ int s_nrows;
+  __shared__ int s_nrows, s_ncols;
   const int nwarps = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31, tid = threadIdx.x;
-  double* m_s = reinterpret_cast<double*>(pcg_smem);
+  double* mp_s = reinterpret_cast<double*>(pcg_smem);  // packed m per owned block row: mp_s[coff + q] = m[cols[q]]
   double* S_s = reinterpret_cast<double*>(pcg_smem + R.off_S);
   double* Minv_s = reinterpret_cast<double*>(pcg_smem + R.off_Minv);
   double* w_s = reinterpret_cast<double*>(pcg_smem + R.off_vec);  // input of the group solves
-  double* n_s = w_s + R.max_rows;                                  // mat-vec output / group-solve output
+  double* n_s = w_s + R.max_rows;                                  // mat-vec output
+  double* g_s = n_s + R.max_rows;                                  // group-solve output (u, then m of the own rows)
   unsigned short* cols_s = reinterpret_cast<unsigned short*>(pcg_smem + R.off_cols);
   int* row_soff = reinterpret_cast<int*>(pcg_smem + R.off_rows);
   int* row_coff = row_soff + R.max_rows;
@@ -1209,9 +1213,10 @@ __global__ void __launch_bounds__(PCG_THREADS, 1)
     }
     grp_row0[ng] = lr;
     s_nrows = lr;
+    s_ncols = c_off;
   }
   __syncthreads();
-  const int nrows = s_nrows;
+  const int nrows = s_nrows, ncols = s_ncols;
   for (int lr = warp; lr < nrows; lr += nwarps) {
     const int i = row_gidx[lr], b = L.row_of[i], M = row_len[lr];
     const double* src = Spcg + L.rowbase[b] + (long long)(i - h.blk_off[b]) * M;
@@ -1232,39 +1237,48 @@ __global__ void __launch_bounds__(PCG_THREADS, 1)
       if (lane < n)
         for (int j = 0; j < n; ++j) sv += M[lane * MAXB + j] * w_s[r0 + j];
       if (lane < n) {
-        n_s[r0 + lane] = sv;
-        if (publish) publish[row_gidx[r0 + lane]] = sv;
+        g_s[r0 + lane] = sv;
+        publish[row_gidx[r0 + lane]] = sv;
       }
     }
   };
-  // n_s[lr] = (S m_s)[row lr]
+  // n_s[lr] = (S m)[row lr], m packed per block row in mp_s.  Eight lanes per row, four rows per warp:
+  // with 16 warps on the SM the mat-vec is latency-bound, so every lane keeps four independent
+  // accumulator chains going and no warp walks more than one batch of rows.
   auto matvec = [&]() {
-    for (int lr = warp; lr < nrows; lr += nwarps) {
-      const double* vals = S_s + row_soff[lr];
-      const unsigned short* cols = cols_s + row_coff[lr];
-      const int M = row_len[lr];
+    const int sub = lane >> 3, l = lane & 7;
+    for (int rb = warp * 4; rb < nrows; rb += nwarps * 4) {
+      const int lr = rb + sub;
       double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-      int q = lane;
-      for (; q + 96 < M; q += 128) {
-        const int c0 = cols[q], c1 = cols[q + 32], c2 = cols[q + 64], c3 = cols[q + 96];
-        const double v0 = vals[q], v1 = vals[q + 32], v2 = vals[q + 64], v3 = vals[q + 96];
-        s0 += v0 * m_s[c0]; s1 += v1 * m_s[c1]; s2 += v2 * m_s[c2]; s3 += v3 * m_s[c3];
+      if (lr < nrows) {
+        const double* vals = S_s + row_soff[lr];
+        const double* mp = mp_s + row_coff[lr];
+        const int M = row_len[lr];
+        int q = l;
+        for (; q + 24 < M; q += 32) {
+          s0 += vals[q] * mp[q]; s1 += vals[q + 8] * mp[q + 8];
+          s2 += vals[q + 16] * mp[q + 16]; s3 += vals[q + 24] * mp[q + 24];
+        }
+        for (; q < M; q += 8) s0 += vals[q] * mp[q];
       }
-      for (; q < M; q += 32) s0 += vals[q] * m_s[cols[q]];
       double sv = (s0 + s1) + (s2 + s3);
-#pragma unroll
-      for (int o = 16; o; o >>= 1) sv += __shfl_xor_sync(0xffffffffu, sv, o);
-      if (lane == 0) n_s[lr] = sv;
+      sv += __shfl_xor_sync(0xffffffffu, sv, 4);
+      sv += __shfl_xor_sync(0xffffffffu, sv, 2);
+      sv += __shfl_xor_sync(0xffffffffu, sv, 1);
+      if (l == 0 && lr < nrows) n_s[lr] = sv;
     }
   };
+  // mp_s[e] = src[cols_s[e]] for every column entry of the owned block rows (gathers from L2, 8 in flight)
   auto stage = [&](const double* src) {
-    int c = tid;
-    for (; c + 3 * (int)blockDim.x < nc; c += 4 * blockDim.x) {
-      const double a0 = ldcg_d(src + c), a1 = ldcg_d(src + c + blockDim.x), a2 = ldcg_d(src + c + 2 * blockDim.x),
-                   a3 = ldcg_d(src + c + 3 * blockDim.x);
-      m_s[c] = a0; m_s[c + blockDim.x] = a1; m_s[c + 2 * blockDim.x] = a2; m_s[c + 3 * blockDim.x] = a3;
+    const int bd = blockDim.x;
+    for (int e = tid; e < ncols; e += 8 * bd) {
+      double a[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) a[k] = (e + k * bd < ncols) ? ldcg_d(src + cols_s[e + k * bd]) : 0.0;
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+        if (e + k * bd < ncols) mp_s[e + k * bd] = a[k];
     }
-    for (; c < nc; c += blockDim.x) m_s[c] = ldcg_d(src + c);
   };
 
   // ---- init: x = 0, r = b, u = M^-1 r, w = S u, m = M^-1 w ----
@@ -1281,7 +1295,7 @@ __global__ void __launch_bounds__(PCG_THREADS, 1)
   double rr = bb;
   int it = 0, converged = 0;
   if (bb > 0.0) {
-    if (mine) u = n_s[tid];
+    if (mine) u = g_s[tid];
     stage(mbuf[0]);
     __syncthreads();
     matvec();
@@ -1311,7 +1325,7 @@ __global__ void __launch_bounds__(PCG_THREADS, 1)
       const double beta = it > 0 ? gamma / gamma_prev : 0.0;
       const double alpha = it > 0 ? gamma / (delta - beta * gamma / alpha_prev) : gamma / delta;
       if (mine) {
-        const double mo = m_s[gi], nn = n_s[tid];
+        const double mo = g_s[tid], nn = n_s[tid];
         z = nn + beta * z;
         q = mo + beta * q;
         sv_ = w + beta * sv_;
