@@ -27,16 +27,18 @@ def main(path):
         a = agg.setdefault(name, [0, 0.0])
         a[0] += 1
         a[1] += v * scale
-    ours = {k: v for k, v in agg.items() if k.startswith("osfm::")}
+    import re
+    pat = re.compile(r"^(osfm::)?(ba_|bf_|pcg_|tc_|ord_|bsr_|pad_rows)")
+    ours = {pat.sub(lambda m: m.group(2), k): v for k, v in agg.items() if pat.match(k)}
     tot = sum(v[1] for v in ours.values())
     print("# %s" % path)
     print("# kernels of libopensfm_b200.so only (cub / torch scene-generation kernels of the same process left out)")
     print("# ncu serialises launches and runs them cold: compare SHARES with bench.py's event timers, not absolute times")
     print("%-44s %8s %12s %12s %7s" % ("kernel", "launches", "total ms", "avg ms", "share"))
     for k, (n, ms) in sorted(ours.items(), key=lambda kv: -kv[1][1]):
-        print("%-44s %8d %12.3f %12.4f %6.1f%%" % (k[6:50], n, ms, ms / n, 100.0 * ms / tot))
+        print("%-44s %8d %12.3f %12.4f %6.1f%%" % (k[:44], n, ms, ms / n, 100.0 * ms / tot))
     print("%-44s %8s %12.3f" % ("total", "", tot))
-    other = sum(v[1] for k, v in agg.items() if not k.startswith("osfm::"))
+    other = sum(v[1] for k, v in agg.items() if not pat.match(k))
     print("%-44s %8s %12.3f" % ("(other kernels in the process)", "", other))
 
 
