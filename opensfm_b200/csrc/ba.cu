@@ -1304,22 +1304,41 @@ void BA::run() {
           OSFM_CUDA(cudaFuncSetAttribute(ba_schur_seg<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SegSmem)));
           seg_attr = true;
         }
-        const long long n_fast = n_fast_obs;
-        d_rowsJ.reserve((size_t)n_fast * wc * 3 + 8); d_rowsW.reserve((size_t)n_fast * wc * 3 + 8);
-        d_rowsY.reserve((size_t)n_fast * wc * 3 + 8); d_Vig.reserve(3 * (size_t)std::max(npf, 1));
+        // default: fused fp64 tensor-core kernel; OSFM_BA_SCHUR_MMA=0 -> the older ba_obs_rows + ba_schur_seg pair
+        static const bool use_mma = []() { const char* e = getenv("OSFM_BA_SCHUR_MMA"); return !(e && e[0] == '0'); }();
+        d_Vig.reserve(3 * (size_t)std::max(npf, 1));
         ba_point_blocks<<<grid_for(P_fast, 128), 128, 0, stream>>>(v, P_fast, d_scale.p, d_diag.p, inv_radius, d_Vinv.p,
                                                                  d_gp.p, d_Vig.p);
         OSFM_LAUNCH_CHECK();
-        ba_obs_rows<<<grid_for(n_fast * wc, 256), 256, 0, stream>>>(v, bm, bsr, n_fast, d_scale.p, d_Vinv.p, d_Vig.p,
-                                                                  d_rowsJ.p, d_rowsW.p, d_rowsY.p, d_rhs_p);
-        OSFM_LAUNCH_CHECK();
-        if (wc == 9)
-          ba_schur_seg<9><<<nseg, SEG_THREADS, sizeof(SegSmem), stream>>>(v, bm, bsr, d_seg_start.p, n_fast, d_rowsJ.p,
-                                                                         d_rowsW.p, d_rowsY.p, d_S_p);
-        else
-          ba_schur_seg<0><<<nseg, SEG_THREADS, sizeof(SegSmem), stream>>>(v, bm, bsr, d_seg_start.p, n_fast, d_rowsJ.p,
-                                                                         d_rowsW.p, d_rowsY.p, d_S_p);
-        OSFM_LAUNCH_CHECK();
+        if (use_mma) {
+          static bool mma_attr = false;
+          if (!mma_attr) {
+            OSFM_CUDA(cudaFuncSetAttribute(ba_schur_mma<9>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SegMmaSmem)));
+            OSFM_CUDA(cudaFuncSetAttribute(ba_schur_mma<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SegMmaSmem)));
+            mma_attr = true;
+          }
+          if (wc == 9)
+            ba_schur_mma<9><<<nseg, SM_THREADS, sizeof(SegMmaSmem), stream>>>(v, bm, bsr, d_seg_start.p, d_scale.p, d_Vinv.p,
+                                                                             d_Vig.p, d_S_p, d_rhs_p);
+          else
+            ba_schur_mma<0><<<nseg, SM_THREADS, sizeof(SegMmaSmem), stream>>>(v, bm, bsr, d_seg_start.p, d_scale.p, d_Vinv.p,
+                                                                             d_Vig.p, d_S_p, d_rhs_p);
+          OSFM_LAUNCH_CHECK();
+        } else {
+          const long long n_fast = n_fast_obs;
+          d_rowsJ.reserve((size_t)n_fast * wc * 3 + 8); d_rowsW.reserve((size_t)n_fast * wc * 3 + 8);
+          d_rowsY.reserve((size_t)n_fast * wc * 3 + 8);
+          ba_obs_rows<<<grid_for(n_fast * wc, 256), 256, 0, stream>>>(v, bm, bsr, n_fast, d_scale.p, d_Vinv.p, d_Vig.p,
+                                                                    d_rowsJ.p, d_rowsW.p, d_rowsY.p, d_rhs_p);
+          OSFM_LAUNCH_CHECK();
+          if (wc == 9)
+            ba_schur_seg<9><<<nseg, SEG_THREADS, sizeof(SegSmem), stream>>>(v, bm, bsr, d_seg_start.p, n_fast, d_rowsJ.p,
+                                                                           d_rowsW.p, d_rowsY.p, d_S_p);
+          else
+            ba_schur_seg<0><<<nseg, SEG_THREADS, sizeof(SegSmem), stream>>>(v, bm, bsr, d_seg_start.p, n_fast, d_rowsJ.p,
+                                                                           d_rowsW.p, d_rowsY.p, d_S_p);
+          OSFM_LAUNCH_CHECK();
+        }
       }
       if (P > P_fast) {
         ba_schur<<<P - P_fast, SCHUR_THREADS, smem, stream>>>(v, bm, bsr, d_scale.p, d_diag.p, inv_radius, d_S_p,

@@ -692,6 +692,224 @@ __global__ void __launch_bounds__(SEG_THREADS, 2)
   }
 }
 
+// ---------------------------------------------------------------------------
+// Segment Schur complement on the fp64 tensor cores, fused with the row construction.
+// One CTA per segment.  Per chunk of SM_PCH points the CTA builds, straight from the residual /
+// Jacobian planes, the operands   Yt[k][col] = -(W V^-1)(col, k),  Wt[k][col] = W(col, k),
+// Jt[k][col] = Js(col, k)   (k = 3 * point-in-chunk + component, col = shot-in-segment * wc + local
+// column) in shared memory, then accumulates the UPPER tiles of
+//     S_seg = sum_p ( U_p - Y_p W_p^T )            (symmetric: Y W^T = W V^-1 W^T)
+// with mma.m8n8k4.f64: C(ti,tj) += Yt^T(ti) Wt(tj), plus Jt^T Jt masked to the same shot for the
+// tiles that touch a diagonal block (U).  The accumulators are flushed once per segment, from the
+// fragments, with fp64 atomics that resolve in L2; g_c - W V^-1 g_p goes to the right-hand side once
+// per segment column.  Leading dimension SM_LD = 4 (mod 16) makes the fragment loads conflict-free.
+// Replaces ba_obs_rows + ba_schur_seg (no materialised rows: the planes are read once).
+// ---------------------------------------------------------------------------
+constexpr int SM_PCH = 8;
+constexpr int SM_KC = 3 * SM_PCH;
+constexpr int SM_LD = 100;
+constexpr int SM_THREADS = 384;
+constexpr int SM_NT = SEG_NA / 8;                    // 12 tiles per side
+constexpr int SM_SLOTS = (SM_NT * (SM_NT + 1) / 2 + SM_THREADS / 32 - 1) / (SM_THREADS / 32);  // 7 tiles per warp
+struct SegMmaSmem {
+  double Yt[SM_KC][SM_LD];
+  double Wt[SM_KC][SM_LD];
+  double Jt[SM_KC][SM_LD];
+  double G[SM_PCH][SEG_NA];   // per (point of the chunk, column): its share of the reduced right-hand side
+  int meta[SEG_NA];
+  int gcol[SEG_NA];
+  int oblk[SEG_KMAX][4];
+  int offt[SEG_KMAX * SEG_KMAX * 9];
+};
+
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(c0), "+d"(c1)
+               : "d"(a), "d"(b));
+}
+
+template <int WC>
+__global__ void __launch_bounds__(SM_THREADS, 2)
+    ba_schur_mma(BAView v, BlkMaps bm, BsrView h, const int* __restrict__ seg_start, const double* __restrict__ scale,
+                 const double* __restrict__ Vinv, const double* __restrict__ Vig, double* __restrict__ Sval,
+                 double* __restrict__ rhs) {
+  extern __shared__ __align__(16) unsigned char seg_raw[];
+  SegMmaSmem& sm = *reinterpret_cast<SegMmaSmem*>(seg_raw);
+  const int wc = WC ? WC : v.wc;
+  const int p_begin = seg_start[blockIdx.x], p_end = seg_start[blockIdx.x + 1];
+  const long long o0 = v.pt_start[p_begin];
+  const int k = (int)(v.pt_start[p_begin + 1] - o0);
+  const int ncols = k * wc;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const bool pfree = v.pt_poff[p_begin] >= 0;   // same for the whole segment (part of the signature)
+  const size_t N = (size_t)v.N;
+  const int nres = v.nres;
+
+  // ---- structure of the segment (from its first point); zero the operand buffers once ----
+  if (tid < SEG_NA) {
+    int g = -1, m = -1;
+    if (tid < ncols) {
+      const int b = tid / wc, c2 = tid - b * wc;
+      const ObsBlk ob = obs_blocks(v, bm, v.obs_shot[o0 + b]);
+      if (c2 == 0) { sm.oblk[b][0] = ob.blk[0]; sm.oblk[b][1] = ob.blk[1]; sm.oblk[b][2] = ob.blk[2]; sm.oblk[b][3] = ob.C; }
+      if (c2 < ob.C + 12) {
+        const int s2 = ob.slot_of(c2);
+        if (ob.blk[s2] >= 0) {
+          const int r2 = c2 - ob.lstart(s2);
+          g = h.blk_off[ob.blk[s2]] + r2;
+          m = (ob.blk[s2] << 12) | (s2 << 10) | (ob.size(s2) << 5) | r2;
+        }
+      }
+    }
+    sm.gcol[tid] = g;
+    sm.meta[tid] = m;
+  }
+  for (int t = tid; t < 3 * SM_KC * SM_LD; t += SM_THREADS) (&sm.Yt[0][0])[t] = 0.0;
+  __syncthreads();
+  for (int idx = tid; idx < k * k * 9; idx += SM_THREADS) {
+    const int ab = idx / 9, ss = idx - ab * 9;
+    const int a = ab / k, bb = ab - a * k;
+    if (a > bb) continue;
+    const int B1 = sm.oblk[a][ss / 3], B2 = sm.oblk[bb][ss % 3];
+    sm.offt[(a * SEG_KMAX + bb) * 9 + ss] = (B1 < 0 || B2 < 0) ? -1 : bsr_lookup(h, min(B1, B2), max(B1, B2));
+  }
+
+  // ---- my tiles: t = warp, warp + 12, ... over the upper triangle of nt x nt tiles ----
+  const int nt = (ncols + 7) >> 3;
+  const int ntiles = nt * (nt + 1) / 2;
+  int tile_i[SM_SLOTS], tile_j[SM_SLOTS];
+  double c[SM_SLOTS][2];
+#pragma unroll
+  for (int sidx = 0; sidx < SM_SLOTS; ++sidx) {
+    c[sidx][0] = 0.0; c[sidx][1] = 0.0;
+    int t = warp + sidx * (SM_THREADS / 32);
+    int ti = -1, tj = -1;
+    if (t < ntiles) {
+      // row ti of the upper triangle starts at ti * nt - ti (ti - 1) / 2
+      ti = 0;
+      while (t >= nt - ti) { t -= nt - ti; ++ti; }
+      tj = ti + t;
+    }
+    tile_i[sidx] = ti; tile_j[sidx] = tj;
+  }
+  const int fr = lane >> 2, fk = lane & 3;   // fragment row / k of this lane
+  double racc = 0.0;                         // reduced right-hand side of column tid (tid < ncols)
+
+  for (int pc0 = p_begin; pc0 < p_end; pc0 += SM_PCH) {
+    const int np = min(SM_PCH, p_end - pc0);
+    const long long ibase = v.pt_start[pc0];
+    const int run = np * k;
+    __syncthreads();  // previous chunk fully consumed (and the structure tables are complete)
+    if (np < SM_PCH) {  // short last chunk: the k rows beyond it must read as zero
+      const int kz0 = 3 * np, kz1 = (3 * np + 3) & ~3;
+      for (int t = tid; t < (kz1 - kz0) * SM_LD; t += SM_THREADS) {
+        const int kk = kz0 + t / SM_LD, cc = t % SM_LD;
+        sm.Yt[kk][cc] = 0.0; sm.Wt[kk][cc] = 0.0; sm.Jt[kk][cc] = 0.0;
+      }
+    }
+    // rows of the chunk: item (c2, observation), observation fastest -> coalesced plane reads
+    for (int t = tid; t < wc * run; t += SM_THREADS) {
+      const int c2 = t / run, off = t - c2 * run;   // off = lp * k + b
+      const int lp = off / k, bb = off - lp * k;
+      const int col = bb * wc + c2;
+      const int g = sm.gcol[col];
+      double js[3] = {0.0, 0.0, 0.0}, w[3] = {0.0, 0.0, 0.0}, y[3] = {0.0, 0.0, 0.0}, gr = 0.0;
+      if (g >= 0) {
+        const size_t i = (size_t)(ibase + off);
+        const double sc = scale[g];
+        const int pf = v.pt_poff[pc0 + lp];
+        double sp0 = 0.0, sp1 = 0.0, sp2 = 0.0;
+        if (pfree) { sp0 = scale[v.nc + 3 * pf]; sp1 = scale[v.nc + 3 * pf + 1]; sp2 = scale[v.nc + 3 * pf + 2]; }
+        for (int q = 0; q < nres; ++q) {
+          const double jc = v.Jc[((size_t)q * wc + c2) * N + i] * sc;
+          js[q] = jc;
+          gr += jc * v.r[q * N + i];
+          if (pfree) {
+            w[0] += jc * v.Jp[((size_t)q * 3 + 0) * N + i] * sp0;
+            w[1] += jc * v.Jp[((size_t)q * 3 + 1) * N + i] * sp1;
+            w[2] += jc * v.Jp[((size_t)q * 3 + 2) * N + i] * sp2;
+          }
+        }
+        if (pfree) {
+          const size_t NP = (size_t)v.npf;
+          const double i00 = Vinv[0 * NP + pf], i01 = Vinv[1 * NP + pf], i02 = Vinv[2 * NP + pf];
+          const double i11 = Vinv[3 * NP + pf], i12 = Vinv[4 * NP + pf], i22 = Vinv[5 * NP + pf];
+          y[0] = w[0] * i00 + w[1] * i01 + w[2] * i02;
+          y[1] = w[0] * i01 + w[1] * i11 + w[2] * i12;
+          y[2] = w[0] * i02 + w[1] * i12 + w[2] * i22;
+          gr -= w[0] * Vig[0 * NP + pf] + w[1] * Vig[1 * NP + pf] + w[2] * Vig[2 * NP + pf];
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        sm.Jt[3 * lp + j][col] = js[j];
+        sm.Wt[3 * lp + j][col] = w[j];
+        sm.Yt[3 * lp + j][col] = -y[j];
+      }
+      sm.G[lp][col] = gr;
+    }
+    __syncthreads();
+    if (tid < ncols)
+      for (int lp = 0; lp < np; ++lp) racc += sm.G[lp][tid];
+    const int ksteps = (3 * np + 3) >> 2;
+#pragma unroll
+    for (int sidx = 0; sidx < SM_SLOTS; ++sidx) {
+      const int ti = tile_i[sidx], tj = tile_j[sidx];
+      if (ti < 0) continue;
+      const int row = 8 * ti + fr, col = 8 * tj + fr;   // A-fragment row / B-fragment column of this lane
+      if (pfree)
+        for (int ks = 0; ks < ksteps; ++ks)
+          dmma884(c[sidx][0], c[sidx][1], sm.Yt[4 * ks + fk][row], sm.Wt[4 * ks + fk][col]);
+      // U: Js^T Js restricted to rows and columns of the same shot
+      const int b_lo = max((8 * ti) / wc, (8 * tj) / wc), b_hi = min(min((8 * ti + 7) / wc, (8 * tj + 7) / wc), k - 1);
+      for (int b = b_lo; b <= b_hi; ++b) {
+        const bool ra = row / wc == b, cb = col / wc == b;
+        for (int ks = 0; ks < ksteps; ++ks) {
+          const double av = sm.Jt[4 * ks + fk][row], bv = sm.Jt[4 * ks + fk][col];
+          dmma884(c[sidx][0], c[sidx][1], ra ? av : 0.0, cb ? bv : 0.0);
+        }
+      }
+    }
+  }
+
+  // ---- flush: right-hand side once per column, the tiles straight from the fragments ----
+  if (tid < ncols && sm.gcol[tid] >= 0) atomicAdd(&rhs[sm.gcol[tid]], racc);
+#pragma unroll
+  for (int sidx = 0; sidx < SM_SLOTS; ++sidx) {
+    const int ti = tile_i[sidx], tj = tile_j[sidx];
+    if (ti < 0) continue;
+    const int row = 8 * ti + fr;
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const int col = 8 * tj + 2 * fk + e;
+      if (row >= ncols || col >= ncols) continue;
+      const int m1 = sm.meta[row], m2 = sm.meta[col];
+      if (m1 < 0 || m2 < 0) continue;
+      const int a = row / wc, bb = col / wc;
+      if (a > bb) continue;
+      const int B1 = m1 >> 12, s1 = (m1 >> 10) & 3, sz1 = (m1 >> 5) & 31, r1 = m1 & 31;
+      const int B2 = m2 >> 12, s2 = (m2 >> 10) & 3, sz2 = (m2 >> 5) & 31, r2 = m2 & 31;
+      double val = c[sidx][e];
+      int pos;
+      if (B1 < B2) {
+        pos = r1 * sz2 + r2;
+      } else if (B1 > B2) {
+        if (a == bb) continue;
+        pos = r2 * sz1 + r1;
+      } else {
+        if (a == bb) {
+          if (r2 < r1) continue;
+          pos = r1 * sz1 + r2;
+        } else {
+          if (r1 == r2) val *= 2.0;
+          pos = min(r1, r2) * sz1 + max(r1, r2);
+        }
+      }
+      atomicAdd(&Sval[sm.offt[(a * SEG_KMAX + bb) * 9 + s1 * 3 + s2] + pos], val);
+    }
+  }
+}
+
 // Priors (after the all-reduce): diagonal entries of the diagonal blocks.
 __global__ void ba_prior_system(PriorView pv, Params p, const double* scale, const int* __restrict__ prior_diag_off,
                                 double* Sval, double* rhs) {
