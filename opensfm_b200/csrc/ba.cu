@@ -625,6 +625,9 @@ struct BA {
   bool pcg_resident = false;
   int pcg_smem = 0;
   DevBuf<int> d_pcg_grplo;
+  DevBuf<unsigned long long> d_prof;
+  DevBuf<long long> d_tab_off, d_tab_sizes;
+  DevBuf<int> d_tab;
   PcgPipe pcg_pipe{};
   bool pcg_pipe_ok = false;
   int pcg_pipe_smem = 0, pcg_pipe_its = 0, pcg_fallbacks = 0;
@@ -1262,6 +1265,24 @@ void BA::run() {
     ba_make_scale<<<grid_for(n, 256), 256, 0, stream>>>(d_colnorm2.p, d_scale.p, n);
     OSFM_LAUNCH_CHECK();
   }
+  // per-segment tables of the tensor-core Schur kernel (columns, block offsets, Jacobi scales): constant from here on
+  static const bool use_mma = []() { const char* e = getenv("OSFM_BA_SCHUR_MMA"); return !(e && e[0] == '0'); }();
+  if (nseg > 0 && use_mma && nblk > 0) {
+    d_tab_off.reserve((size_t)nseg + 1); d_tab_sizes.reserve((size_t)nseg + 1);
+    ba_seg_table_sizes<<<grid_for(nseg + 1, 256), 256, 0, stream>>>(v, d_seg_start.p, nseg, d_tab_sizes.p);
+    OSFM_LAUNCH_CHECK();
+    size_t tb = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, tb, d_tab_sizes.p, d_tab_off.p, nseg + 1, stream);
+    d_cub.reserve(tb + 256);
+    tb = d_cub.cap;
+    OSFM_CUDA(cub::DeviceScan::ExclusiveSum(d_cub.p, tb, d_tab_sizes.p, d_tab_off.p, nseg + 1, stream));
+    long long total_ints = 0;
+    OSFM_CUDA(cudaMemcpyAsync(&total_ints, d_tab_off.p + nseg, sizeof(long long), cudaMemcpyDeviceToHost, stream));
+    OSFM_CUDA(cudaStreamSynchronize(stream));
+    d_tab.reserve((size_t)total_ints + 2);
+    ba_seg_tables<<<nseg, 128, 0, stream>>>(v, bm, bsr, d_seg_start.p, d_scale.p, d_tab_off.p, d_tab.p);
+    OSFM_LAUNCH_CHECK();
+  }
   // |x| of the free parameters
   auto x_norm_of = [&](int b) -> double {
     OSFM_CUDA(cudaMemsetAsync(&d_sc.p->x_norm2, 0, sizeof(double), stream));
@@ -1305,7 +1326,6 @@ void BA::run() {
           seg_attr = true;
         }
         // default: fused fp64 tensor-core kernel; OSFM_BA_SCHUR_MMA=0 -> the older ba_obs_rows + ba_schur_seg pair
-        static const bool use_mma = []() { const char* e = getenv("OSFM_BA_SCHUR_MMA"); return !(e && e[0] == '0'); }();
         d_Vig.reserve(3 * (size_t)std::max(npf, 1));
         ba_point_blocks<<<grid_for(P_fast, 128), 128, 0, stream>>>(v, P_fast, d_scale.p, d_diag.p, inv_radius, d_Vinv.p,
                                                                  d_gp.p, d_Vig.p);
@@ -1317,13 +1337,26 @@ void BA::run() {
             OSFM_CUDA(cudaFuncSetAttribute(ba_schur_mma<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SegMmaSmem)));
             mma_attr = true;
           }
+          unsigned long long* prof = nullptr;
+          if (trace_on) {
+            d_prof.reserve(8);
+            OSFM_CUDA(cudaMemsetAsync(d_prof.p, 0, 8 * sizeof(unsigned long long), stream));
+            prof = d_prof.p;
+          }
           if (wc == 9)
-            ba_schur_mma<9><<<nseg, SM_THREADS, sizeof(SegMmaSmem), stream>>>(v, bm, bsr, d_seg_start.p, d_scale.p, d_Vinv.p,
-                                                                             d_Vig.p, d_S_p, d_rhs_p);
+            ba_schur_mma<9><<<nseg, SM_THREADS, sizeof(SegMmaSmem), stream>>>(v, d_seg_start.p, d_tab_off.p, d_tab.p, d_scale.p,
+                                                                             d_Vinv.p, d_Vig.p, d_S_p, d_rhs_p, prof);
           else
-            ba_schur_mma<0><<<nseg, SM_THREADS, sizeof(SegMmaSmem), stream>>>(v, bm, bsr, d_seg_start.p, d_scale.p, d_Vinv.p,
-                                                                             d_Vig.p, d_S_p, d_rhs_p);
+            ba_schur_mma<0><<<nseg, SM_THREADS, sizeof(SegMmaSmem), stream>>>(v, d_seg_start.p, d_tab_off.p, d_tab.p, d_scale.p,
+                                                                             d_Vinv.p, d_Vig.p, d_S_p, d_rhs_p, prof);
           OSFM_LAUNCH_CHECK();
+          if (trace_on) {
+            unsigned long long hp[8];
+            OSFM_CUDA(cudaMemcpyAsync(hp, d_prof.p, sizeof(hp), cudaMemcpyDeviceToHost, stream));
+            OSFM_CUDA(cudaStreamSynchronize(stream));
+            fprintf(stderr, "[osfm_ba] ba_schur_mma clocks / segment (thread 0): structure %llu offsets %llu loads %llu rows %llu mma %llu flush %llu\n",
+                    hp[0] / nseg, hp[1] / nseg, hp[2] / nseg, hp[3] / nseg, hp[4] / nseg, hp[5] / nseg);
+          }
         } else {
           const long long n_fast = n_fast_obs;
           d_rowsJ.reserve((size_t)n_fast * wc * 3 + 8); d_rowsW.reserve((size_t)n_fast * wc * 3 + 8);

@@ -710,17 +710,84 @@ constexpr int SM_KC = 3 * SM_PCH;
 constexpr int SM_LD = 100;
 constexpr int SM_THREADS = 384;
 constexpr int SM_NT = SEG_NA / 8;                    // 12 tiles per side
-constexpr int SM_SLOTS = (SM_NT * (SM_NT + 1) / 2 + SM_THREADS / 32 - 1) / (SM_THREADS / 32);  // 7 tiles per warp
+constexpr int SM_NEAR = (2 * SM_NT - 1 + SM_THREADS / 32 - 1) / (SM_THREADS / 32);                       // 2 near-diagonal tiles per warp
+constexpr int SM_SLOTS = SM_NEAR + ((SM_NT - 1) * (SM_NT - 2) / 2 + SM_THREADS / 32 - 1) / (SM_THREADS / 32);  // + 5 far tiles
 struct SegMmaSmem {
   double Yt[SM_KC][SM_LD];
   double Wt[SM_KC][SM_LD];
   double Jt[SM_KC][SM_LD];
   double G[SM_PCH][SEG_NA];   // per (point of the chunk, column): its share of the reduced right-hand side
+  double obsd[SM_PCH * SEG_KMAX][12];  // per observation of the chunk: r[3], (Jp * point scale)[3][3]
+  double ptd[SM_PCH][9];               // per point of the chunk: V^-1 (6), V^-1 g_p (3)
+  double scol[SEG_NA];                 // Jacobi scale of every column
+  unsigned char lp_of[SM_PCH * SEG_KMAX], bb_of[SM_PCH * SEG_KMAX];  // observation-in-chunk -> (point, shot)
   int meta[SEG_NA];
   int gcol[SEG_NA];
   int oblk[SEG_KMAX][4];
   int offt[SEG_KMAX * SEG_KMAX * 9];
 };
+
+// Per-segment tables (constant over the LM iterations of a run, built once by ba_seg_tables):
+//   [ gcol (ncols) | meta (ncols) | offt (k (k + 1) / 2 shot pairs a <= b, 9 slot pairs each) ] ints, then
+//   scol (ncols doubles, 8-byte aligned).  tab_off[s] = offset of segment s in ints.
+__host__ __device__ inline int seg_pair_index(int a, int b, int k) { return a * k - a * (a - 1) / 2 + (b - a); }
+__host__ __device__ inline long long seg_table_ints(int k, int wc) {
+  const int ncols = k * wc;
+  long long n = 2LL * ncols + 9LL * (k * (k + 1) / 2);
+  n += n & 1;              // doubles start on an 8-byte boundary
+  return n + 2LL * ncols;  // scol
+}
+// tab_off[s] for every segment (then an exclusive scan on the host side via cub)
+__global__ void ba_seg_table_sizes(BAView v, const int* __restrict__ seg_start, int nseg, long long* __restrict__ sizes) {
+  const int sidx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (sidx > nseg) return;
+  if (sidx == nseg) { sizes[sidx] = 0; return; }
+  const int p0 = seg_start[sidx];
+  const int k = (int)(v.pt_start[p0 + 1] - v.pt_start[p0]);
+  sizes[sidx] = seg_table_ints(k, v.wc);
+}
+__global__ void __launch_bounds__(128)
+    ba_seg_tables(BAView v, BlkMaps bm, BsrView h, const int* __restrict__ seg_start, const double* __restrict__ scale,
+                  const long long* __restrict__ tab_off, int* __restrict__ tab) {
+  __shared__ int oblk[SEG_KMAX][4];
+  const int wc = v.wc;
+  const int p0 = seg_start[blockIdx.x];
+  const long long o0 = v.pt_start[p0];
+  const int k = (int)(v.pt_start[p0 + 1] - o0);
+  const int ncols = k * wc;
+  int* T = tab + tab_off[blockIdx.x];
+  int* gcol = T;
+  int* meta = T + ncols;
+  int* offt = T + 2 * ncols;
+  long long nints = 2LL * ncols + 9LL * (k * (k + 1) / 2);
+  nints += nints & 1;
+  double* scol = reinterpret_cast<double*>(T + nints);
+  for (int t = threadIdx.x; t < ncols; t += blockDim.x) {
+    const int b = t / wc, c2 = t - b * wc;
+    const ObsBlk ob = obs_blocks(v, bm, v.obs_shot[o0 + b]);
+    if (c2 == 0) { oblk[b][0] = ob.blk[0]; oblk[b][1] = ob.blk[1]; oblk[b][2] = ob.blk[2]; oblk[b][3] = ob.C; }
+    int g = -1, m = -1;
+    if (c2 < ob.C + 12) {
+      const int s2 = ob.slot_of(c2);
+      if (ob.blk[s2] >= 0) {
+        const int r2 = c2 - ob.lstart(s2);
+        g = h.blk_off[ob.blk[s2]] + r2;
+        m = (ob.blk[s2] << 12) | (s2 << 10) | (ob.size(s2) << 5) | r2;
+      }
+    }
+    gcol[t] = g;
+    meta[t] = m;
+    scol[t] = g >= 0 ? scale[g] : 0.0;
+  }
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < k * k * 9; idx += blockDim.x) {
+    const int ab = idx / 9, ss = idx - ab * 9;
+    const int a = ab / k, bb = ab - a * k;
+    if (a > bb) continue;
+    const int B1 = oblk[a][ss / 3], B2 = oblk[bb][ss % 3];
+    offt[seg_pair_index(a, bb, k) * 9 + ss] = (B1 < 0 || B2 < 0) ? -1 : bsr_lookup(h, min(B1, B2), max(B1, B2));
+  }
+}
 
 __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
@@ -730,11 +797,20 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
 
 template <int WC>
 __global__ void __launch_bounds__(SM_THREADS, 2)
-    ba_schur_mma(BAView v, BlkMaps bm, BsrView h, const int* __restrict__ seg_start, const double* __restrict__ scale,
-                 const double* __restrict__ Vinv, const double* __restrict__ Vig, double* __restrict__ Sval,
-                 double* __restrict__ rhs) {
+    ba_schur_mma(BAView v, const int* __restrict__ seg_start, const long long* __restrict__ tab_off,
+                 const int* __restrict__ tab, const double* __restrict__ scale, const double* __restrict__ Vinv, const double* __restrict__ Vig, double* __restrict__ Sval,
+                 double* __restrict__ rhs, unsigned long long* prof) {
   extern __shared__ __align__(16) unsigned char seg_raw[];
   SegMmaSmem& sm = *reinterpret_cast<SegMmaSmem*>(seg_raw);
+  // prof != null (OSFM_BA_TRACE): thread 0 adds its clocks per phase: structure, block offsets, loads, rows, mma, flush
+  long long tk = prof ? clock64() : 0;
+  auto mark = [&](int slot) {
+    if (prof && threadIdx.x == 0) {
+      const long long now = clock64();
+      atomicAdd(&prof[slot], (unsigned long long)(now - tk));
+      tk = now;
+    }
+  };
   const int wc = WC ? WC : v.wc;
   const int p_begin = seg_start[blockIdx.x], p_end = seg_start[blockIdx.x + 1];
   const long long o0 = v.pt_start[p_begin];
@@ -745,52 +821,57 @@ __global__ void __launch_bounds__(SM_THREADS, 2)
   const size_t N = (size_t)v.N;
   const int nres = v.nres;
 
-  // ---- structure of the segment (from its first point); zero the operand buffers once ----
-  if (tid < SEG_NA) {
-    int g = -1, m = -1;
-    if (tid < ncols) {
-      const int b = tid / wc, c2 = tid - b * wc;
-      const ObsBlk ob = obs_blocks(v, bm, v.obs_shot[o0 + b]);
-      if (c2 == 0) { sm.oblk[b][0] = ob.blk[0]; sm.oblk[b][1] = ob.blk[1]; sm.oblk[b][2] = ob.blk[2]; sm.oblk[b][3] = ob.C; }
-      if (c2 < ob.C + 12) {
-        const int s2 = ob.slot_of(c2);
-        if (ob.blk[s2] >= 0) {
-          const int r2 = c2 - ob.lstart(s2);
-          g = h.blk_off[ob.blk[s2]] + r2;
-          m = (ob.blk[s2] << 12) | (s2 << 10) | (ob.size(s2) << 5) | r2;
-        }
-      }
+  // ---- tables of the segment (ba_seg_tables) -> shared memory; zero the operand buffers once ----
+  {
+    const int* T = tab + tab_off[blockIdx.x];
+    const int npair9 = 9 * (k * (k + 1) / 2);
+    for (int t = tid; t < 2 * ncols + npair9; t += SM_THREADS) {
+      const int val = T[t];
+      if (t < ncols) sm.gcol[t] = val;
+      else if (t < 2 * ncols) sm.meta[t - ncols] = val;
+      else sm.offt[t - 2 * ncols] = val;
     }
-    sm.gcol[tid] = g;
-    sm.meta[tid] = m;
+    long long nints = 2LL * ncols + npair9;
+    nints += nints & 1;
+    const double* scol = reinterpret_cast<const double*>(T + nints);
+    if (tid < SEG_NA) {
+      sm.scol[tid] = tid < ncols ? scol[tid] : 0.0;
+      if (tid >= ncols) { sm.gcol[tid] = -1; sm.meta[tid] = -1; }
+    }
+  }
+  if (tid < SM_PCH * SEG_KMAX) {
+    const int lp = tid / k;
+    sm.lp_of[tid] = (unsigned char)lp;
+    sm.bb_of[tid] = (unsigned char)(tid - lp * k);
   }
   for (int t = tid; t < 3 * SM_KC * SM_LD; t += SM_THREADS) (&sm.Yt[0][0])[t] = 0.0;
-  __syncthreads();
-  for (int idx = tid; idx < k * k * 9; idx += SM_THREADS) {
-    const int ab = idx / 9, ss = idx - ab * 9;
-    const int a = ab / k, bb = ab - a * k;
-    if (a > bb) continue;
-    const int B1 = sm.oblk[a][ss / 3], B2 = sm.oblk[bb][ss % 3];
-    sm.offt[(a * SEG_KMAX + bb) * 9 + ss] = (B1 < 0 || B2 < 0) ? -1 : bsr_lookup(h, min(B1, B2), max(B1, B2));
-  }
+  mark(0);
 
-  // ---- my tiles: t = warp, warp + 12, ... over the upper triangle of nt x nt tiles ----
+  // ---- my tiles of the upper triangle of nt x nt 8x8 tiles.  Slots 0..SM_NEAR-1 take the tiles that can
+  //      touch a diagonal (same-shot) block, (t, t) and (t, t + 1): they also accumulate Jt^T Jt in d[];
+  //      the other slots take the tiles with tj >= ti + 2 (Y W^T only). ----
   const int nt = (ncols + 7) >> 3;
-  const int ntiles = nt * (nt + 1) / 2;
-  int tile_i[SM_SLOTS], tile_j[SM_SLOTS];
-  double c[SM_SLOTS][2];
+  const int n_near = 2 * nt - 1, n_far = (nt - 1) * (nt - 2) / 2;
+  int tile_ij[SM_SLOTS];   // ti | tj << 8, or -1
+  double c[SM_SLOTS][2], d[SM_NEAR][2];
 #pragma unroll
   for (int sidx = 0; sidx < SM_SLOTS; ++sidx) {
     c[sidx][0] = 0.0; c[sidx][1] = 0.0;
-    int t = warp + sidx * (SM_THREADS / 32);
     int ti = -1, tj = -1;
-    if (t < ntiles) {
-      // row ti of the upper triangle starts at ti * nt - ti (ti - 1) / 2
-      ti = 0;
-      while (t >= nt - ti) { t -= nt - ti; ++ti; }
-      tj = ti + t;
+    if (sidx < SM_NEAR) {
+      d[sidx][0] = 0.0; d[sidx][1] = 0.0;
+      const int t = warp + sidx * (SM_THREADS / 32);
+      if (t < nt) { ti = t; tj = t; }
+      else if (t < n_near) { ti = t - nt; tj = ti + 1; }
+    } else {
+      int t = warp + (sidx - SM_NEAR) * (SM_THREADS / 32);
+      if (t < n_far) {
+        ti = 0;
+        while (t >= nt - 2 - ti) { t -= nt - 2 - ti; ++ti; }
+        tj = ti + 2 + t;
+      }
     }
-    tile_i[sidx] = ti; tile_j[sidx] = tj;
+    tile_ij[sidx] = ti < 0 ? -1 : (ti | (tj << 8));
   }
   const int fr = lane >> 2, fk = lane & 3;   // fragment row / k of this lane
   double racc = 0.0;                         // reduced right-hand side of column tid (tid < ncols)
@@ -800,6 +881,7 @@ __global__ void __launch_bounds__(SM_THREADS, 2)
     const long long ibase = v.pt_start[pc0];
     const int run = np * k;
     __syncthreads();  // previous chunk fully consumed (and the structure tables are complete)
+    mark(pc0 == p_begin ? 1 : 4);
     if (np < SM_PCH) {  // short last chunk: the k rows beyond it must read as zero
       const int kz0 = 3 * np, kz1 = (3 * np + 3) & ~3;
       for (int t = tid; t < (kz1 - kz0) * SM_LD; t += SM_THREADS) {
@@ -807,38 +889,64 @@ __global__ void __launch_bounds__(SM_THREADS, 2)
         sm.Yt[kk][cc] = 0.0; sm.Wt[kk][cc] = 0.0; sm.Jt[kk][cc] = 0.0;
       }
     }
-    // rows of the chunk: item (c2, observation), observation fastest -> coalesced plane reads
-    for (int t = tid; t < wc * run; t += SM_THREADS) {
-      const int c2 = t / run, off = t - c2 * run;   // off = lp * k + b
-      const int lp = off / k, bb = off - lp * k;
-      const int col = bb * wc + c2;
-      const int g = sm.gcol[col];
-      double js[3] = {0.0, 0.0, 0.0}, w[3] = {0.0, 0.0, 0.0}, y[3] = {0.0, 0.0, 0.0}, gr = 0.0;
-      if (g >= 0) {
-        const size_t i = (size_t)(ibase + off);
-        const double sc = scale[g];
+    // per-observation / per-point data of the chunk, loaded once (not once per camera-side column)
+    if (tid < run) {
+      const size_t i = (size_t)(ibase + tid);
+      const int pf = v.pt_poff[pc0 + sm.lp_of[tid]];
+      double sp[3] = {0.0, 0.0, 0.0};
+      if (pfree) { sp[0] = scale[v.nc + 3 * pf]; sp[1] = scale[v.nc + 3 * pf + 1]; sp[2] = scale[v.nc + 3 * pf + 2]; }
+#pragma unroll
+      for (int q = 0; q < 3; ++q) {
+        const bool on = q < nres;
+        sm.obsd[tid][q] = on ? v.r[q * N + i] : 0.0;
+#pragma unroll
+        for (int j = 0; j < 3; ++j) sm.obsd[tid][3 + 3 * q + j] = (on && pfree) ? v.Jp[((size_t)q * 3 + j) * N + i] * sp[j] : 0.0;
+      }
+    } else if (tid >= SM_THREADS - SM_PCH && pfree) {
+      const int lp = tid - (SM_THREADS - SM_PCH);
+      if (lp < np) {
         const int pf = v.pt_poff[pc0 + lp];
-        double sp0 = 0.0, sp1 = 0.0, sp2 = 0.0;
-        if (pfree) { sp0 = scale[v.nc + 3 * pf]; sp1 = scale[v.nc + 3 * pf + 1]; sp2 = scale[v.nc + 3 * pf + 2]; }
-        for (int q = 0; q < nres; ++q) {
-          const double jc = v.Jc[((size_t)q * wc + c2) * N + i] * sc;
-          js[q] = jc;
-          gr += jc * v.r[q * N + i];
-          if (pfree) {
-            w[0] += jc * v.Jp[((size_t)q * 3 + 0) * N + i] * sp0;
-            w[1] += jc * v.Jp[((size_t)q * 3 + 1) * N + i] * sp1;
-            w[2] += jc * v.Jp[((size_t)q * 3 + 2) * N + i] * sp2;
-          }
-        }
-        if (pfree) {
-          const size_t NP = (size_t)v.npf;
-          const double i00 = Vinv[0 * NP + pf], i01 = Vinv[1 * NP + pf], i02 = Vinv[2 * NP + pf];
-          const double i11 = Vinv[3 * NP + pf], i12 = Vinv[4 * NP + pf], i22 = Vinv[5 * NP + pf];
-          y[0] = w[0] * i00 + w[1] * i01 + w[2] * i02;
-          y[1] = w[0] * i01 + w[1] * i11 + w[2] * i12;
-          y[2] = w[0] * i02 + w[1] * i12 + w[2] * i22;
-          gr -= w[0] * Vig[0 * NP + pf] + w[1] * Vig[1 * NP + pf] + w[2] * Vig[2 * NP + pf];
-        }
+        const size_t NP = (size_t)v.npf;
+#pragma unroll
+        for (int e = 0; e < 6; ++e) sm.ptd[lp][e] = Vinv[e * NP + pf];
+#pragma unroll
+        for (int e = 0; e < 3; ++e) sm.ptd[lp][6 + e] = Vig[e * NP + pf];
+      }
+    }
+    __syncthreads();
+    mark(2);
+    // items (c2 = item >> 7, observation = item & 127): coalesced plane reads of the camera-side Jacobian
+    constexpr int ITEMS = ((WC ? WC : SEG_WCMAX) * 128 + SM_THREADS - 1) / SM_THREADS;
+#pragma unroll 1
+    for (int it = 0; it < ITEMS; ++it) {
+      const int t = tid + it * SM_THREADS;
+      const int c2 = t >> 7, off = t & 127;
+      if (c2 >= wc || off >= run) continue;
+      double jcv[3] = {0.0, 0.0, 0.0};
+      {
+        const size_t i = (size_t)(ibase + off);
+#pragma unroll
+        for (int q = 0; q < 3; ++q)
+          if (q < nres) jcv[q] = v.Jc[((size_t)q * wc + c2) * N + i];
+      }
+      const int lp = sm.lp_of[off], bb = sm.bb_of[off];
+      const int col = bb * wc + c2;
+      const double sc = sm.scol[col];
+      const double* od = sm.obsd[off];
+      double js[3], w[3] = {0.0, 0.0, 0.0}, y[3] = {0.0, 0.0, 0.0}, gr = 0.0;
+#pragma unroll
+      for (int q = 0; q < 3; ++q) {
+        js[q] = jcv[q] * sc;
+        gr += js[q] * od[q];
+#pragma unroll
+        for (int j = 0; j < 3; ++j) w[j] += js[q] * od[3 + 3 * q + j];
+      }
+      if (pfree) {
+        const double* pd = sm.ptd[lp];
+        y[0] = w[0] * pd[0] + w[1] * pd[1] + w[2] * pd[2];
+        y[1] = w[0] * pd[1] + w[1] * pd[3] + w[2] * pd[4];
+        y[2] = w[0] * pd[2] + w[1] * pd[4] + w[2] * pd[5];
+        gr -= w[0] * pd[6] + w[1] * pd[7] + w[2] * pd[8];
       }
 #pragma unroll
       for (int j = 0; j < 3; ++j) {
@@ -849,35 +957,37 @@ __global__ void __launch_bounds__(SM_THREADS, 2)
       sm.G[lp][col] = gr;
     }
     __syncthreads();
+    mark(3);
     if (tid < ncols)
       for (int lp = 0; lp < np; ++lp) racc += sm.G[lp][tid];
     const int ksteps = (3 * np + 3) >> 2;
 #pragma unroll
     for (int sidx = 0; sidx < SM_SLOTS; ++sidx) {
-      const int ti = tile_i[sidx], tj = tile_j[sidx];
-      if (ti < 0) continue;
-      const int row = 8 * ti + fr, col = 8 * tj + fr;   // A-fragment row / B-fragment column of this lane
-      if (pfree)
-        for (int ks = 0; ks < ksteps; ++ks)
-          dmma884(c[sidx][0], c[sidx][1], sm.Yt[4 * ks + fk][row], sm.Wt[4 * ks + fk][col]);
-      // U: Js^T Js restricted to rows and columns of the same shot
-      const int b_lo = max((8 * ti) / wc, (8 * tj) / wc), b_hi = min(min((8 * ti + 7) / wc, (8 * tj + 7) / wc), k - 1);
-      for (int b = b_lo; b <= b_hi; ++b) {
-        const bool ra = row / wc == b, cb = col / wc == b;
-        for (int ks = 0; ks < ksteps; ++ks) {
-          const double av = sm.Jt[4 * ks + fk][row], bv = sm.Jt[4 * ks + fk][col];
-          dmma884(c[sidx][0], c[sidx][1], ra ? av : 0.0, cb ? bv : 0.0);
-        }
+      if (tile_ij[sidx] < 0) continue;
+      // A-fragment row / B-fragment column of this lane, at k = fk
+      const int arow = fk * SM_LD + 8 * (tile_ij[sidx] & 255) + fr, bcol = fk * SM_LD + 8 * (tile_ij[sidx] >> 8) + fr;
+      if (pfree) {
+        const double* yk = &sm.Yt[0][0] + arow;
+        const double* wk = &sm.Wt[0][0] + bcol;
+#pragma unroll 2
+        for (int ks = 0; ks < ksteps; ++ks) dmma884(c[sidx][0], c[sidx][1], yk[ks * 4 * SM_LD], wk[ks * 4 * SM_LD]);
+      }
+      if (sidx < SM_NEAR) {   // Js^T Js; the flush keeps it only where row and column belong to the same shot
+        const double* ja = &sm.Jt[0][0] + arow;
+        const double* jb = &sm.Jt[0][0] + bcol;
+#pragma unroll 2
+        for (int ks = 0; ks < ksteps; ++ks) dmma884(d[sidx][0], d[sidx][1], ja[ks * 4 * SM_LD], jb[ks * 4 * SM_LD]);
       }
     }
   }
 
   // ---- flush: right-hand side once per column, the tiles straight from the fragments ----
+  mark(4);
   if (tid < ncols && sm.gcol[tid] >= 0) atomicAdd(&rhs[sm.gcol[tid]], racc);
 #pragma unroll
   for (int sidx = 0; sidx < SM_SLOTS; ++sidx) {
-    const int ti = tile_i[sidx], tj = tile_j[sidx];
-    if (ti < 0) continue;
+    if (tile_ij[sidx] < 0) continue;
+    const int ti = tile_ij[sidx] & 255, tj = tile_ij[sidx] >> 8;
     const int row = 8 * ti + fr;
 #pragma unroll
     for (int e = 0; e < 2; ++e) {
@@ -890,6 +1000,7 @@ __global__ void __launch_bounds__(SM_THREADS, 2)
       const int B1 = m1 >> 12, s1 = (m1 >> 10) & 3, sz1 = (m1 >> 5) & 31, r1 = m1 & 31;
       const int B2 = m2 >> 12, s2 = (m2 >> 10) & 3, sz2 = (m2 >> 5) & 31, r2 = m2 & 31;
       double val = c[sidx][e];
+      if (sidx < SM_NEAR && a == bb) val += d[sidx < SM_NEAR ? sidx : 0][e];
       int pos;
       if (B1 < B2) {
         pos = r1 * sz2 + r2;
@@ -905,9 +1016,10 @@ __global__ void __launch_bounds__(SM_THREADS, 2)
           pos = min(r1, r2) * sz1 + max(r1, r2);
         }
       }
-      atomicAdd(&Sval[sm.offt[(a * SEG_KMAX + bb) * 9 + s1 * 3 + s2] + pos], val);
+      atomicAdd(&Sval[sm.offt[seg_pair_index(a, bb, k) * 9 + s1 * 3 + s2] + pos], val);
     }
   }
+  mark(5);
 }
 
 // Priors (after the all-reduce): diagonal entries of the diagonal blocks.
