@@ -917,18 +917,20 @@ __global__ void __launch_bounds__(SM_THREADS, 2)
     mark(2);
     // items (c2 = item >> 7, observation = item & 127): coalesced plane reads of the camera-side Jacobian
     constexpr int ITEMS = ((WC ? WC : SEG_WCMAX) * 128 + SM_THREADS - 1) / SM_THREADS;
-#pragma unroll 1
+    double jall[ITEMS][3];   // all of this thread's plane reads in flight before the first use
+#pragma unroll
+    for (int it = 0; it < ITEMS; ++it) {
+      const int t = tid + it * SM_THREADS;
+      const int c2 = t >> 7, off = t & 127;
+#pragma unroll
+      for (int q = 0; q < 3; ++q)
+        jall[it][q] = (c2 < wc && off < run && q < nres) ? v.Jc[((size_t)q * wc + c2) * N + (size_t)(ibase + off)] : 0.0;
+    }
+#pragma unroll
     for (int it = 0; it < ITEMS; ++it) {
       const int t = tid + it * SM_THREADS;
       const int c2 = t >> 7, off = t & 127;
       if (c2 >= wc || off >= run) continue;
-      double jcv[3] = {0.0, 0.0, 0.0};
-      {
-        const size_t i = (size_t)(ibase + off);
-#pragma unroll
-        for (int q = 0; q < 3; ++q)
-          if (q < nres) jcv[q] = v.Jc[((size_t)q * wc + c2) * N + i];
-      }
       const int lp = sm.lp_of[off], bb = sm.bb_of[off];
       const int col = bb * wc + c2;
       const double sc = sm.scol[col];
@@ -936,7 +938,7 @@ __global__ void __launch_bounds__(SM_THREADS, 2)
       double js[3], w[3] = {0.0, 0.0, 0.0}, y[3] = {0.0, 0.0, 0.0}, gr = 0.0;
 #pragma unroll
       for (int q = 0; q < 3; ++q) {
-        js[q] = jcv[q] * sc;
+        js[q] = jall[it][q] * sc;
         gr += js[q] * od[q];
 #pragma unroll
         for (int j = 0; j < 3; ++j) w[j] += js[q] * od[3 + 3 * q + j];
