@@ -1221,7 +1221,7 @@ void BA::run() {
       const long long off_S = up16(8 * col_max), off_Minv = off_S + up16(8 * ent_max);
       const long long off_vec = off_Minv + 8LL * grp_max * MAXB * MAXB, off_cols = off_vec + up16(24LL * rows_max);
       const long long off_rows = off_cols + up16(2 * col_max);
-      const long long total = off_rows + 16LL * rows_max + 4LL * (grp_max + 1);
+      const long long total = off_rows + 36LL * rows_max + 4LL * (grp_max + 1);
       static const bool allow_pipe = []() { const char* e = getenv("OSFM_BA_PCG_PIPELINED"); return !(e && e[0] == '0'); }();
       int max_smem = 0;
       OSFM_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));

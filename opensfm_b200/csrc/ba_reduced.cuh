@@ -1521,6 +1521,14 @@ __global__ void __launch_bounds__(PCG_THREADS, 1)
   int* row_len = row_coff + R.max_rows;
   int* row_gidx = row_len + R.max_rows;
   int* grp_row0 = row_gidx + R.max_rows;  // [max_groups + 1]
+  // mat-vec units: up to three consecutive rows of one block row (they share the packed m of that block row)
+  int* unit_soff = grp_row0 + R.max_groups + 1;  // [max_rows] each
+  int* unit_coff = unit_soff + R.max_rows;
+  int* unit_len = unit_coff + R.max_rows;
+  int* unit_lr0 = unit_len + R.max_rows;
+  int* unit_nr = unit_lr0 + R.max_rows;
+  __shared__ double part_s[PCG_THREADS / 8][3];   // per 8-lane group: partial sums of its unit's rows
+  __shared__ int s_nunits;
   double* mbuf[2] = {mbuf0, mbuf1};
   unsigned bar_gen = 0;
 
@@ -1546,6 +1554,15 @@ __global__ void __launch_bounds__(PCG_THREADS, 1)
     grp_row0[ng] = lr;
     s_nrows = lr;
     s_ncols = c_off;
+    int nu = 0;
+    for (int r0 = 0; r0 < lr;) {
+      int nr = 1;  // rows r0 .. r0 + nr - 1 belong to the same block row iff they share the column list
+      while (nr < 3 && r0 + nr < lr && row_coff[r0 + nr] == row_coff[r0] && row_soff[r0 + nr] == row_soff[r0] + nr * row_len[r0]) ++nr;
+      unit_soff[nu] = row_soff[r0]; unit_coff[nu] = row_coff[r0]; unit_len[nu] = row_len[r0]; unit_lr0[nu] = r0; unit_nr[nu] = nr;
+      ++nu;
+      r0 += nr;
+    }
+    s_nunits = nu;
   }
   __syncthreads();
   const int nrows = s_nrows, ncols = s_ncols;
@@ -1574,30 +1591,52 @@ __global__ void __launch_bounds__(PCG_THREADS, 1)
       }
     }
   };
-  // n_s[lr] = (S m)[row lr], m packed per block row in mp_s.  Eight lanes per row, four rows per warp:
-  // with 16 warps on the SM the mat-vec is latency-bound, so every lane keeps four independent
-  // accumulator chains going and no warp walks more than one batch of rows.
+  // n_s[lr] = (S m)[row lr], m packed per block row in mp_s.  The mat-vec is bound by shared-memory
+  // bandwidth, so a lane multiplies one loaded m entry into up to three rows (a unit) and the 64
+  // eight-lane groups of the CTA split the units' columns among them; partial sums meet in part_s.
   auto matvec = [&]() {
-    const int sub = lane >> 3, l = lane & 7;
-    for (int rb = warp * 4; rb < nrows; rb += nwarps * 4) {
-      const int lr = rb + sub;
-      double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-      if (lr < nrows) {
-        const double* vals = S_s + row_soff[lr];
-        const double* mp = mp_s + row_coff[lr];
-        const int M = row_len[lr];
-        int q = l;
-        for (; q + 24 < M; q += 32) {
-          s0 += vals[q] * mp[q]; s1 += vals[q + 8] * mp[q + 8];
-          s2 += vals[q + 16] * mp[q + 16]; s3 += vals[q + 24] * mp[q + 24];
+    const int nunits = s_nunits;
+    const int gidx = tid >> 3, l = tid & 7, ngroups8 = blockDim.x >> 3;
+    const int gpu = max(1, ngroups8 / nunits);   // groups per unit
+    for (int ub = 0; ub < nunits; ub += ngroups8) {   // one pass unless a CTA has more than 64 units
+      const int upass = min(nunits - ub, ngroups8 / gpu);   // units handled in this pass
+      const int ul = gidx / gpu, sub = gidx - ul * gpu;
+      const int u = ub + ul;
+      double a0 = 0.0, a1 = 0.0, a2 = 0.0;
+      const bool on = ul < upass;
+      if (on) {
+        const int M = unit_len[u], nr = unit_nr[u];
+        const double* v0 = S_s + unit_soff[u];
+        const double* v1 = v0 + (nr > 1 ? M : 0);
+        const double* v2 = v0 + (nr > 2 ? 2 * M : 0);
+        const double* mp = mp_s + unit_coff[u];
+        const int step = gpu * 8;
+        int q = sub * 8 + l;
+        for (; q + step < M; q += 2 * step) {
+          const double m0 = mp[q], m1 = mp[q + step];
+          a0 += v0[q] * m0; a1 += v1[q] * m0; a2 += v2[q] * m0;
+          a0 += v0[q + step] * m1; a1 += v1[q + step] * m1; a2 += v2[q + step] * m1;
         }
-        for (; q < M; q += 8) s0 += vals[q] * mp[q];
+        if (q < M) { const double m0 = mp[q]; a0 += v0[q] * m0; a1 += v1[q] * m0; a2 += v2[q] * m0; }
       }
-      double sv = (s0 + s1) + (s2 + s3);
-      sv += __shfl_xor_sync(0xffffffffu, sv, 4);
-      sv += __shfl_xor_sync(0xffffffffu, sv, 2);
-      sv += __shfl_xor_sync(0xffffffffu, sv, 1);
-      if (l == 0 && lr < nrows) n_s[lr] = sv;
+#pragma unroll
+      for (int o = 4; o; o >>= 1) {
+        a0 += __shfl_xor_sync(0xffffffffu, a0, o);
+        a1 += __shfl_xor_sync(0xffffffffu, a1, o);
+        a2 += __shfl_xor_sync(0xffffffffu, a2, o);
+      }
+      if (l == 0) { part_s[gidx][0] = a0; part_s[gidx][1] = a1; part_s[gidx][2] = a2; }
+      __syncthreads();
+      if (tid < upass * 3) {
+        const int uu = tid / 3, r = tid - uu * 3;
+        const int u2 = ub + uu;
+        if (r < unit_nr[u2]) {
+          double sv = 0.0;
+          for (int g2 = 0; g2 < gpu; ++g2) sv += part_s[uu * gpu + g2][r];
+          n_s[unit_lr0[u2] + r] = sv;
+        }
+      }
+      __syncthreads();
     }
   };
   // mp_s[e] = src[cols_s[e]] for every column entry of the owned block rows (gathers from L2, 8 in flight)
