@@ -227,7 +227,7 @@ def main():
         odist.init_from_env("nccl")
         import torch.distributed as tdist
 
-        allreduce = odist.make_allreduce(device=local)
+        allreduce = "nccl"  # the library's own NCCL communicator (opensfm_b200.dist.make_allreduce is the callback form)
     L = _lib.load()
     pk = peaks()
 

@@ -128,6 +128,12 @@ int osfm_ba_set_options(osfm_ba* ba, int loss, double loss_threshold, int max_it
  * at device pointer `buf` across ranks on `stream` (NCCL); NULL when world == 1. */
 typedef int (*osfm_allreduce_fn)(void* device_buf, int64_t count, void* stream, void* user);
 int osfm_ba_set_distributed(osfm_ba* ba, int rank, int world, osfm_allreduce_fn fn, void* user);
+/* Alternative to the callback: the library opens libnccl.so.2 itself and owns a communicator.
+ * Rank 0 calls osfm_nccl_unique_id, the caller broadcasts the 128 bytes by its own means, every rank calls
+ * osfm_ba_set_nccl (collective), then osfm_ba_set_distributed(ba, rank, world, NULL, NULL).  The all-reduces
+ * of a run are then plain ncclAllReduce calls on the library's stream (no host code in between). */
+int osfm_nccl_unique_id(char* out128);
+int osfm_ba_set_nccl(osfm_ba* ba, int rank, int world, const char* id128);
 /* Use an externally owned stream (e.g. torch's current stream); NULL = own stream. */
 int osfm_ba_set_stream(osfm_ba* ba, void* cuda_stream);
 

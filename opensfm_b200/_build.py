@@ -52,7 +52,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     with ThreadPoolExecutor(max_workers=len(SOURCES)) as ex:
         objs = list(ex.map(compile_one, SOURCES))
     cmd = [nvcc, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-ccbin", "/usr/bin/g++",
-                                                "-cudart", "static"]
+                                                "-cudart", "static", "-ldl"]
     subprocess.check_call(cmd)
     return LIB
 

@@ -63,6 +63,8 @@ SIGNATURES = {
     "osfm_ba_set_observations": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]),
     "osfm_ba_set_options": (c_int, [c_void_p, c_int, c_double, c_int, c_char_p, c_int]),
     "osfm_ba_set_distributed": (c_int, [c_void_p, c_int, c_int, ALLREDUCE_FN, c_void_p]),
+    "osfm_nccl_unique_id": (c_int, [c_void_p]),
+    "osfm_ba_set_nccl": (c_int, [c_void_p, c_int, c_int, c_void_p]),
     "osfm_ba_set_stream": (c_int, [c_void_p, c_void_p]),
     "osfm_ba_run": (c_int, [c_void_p]),
     "osfm_ba_get_summary": (c_int, [c_void_p, POINTER(BASummary)]),

@@ -63,8 +63,10 @@ def solve(pb: bp.BAProblem, device: int = 0, rank: int = 0, world: int = 1, allr
     """Run the GPU bundle adjustment on a BAProblem.  Returns updated parameter arrays,
     unscaled reprojection errors (bundle_adjuster.cc:1196-1208) and the run summary.
 
-    Multi-GPU: pass rank/world and `allreduce(ptr:int, count:int, stream:int) -> None`
-    that sums `count` float64 at device pointer `ptr` across ranks (see opensfm_b200.dist).
+    Multi-GPU: pass rank/world and either allreduce="nccl" (the library opens its own NCCL
+    communicator; torch.distributed must be initialised, it only carries the 128-byte id once) or a
+    callable `allreduce(ptr:int, count:int, stream:int) -> None` that sums `count` float64 at device
+    pointer `ptr` across ranks (see opensfm_b200.dist; used with gloo in the CPU tests).
 
     `out` may hold preallocated C-contiguous float64 arrays "points" (P, 3) and "reprojection_errors"
     (N, 3) to receive the results (page-locked buffers make the device->host copy a plain DMA)."""
@@ -97,20 +99,37 @@ def solve(pb: bp.BAProblem, device: int = 0, rank: int = 0, world: int = 1, allr
         cb = None
         if world > 1:
             if allreduce is None:
-                raise ValueError("world > 1 needs an allreduce callable")
+                raise ValueError("world > 1 needs allreduce: a callable or the string 'nccl'")
+            if isinstance(allreduce, str):
+                if allreduce != "nccl":
+                    raise ValueError("allreduce must be a callable or 'nccl'")
+                # the library's own NCCL communicator (one per handle; the 128-byte id travels over torch.distributed)
+                hd = _handle(int(device))
+                if getattr(hd, "nccl", None) != (int(rank), int(world)):
+                    import torch.distributed as tdist
 
-            def _cb(buf, count, strm, user):
-                try:
-                    allreduce(int(buf), int(count), int(strm or 0))
-                    return 0
-                except Exception:  # surfaces as RuntimeError from run()
-                    import traceback
+                    buf = ctypes.create_string_buffer(128)
+                    if rank == 0:
+                        _lib.check(L.osfm_nccl_unique_id(buf))
+                    box = [buf.raw]
+                    tdist.broadcast_object_list(box, src=0)
+                    idb = ctypes.create_string_buffer(box[0], 128)
+                    _lib.check(L.osfm_ba_set_nccl(h, int(rank), int(world), idb))
+                    hd.nccl = (int(rank), int(world))
+                _lib.check(L.osfm_ba_set_distributed(h, int(rank), int(world), ctypes.cast(None, _lib.ALLREDUCE_FN), None))
+            else:
+                def _cb(buf, count, strm, user):
+                    try:
+                        allreduce(int(buf), int(count), int(strm or 0))
+                        return 0
+                    except Exception:  # surfaces as RuntimeError from run()
+                        import traceback
 
-                    traceback.print_exc()
-                    return 1
+                        traceback.print_exc()
+                        return 1
 
-            cb = _lib.ALLREDUCE_FN(_cb)
-            _lib.check(L.osfm_ba_set_distributed(h, int(rank), int(world), cb, None))
+                cb = _lib.ALLREDUCE_FN(_cb)
+                _lib.check(L.osfm_ba_set_distributed(h, int(rank), int(world), cb, None))
         else:
             # the handle is reused between calls: reset whatever a previous distributed solve left
             _lib.check(L.osfm_ba_set_distributed(h, 0, 1, ctypes.cast(None, _lib.ALLREDUCE_FN), None))

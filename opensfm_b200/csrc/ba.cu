@@ -18,7 +18,11 @@
 // U, g_c, V^-1 and W V^-1 W^T scattered to S with fp64 atomics), ba_finish_system,
 // PCG kernels (block-Jacobi), ba_backsub (warp per point), ba_model_change, ba_update.
 #include <algorithm>
+#include <dlfcn.h>
+
 #include <chrono>
+#include <cstring>
+#include <mutex>
 #include <cmath>
 #include <cstdlib>
 #include <string>
@@ -26,6 +30,9 @@
 
 #include "ba_models.cuh"
 #include "common.cuh"
+
+// ncclUniqueId is 128 opaque bytes passed BY VALUE to ncclCommInitRank (nccl.h: NCCL_UNIQUE_ID_BYTES)
+struct OsfmNcclId { char internal[128]; };
 
 namespace osfm {
 
@@ -559,6 +566,45 @@ static void upload(DevBuf<T>& d, const std::vector<T>& h, cudaStream_t st) {
   if (!h.empty()) OSFM_CUDA(cudaMemcpyAsync(d.p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice, st));
 }
 
+// ---------------------------------------------------------------------------
+// NCCL, loaded at run time (libnccl.so.2: the copy torch already mapped if there is one, so that one
+// process never mixes two NCCL versions).  Only the five entry points the all-reduce needs; the
+// constants are nccl.h's (ncclFloat64 = 8, ncclSum = 0, ncclUniqueId = 128 bytes).
+// ---------------------------------------------------------------------------
+struct NcclApi {
+  void* lib = nullptr;
+  int (*GetUniqueId)(void*) = nullptr;
+  int (*CommInitRank)(void**, int, OsfmNcclId, int) = nullptr;
+  int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+  int (*CommDestroy)(void*) = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+};
+static NcclApi& nccl_api() {
+  static NcclApi api;
+  static std::once_flag once;
+  std::call_once(once, []() {
+    void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);
+    if (!h) h = dlopen("libnccl.so.2", RTLD_NOW);
+    if (!h) h = dlopen("libnccl.so", RTLD_NOW);
+    if (!h) return;
+    api.lib = h;
+    api.GetUniqueId = reinterpret_cast<int (*)(void*)>(dlsym(h, "ncclGetUniqueId"));
+    api.CommInitRank = reinterpret_cast<int (*)(void**, int, OsfmNcclId, int)>(dlsym(h, "ncclCommInitRank"));
+    api.AllReduce = reinterpret_cast<int (*)(const void*, void*, size_t, int, int, void*, cudaStream_t)>(dlsym(h, "ncclAllReduce"));
+    api.CommDestroy = reinterpret_cast<int (*)(void*)>(dlsym(h, "ncclCommDestroy"));
+    api.GetErrorString = reinterpret_cast<const char* (*)(int)>(dlsym(h, "ncclGetErrorString"));
+  });
+  if (!api.lib || !api.GetUniqueId || !api.CommInitRank || !api.AllReduce || !api.CommDestroy)
+    throw std::runtime_error("NCCL (libnccl.so.2) is not available in this process");
+  return api;
+}
+static void nccl_check(int rc, const char* what) {
+  if (rc != 0) {
+    NcclApi& a = nccl_api();
+    throw std::runtime_error(std::string(what) + ": " + (a.GetErrorString ? a.GetErrorString(rc) : "NCCL error"));
+  }
+}
+
 struct BA {
   int device = 0;
   cudaStream_t own_stream = nullptr, stream = nullptr;
@@ -581,6 +627,8 @@ struct BA {
   int rank = 0, world = 1;
   osfm_allreduce_fn allreduce = nullptr;
   void* allreduce_user = nullptr;
+  void* nccl_comm = nullptr;   // own communicator (osfm_ba_set_nccl); used when no callback is set
+  int nccl_rank = -1, nccl_world = 0;
   // results
   bool reproj_valid = false;
   osfm_ba_summary summary{};
@@ -648,6 +696,7 @@ struct BA {
   }
   ~BA() {
     cudaSetDevice(device);
+    if (nccl_comm) { try { nccl_api().CommDestroy(nccl_comm); } catch (...) {} }
     if (own_stream) cudaStreamDestroy(own_stream);
   }
 
@@ -658,8 +707,13 @@ struct BA {
   }
   void allreduce_dev(double* buf, long long count) {
     if (world > 1) {
-      if (!allreduce) throw ArgError("world > 1 but no all-reduce callback set");
-      if (allreduce(buf, count, stream, allreduce_user) != 0) throw std::runtime_error("all-reduce callback failed");
+      if (allreduce) {
+        if (allreduce(buf, count, stream, allreduce_user) != 0) throw std::runtime_error("all-reduce callback failed");
+      } else if (nccl_comm && nccl_world == world && nccl_rank == rank) {
+        nccl_check(nccl_api().AllReduce(buf, buf, (size_t)count, /*ncclFloat64*/ 8, /*ncclSum*/ 0, nccl_comm, stream), "ncclAllReduce");
+      } else {
+        throw ArgError("world > 1 but neither an all-reduce callback nor an NCCL communicator is set");
+      }
     }
   }
   void run();
@@ -1729,8 +1783,30 @@ int osfm_ba_set_distributed(osfm_ba* ba, int rank, int world, osfm_allreduce_fn 
   OSFM_API_BEGIN
   OSFM_BA_CHECK
   if (world < 1 || rank < 0 || rank >= world) throw ArgError("bad rank/world");
-  if (world > 1 && !fn) throw ArgError("world > 1 needs an all-reduce callback");
+  if (world > 1 && !fn && !(ba->impl.nccl_comm && ba->impl.nccl_world == world && ba->impl.nccl_rank == rank))
+    throw ArgError("world > 1 needs an all-reduce callback or osfm_ba_set_nccl");
   ba->impl.rank = rank; ba->impl.world = world; ba->impl.allreduce = fn; ba->impl.allreduce_user = user;
+  OSFM_API_END
+}
+int osfm_nccl_unique_id(char* out128) {
+  OSFM_API_BEGIN
+  if (!out128) throw ArgError("null id buffer");
+  OsfmNcclId id;
+  osfm::nccl_check(osfm::nccl_api().GetUniqueId(&id), "ncclGetUniqueId");
+  std::memcpy(out128, id.internal, 128);
+  OSFM_API_END
+}
+int osfm_ba_set_nccl(osfm_ba* ba, int rank, int world, const char* id128) {
+  OSFM_API_BEGIN
+  OSFM_BA_CHECK
+  if (world < 2 || rank < 0 || rank >= world || !id128) throw ArgError("bad rank/world/id");
+  auto& b = ba->impl;
+  OSFM_CUDA(cudaSetDevice(b.device));
+  if (b.nccl_comm) { osfm::nccl_api().CommDestroy(b.nccl_comm); b.nccl_comm = nullptr; }
+  OsfmNcclId id;
+  std::memcpy(id.internal, id128, 128);
+  osfm::nccl_check(osfm::nccl_api().CommInitRank(&b.nccl_comm, world, id, rank), "ncclCommInitRank");
+  b.nccl_rank = rank; b.nccl_world = world;
   OSFM_API_END
 }
 int osfm_ba_set_stream(osfm_ba* ba, void* cuda_stream) {

@@ -18,8 +18,12 @@ allreduce = odist.make_allreduce(device=local)
 
 sc = syn.cube_scene(16, 3000, 1.0, max_obs_per_point=8)
 pb = syn.scene_to_problem(sc)
-multi = bundle.solve(pb, device=local, rank=rank, world=world, allreduce=allreduce)
+multi_cb = bundle.solve(pb, device=local, rank=rank, world=world, allreduce=allreduce)   # torch.distributed callback
+multi = bundle.solve(pb, device=local, rank=rank, world=world, allreduce="nccl")         # the library's own communicator
 single = bundle.solve(pb, device=local)
+assert multi_cb["summary"]["iterations"] == multi["summary"]["iterations"]
+assert abs(multi_cb["summary"]["final_cost"] - multi["summary"]["final_cost"]) <= 1e-9 * multi["summary"]["final_cost"]
+assert np.abs(multi_cb["points"] - multi["points"]).max() < 1e-8
 sm, ss = multi["summary"], single["summary"]
 assert sm["termination"] == "CONVERGENCE", sm
 assert sm["iterations"] == ss["iterations"], (sm, ss)
