@@ -384,6 +384,26 @@ __global__ void ba_make_diag(const double* colnorm2, const double* scale, double
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) diag[i] = fmin(fmax(colnorm2[i] * scale[i] * scale[i], 1e-6), 1e32);
 }
+// Multi-GPU: everything rank-summed after a linearisation travels in ONE buffer
+//   pack = [ colnorm2 (nc) | grad (nc) | cost | per-rank max |point gradient| (world) ]
+__global__ void ba_pack_lin(const double* __restrict__ colnorm2, const double* __restrict__ grad, const Scalars* sc, int nc,
+                            int rank, int world, double* __restrict__ pack) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < nc) { pack[i] = colnorm2[i]; pack[nc + i] = grad[i]; }
+  if (i == 0) pack[2 * nc] = sc->cost;
+  if (i < world) pack[2 * nc + 1 + i] = i == rank ? sc->grad_max_bits : 0.0;
+}
+__global__ void ba_unpack_lin(const double* __restrict__ pack, int nc, int world, double* __restrict__ colnorm2,
+                              double* __restrict__ grad, Scalars* sc) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  double v = 0.0;
+  if (i < nc) { colnorm2[i] = pack[i]; grad[i] = pack[nc + i]; v = fabs(pack[nc + i]); }
+  if (i < world) v = fmax(v, pack[2 * nc + 1 + i]);
+  if (i == 0) sc->cost = pack[2 * nc];
+#pragma unroll
+  for (int o = 16; o; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+  if ((threadIdx.x & 31) == 0 && v > 0.0) atomic_max_nonneg(&sc->grad_max_bits, v);
+}
 __global__ void ba_grad_max(const double* grad, int n, Scalars* sc) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   double v = i < n ? fabs(grad[i]) : 0.0;
@@ -705,8 +725,27 @@ struct BA {
     OSFM_CUDA(cudaStreamSynchronize(stream));
     return *h_sc.p;
   }
+  // OSFM_BA_TRACE: number of all-reduces and the host time spent issuing them (+ device time when traced)
+  int ar_calls = 0;
+  double ar_host_ms = 0.0, ar_dev_ms = 0.0;
+  bool ar_trace = false;
   void allreduce_dev(double* buf, long long count) {
     if (world > 1) {
+      const auto t0 = std::chrono::high_resolution_clock::now();
+      cudaEvent_t e0 = nullptr, e1 = nullptr;
+      if (ar_trace) { cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventRecord(e0, stream); }
+      struct Done {
+        BA* self; std::chrono::high_resolution_clock::time_point t0; cudaEvent_t e0, e1;
+        ~Done() {
+          if (self->ar_trace) {
+            cudaEventRecord(e1, self->stream); cudaEventSynchronize(e1);
+            float ms = 0.f; cudaEventElapsedTime(&ms, e0, e1); self->ar_dev_ms += ms;
+            cudaEventDestroy(e0); cudaEventDestroy(e1);
+          }
+          ++self->ar_calls;
+          self->ar_host_ms += std::chrono::duration<double, std::milli>(std::chrono::high_resolution_clock::now() - t0).count();
+        }
+      } done{this, t0, e0, e1};
       if (allreduce) {
         if (allreduce(buf, count, stream, allreduce_user) != 0) throw std::runtime_error("all-reduce callback failed");
       } else if (nccl_comm && nccl_world == world && nccl_rank == rank) {
@@ -727,6 +766,7 @@ void BA::run() {
   // OSFM_BA_TRACE=1: host wall-clock per phase of run() on stderr (diagnostics only)
   static const bool trace_on = []() { const char* e = getenv("OSFM_BA_TRACE"); return e && e[0] == '1'; }();
   auto t_prev = t_start;
+  ar_trace = trace_on; ar_calls = 0; ar_host_ms = 0.0; ar_dev_ms = 0.0;
   auto trace = [&](const char* what) {
     if (!trace_on) return;
     const auto now = std::chrono::high_resolution_clock::now();
@@ -1055,26 +1095,25 @@ void BA::run() {
       OSFM_LAUNCH_CHECK();
     }
     if (world > 1) {
-      allreduce_dev(&d_sc.p->cost, 1);
-      if (nc > 0) { allreduce_dev(d_colnorm2.p, nc); allreduce_dev(d_grad.p, nc); }
-    }
-    if (n > 0) {
+      // local max over the point part, then one all-reduce for cost, camera-side sums and the per-rank maxima
+      if (n > nc) {
+        ba_grad_max<<<grid_for(n - nc, 256), 256, 0, stream>>>(d_grad.p + nc, n - nc, d_sc.p);
+        OSFM_LAUNCH_CHECK();
+      }
+      const int npack = 2 * nc + 1 + world;
+      d_slots.reserve(npack);
+      const int gsz = std::max(nc, world);
+      ba_pack_lin<<<grid_for(gsz, 256), 256, 0, stream>>>(d_colnorm2.p, d_grad.p, d_sc.p, nc, rank, world, d_slots.p);
+      OSFM_LAUNCH_CHECK();
+      allreduce_dev(d_slots.p, npack);
+      ba_unpack_lin<<<grid_for(gsz, 256), 256, 0, stream>>>(d_slots.p, nc, world, d_colnorm2.p, d_grad.p, d_sc.p);
+      OSFM_LAUNCH_CHECK();
+    } else if (n > 0) {
       ba_grad_max<<<grid_for(n, 256), 256, 0, stream>>>(d_grad.p, n, d_sc.p);
       OSFM_LAUNCH_CHECK();
     }
     const Scalars s = read_scalars();
-    double gm = s.grad_max_bits;
-    if (world > 1) {
-      // max over ranks of the local point-gradient maxima: sum of one-hot slots
-      std::vector<double> slots(world, 0.0);
-      slots[rank] = gm;
-      d_slots.reserve(world);
-      OSFM_CUDA(cudaMemcpyAsync(d_slots.p, slots.data(), sizeof(double) * world, cudaMemcpyHostToDevice, stream));
-      allreduce_dev(d_slots.p, world);
-      OSFM_CUDA(cudaMemcpyAsync(slots.data(), d_slots.p, sizeof(double) * world, cudaMemcpyDeviceToHost, stream));
-      OSFM_CUDA(cudaStreamSynchronize(stream));
-      for (double x : slots) gm = std::max(gm, x);
-    }
+    const double gm = s.grad_max_bits;
     *grad_max = gm;
     return s.cost;
   };
@@ -1301,6 +1340,11 @@ void BA::run() {
 
   trace("structure");
   // ---- Levenberg-Marquardt (Ceres trust_region_minimizer / levenberg_marquardt_strategy) ----
+  if (world > 1) {  // all ranks enter the timed region together (their set-up times differ)
+    OSFM_CUDA(cudaMemsetAsync(d_sc.p, 0, sizeof(Scalars), stream));
+    allreduce_dev(&d_sc.p->cost, 1);
+    OSFM_CUDA(cudaStreamSynchronize(stream));
+  }
   OSFM_CUDA(cudaEventRecord(ev0, stream));
   double radius = 1e4;
   const double max_radius = 1e16, min_radius = 1e-32, min_rel_decrease = 1e-3;
@@ -1604,6 +1648,9 @@ void BA::run() {
   }
   OSFM_CUDA(cudaStreamSynchronize(stream));
   trace("results");
+  if (trace_on && world > 1)
+    fprintf(stderr, "[osfm_ba] rank %d: %d all-reduces, host %.3f ms, device (traced, serialised) %.3f ms\n", rank, ar_calls,
+            ar_host_ms, ar_dev_ms);
   float dev_ms = 0.f;
   OSFM_CUDA(cudaEventElapsedTime(&dev_ms, ev0, ev1));
   cudaEventDestroy(ev0); cudaEventDestroy(ev1);
