@@ -305,7 +305,7 @@ __global__ void __launch_bounds__(256) ba_colnorm_grad_points(BAView v, double* 
 // warp per segment, lane = (point slot g, shot c) so that a lane always works on the same shot; the
 // running sums stay in registers and a segment issues k * wc atomics instead of points * k * wc.
 template <int WCT>
-__global__ void __launch_bounds__(256) ba_colnorm_grad_seg(BAView v, const int* __restrict__ seg_start, int nseg,
+__global__ void __launch_bounds__(256, WCT ? 3 : 2) ba_colnorm_grad_seg(BAView v, const int* __restrict__ seg_start, int nseg,
                                                            double* colnorm2, double* grad) {
   const int s = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (s >= nseg) return;

@@ -99,6 +99,23 @@ def match_brute_force_symmetric(fi: np.ndarray, fj: np.ndarray, config: Dict[str
     return [(int(i), int(idx[i])) for i in q]
 
 
+def split_match_lists(raw: np.ndarray, counts: np.ndarray) -> List[np.ndarray]:
+    """raw = the concatenated per-query train indices (-1 = no match) of consecutive pairs with `counts[p]`
+    queries each -> one int64 [K, 2] array of (query, train) per pair, in one vectorised pass (the
+    reference builds the same list pair by pair, matching.py:744-756)."""
+    npairs = len(counts)
+    if npairs == 0:
+        return []
+    starts = np.concatenate([[0], np.cumsum(counts)])
+    hit = np.flatnonzero(raw >= 0)
+    pair_of = np.searchsorted(starts, hit, side="right") - 1
+    both = np.empty((len(hit), 2), dtype=np.int64)
+    both[:, 0] = hit - starts[pair_of]
+    both[:, 1] = raw[hit]
+    cuts = np.searchsorted(pair_of, np.arange(1, npairs))
+    return np.split(both, cuts)
+
+
 class PairMatcher:
     """Descriptors resident in HBM + a pair list matched in one submission.
 
@@ -187,17 +204,8 @@ class PairMatcher:
             symmetric = bool(config.get("symmetric_matching", True))  # config.py:101
         self.submit(pairs, config["lowes_ratio"], symmetric)
         raw = self.fetch_raw()
-        # one vectorised pass over all pairs' match lists instead of a numpy call per pair
         counts = np.array([self._n[a] for a, _ in self._pairs], dtype=np.int64)
-        starts = np.concatenate([[0], np.cumsum(counts)])
-        hit = np.flatnonzero(raw >= 0)
-        pair_of = np.searchsorted(starts, hit, side="right") - 1
-        both = np.empty((len(hit), 2), dtype=np.int64)
-        both[:, 0] = hit - starts[pair_of]
-        both[:, 1] = raw[hit]
-        cuts = np.searchsorted(pair_of, np.arange(1, len(self._pairs)))
-        parts = np.split(both, cuts) if len(self._pairs) else []
-        return dict(zip(self._pairs, parts))
+        return dict(zip(self._pairs, split_match_lists(raw, counts)))
 
 
 def shard_pairs(pairs: Sequence[Tuple[Any, Any]], sizes: Dict[Any, int], world: int) -> List[List[Tuple[Any, Any]]]:

@@ -136,3 +136,23 @@ def test_world_size_2_gloo_plumbing(tmp_path):
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
     assert out.returncode == 0, out.stderr[-2000:]
     assert "GLOO_OK" in out.stdout
+
+
+def test_split_match_lists_matches_the_per_pair_loop():
+    from opensfm_b200.matching import split_match_lists
+
+    rng = np.random.default_rng(3)
+    assert split_match_lists(np.zeros(0, np.int32), np.zeros(0, np.int64)) == []
+    for _ in range(200):
+        npairs = int(rng.integers(1, 7))
+        counts = rng.integers(0, 9, size=npairs).astype(np.int64)
+        raw = rng.integers(-1, 6, size=int(counts.sum())).astype(np.int32)
+        parts = split_match_lists(raw, counts)
+        assert len(parts) == npairs
+        off = 0
+        for n, got in zip(counts, parts):
+            idx = raw[off:off + n]
+            off += n
+            q = np.nonzero(idx >= 0)[0]
+            want = np.stack([q, idx[q]], axis=1).astype(np.int64) if len(q) else np.zeros((0, 2), dtype=np.int64)
+            assert got.dtype == np.int64 and got.shape == want.shape and np.array_equal(got, want)
