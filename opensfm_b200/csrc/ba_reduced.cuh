@@ -1238,7 +1238,7 @@ __device__ __forceinline__ void grid_reduce2(PcgState* st, unsigned nblocks, uns
     do {
       asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(cur) : "l"(&st->flags[threadIdx.x * PCG_FLAG_STRIDE]) : "memory");
       if (clock64() - t0 > 8000000000LL) __trap();  // a protocol bug must not hang the GPU
-    } while (cur != gen);
+    } while ((int)(cur - gen) < 0);  // monotonic: a fast CTA may already have published generation gen + 1
     va = ldcg_d(&st->slot[gen & 1][threadIdx.x][0]);
     vb = ldcg_d(&st->slot[gen & 1][threadIdx.x][1]);
   }
@@ -1479,7 +1479,7 @@ __device__ __forceinline__ void grid_reduce3(PcgState* st, unsigned nblocks, uns
     do {
       asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(cur) : "l"(&st->flags[threadIdx.x * PCG_FLAG_STRIDE]) : "memory");
       if (clock64() - t0 > 8000000000LL) __trap();  // a protocol bug must not hang the GPU
-    } while (cur != gen);
+    } while ((int)(cur - gen) < 0);  // monotonic: a fast CTA may already have published generation gen + 1
     const double* sl = st->slot[gen & 1][threadIdx.x];
     const double2 ab = __ldcg(reinterpret_cast<const double2*>(sl));
     va = ab.x; vb = ab.y;
