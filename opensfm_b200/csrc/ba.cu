@@ -694,6 +694,7 @@ struct BA {
   int pcg_smem = 0;
   DevBuf<int> d_pcg_grplo;
   DevBuf<unsigned long long> d_prof;
+  bool seg_attr = false, mma_attr = false;   // per handle (= per device): dynamic shared-memory opt-in done
   DevBuf<long long> d_tab_off, d_tab_sizes;
   DevBuf<int> d_tab;
   PcgPipe pcg_pipe{};
@@ -1417,7 +1418,6 @@ void BA::run() {
                           (size_t)SCHUR_KC * 8 * sizeof(int) + (size_t)SCHUR_KC * SCHUR_KC * 9 * sizeof(int);
       tm_schur.start(stream);
       if (nseg > 0) {
-        static bool seg_attr = false;
         if (!seg_attr) {
           OSFM_CUDA(cudaFuncSetAttribute(ba_schur_seg<9>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SegSmem)));
           OSFM_CUDA(cudaFuncSetAttribute(ba_schur_seg<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SegSmem)));
@@ -1429,7 +1429,6 @@ void BA::run() {
                                                                  d_gp.p, d_Vig.p);
         OSFM_LAUNCH_CHECK();
         if (use_mma) {
-          static bool mma_attr = false;
           if (!mma_attr) {
             OSFM_CUDA(cudaFuncSetAttribute(ba_schur_mma<9>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SegMmaSmem)));
             OSFM_CUDA(cudaFuncSetAttribute(ba_schur_mma<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SegMmaSmem)));

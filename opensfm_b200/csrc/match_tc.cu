@@ -476,10 +476,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
 }
 
 void launch_tc(Matcher& m, int njobs, int ntasks) {
-  static bool attr_set = false;
-  if (!attr_set) {
+  if (!m.tc_attr_set) {   // per matcher (= per device)
     OSFM_CUDA(cudaFuncSetAttribute(bf_top2_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
-    attr_set = true;
+    m.tc_attr_set = true;
   }
   m.d_flags.reserve(4);
   OSFM_CUDA(cudaMemsetAsync(m.d_flags.p + 1, 0, sizeof(int), m.stream));
