@@ -156,3 +156,22 @@ def test_split_match_lists_matches_the_per_pair_loop():
             q = np.nonzero(idx >= 0)[0]
             want = np.stack([q, idx[q]], axis=1).astype(np.int64) if len(q) else np.zeros((0, 2), dtype=np.int64)
             assert got.dtype == np.int64 and got.shape == want.shape and np.array_equal(got, want)
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the CPU arm: oracle port for BA, cv2 for MATCH) needs no GPU."""
+    import json
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--workload", "tiny",
+                          "--steps", "1", "--warmup", "0"], capture_output=True, text=True, timeout=600, cwd=root)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["value"] > 0 and line["higher_is_better"] is True
+    for key in ("metric", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "scaling", "dtype", "data", "config", "e2e",
+                "cpu_baseline"):
+        assert key in line, key
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["cpu_baseline"]["kind"] in ("port", "reference")
+    assert line["match"]["value"] > 0
