@@ -94,8 +94,10 @@ __device__ __forceinline__ void atomic_max_nonneg(double* addr, double v) {
 // ---------------------------------------------------------------------------
 // MODE 0: cost only (candidate evaluation).  MODE 1: residual + Jacobian planes (robustified).
 // MODE 2: unscaled reprojection errors (bundle_adjuster.cc:531-566), written in original order.
-template <int MODE>
-__global__ void __launch_bounds__(128) ba_linearize(BAView v, Params p, Scalars* sc, double* reproj) {
+// NB = minimum resident CTAs per SM the register allocation is held to (the kernel is latency-bound: at its
+// natural 156 registers only 12 warps fit on an SM).
+template <int MODE, int NB = 3>
+__global__ void __launch_bounds__(128, NB) ba_linearize(BAView v, Params p, Scalars* sc, double* reproj) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   double cost = 0.0;
   if (i < v.N) {
@@ -759,6 +761,7 @@ struct BA {
   void run();
 };
 
+constexpr int LIN_NB_DEFAULT = 3;
 static int grid_for(long long n, int threads) { return (int)std::max<long long>(1, (n + threads - 1) / threads); }
 
 void BA::run() {
@@ -864,6 +867,8 @@ void BA::run() {
   // per launch for the per-point kernel on the 2M-observation scene (profiles/README.md).
   // OSFM_BA_SEGMENT_SCHUR=0 forces every point through ba_schur (kept for A/B runs and tests).
   static const bool use_seg = []() { const char* e = getenv("OSFM_BA_SEGMENT_SCHUR"); return !(e && e[0] == '0'); }();
+  // register budget of ba_linearize<1> (A/B switch): 3, 4 or 5 resident CTAs per SM
+  static const int lin_nb = []() { const char* e = getenv("OSFM_BA_LIN_NB"); return e ? atoi(e) : LIN_NB_DEFAULT; }();
   if (Nfull >= (1LL << 31)) throw ArgError("too many observations");
   const int P = Pfull > rank ? (Pfull - rank + world - 1) / world : 0;
   const size_t Nfz = (size_t)std::max<long long>(Nfull, 1), Pz = (size_t)std::max(P, 1);
@@ -1072,7 +1077,9 @@ void BA::run() {
     OSFM_CUDA(cudaMemsetAsync(d_grad.p, 0, sizeof(double) * nz, stream));
     if (N > 0) {
       tm_lin.start(stream);
-      ba_linearize<1><<<grid_for(N, 128), 128, 0, stream>>>(v, params_of(b), d_sc.p, nullptr);
+      if (lin_nb == 5) ba_linearize<1, 5><<<grid_for(N, 128), 128, 0, stream>>>(v, params_of(b), d_sc.p, nullptr);
+      else if (lin_nb == 4) ba_linearize<1, 4><<<grid_for(N, 128), 128, 0, stream>>>(v, params_of(b), d_sc.p, nullptr);
+      else ba_linearize<1, 3><<<grid_for(N, 128), 128, 0, stream>>>(v, params_of(b), d_sc.p, nullptr);
       OSFM_LAUNCH_CHECK();
       tm_lin.stop(stream);
       ba_colnorm_grad_points<<<grid_for(N, 256), 256, 0, stream>>>(v, d_colnorm2.p, d_grad.p);
