@@ -1186,6 +1186,12 @@ __global__ void pcg_factor_groups(const double* __restrict__ Sval, BsrView h, co
 
 constexpr int PCG_MAX_CTAS = 256;
 constexpr int PCG_FLAG_STRIDE = 32;
+// Barrier word of the 128-bit variant: a partial sum and the generation it belongs to travel together, so a
+// reader that sees the generation also has the value (one L2 round trip less than flag + slot).
+struct alignas(16) PcgWord {
+  double v;
+  unsigned long long tag;
+};
 struct PcgState {
   // header: what the host reads back after a solve
   int iterations;
@@ -1197,6 +1203,8 @@ struct PcgState {
   // per-CTA arrival generation, one 128-byte line each (packed flags cost 9.3k clk per barrier,
   // strided ones 4.4k: scripts/bench_barrier.cu)
   unsigned flags[PCG_MAX_CTAS * PCG_FLAG_STRIDE];
+  // 128-bit barrier words (value, generation), double-buffered by generation parity: [parity][CTA][3 sums + pad]
+  PcgWord words[2][PCG_MAX_CTAS][4];
 };
 constexpr size_t PCG_STATE_HEADER = offsetof(PcgState, slot);
 
@@ -1450,7 +1458,66 @@ struct PcgPipe {
   int off_S, off_Minv, off_vec, off_cols, off_rows;  // byte offsets into dynamic shared memory; mp at 0
   int max_cols;
   int max_rows, max_groups;
+  int b128;   // 1: grid_reduce3_b128 (<= 160 CTAs, >= 480 threads), 0: flags + slots
 };
+
+__device__ __forceinline__ PcgWord ld_acquire_b128(const PcgWord* p) {
+  PcgWord r;
+  unsigned long long lo, hi;
+  asm volatile("{\n.reg .b128 t;\nld.acquire.gpu.global.b128 t, [%2];\nmov.b128 {%0, %1}, t;\n}" : "=l"(lo), "=l"(hi) : "l"(p) : "memory");
+  r.v = __longlong_as_double((long long)lo);
+  r.tag = hi;
+  return r;
+}
+__device__ __forceinline__ void st_release_b128(PcgWord* p, double v, unsigned long long tag) {
+  asm volatile("{\n.reg .b128 t;\nmov.b128 t, {%1, %2};\nst.release.gpu.global.b128 [%0], t;\n}" ::"l"(p),
+               "l"((unsigned long long)__double_as_longlong(v)), "l"(tag)
+               : "memory");
+}
+// grid_reduce3 with 128-bit words (SASS LDG/STG.E.128.STRONG.GPU): threads 0..2 publish the three block sums,
+// thread t polls word t / 160 of CTA t % 160 and gets the value with the generation.  Needs <= 160 CTAs and
+// >= 480 threads; the sums are formed in a fixed order, as in grid_reduce3.
+constexpr int PCG_B128_GROUP = 160;
+__device__ __forceinline__ void grid_reduce3_b128(PcgState* st, unsigned nblocks, unsigned& gen, double a, double b, double c,
+                                                  double& A, double& B, double& C, double (*red)[3]) {
+  ++gen;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+#pragma unroll
+  for (int o = 16; o; o >>= 1) {
+    a += __shfl_xor_sync(0xffffffffu, a, o);
+    b += __shfl_xor_sync(0xffffffffu, b, o);
+    c += __shfl_xor_sync(0xffffffffu, c, o);
+  }
+  if (lane == 0) { red[warp][0] = a; red[warp][1] = b; red[warp][2] = c; }
+  __syncthreads();  // also: every global write of this CTA happens-before the releases below
+  if (threadIdx.x < 3) {
+    double sv = 0.0;
+    for (int w = 0; w < nwarps; ++w) sv += red[w][threadIdx.x];
+    st_release_b128(&st->words[gen & 1][blockIdx.x][threadIdx.x], sv, gen);
+  }
+  const int grp = threadIdx.x / PCG_B128_GROUP, idx = threadIdx.x - grp * PCG_B128_GROUP;
+  double val = 0.0;
+  if (grp < 3 && idx < (int)nblocks) {
+    const PcgWord* wp = &st->words[gen & 1][idx][grp];
+    const long long t0 = clock64();
+    PcgWord wv;
+    do {
+      wv = ld_acquire_b128(wp);
+      if (clock64() - t0 > 8000000000LL) __trap();  // a protocol bug must not hang the GPU
+    } while ((long long)(wv.tag - gen) < 0);
+    val = wv.v;
+  }
+  __syncthreads();  // red[] is free again; the acquires above order every thread's later loads
+#pragma unroll
+  for (int o = 16; o; o >>= 1) val += __shfl_xor_sync(0xffffffffu, val, o);
+  if (lane == 0) red[warp][0] = val;
+  __syncthreads();
+  constexpr int WPG = PCG_B128_GROUP / 32;   // warps per group
+  double sa = 0.0, sb = 0.0, sc = 0.0;
+  for (int w = 0; w < WPG; ++w) { sa += red[w][0]; sb += red[WPG + w][0]; sc += red[2 * WPG + w][0]; }
+  A = sa; B = sb; C = sc;
+  __syncthreads();
+}
 
 __device__ __forceinline__ void grid_reduce3(PcgState* st, unsigned nblocks, unsigned& gen, double a, double b, double c,
                                              double& A, double& B, double& C, double (*red)[3]) {
@@ -1660,7 +1727,8 @@ __global__ void __launch_bounds__(PCG_THREADS, 1)
   __syncthreads();
   group_solve(mbuf[0]);
   double d0, d1, d2;
-  grid_reduce3(st, gridDim.x, bar_gen, 0.0, 0.0, mine ? rr_ * rr_ : 0.0, d0, d1, d2, red);
+  if (R.b128) grid_reduce3_b128(st, gridDim.x, bar_gen, 0.0, 0.0, mine ? rr_ * rr_ : 0.0, d0, d1, d2, red);
+  else grid_reduce3(st, gridDim.x, bar_gen, 0.0, 0.0, mine ? rr_ * rr_ : 0.0, d0, d1, d2, red);
   const double bb = d2;
   const double tol2 = tol2_rel * bb;
   double rr = bb;
@@ -1679,7 +1747,11 @@ __global__ void __launch_bounds__(PCG_THREADS, 1)
     for (;; ++it) {
       const long long tk0 = clock64();
       double gamma, delta;
-      grid_reduce3(st, gridDim.x, bar_gen, mine ? rr_ * u : 0.0, mine ? w * u : 0.0, mine ? rr_ * rr_ : 0.0, gamma, delta, rr,
+      if (R.b128)
+        grid_reduce3_b128(st, gridDim.x, bar_gen, mine ? rr_ * u : 0.0, mine ? w * u : 0.0, mine ? rr_ * rr_ : 0.0, gamma, delta, rr,
+                   red);
+      else
+        grid_reduce3(st, gridDim.x, bar_gen, mine ? rr_ * u : 0.0, mine ? w * u : 0.0, mine ? rr_ * rr_ : 0.0, gamma, delta, rr,
                    red);
       const long long tk1 = clock64();
       if (!(rr == rr)) break;
