@@ -1334,8 +1334,9 @@ void BA::run() {
         pcg_pipe.grp_lo = d_pcg_grplo.p; pcg_pipe.off_S = (int)off_S; pcg_pipe.off_Minv = (int)off_Minv;
         pcg_pipe.off_vec = (int)off_vec; pcg_pipe.off_cols = (int)off_cols; pcg_pipe.off_rows = (int)off_rows;
         pcg_pipe.max_rows = rows_max; pcg_pipe.max_groups = grp_max; pcg_pipe.max_cols = (int)col_max;
-        // 128-bit barrier words: A/B switch OSFM_BA_PCG_B128 (default on when the grid fits the polling layout)
-        static const bool allow_b128 = []() { const char* e = getenv("OSFM_BA_PCG_B128"); return !(e && e[0] == '0'); }();
+        // 128-bit barrier words (value + generation in one strong 16-byte access): measured SLOWER than flags + slots
+        // on B200 (PCG 8.69 vs 8.05 ms at C4), so it is opt-in: OSFM_BA_PCG_B128=1
+        static const bool allow_b128 = []() { const char* e = getenv("OSFM_BA_PCG_B128"); return e && e[0] == '1'; }();
         pcg_pipe.b128 = (allow_b128 && pcg_grid <= PCG_B128_GROUP && PCG_THREADS >= 3 * PCG_B128_GROUP) ? 1 : 0;
         OSFM_CUDA(cudaFuncSetAttribute(pcg_pipelined, cudaFuncAttributeMaxDynamicSharedMemorySize, pcg_pipe_smem));
       }
