@@ -96,7 +96,8 @@ enum {
   OSFM_FISHEYE624 = 5, OSFM_SPHERICAL = 6, OSFM_DUAL = 7, OSFM_RADIAL = 8, OSFM_SIMPLE_RADIAL = 9
 };
 /* ceres loss names accepted by CreateLossFunction (bundle_adjuster.cc:414-429) */
-enum { OSFM_LOSS_TRIVIAL = 0, OSFM_LOSS_HUBER = 1, OSFM_LOSS_SOFTLONE = 2, OSFM_LOSS_CAUCHY = 3, OSFM_LOSS_ARCTAN = 4 };
+enum { OSFM_LOSS_TRIVIAL = 0, OSFM_LOSS_HUBER = 1, OSFM_LOSS_SOFTLONE = 2, OSFM_LOSS_CAUCHY = 3, OSFM_LOSS_ARCTAN = 4,
+       OSFM_LOSS_TUKEY = 5 /* side terms only (common position, bundle_adjuster.cc:905) */ };
 
 int osfm_ba_create(int device, osfm_ba** out);
 int osfm_ba_destroy(osfm_ba* ba);
@@ -117,6 +118,55 @@ int osfm_ba_set_shots(osfm_ba* ba, int n, const int32_t* rig_instance, const int
 int osfm_ba_set_points(osfm_ba* ba, int n, const double* xyz, const int32_t* constant);
 int osfm_ba_set_observations(osfm_ba* ba, int64_t n, const int32_t* shot, const int32_t* point,
                              const double* xy, const double* std_deviation);
+
+/* Rig-camera pose priors: DataPriorError<Pose> with sigma GetDefaultRigPoseSigma, one per rig camera
+ * (bundle_adjuster.cc:779-790; residual dropped when the rig camera is constant).  prior6 / sigma6: n x 6
+ * in the order [rx, ry, rz, tx, ty, tz]; NULL removes the priors.  Call after osfm_ba_set_rig_cameras. */
+int osfm_ba_set_rig_camera_priors(osfm_ba* ba, const double* prior6, const double* sigma6);
+/* Point priors (GCP): AddPointPrior (bundle_adjuster.cc:224-236, residual :688-708): residuals on x, y
+ * (and z when has_altitude) with scale 1 / max(sigma, eps).  n priors on points point[i]. */
+int osfm_ba_set_point_priors(osfm_ba* ba, int n, const int32_t* point, const double* prior3, const double* sigma3,
+                             const int32_t* has_altitude);
+/* Extra parameter blocks of the camera side: camera biases (7: [R | t | scale], data/bias.h:10-31), per-instance
+ * reconstruction scales (1, lower bound 0, bundle_adjuster.cc:672-685), std-deviation scales of the position-prior
+ * groups (1, lower bound 1e-10, :727-736).  values / lower_bound are flat over the blocks (-inf = unbounded). */
+int osfm_ba_set_ext_blocks(osfm_ba* ba, int n, const int32_t* size, const double* values, const int32_t* constant,
+                           const double* lower_bound);
+int osfm_ba_get_ext_blocks(osfm_ba* ba, double* values);
+
+/* Side terms: the O(#shots) residual blocks next to the point projections.  Each names up to 6 parameter blocks
+ * (kind: 0 camera, 1 rig instance, 2 rig camera, 3 ext block; idx within the kind), a ceres loss (-1 = none) and
+ * `nconst` constants starting at consts[cofs].  Types, blocks and constants (reference functor):
+ *   UP_VECTOR           [inst, rigcam]  c = unit acceleration[3], 1/std          absolute_motion_errors.h:12-39
+ *   PAN / TILT / ROLL   [inst, rigcam]  c = angle, 1/std                         :41-136
+ *   RELATIVE_MOTION     [inst_i, inst_j, scale_i(, scale_j)]  c = Rts[7], scale_matrix[49] row-major,
+ *                       observed_scale; aux[0] = block of scale_j (2 or 3)       relative_motion_errors.h:14-72
+ *   RELATIVE_ROTATION   [inst_i, inst_j(, rigcam_i)(, rigcam_j)]  c = Rij[3], scale_matrix[9];
+ *                       aux[0], aux[1] = rig-camera block of i, j or -1          :74-103
+ *   COMMON_POSITION     same blocks / aux; c = margin, 1/std                     :105-138
+ *   LINEAR_MOTION       [inst0, inst1, inst2(, rigcams)]  c = alpha, 1/pos_std, 1/ori_std; aux[0..2] = rig-camera
+ *                       blocks or -1                                             motion_prior_errors.h:13-76
+ *   TRANSLATION_PRIOR   [inst1, inst2]  c = max(prior norm, 1e-20)               absolute_motion_errors.h:180-202
+ *   PARAMETER_BARRIER   [camera]  c = lower, upper; aux[0] = parameter index     parameters_errors.h:20-36
+ *   STD_DEVIATION       [ext]                                                    parameters_errors.h:7-18
+ *   POSITION_PRIOR      [inst, bias ext(7), std-scale ext(1)]  c = prior[3], 1/sigma[3], adjust flag
+ *                       (the general form of the position prior: bias transform + scale group,
+ *                        bundle_adjuster.cc:745-778, data/bias.h:33-53) */
+enum {
+  OSFM_SIDE_UP_VECTOR = 0, OSFM_SIDE_PAN = 1, OSFM_SIDE_TILT = 2, OSFM_SIDE_ROLL = 3, OSFM_SIDE_RELATIVE_MOTION = 4,
+  OSFM_SIDE_RELATIVE_ROTATION = 5, OSFM_SIDE_COMMON_POSITION = 6, OSFM_SIDE_LINEAR_MOTION = 7,
+  OSFM_SIDE_TRANSLATION_PRIOR = 8, OSFM_SIDE_PARAMETER_BARRIER = 9, OSFM_SIDE_STD_DEVIATION = 10,
+  OSFM_SIDE_POSITION_PRIOR = 11, OSFM_SIDE_NUM_TYPES = 12
+};
+typedef struct {
+  int32_t type, nres, nblocks;
+  int32_t kind[6], idx[6];
+  int32_t loss;          /* OSFM_LOSS_*, or -1 for no loss function */
+  double loss_a;
+  int32_t cofs;          /* index of the term's first constant in `consts` */
+  int32_t aux[4];
+} osfm_side_term;
+int osfm_ba_set_side_terms(osfm_ba* ba, int n, const osfm_side_term* terms, int64_t nconsts, const double* consts);
 /* SetPointProjectionLossFunction / SetMaxNumIterations / SetLinearSolverType
  * (bundle_adjuster.cc:262-372).  linear_solver: "SPARSE_SCHUR", "DENSE_SCHUR",
  * "ITERATIVE_SCHUR" are all served by Schur elimination + PCG; unknown names fail

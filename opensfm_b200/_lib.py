@@ -16,6 +16,16 @@ OSFM_OK = 0
 PROJECTION_TYPES = dict(PERSPECTIVE=0, BROWN=1, FISHEYE=2, FISHEYE_OPENCV=3, FISHEYE62=4, FISHEYE624=5,
                         SPHERICAL=6, DUAL=7, RADIAL=8, SIMPLE_RADIAL=9)
 LOSS_IDS = {"TrivialLoss": 0, "HuberLoss": 1, "SoftLOneLoss": 2, "CauchyLoss": 3, "ArctanLoss": 4}
+LOSS_TUKEY = 5  # side terms only (common position)
+SIDE_TYPES = dict(UP_VECTOR=0, PAN=1, TILT=2, ROLL=3, RELATIVE_MOTION=4, RELATIVE_ROTATION=5, COMMON_POSITION=6,
+                  LINEAR_MOTION=7, TRANSLATION_PRIOR=8, PARAMETER_BARRIER=9, STD_DEVIATION=10, POSITION_PRIOR=11)
+SB_CAM, SB_INST, SB_RIGCAM, SB_EXT = 0, 1, 2, 3
+
+
+class SideTerm(ctypes.Structure):
+    """osfm_side_term (include/opensfm_b200.h)."""
+    _fields_ = [("type", c_int32), ("nres", c_int32), ("nblocks", c_int32), ("kind", c_int32 * 6), ("idx", c_int32 * 6),
+                ("loss", c_int32), ("loss_a", c_double), ("cofs", c_int32), ("aux", c_int32 * 4)]
 
 
 class BASummary(ctypes.Structure):
@@ -61,6 +71,11 @@ SIGNATURES = {
     "osfm_ba_set_shots": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "osfm_ba_set_points": (c_int, [c_void_p, c_int, c_void_p, c_void_p]),
     "osfm_ba_set_observations": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "osfm_ba_set_rig_camera_priors": (c_int, [c_void_p, c_void_p, c_void_p]),
+    "osfm_ba_set_point_priors": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "osfm_ba_set_ext_blocks": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "osfm_ba_get_ext_blocks": (c_int, [c_void_p, c_void_p]),
+    "osfm_ba_set_side_terms": (c_int, [c_void_p, c_int, c_void_p, c_int64, c_void_p]),
     "osfm_ba_set_options": (c_int, [c_void_p, c_int, c_double, c_int, c_char_p, c_int]),
     "osfm_ba_set_distributed": (c_int, [c_void_p, c_int, c_int, ALLREDUCE_FN, c_void_p]),
     "osfm_nccl_unique_id": (c_int, [c_void_p]),

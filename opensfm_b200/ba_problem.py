@@ -18,7 +18,7 @@ Parameter conventions follow the reference:
 from __future__ import annotations
 
 from dataclasses import dataclass, field
-from typing import Optional
+from typing import List, Optional, Sequence, Tuple
 
 import numpy as np
 
@@ -47,6 +47,116 @@ CAMERA_PARAM_NAMES = {
 }
 
 LOSS_NAMES = ("TrivialLoss", "HuberLoss", "SoftLOneLoss", "CauchyLoss", "ArctanLoss")
+LOSS_IDS = {n: i for i, n in enumerate(LOSS_NAMES)}
+LOSS_NONE, LOSS_CAUCHY, LOSS_TUKEY = -1, 3, 5
+
+# block kinds of a side term / ids of the side-term types (include/opensfm_b200.h)
+SB_CAM, SB_INST, SB_RIGCAM, SB_EXT = 0, 1, 2, 3
+(SIDE_UP_VECTOR, SIDE_PAN, SIDE_TILT, SIDE_ROLL, SIDE_RELATIVE_MOTION, SIDE_RELATIVE_ROTATION, SIDE_COMMON_POSITION,
+ SIDE_LINEAR_MOTION, SIDE_TRANSLATION_PRIOR, SIDE_PARAMETER_BARRIER, SIDE_STD_DEVIATION, SIDE_POSITION_PRIOR) = range(12)
+
+
+@dataclass
+class SideTerm:
+    """One secondary residual block: its type, the parameter blocks it reads ((kind, index) pairs, at most 6),
+    its constants and its ceres loss (LOSS_NONE = nullptr in the reference).  The constructors below restate the
+    reference functors' constructors (argument checks and pre-computed constants included)."""
+    type: int
+    nres: int
+    blocks: List[Tuple[int, int]]
+    consts: np.ndarray
+    loss: int = LOSS_NONE
+    loss_a: float = 1.0
+    aux: Tuple[int, ...] = ()
+
+
+def up_vector_term(inst: int, rigcam: int, up_vector, std_deviation: float) -> SideTerm:
+    """UpVectorError (absolute_motion_errors.h:12-39) under CauchyLoss(1) (bundle_adjuster.cc:956-971)."""
+    a = np.asarray(up_vector, dtype=np.float64)
+    n = float(np.linalg.norm(a))
+    if n < 1e-10:
+        raise RuntimeError("UpVectorError: acceleration vector has near-zero magnitude")
+    return SideTerm(SIDE_UP_VECTOR, 3, [(SB_INST, inst), (SB_RIGCAM, rigcam)],
+                    np.concatenate([a / n, [1.0 / std_deviation]]), LOSS_CAUCHY, 1.0)
+
+
+def angle_term(which: int, inst: int, rigcam: int, angle: float, std_deviation: float) -> SideTerm:
+    """Pan / Tilt / RollAngleError (absolute_motion_errors.h:41-136) under CauchyLoss(1) (:973-1022)."""
+    assert which in (SIDE_PAN, SIDE_TILT, SIDE_ROLL)
+    return SideTerm(which, 1, [(SB_INST, inst), (SB_RIGCAM, rigcam)], np.array([angle, 1.0 / std_deviation]),
+                    LOSS_CAUCHY, 1.0)
+
+
+def relative_motion_term(inst_i: int, inst_j: int, scale_i_ext: int, scale_j_ext: int, rts7, scale_matrix7x7,
+                         observed_scale: bool, loss: int, loss_a: float) -> SideTerm:
+    """RelativeMotionError (relative_motion_errors.h:14-72; blocks bundle_adjuster.cc:817-856)."""
+    blocks = [(SB_INST, inst_i), (SB_INST, inst_j), (SB_EXT, scale_i_ext)]
+    sj = 2
+    if scale_j_ext != scale_i_ext:
+        blocks.append((SB_EXT, scale_j_ext))
+        sj = 3
+    c = np.concatenate([np.asarray(rts7, dtype=np.float64).reshape(7),
+                        np.asarray(scale_matrix7x7, dtype=np.float64).reshape(49), [1.0 if observed_scale else 0.0]])
+    return SideTerm(SIDE_RELATIVE_MOTION, 7, blocks, c, loss, loss_a, (sj,))
+
+
+def _with_rigcams(insts: Sequence[int], rigcams: Sequence[Optional[int]]):
+    """Block list [instances..., distinct useful rig cameras...] and, per shot, the block of its rig camera or -1
+    (the de-duplication of bundle_adjuster.cc:880-898 / 1048-1081: a rig camera shared by two shots is one block)."""
+    blocks = [(SB_INST, i) for i in insts]
+    where = {}
+    aux = []
+    for rc in rigcams:
+        if rc is None:
+            aux.append(-1)
+            continue
+        if rc not in where:
+            where[rc] = len(blocks)
+            blocks.append((SB_RIGCAM, rc))
+        aux.append(where[rc])
+    return blocks, tuple(aux)
+
+
+def relative_rotation_term(inst_i, inst_j, rigcam_i, rigcam_j, rij3, scale_matrix3x3, loss, loss_a) -> SideTerm:
+    """RelativeRotationError (relative_motion_errors.h:74-103); rigcam_* = None when not 'useful'."""
+    blocks, aux = _with_rigcams([inst_i, inst_j], [rigcam_i, rigcam_j])
+    c = np.concatenate([np.asarray(rij3, dtype=np.float64).reshape(3), np.asarray(scale_matrix3x3, dtype=np.float64).reshape(9)])
+    return SideTerm(SIDE_RELATIVE_ROTATION, 3, blocks, c, loss, loss_a, aux)
+
+
+def common_position_term(inst_i, inst_j, rigcam_i, rigcam_j, margin: float, std_deviation: float) -> SideTerm:
+    """CommonPositionError under TukeyLoss(1) (relative_motion_errors.h:105-138, bundle_adjuster.cc:902-944)."""
+    blocks, aux = _with_rigcams([inst_i, inst_j], [rigcam_i, rigcam_j])
+    return SideTerm(SIDE_COMMON_POSITION, 3, blocks, np.array([margin, 1.0 / std_deviation]), LOSS_TUKEY, 1.0, aux)
+
+
+def linear_motion_term(insts3, rigcams3, alpha: float, position_std: float, orientation_std: float) -> SideTerm:
+    """LinearMotionError under CauchyLoss(1) (motion_prior_errors.h:13-76, bundle_adjuster.cc:1024-1084)."""
+    blocks, aux = _with_rigcams(list(insts3), list(rigcams3))
+    return SideTerm(SIDE_LINEAR_MOTION, 6, blocks, np.array([alpha, 1.0 / position_std, 1.0 / orientation_std]),
+                    LOSS_CAUCHY, 1.0, aux)
+
+
+def translation_prior_term(inst1: int, inst2: int, prior_norm: float) -> SideTerm:
+    """TranslationPriorError: the gauge-fix scale constraint (absolute_motion_errors.h:180-202)."""
+    return SideTerm(SIDE_TRANSLATION_PRIOR, 1, [(SB_INST, inst1), (SB_INST, inst2)], np.array([max(prior_norm, 1e-20)]))
+
+
+def parameter_barrier_term(cam: int, index: int, lower: float = 0.0, upper: float = 1.0) -> SideTerm:
+    """ParameterBarrier on the DUAL transition (parameters_errors.h:20-36, bundle_adjuster.cc:610-625)."""
+    return SideTerm(SIDE_PARAMETER_BARRIER, 1, [(SB_CAM, cam)], np.array([lower, upper]), aux=(index,))
+
+
+def std_deviation_term(ext: int) -> SideTerm:
+    """StdDeviationConstraint (parameters_errors.h:7-18, bundle_adjuster.cc:727-736)."""
+    return SideTerm(SIDE_STD_DEVIATION, 1, [(SB_EXT, ext)], np.zeros(0))
+
+
+def position_prior_term(inst: int, bias_ext: int, std_ext: int, position, std_deviation, adjust_scales: bool) -> SideTerm:
+    """DataPriorError<Pose, SimilarityPriorTransform> on TX, TY, TZ (bundle_adjuster.cc:745-778)."""
+    sig = np.maximum(np.asarray(std_deviation, dtype=np.float64).reshape(3), np.finfo(np.float64).eps)
+    c = np.concatenate([np.asarray(position, dtype=np.float64).reshape(3), 1.0 / sig, [1.0 if adjust_scales else 0.0]])
+    return SideTerm(SIDE_POSITION_PRIOR, 3, [(SB_INST, inst), (SB_EXT, bias_ext), (SB_EXT, std_ext)], c)
 
 
 def camera_num_params(ptype: int) -> int:
@@ -109,6 +219,49 @@ class BAProblem:
     max_iterations: int = 500
     linear_solver_type: str = "SPARSE_SCHUR"
     num_threads: int = 1
+    # --- secondary residuals; all optional -------------------------------------
+    # rig-camera pose priors DataPriorError<Pose> (bundle_adjuster.cc:779-790): NR x 6 each, or None
+    rigcam_prior: Optional[np.ndarray] = None
+    rigcam_prior_sigma: Optional[np.ndarray] = None
+    # point priors (AddPointPrior): point index, prior xyz, sigma xyz, has_altitude
+    pp_point: np.ndarray = field(default_factory=lambda: np.zeros(0, dtype=np.int32))
+    pp_prior: np.ndarray = field(default_factory=lambda: np.zeros((0, 3)))
+    pp_sigma: np.ndarray = field(default_factory=lambda: np.ones((0, 3)))
+    pp_alt: np.ndarray = field(default_factory=lambda: np.zeros(0, dtype=np.int32))
+    # ext blocks: camera biases (7), reconstruction scales (1), std-deviation scales (1)
+    ext_size: np.ndarray = field(default_factory=lambda: np.zeros(0, dtype=np.int32))
+    ext_values: np.ndarray = field(default_factory=lambda: np.zeros(0))
+    ext_const: np.ndarray = field(default_factory=lambda: np.zeros(0, dtype=np.int32))
+    ext_lower: np.ndarray = field(default_factory=lambda: np.zeros(0))
+    side_terms: List[SideTerm] = field(default_factory=list)
+
+    def add_ext_block(self, values, constant: bool, lower: Optional[Sequence[float]] = None) -> int:
+        v = np.atleast_1d(np.asarray(values, dtype=np.float64))
+        lo = np.full(len(v), -np.inf) if lower is None else np.atleast_1d(np.asarray(lower, dtype=np.float64))
+        self.ext_size = np.append(self.ext_size, len(v)).astype(np.int32)
+        self.ext_values = np.concatenate([self.ext_values, v])
+        self.ext_const = np.append(self.ext_const, int(constant)).astype(np.int32)
+        self.ext_lower = np.concatenate([self.ext_lower, lo])
+        return len(self.ext_size) - 1
+
+    @property
+    def ext_off(self) -> np.ndarray:
+        return np.concatenate([[0], np.cumsum(self.ext_size)]).astype(np.int32)
+
+    def packed_side_terms(self):
+        """(records, constants): per term (type, nres, nblocks, kind[6], idx[6], loss, loss_a, cofs, aux[4])."""
+        recs, consts, cofs = [], [], 0
+        for t in self.side_terms:
+            if len(t.blocks) > 6 or len(t.aux) > 4:
+                raise ValueError("side term with too many blocks")
+            kind = [b[0] for b in t.blocks] + [0] * (6 - len(t.blocks))
+            idx = [b[1] for b in t.blocks] + [0] * (6 - len(t.blocks))
+            aux = list(t.aux) + [-1] * (4 - len(t.aux))
+            recs.append((int(t.type), int(t.nres), len(t.blocks), kind, idx, int(t.loss), float(t.loss_a), cofs, aux))
+            c = np.asarray(t.consts, dtype=np.float64).ravel()
+            consts.append(c)
+            cofs += len(c)
+        return recs, (np.concatenate(consts) if consts else np.zeros(0))
 
     @property
     def cam_off(self) -> np.ndarray:
@@ -122,7 +275,7 @@ class BAProblem:
     def copy(self) -> "BAProblem":
         kw = {}
         for k, v in self.__dict__.items():
-            kw[k] = v.copy() if isinstance(v, np.ndarray) else v
+            kw[k] = v.copy() if isinstance(v, np.ndarray) else (list(v) if isinstance(v, list) else v)
         return BAProblem(**kw)
 
     def validate(self) -> None:

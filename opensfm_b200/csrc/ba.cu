@@ -56,7 +56,7 @@ struct BAView {
 };
 
 struct Params {
-  double *cam, *inst, *rc, *pts;
+  double *cam, *inst, *rc, *pts, *ext;
 };
 
 // scalar accumulators (device)
@@ -191,7 +191,9 @@ struct PriorView {
   int n_cam_rows, n_pos_rows;
   const int *cam_row_param, *cam_row_col, *cam_row_log;  // index into cam params / reduced column
   const double *cam_row_prior, *cam_row_scale;
-  const int *pos_row_inst, *pos_row_axis, *pos_row_col;
+  // linear rows on one component of a rig instance (kind 1: GPS position prior) or of a rig camera
+  // (kind 2: DataPriorError<Pose>, bundle_adjuster.cc:779-790)
+  const int *pos_row_kind, *pos_row_inst, *pos_row_axis, *pos_row_col;
   const double *pos_row_prior, *pos_row_scale;
 };
 __device__ __forceinline__ void prior_row(const PriorView& pv, const Params& p, int row, double* r, int* col,
@@ -211,7 +213,8 @@ __device__ __forceinline__ void prior_row(const PriorView& pv, const Params& p, 
     const int q = row - pv.n_cam_rows;
     const double sc = pv.pos_row_scale[q];
     *col = pv.pos_row_col[q];
-    *r = sc * (p.inst[6 * (size_t)pv.pos_row_inst[q] + 3 + pv.pos_row_axis[q]] - pv.pos_row_prior[q]);
+    const double* base = pv.pos_row_kind[q] == 2 ? p.rc : p.inst;
+    *r = sc * (base[6 * (size_t)pv.pos_row_inst[q] + pv.pos_row_axis[q]] - pv.pos_row_prior[q]);
     *d = sc;
   }
 }
@@ -227,6 +230,45 @@ __global__ void ba_prior_cost(PriorView pv, Params p, Scalars* sc) {
   }
   const double tot = block_reduce_sum(c);
   if (threadIdx.x == 0 && tot != 0.0) atomicAdd(&sc->cost, tot);
+}
+
+// Point priors (AddPointPrior, bundle_adjuster.cc:224-236; residual block :688-708, DataPriorError<Vec3d>):
+// r_j = d_j (X_j - x0_j), d_j = 1 / max(sigma_j, eps), j over x, y (and z with an altitude prior).  Dense arrays in
+// the caller's point order (d = 0: no row); local point np -> global_of[np].  Points with a prior are kept off the
+// segment path (ba_order.cuh), so only ba_schur has to add them to V_p and g_p.
+struct PointPriorView {
+  const double* d;   // [3 * Pfull], nullptr when no point has a prior
+  const double* x0;
+  const int* global_of;
+};
+// MODE 0: cost.  1: cost + squared column norms + gradient.  2: model cost change.  3: adds J_p^T r to the
+// right-hand side t[3][npf] of the back-substitution.  One thread per local point.
+template <int MODE>
+__global__ void ba_point_prior(PointPriorView pp, BAView v, Params p, const double* __restrict__ scale,
+                               const double* __restrict__ y, double* colnorm2, double* grad, double* t, Scalars* sc) {
+  const int np = blockIdx.x * blockDim.x + threadIdx.x;
+  double acc = 0.0;
+  if (np < v.P) {
+    const int pf = v.pt_poff[np];
+    const size_t g = (size_t)pp.global_of[np];
+    if (pf >= 0) {
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        const double d = pp.d[3 * g + j];
+        if (d == 0.0) continue;
+        const double r = d * (p.pts[3 * (size_t)np + j] - pp.x0[3 * g + j]);
+        const int col = v.nc + 3 * pf + j;
+        if (MODE <= 1) acc += 0.5 * r * r;
+        if (MODE == 1) { colnorm2[col] += d * d; grad[col] += d * r; }   // only this thread touches the point's columns here
+        if (MODE == 2) { const double m = -d * scale[col] * y[col]; acc += -m * (r + 0.5 * m); }
+        if (MODE == 3) t[(size_t)j * v.npf + pf] += d * r;
+      }
+    }
+  }
+  if (MODE <= 2) {
+    const double tot = block_reduce_sum(acc);
+    if (threadIdx.x == 0 && tot != 0.0) atomicAdd(MODE == 2 ? &sc->model_change : &sc->cost, tot);
+  }
 }
 
 // Squared column norms and gradient of the (unscaled, robustified) Jacobian.
@@ -416,6 +458,7 @@ __global__ void ba_grad_max(const double* grad, int n, Scalars* sc) {
 
 }  // namespace osfm
 #include "ba_reduced.cuh"
+#include "ba_side.cuh"
 #include "ba_order.cuh"
 namespace osfm {
 
@@ -516,7 +559,7 @@ __global__ void ba_prior_model_change(PriorView pv, Params p, const double* scal
 __global__ void ba_update(int which, int count, const int* __restrict__ poff, const int* __restrict__ off,
                           const int* __restrict__ np, int stride, int base, const double* __restrict__ src,
                           double* __restrict__ dst, const double* __restrict__ scale, const double* __restrict__ y,
-                          Scalars* sc, int accumulate_norms) {
+                          Scalars* sc, int accumulate_norms, const double* __restrict__ lower = nullptr) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   double sn = 0.0, xn = 0.0;
   if (b < count) {
@@ -527,7 +570,8 @@ __global__ void ba_update(int which, int count, const int* __restrict__ poff, co
       double val = src[o + j];
       if (g >= 0) {
         const int gi = which == 3 ? base + 3 * g + j : g + j;
-        const double d = -scale[gi] * y[gi];
+        double d = -scale[gi] * y[gi];
+        if (lower && val + d < lower[o + j]) d = lower[o + j] - val;   // projection onto the bound (ceres bounded LM)
         xn += val * val;
         sn += d * d;
         val += d;
@@ -635,8 +679,15 @@ struct BA {
   std::vector<double> cam_params, cam_prior, cam_prior_sigma;
   std::vector<double> inst, inst_prior_pos, inst_prior_std;
   std::vector<int> inst_const, inst_has_prior;
-  std::vector<double> rc;
+  std::vector<double> rc, rc_prior, rc_prior_sigma;   // rig-camera pose priors: empty = none
   std::vector<int> rc_const;
+  // ext blocks (biases, reconstruction scales, std-deviation scales), side terms, point priors
+  std::vector<int> ext_size, ext_const;
+  std::vector<double> ext_values, ext_lower;
+  std::vector<osfm_side_term> side_terms;
+  std::vector<double> side_consts;
+  std::vector<int> pp_point, pp_alt;
+  std::vector<double> pp_prior, pp_sigma;
   std::vector<int> shot_inst, shot_cam, shot_rc, shot_use_rc;
   std::vector<double> pts;
   std::vector<int> pt_const;
@@ -708,6 +759,9 @@ struct BA {
   DevBuf<Scalars> d_sc;
   PinnedBuf<Scalars> h_sc;
   DevBuf<double> d_eval;
+  DevBuf<int> d_pr_pos_kind, d_ext_off, d_ext_np, d_ext_poff, d_ext_blk, d_side_jofs, d_side_rofs;
+  DevBuf<double> d_ext[2], d_ext_lower, d_side_consts, d_side_J, d_side_r, d_pp_d, d_pp_x0;
+  DevBuf<SideTerm> d_side_terms;
 
   explicit BA(int dev) : device(dev) {
     OSFM_CUDA(cudaSetDevice(device));
@@ -813,16 +867,46 @@ void BA::run() {
     rc_poff[i] = rc_const[i] ? -1 : off;
     if (!rc_const[i]) { blk_off.push_back(off); blk_sz.push_back(6); off += 6; }
   }
+  const int NE = (int)ext_size.size();
+  std::vector<int> ext_off(NE + 1, 0), ext_poff(std::max(NE, 1), -1);
+  for (int i = 0; i < NE; ++i) {
+    if (ext_size[i] < 1 || ext_size[i] > MAXB) throw ArgError("ext block size must be in [1, 16]");
+    ext_off[i + 1] = ext_off[i] + ext_size[i];
+    ext_poff[i] = ext_const[i] ? -1 : off;
+    if (!ext_const[i]) { blk_off.push_back(off); blk_sz.push_back(ext_size[i]); off += ext_size[i]; }
+  }
   const int nc = off;
   const int nblk = (int)blk_off.size();
   const int nc_pad = (nc + 15) / 16 * 16;  // rhs sits in front of the reduced system in one buffer
-  // parameter-block id of every camera / rig instance / rig camera (-1 = constant)
-  std::vector<int> cam_blk(std::max(K, 1), -1), inst_blk(std::max(NI, 1), -1), rc_blk(std::max(NR, 1), -1);
+  // parameter-block id of every camera / rig instance / rig camera / ext block (-1 = constant)
+  std::vector<int> cam_blk(std::max(K, 1), -1), inst_blk(std::max(NI, 1), -1), rc_blk(std::max(NR, 1), -1),
+      ext_blk(std::max(NE, 1), -1);
   {
     int b = 0;
     for (int k = 0; k < K; ++k) if (!cam_const[k]) cam_blk[k] = b++;
     for (int i = 0; i < NI; ++i) if (!inst_const[i]) inst_blk[i] = b++;
     for (int i = 0; i < NR; ++i) if (!rc_const[i]) rc_blk[i] = b++;
+    for (int i = 0; i < NE; ++i) if (!ext_const[i]) ext_blk[i] = b++;
+  }
+  // side terms: block references checked here (the reference's std::map::at / "doesn't exist" errors)
+  const int NT = (int)side_terms.size();
+  std::vector<int> side_jofs(NT + 1, 0), side_rofs(NT + 1, 0);
+  for (int t = 0; t < NT; ++t) {
+    const osfm_side_term& st = side_terms[t];
+    if (st.type < 0 || st.type >= OSFM_SIDE_NUM_TYPES) throw ArgError("unknown side term type");
+    if (st.nblocks < 1 || st.nblocks > SIDE_MAX_BLOCKS || st.nres < 1 || st.nres > SIDE_MAX_RES)
+      throw ArgError("side term with a bad block / residual count");
+    int np = 0;
+    for (int b = 0; b < st.nblocks; ++b) {
+      const int kd = st.kind[b], ix = st.idx[b];
+      const int cnt = kd == SB_CAM ? K : kd == SB_INST ? NI : kd == SB_RIGCAM ? NR : kd == SB_EXT ? NE : -1;
+      if (ix < 0 || ix >= cnt) throw ArgError("side term references a parameter block that doesn't exist");
+      np += kd == SB_CAM ? model_num_params(cam_type[ix]) : kd == SB_EXT ? ext_size[ix] : 6;
+    }
+    if (np > SIDE_MAX_PARAMS) throw ArgError("side term with too many parameters");
+    if (st.cofs < 0 || (size_t)st.cofs > side_consts.size()) throw ArgError("side term constants out of range");
+    side_jofs[t + 1] = side_jofs[t] + st.nres * np;
+    side_rofs[t + 1] = side_rofs[t] + st.nres;
   }
 
   // preconditioner groups: a camera and the rig instance that is its only user (and vice versa) are
@@ -849,6 +933,8 @@ void BA::run() {
       if (inst_blk[i] >= 0 && !inst_done[i]) { grp_b1.push_back(inst_blk[i]); grp_b2.push_back(-1); }
     for (int i = 0; i < NR; ++i)
       if (rc_blk[i] >= 0) { grp_b1.push_back(rc_blk[i]); grp_b2.push_back(-1); }
+    for (int i = 0; i < NE; ++i)
+      if (ext_blk[i] >= 0) { grp_b1.push_back(ext_blk[i]); grp_b2.push_back(-1); }
   }
   const int ngroups = (int)grp_b1.size();
 
@@ -872,7 +958,17 @@ void BA::run() {
   if (Nfull >= (1LL << 31)) throw ArgError("too many observations");
   const int P = Pfull > rank ? (Pfull - rank + world - 1) / world : 0;
   const size_t Nfz = (size_t)std::max<long long>(Nfull, 1), Pz = (size_t)std::max(P, 1);
-  upload(d_ptc_full, pt_const, stream);
+  const bool have_pp = !pp_point.empty();
+  {
+    std::vector<int> ptc = pt_const;
+    for (int& c : ptc) c = c ? 1 : 0;
+    for (int q : pp_point) {
+      if (q < 0 || q >= Pfull) throw ArgError("point prior on a point that doesn't exist");
+      ptc[q] |= 2;
+    }
+    upload(d_ptc_full, ptc, stream);
+    OSFM_CUDA(cudaStreamSynchronize(stream));  // ptc goes out of scope
+  }
   upload(d_pts_in, pts, stream);
   d_okeys.reserve(Nfz); d_okeys2.reserve(Nfz); d_ovals.reserve(Nfz); d_ovals2.reserve(Nfz);
   d_g_pt_start.reserve((size_t)Pfull + 1);
@@ -963,7 +1059,7 @@ void BA::run() {
 
   trace("sort");
   // ---- prior rows (rank 0 adds them; Ceres drops residuals of constant blocks) ----
-  std::vector<int> pr_cam_param, pr_cam_col, pr_cam_log, pr_pos_inst, pr_pos_axis, pr_pos_col;
+  std::vector<int> pr_cam_param, pr_cam_col, pr_cam_log, pr_pos_kind, pr_pos_inst, pr_pos_axis, pr_pos_col;
   std::vector<double> pr_cam_prior, pr_cam_scale, pr_pos_prior, pr_pos_scale;
   for (int k = 0; k < K; ++k) {
     if (cam_poff[k] < 0) continue;
@@ -979,9 +1075,18 @@ void BA::run() {
   for (int i = 0; i < NI; ++i) {
     if (!inst_has_prior[i] || inst_poff[i] < 0) continue;
     for (int j = 0; j < 3; ++j) {
-      pr_pos_inst.push_back(i); pr_pos_axis.push_back(j); pr_pos_col.push_back(inst_poff[i] + 3 + j);
+      pr_pos_kind.push_back(1); pr_pos_inst.push_back(i); pr_pos_axis.push_back(3 + j); pr_pos_col.push_back(inst_poff[i] + 3 + j);
       pr_pos_prior.push_back(inst_prior_pos[3 * (size_t)i + j]);
       pr_pos_scale.push_back(1.0 / std::max(inst_prior_std[3 * (size_t)i + j], DBL_EPSILON));
+    }
+  }
+  const bool have_rc_prior = !rc_prior.empty();
+  for (int i = 0; i < NR && have_rc_prior; ++i) {   // DataPriorError<Pose> on every free rig camera (:779-790)
+    if (rc_poff[i] < 0) continue;
+    for (int j = 0; j < 6; ++j) {
+      pr_pos_kind.push_back(2); pr_pos_inst.push_back(i); pr_pos_axis.push_back(j); pr_pos_col.push_back(rc_poff[i] + j);
+      pr_pos_prior.push_back(rc_prior[6 * (size_t)i + j]);
+      pr_pos_scale.push_back(1.0 / std::max(rc_prior_sigma[6 * (size_t)i + j], DBL_EPSILON));
     }
   }
   const int npr = (int)(pr_cam_param.size() + pr_pos_inst.size());
@@ -994,6 +1099,10 @@ void BA::run() {
   for (int i = 0; i < NI; ++i) {
     if (!inst_has_prior[i] || inst_poff[i] < 0) continue;
     for (int j = 0; j < 3; ++j) { pr_blk.push_back(inst_blk[i]); pr_local.push_back(3 + j); }
+  }
+  for (int i = 0; i < NR && have_rc_prior; ++i) {
+    if (rc_poff[i] < 0) continue;
+    for (int j = 0; j < 6; ++j) { pr_blk.push_back(rc_blk[i]); pr_local.push_back(j); }
   }
 
   trace("priors");
@@ -1015,6 +1124,30 @@ void BA::run() {
   upload(d_pr_cam_log, pr_cam_log, stream); upload(d_pr_cam_prior, pr_cam_prior, stream);
   upload(d_pr_cam_scale, pr_cam_scale, stream); upload(d_pr_pos_inst, pr_pos_inst, stream);
   upload(d_pr_pos_axis, pr_pos_axis, stream); upload(d_pr_pos_col, pr_pos_col, stream);
+  upload(d_pr_pos_kind, pr_pos_kind, stream);
+  // ext blocks, side terms, point priors
+  {
+    std::vector<double> ev = ext_values, el = ext_lower;
+    if (ev.empty()) { ev.assign(1, 0.0); el.assign(1, 0.0); }
+    upload(d_ext[0], ev, stream); upload(d_ext[1], ev, stream); upload(d_ext_lower, el, stream);
+    upload(d_ext_off, ext_off, stream); upload(d_ext_np, ext_size, stream); upload(d_ext_poff, ext_poff, stream);
+    upload(d_ext_blk, ext_blk, stream);
+    upload(d_side_terms, side_terms, stream); upload(d_side_consts, side_consts, stream);
+    upload(d_side_jofs, side_jofs, stream); upload(d_side_rofs, side_rofs, stream);
+    d_side_J.reserve((size_t)side_jofs[NT] + 1); d_side_r.reserve((size_t)side_rofs[NT] + 1);
+    if (have_pp) {
+      std::vector<double> ppd(3 * (size_t)Pfull, 0.0), ppx(3 * (size_t)Pfull, 0.0);
+      for (size_t q = 0; q < pp_point.size(); ++q) {
+        const size_t g = (size_t)pp_point[q];
+        for (int j = 0; j < (pp_alt[q] ? 3 : 2); ++j) {
+          ppd[3 * g + j] = 1.0 / std::max(pp_sigma[3 * q + j], DBL_EPSILON);   // prior_error.h:31-35
+          ppx[3 * g + j] = pp_prior[3 * q + j];
+        }
+      }
+      upload(d_pp_d, ppd, stream); upload(d_pp_x0, ppx, stream);
+    }
+    OSFM_CUDA(cudaStreamSynchronize(stream));  // local vectors go out of scope
+  }
   upload(d_pr_pos_prior, pr_pos_prior, stream); upload(d_pr_pos_scale, pr_pos_scale, stream);
   const size_t Nz = (size_t)std::max<long long>(N, 1);
   d_r.reserve(nres * Nz); d_Jc.reserve((size_t)nres * wc * Nz); d_Jp.reserve((size_t)nres * 3 * Nz);
@@ -1042,13 +1175,20 @@ void BA::run() {
   pv.n_pos_rows = add_priors ? (int)pr_pos_inst.size() : 0;
   pv.cam_row_param = d_pr_cam_param.p; pv.cam_row_col = d_pr_cam_col.p; pv.cam_row_log = d_pr_cam_log.p;
   pv.cam_row_prior = d_pr_cam_prior.p; pv.cam_row_scale = d_pr_cam_scale.p;
+  pv.pos_row_kind = d_pr_pos_kind.p;
   pv.pos_row_inst = d_pr_pos_inst.p; pv.pos_row_axis = d_pr_pos_axis.p; pv.pos_row_col = d_pr_pos_col.p;
   pv.pos_row_prior = d_pr_pos_prior.p; pv.pos_row_scale = d_pr_pos_scale.p;
   const int npr_local = pv.n_cam_rows + pv.n_pos_rows;
   (void)npr;
 
   int cur = 0;  // index of the accepted parameter set
-  auto params_of = [&](int b) { return Params{d_cam[b].p, d_inst[b].p, d_rc[b].p, d_pts[b].p}; };
+  auto params_of = [&](int b) { return Params{d_cam[b].p, d_inst[b].p, d_rc[b].p, d_pts[b].p, d_ext[b].p}; };
+  SideView sv{};
+  sv.n = NT; sv.terms = d_side_terms.p; sv.consts = d_side_consts.p; sv.jofs = d_side_jofs.p; sv.rofs = d_side_rofs.p;
+  sv.J = d_side_J.p; sv.r = d_side_r.p;
+  sv.ext_off = d_ext_off.p; sv.ext_np = d_ext_np.p; sv.ext_poff = d_ext_poff.p; sv.ext_blk = d_ext_blk.p;
+  PointPriorView ppv{have_pp ? d_pp_d.p : nullptr, d_pp_x0.p, d_global_of.p};
+  BlkMaps bm{d_cam_blk.p, d_inst_blk.p, d_rc_blk.p};
 
   cudaEvent_t ev0, ev1;
   OSFM_CUDA(cudaEventCreate(&ev0)); OSFM_CUDA(cudaEventCreate(&ev1));
@@ -1065,6 +1205,14 @@ void BA::run() {
     }
     if (npr_local > 0) {
       ba_prior_cost<<<grid_for(npr_local, 128), 128, 0, stream>>>(pv, params_of(b), d_sc.p);
+      OSFM_LAUNCH_CHECK();
+    }
+    if (NT > 0 && add_priors) {
+      side_cost<<<grid_for(NT, 128), 128, 0, stream>>>(sv, v, bm, params_of(b), d_sc.p);
+      OSFM_LAUNCH_CHECK();
+    }
+    if (have_pp && P > 0) {
+      ba_point_prior<0><<<grid_for(P, 128), 128, 0, stream>>>(ppv, v, params_of(b), nullptr, nullptr, nullptr, nullptr, nullptr, d_sc.p);
       OSFM_LAUNCH_CHECK();
     }
     allreduce_dev(&d_sc.p->cost, 1);
@@ -1102,6 +1250,18 @@ void BA::run() {
       ba_prior_colnorm_grad<<<grid_for(npr_local, 128), 128, 0, stream>>>(pv, params_of(b), d_colnorm2.p, d_grad.p);
       OSFM_LAUNCH_CHECK();
     }
+    if (NT > 0) {   // every rank keeps the terms' Jacobians (the system part is added after the all-reduce)
+      side_linearize<<<NT, SIDE_THREADS, 0, stream>>>(sv, v, bm, params_of(b), d_sc.p, add_priors ? 1 : 0);
+      OSFM_LAUNCH_CHECK();
+      if (add_priors) {
+        side_colnorm_grad<<<NT, SIDE_THREADS, 0, stream>>>(sv, v, bm, params_of(b), d_colnorm2.p, d_grad.p);
+        OSFM_LAUNCH_CHECK();
+      }
+    }
+    if (have_pp && P > 0) {
+      ba_point_prior<1><<<grid_for(P, 128), 128, 0, stream>>>(ppv, v, params_of(b), nullptr, nullptr, d_colnorm2.p, d_grad.p, nullptr, d_sc.p);
+      OSFM_LAUNCH_CHECK();
+    }
     if (world > 1) {
       // local max over the point part, then one all-reduce for cost, camera-side sums and the per-rank maxima
       if (n > nc) {
@@ -1130,7 +1290,6 @@ void BA::run() {
   const int pcg_grid = std::max(1, std::min(std::min(num_sms, PCG_MAX_CTAS), (nc + PCG_THREADS / 32 - 1) / (PCG_THREADS / 32)));
   trace("pre-struct");
   // ---- block-sparse structure of the reduced camera system (identical on every rank) ----
-  BlkMaps bm{d_cam_blk.p, d_inst_blk.p, d_rc_blk.p};
   BsrView bsr{};
   int n_upper = 0, n_blocks_all = 0;
   long long s_upper_total = 0, s_total = 0;
@@ -1141,7 +1300,7 @@ void BA::run() {
     const long long* g_start = d_pt_start.p;
     const long long pair_bound = pair_bound_all;
     if (world > 1) { g_shot = d_g_obs_shot.p; g_point = d_g_obs_point.p; g_start = d_g_pt_start.p; }
-    const long long bound = std::min<long long>((long long)nblk * (nblk + 1) / 2, 9 * pair_bound + nblk);
+    const long long bound = std::min<long long>((long long)nblk * (nblk + 1) / 2, 9 * pair_bound + nblk + 21LL * NT);
     unsigned tsize = 1024;
     while ((long long)tsize < 4 * bound) {
       if (tsize >= (1u << 28)) throw std::runtime_error("reduced camera system has too many block pairs");
@@ -1154,6 +1313,10 @@ void BA::run() {
     if (n_enum > 0) {
       bsr_enum_pairs<<<grid_for(n_enum, 128), 128, 0, stream>>>(vg, bm, g_shot, g_start, g_point, n_enum, d_tkeys.p,
                                                               tsize - 1, nblk);
+      OSFM_LAUNCH_CHECK();
+    }
+    if (NT > 0) {
+      side_enum_pairs<<<grid_for(NT, 128), 128, 0, stream>>>(sv, v, bm, params_of(0), d_tkeys.p, tsize - 1, nblk);
       OSFM_LAUNCH_CHECK();
     }
     bsr_insert_diagonal<<<grid_for(nblk, 128), 128, 0, stream>>>(d_tkeys.p, tsize - 1, nblk);
@@ -1402,6 +1565,7 @@ void BA::run() {
     if (NI) { ba_update<<<grid_for(NI, 128), 128, 0, stream>>>(1, NI, d_inst_poff.p, nullptr, nullptr, 6, 0, pp.inst, pp.inst, d_scale.p, d_y.p, d_sc.p, rank == 0); OSFM_LAUNCH_CHECK(); }
     if (NR) { ba_update<<<grid_for(NR, 128), 128, 0, stream>>>(2, NR, d_rc_poff.p, nullptr, nullptr, 6, 0, pp.rc, pp.rc, d_scale.p, d_y.p, d_sc.p, rank == 0); OSFM_LAUNCH_CHECK(); }
     if (P) { ba_update<<<grid_for(P, 128), 128, 0, stream>>>(3, P, d_pt_poff.p, nullptr, nullptr, 3, nc, pp.pts, pp.pts, d_scale.p, d_y.p, d_sc.p, 1); OSFM_LAUNCH_CHECK(); }
+    if (NE) { ba_update<<<grid_for(NE, 128), 128, 0, stream>>>(0, NE, d_ext_poff.p, d_ext_off.p, d_ext_np.p, 0, 0, pp.ext, pp.ext, d_scale.p, d_y.p, d_sc.p, rank == 0); OSFM_LAUNCH_CHECK(); }
     allreduce_dev(&d_sc.p->x_norm2, 1);
     return std::sqrt(read_scalars().x_norm2);
   };
@@ -1483,7 +1647,7 @@ void BA::run() {
       }
       if (P > P_fast) {
         ba_schur<<<P - P_fast, SCHUR_THREADS, smem, stream>>>(v, bm, bsr, d_scale.p, d_diag.p, inv_radius, d_S_p,
-                                                             d_rhs_p, d_Vinv.p, d_gp.p, P_fast);
+                                                             d_rhs_p, d_Vinv.p, d_gp.p, P_fast, ppv, d_pts[cur].p);
         OSFM_LAUNCH_CHECK();
       }
       tm_schur.stop(stream);
@@ -1504,6 +1668,10 @@ void BA::run() {
         if (nall > 0) {
           ba_prior_system<<<grid_for(nall, 128), 128, 0, stream>>>(pall, params_of(cur), d_scale.p, d_prior_diag_off.p,
                                                                   d_S_p, d_rhs_p);
+          OSFM_LAUNCH_CHECK();
+        }
+        if (NT > 0) {
+          side_system<<<NT, SIDE_THREADS, 0, stream>>>(sv, v, bm, params_of(cur), bsr, d_scale.p, d_S_p, d_rhs_p);
           OSFM_LAUNCH_CHECK();
         }
       }
@@ -1561,8 +1729,14 @@ void BA::run() {
       tm_back.start(stream);
       d_bs_t.reserve(3 * (size_t)npf);
       OSFM_CUDA(cudaMemsetAsync(d_bs_t.p, 0, sizeof(double) * 3 * (size_t)npf, stream));
-      ba_backsub_rows<<<grid_for(N, 256), 256, 0, stream>>>(v, d_scale.p, d_y.p, d_bs_t.p);
-      OSFM_LAUNCH_CHECK();
+      if (N > 0) {
+        ba_backsub_rows<<<grid_for(N, 256), 256, 0, stream>>>(v, d_scale.p, d_y.p, d_bs_t.p);
+        OSFM_LAUNCH_CHECK();
+      }
+      if (have_pp) {
+        ba_point_prior<3><<<grid_for(P, 128), 128, 0, stream>>>(ppv, v, params_of(cur), nullptr, nullptr, nullptr, nullptr, d_bs_t.p, d_sc.p);
+        OSFM_LAUNCH_CHECK();
+      }
       ba_backsub_points<<<grid_for(npf, 256), 256, 0, stream>>>(v, d_scale.p, d_Vinv.p, d_bs_t.p, d_y.p);
       OSFM_LAUNCH_CHECK();
       tm_back.stop(stream);
@@ -1576,6 +1750,14 @@ void BA::run() {
       ba_prior_model_change<<<grid_for(npr_local, 128), 128, 0, stream>>>(pv, params_of(cur), d_scale.p, d_y.p, d_sc.p);
       OSFM_LAUNCH_CHECK();
     }
+    if (NT > 0 && add_priors) {
+      side_model_change<<<grid_for(NT, 128), 128, 0, stream>>>(sv, v, bm, params_of(cur), d_scale.p, d_y.p, d_sc.p);
+      OSFM_LAUNCH_CHECK();
+    }
+    if (have_pp && P > 0) {
+      ba_point_prior<2><<<grid_for(P, 128), 128, 0, stream>>>(ppv, v, params_of(cur), d_scale.p, d_y.p, nullptr, nullptr, nullptr, d_sc.p);
+      OSFM_LAUNCH_CHECK();
+    }
     // --- candidate point ---
     const int cand = cur ^ 1;
     {
@@ -1584,6 +1766,7 @@ void BA::run() {
       if (NI) { ba_update<<<grid_for(NI, 128), 128, 0, stream>>>(1, NI, d_inst_poff.p, nullptr, nullptr, 6, 0, a.inst, b.inst, d_scale.p, d_y.p, d_sc.p, rank == 0); OSFM_LAUNCH_CHECK(); }
       if (NR) { ba_update<<<grid_for(NR, 128), 128, 0, stream>>>(2, NR, d_rc_poff.p, nullptr, nullptr, 6, 0, a.rc, b.rc, d_scale.p, d_y.p, d_sc.p, rank == 0); OSFM_LAUNCH_CHECK(); }
       if (P) { ba_update<<<grid_for(P, 128), 128, 0, stream>>>(3, P, d_pt_poff.p, nullptr, nullptr, 3, nc, a.pts, b.pts, d_scale.p, d_y.p, d_sc.p, 1); OSFM_LAUNCH_CHECK(); }
+      if (NE) { ba_update<<<grid_for(NE, 128), 128, 0, stream>>>(0, NE, d_ext_poff.p, d_ext_off.p, d_ext_np.p, 0, 0, a.ext, b.ext, d_scale.p, d_y.p, d_sc.p, rank == 0, d_ext_lower.p); OSFM_LAUNCH_CHECK(); }
     }
     if (world > 1) allreduce_dev(&d_sc.p->model_change, 3);
     const Scalars sm = read_scalars();
@@ -1636,6 +1819,8 @@ void BA::run() {
   OSFM_CUDA(cudaMemcpyAsync(inst.data(), d_inst[cur].p, sizeof(double) * inst.size(), cudaMemcpyDeviceToHost, stream));
   if (!rc.empty())
     OSFM_CUDA(cudaMemcpyAsync(rc.data(), d_rc[cur].p, sizeof(double) * rc.size(), cudaMemcpyDeviceToHost, stream));
+  if (!ext_values.empty())
+    OSFM_CUDA(cudaMemcpyAsync(ext_values.data(), d_ext[cur].p, sizeof(double) * ext_values.size(), cudaMemcpyDeviceToHost, stream));
   d_full_pts.reserve(3 * (size_t)std::max(Pfull, 1));
   if (world > 1) OSFM_CUDA(cudaMemsetAsync(d_full_pts.p, 0, sizeof(double) * 3 * (size_t)Pfull, stream));
   if (P > 0) {
@@ -1774,6 +1959,63 @@ int osfm_ba_set_rig_cameras(osfm_ba* ba, int n, const double* pose6, const int32
   if (n < 0 || (n > 0 && (!pose6 || !constant))) throw ArgError("bad rig camera arrays");
   ba->impl.rc.assign(pose6, pose6 + 6 * (size_t)n);
   ba->impl.rc_const.assign(constant, constant + n);
+  ba->impl.rc_prior.clear();
+  ba->impl.rc_prior_sigma.clear();
+  OSFM_API_END
+}
+int osfm_ba_set_rig_camera_priors(osfm_ba* ba, const double* prior6, const double* sigma6) {
+  OSFM_API_BEGIN
+  OSFM_BA_CHECK
+  auto& b = ba->impl;
+  const size_t n = b.rc_const.size();
+  if (!prior6 || !sigma6) { b.rc_prior.clear(); b.rc_prior_sigma.clear(); }
+  else { b.rc_prior.assign(prior6, prior6 + 6 * n); b.rc_prior_sigma.assign(sigma6, sigma6 + 6 * n); }
+  OSFM_API_END
+}
+int osfm_ba_set_point_priors(osfm_ba* ba, int n, const int32_t* point, const double* prior3, const double* sigma3,
+                             const int32_t* has_altitude) {
+  OSFM_API_BEGIN
+  OSFM_BA_CHECK
+  if (n < 0 || (n > 0 && (!point || !prior3 || !sigma3 || !has_altitude))) throw ArgError("bad point prior arrays");
+  auto& b = ba->impl;
+  b.pp_point.assign(point, point + n);
+  b.pp_prior.assign(prior3, prior3 + 3 * (size_t)n);
+  b.pp_sigma.assign(sigma3, sigma3 + 3 * (size_t)n);
+  b.pp_alt.assign(has_altitude, has_altitude + n);
+  OSFM_API_END
+}
+int osfm_ba_set_ext_blocks(osfm_ba* ba, int n, const int32_t* size, const double* values, const int32_t* constant,
+                           const double* lower_bound) {
+  OSFM_API_BEGIN
+  OSFM_BA_CHECK
+  if (n < 0 || (n > 0 && (!size || !values || !constant || !lower_bound))) throw ArgError("bad ext block arrays");
+  auto& b = ba->impl;
+  size_t total = 0;
+  for (int i = 0; i < n; ++i) {
+    if (size[i] < 1 || size[i] > 16) throw ArgError("ext block size must be in [1, 16]");
+    total += (size_t)size[i];
+  }
+  b.ext_size.assign(size, size + n);
+  b.ext_const.assign(constant, constant + n);
+  b.ext_values.assign(values, values + total);
+  b.ext_lower.assign(lower_bound, lower_bound + total);
+  OSFM_API_END
+}
+int osfm_ba_get_ext_blocks(osfm_ba* ba, double* values) {
+  OSFM_API_BEGIN
+  OSFM_BA_CHECK
+  std::copy(ba->impl.ext_values.begin(), ba->impl.ext_values.end(), values);
+  OSFM_API_END
+}
+int osfm_ba_set_side_terms(osfm_ba* ba, int n, const osfm_side_term* terms, int64_t nconsts, const double* consts) {
+  OSFM_API_BEGIN
+  OSFM_BA_CHECK
+  if (n < 0 || nconsts < 0 || (n > 0 && !terms) || (nconsts > 0 && !consts)) throw ArgError("bad side term arrays");
+  auto& b = ba->impl;
+  b.side_terms.assign(terms, terms + n);
+  b.side_consts.assign(consts, consts + nconsts);
+  for (const auto& t : b.side_terms)
+    if (t.loss < -1 || t.loss > OSFM_LOSS_TUKEY) throw ArgError("ceres::LossFunction with that name not found.");
   OSFM_API_END
 }
 int osfm_ba_set_shots(osfm_ba* ba, int n, const int32_t* rig_instance, const int32_t* camera,

@@ -90,13 +90,15 @@ __global__ void ord_signatures(const unsigned long long* __restrict__ keys, cons
   if (lp >= P) return;
   const int p = lp * world + rank;
   const long long b = g_start[p], e = g_start[p + 1];
-  unsigned long long h = 1469598103934665603ULL ^ (unsigned long long)(pt_const[p] ? 1 : 0);
+  // pt_const: bit 0 = constant point, bit 1 = the point has a prior (kept off the segment path: only the
+  // per-point kernel ba_schur adds prior rows to V_p / g_p)
+  unsigned long long h = 1469598103934665603ULL ^ (unsigned long long)((pt_const[p] & 1) ? 1 : 0);
   for (long long j = b; j < e; ++j) {
     h ^= (keys[j] & 0xffffffffULL) + 0x9e3779b97f4a7c15ULL;
     h *= 1099511628211ULL;
   }
   const long long k = e - b;
-  const bool eligible = use_seg && k >= 1 && k <= kmax && k * wc <= na && wc <= wcmax;
+  const bool eligible = use_seg && k >= 1 && k <= kmax && k * wc <= na && wc <= wcmax && !(pt_const[p] & 2);
   key2[lp] = (eligible ? 0ULL : ORD_SLOW) | (h >> 1);
   val2[lp] = lp;
 }
@@ -111,7 +113,7 @@ __global__ void ord_counts(const int* __restrict__ order, const long long* __res
   const int op = order[np];
   const int p = op * world + rank;
   kk[np] = g_start[p + 1] - g_start[p];
-  free_flag[np] = pt_const[p] ? 0 : 1;
+  free_flag[np] = (pt_const[p] & 1) ? 0 : 1;
   inv_order[op] = np;
   global_of[np] = p;
 }
@@ -168,7 +170,7 @@ __global__ void ord_seg_heads(int P, const unsigned long long* __restrict__ key2
     const int pa = order[np - 1] * world + rank, pb = order[np] * world + rank;
     const long long a0 = g_start[pa], b0 = g_start[pb];
     const long long k = g_start[pb + 1] - b0;
-    same = (g_start[pa + 1] - a0) == k && (pt_const[pa] != 0) == (pt_const[pb] != 0);
+    same = (g_start[pa + 1] - a0) == k && (pt_const[pa] & 1) == (pt_const[pb] & 1);
     for (long long t = 0; t < k && same; ++t) same = (keys[a0 + t] & 0xffffffffULL) == (keys[b0 + t] & 0xffffffffULL);
   }
   head[np] = same ? -1 : np;

@@ -195,7 +195,7 @@ constexpr int SCHUR_KC = 16;  // observations staged per chunk
 __global__ void __launch_bounds__(SCHUR_THREADS)
     ba_schur(BAView v, BlkMaps bm, BsrView h, const double* __restrict__ scale, const double* __restrict__ diag,
              double inv_radius, double* __restrict__ Sval, double* __restrict__ rhs, double* __restrict__ Vinv,
-             double* __restrict__ gpo, int p_off) {
+             double* __restrict__ gpo, int p_off, PointPriorView pp, const double* __restrict__ pts) {
   extern __shared__ double sm[];
   const int wc = v.wc, nres = v.nres, nc = v.nc;
   double* Ya = sm;                                   // [KC][wc][3]
@@ -210,8 +210,8 @@ __global__ void __launch_bounds__(SCHUR_THREADS)
   const int p = p_off + blockIdx.x;
   const long long b0 = v.pt_start[p], e0 = v.pt_start[p + 1];
   const int k = (int)(e0 - b0);
-  if (k == 0) return;
   const int pf = v.pt_poff[p];
+  if (k == 0 && pf < 0) return;   // a free point without observations still needs V^-1 = (D_p + prior)^-1
   const size_t N = (size_t)v.N;
   const int tid = threadIdx.x;
 
@@ -275,6 +275,18 @@ __global__ void __launch_bounds__(SCHUR_THREADS)
       for (int o = 16; o; o >>= 1) acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], o);
     }
     if (tid == 0) {
+      if (pp.d) {  // point prior rows (diagonal): V_jj += (d_j s_j)^2, g_j += d_j s_j r_j
+        const size_t g = (size_t)pp.global_of[p];
+        const double sps[3] = {sp0, sp1, sp2};
+        const int vi[3] = {0, 3, 5};
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+          const double dj = pp.d[3 * g + j] * sps[j];
+          if (dj == 0.0) continue;
+          acc[vi[j]] += dj * dj;
+          acc[6 + j] += dj * pp.d[3 * g + j] * (pts[3 * (size_t)p + j] - pp.x0[3 * g + j]);
+        }
+      }
       const double a = acc[0] + diag[nc + 3 * pf] * inv_radius, b = acc[1], c = acc[2];
       const double d = acc[3] + diag[nc + 3 * pf + 1] * inv_radius, e = acc[4];
       const double f = acc[5] + diag[nc + 3 * pf + 2] * inv_radius;

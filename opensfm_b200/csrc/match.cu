@@ -146,6 +146,171 @@ __global__ void __launch_bounds__(256) bf_top2_simt(const MatchJob* __restrict__
 }
 
 // ---------------------------------------------------------------------------
+// General float32 descriptors, bit-exact with cv2's summation order.
+//
+// cv2::batchDistance -> normL2Sqr_(const float*, const float*, int) (OpenCV core, the x86-64 baseline
+// build of the opencv-python wheels: 4-lane universal intrinsics, no FMA) accumulates
+//     acc[a][l] += t*t   for element e = 16*blk + 4*a + l   (four 4-lane accumulators, mul then add),
+// combines  v[l] = ((acc[0][l] + acc[1][l]) + acc[2][l]) + acc[3][l],
+// reduces   d = (v[0] + v[2]) + (v[1] + v[3]),
+// and adds the dim % 16 tail sequentially, d += t*t.  (Probed against live cv2 4.13 in
+// tests/test_match_oracle.py::test_cv2_float_sum_order; integer-valued descriptors are exact in any order.)
+// Every accumulator receives one term per 16-element block, so the kernel walks the 16 (a, l) slots in
+// the outer loop and the blocks in the inner loop: one live accumulator per pair instead of sixteen.
+// Both operand tiles hold whole rows in shared memory ([element][row], 128-bit conflict-free reads).
+// MT = micro-tile edge per thread (4 -> 64x64 CTA tile, 2 -> 32x32 for long descriptors).
+// ---------------------------------------------------------------------------
+template <int MT>
+__global__ void __launch_bounds__(256) bf_top2_f32_cv(const MatchJob* __restrict__ jobs,
+                                                      const int* __restrict__ tile_prefix, int njobs,
+                                                      Top2* __restrict__ partial) {
+  constexpr int TS = 16 * MT;      // rows per tile side
+  constexpr int LD = TS + 4;       // floats per element row (keeps 16-byte alignment, staggers banks)
+  extern __shared__ __align__(16) float fx_smem[];
+  __shared__ Top2 cand[TS][16];
+
+  int lo = 0, hi = njobs - 1;
+  const int cta = blockIdx.x;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (tile_prefix[mid] <= cta) lo = mid; else hi = mid - 1;
+  }
+  const MatchJob job = jobs[lo];
+  const int local = cta - tile_prefix[lo];
+  const int qtile = local / job.nchunks;
+  const int chunk = local % job.nchunks;
+  const int q0 = qtile * TS;
+  const int t_begin = chunk * job.chunk_len;
+  const int t_end = min(job.nt, t_begin + job.chunk_len);
+  const int D = job.dim_padded;
+  const int nblk = job.dim / 16;   // full 16-element blocks of the TRUE dimension; the rest is cv2's scalar tail
+  const float* __restrict__ Q = static_cast<const float*>(job.q);
+  const float* __restrict__ T = static_cast<const float*>(job.t);
+  float* As = fx_smem;
+  float* Bs = fx_smem + (size_t)D * LD;
+
+  const int tid = threadIdx.x;
+  const int ty = tid >> 4, tx = tid & 15;
+  const int nvec = D >> 2;
+
+  auto load_tile = [&](float* dst, const float* __restrict__ src, int r0, int rend) {
+    for (int idx = tid; idx < TS * nvec; idx += 256) {
+      const int row = idx % TS, v = idx / TS;
+      float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (r0 + row < rend) x = *reinterpret_cast<const float4*>(src + (size_t)(r0 + row) * D + v * 4);
+      dst[(v * 4 + 0) * LD + row] = x.x;
+      dst[(v * 4 + 1) * LD + row] = x.y;
+      dst[(v * 4 + 2) * LD + row] = x.z;
+      dst[(v * 4 + 3) * LD + row] = x.w;
+    }
+  };
+  load_tile(As, Q, q0, job.nq);
+
+  Top2 best[MT];
+#pragma unroll
+  for (int i = 0; i < MT; ++i) best[i] = top2_empty();
+
+  for (int t0 = t_begin; t0 < t_end; t0 += TS) {
+    __syncthreads();  // previous tile's readers are done (and As is complete on the first pass)
+    load_tile(Bs, T, t0, t_end);
+    __syncthreads();
+    float u[MT][MT], w[MT][MT];
+#pragma unroll
+    for (int li = 0; li < 4; ++li) {
+      const int l = (li == 0) ? 0 : (li == 1) ? 2 : (li == 2) ? 1 : 3;  // lanes 0, 2 feed u; 1, 3 feed w
+      float s[MT][MT];
+#pragma unroll
+      for (int a = 0; a < 4; ++a) {
+        float acc[MT][MT];
+#pragma unroll
+        for (int i = 0; i < MT; ++i)
+#pragma unroll
+          for (int j = 0; j < MT; ++j) acc[i][j] = 0.f;
+        const float* pa = As + (size_t)(4 * a + l) * LD + ty * MT;
+        const float* pb = Bs + (size_t)(4 * a + l) * LD + tx * MT;
+        for (int blk = 0; blk < nblk; ++blk) {
+          float av[MT], bv[MT];
+          if constexpr (MT == 4) {
+            const float4 a4 = *reinterpret_cast<const float4*>(pa);
+            const float4 b4 = *reinterpret_cast<const float4*>(pb);
+            av[0] = a4.x; av[1] = a4.y; av[2] = a4.z; av[3] = a4.w;
+            bv[0] = b4.x; bv[1] = b4.y; bv[2] = b4.z; bv[3] = b4.w;
+          } else {
+            const float2 a2 = *reinterpret_cast<const float2*>(pa);
+            const float2 b2 = *reinterpret_cast<const float2*>(pb);
+            av[0] = a2.x; av[1] = a2.y; bv[0] = b2.x; bv[1] = b2.y;
+          }
+#pragma unroll
+          for (int i = 0; i < MT; ++i)
+#pragma unroll
+            for (int j = 0; j < MT; ++j) {
+              const float t = __fsub_rn(av[i], bv[j]);
+              acc[i][j] = __fadd_rn(acc[i][j], __fmul_rn(t, t));   // mul, then add: no FMA contraction
+            }
+          pa += 16 * LD;
+          pb += 16 * LD;
+        }
+#pragma unroll
+        for (int i = 0; i < MT; ++i)
+#pragma unroll
+          for (int j = 0; j < MT; ++j) s[i][j] = a == 0 ? acc[i][j] : __fadd_rn(s[i][j], acc[i][j]);
+      }
+#pragma unroll
+      for (int i = 0; i < MT; ++i)
+#pragma unroll
+        for (int j = 0; j < MT; ++j) {
+          if (li == 0) u[i][j] = s[i][j];
+          else if (li == 1) u[i][j] = __fadd_rn(u[i][j], s[i][j]);
+          else if (li == 2) w[i][j] = s[i][j];
+          else w[i][j] = __fadd_rn(w[i][j], s[i][j]);
+        }
+    }
+    float d2[MT][MT];
+#pragma unroll
+    for (int i = 0; i < MT; ++i)
+#pragma unroll
+      for (int j = 0; j < MT; ++j) d2[i][j] = __fadd_rn(u[i][j], w[i][j]);
+    // scalar tail of the true dimension (zero padding beyond it adds +0)
+    for (int e = nblk * 16; e < D; ++e) {
+      float av[MT], bv[MT];
+#pragma unroll
+      for (int i = 0; i < MT; ++i) { av[i] = As[(size_t)e * LD + ty * MT + i]; bv[i] = Bs[(size_t)e * LD + tx * MT + i]; }
+#pragma unroll
+      for (int i = 0; i < MT; ++i)
+#pragma unroll
+        for (int j = 0; j < MT; ++j) {
+          const float t = __fsub_rn(av[i], bv[j]);
+          d2[i][j] = __fadd_rn(d2[i][j], __fmul_rn(t, t));
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < MT; ++i) {
+      const int gq = q0 + ty * MT + i;
+#pragma unroll
+      for (int j = 0; j < MT; ++j) {
+        const int gt = t0 + tx * MT + j;
+        if (gq >= job.nq || gt >= t_end) continue;
+        if (job.mask && job.mask[(size_t)gq * job.mask_sq + (size_t)gt * job.mask_st] == 0) continue;
+        top2_insert(best[i], __fsqrt_rn(d2[i][j]), gt);
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < MT; ++i) cand[ty * MT + i][tx] = best[i];
+  __syncthreads();
+  if (tid < TS) {
+    const int gq = q0 + tid;
+    if (gq < job.nq) {
+      Top2 m = top2_empty();
+      for (int x = 0; x < 16; ++x) top2_merge(m, cand[tid][x]);
+      partial[job.partial_off + (size_t)chunk * job.nq + gq] = m;
+    }
+  }
+}
+constexpr int FX_MAX_DIM_T64 = 320;   // padded elements: 2 * 320 * 68 * 4 B = 174 KB of shared memory
+constexpr int FX_MAX_DIM_T32 = 704;   // 2 * 704 * 36 * 4 B = 203 KB
+
+// ---------------------------------------------------------------------------
 // Merge chunks + ratio test.  grid = (ceil(max_nq/256), njobs)
 // ---------------------------------------------------------------------------
 // squared != 0: the partials hold squared distances (tcgen05 kernel; only used when float32 sqrt is
@@ -369,7 +534,7 @@ void Matcher::match_pairs_async(int npairs, const int* ids_a, const int* ids_b, 
   h_out_off.assign(npairs + 1, 0);
   bool any_u8 = false, any_f32 = false, all_tc = true;
   long long total_qtiles = 0;
-  int max_nq = 0;
+  int max_nq = 0, max_dim_padded = 0;
   for (int p = 0; p < npairs; ++p) {
     auto ia = sets.find(ids_a[p]), ib = sets.find(ids_b[p]);
     if (ia == sets.end() || ib == sets.end()) throw ArgError("unknown descriptor set id in pair list");
@@ -379,6 +544,7 @@ void Matcher::match_pairs_async(int npairs, const int* ids_a, const int* ids_b, 
     if (A.u8 != B.u8 || A.dim != B.dim) throw ArgError("descriptor sets of a pair differ in dtype or dimension");
     any_u8 |= A.u8;
     any_f32 |= !A.u8;
+    max_dim_padded = std::max(max_dim_padded, A.dim_padded);
     // d^2 <= (|a| + |b|)^2 <= 2 (|a|^2 + |b|^2) must stay below 2^22 for the d^2-space ranking of the
     // tcgen05 kernel to equal cv2's sqrt-space ranking (float32 sqrt injective on integers < 2^22)
     all_tc &= (!A.u8 && A.tc_ok && B.tc_ok && 2.0f * (A.tc_max_norm + B.tc_max_norm) < 4194304.0f);
@@ -418,10 +584,17 @@ void Matcher::match_pairs_async(int npairs, const int* ids_a, const int* ids_b, 
   last_npairs = npairs;
 
   // split the train dimension when there are too few query tiles to fill the GPU
-  const int tile_m = use == 2 ? tc_tile_m() : BM;
-  const int chunk_unit = use == 2 ? tc_tile_n() : BN;
+  // float32 SIMT path: the cv2-order kernel keeps whole rows in shared memory -> tile edge by descriptor length
+  int simt_tile = BM;
+  if (use == 1 && any_f32) {
+    if (max_dim_padded > FX_MAX_DIM_T32)
+      throw ArgError("float32 descriptors longer than 704 elements are not supported by the exact matcher");
+    simt_tile = max_dim_padded > FX_MAX_DIM_T64 ? 32 : 64;
+  }
+  const int tile_m = use == 2 ? tc_tile_m() : simt_tile;
+  const int chunk_unit = use == 2 ? tc_tile_n() : simt_tile;
   long long tiles_total = 0;
-  if (use == 2) {
+  if (use == 2 || simt_tile != BM) {
     total_qtiles = 0;
     for (auto& j : h_jobs) { j.qtiles = (j.nq + tile_m - 1) / tile_m; total_qtiles += j.qtiles; }
   }
@@ -482,7 +655,18 @@ void Matcher::match_pairs_async(int npairs, const int* ids_a, const int* ids_b, 
       bf_top2_simt<true><<<(unsigned)tiles_total, 256, 0, stream>>>(d_jobs.p, d_prefix.p, njobs, d_partial.p);
       OSFM_LAUNCH_CHECK();
     } else {
-      bf_top2_simt<false><<<(unsigned)tiles_total, 256, 0, stream>>>(d_jobs.p, d_prefix.p, njobs, d_partial.p);
+      const size_t smem = 2 * (size_t)max_dim_padded * (simt_tile + 4) * sizeof(float);
+      if (!fx_attr_set) {
+        OSFM_CUDA(cudaFuncSetAttribute(bf_top2_f32_cv<4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       2 * FX_MAX_DIM_T64 * 68 * (int)sizeof(float)));
+        OSFM_CUDA(cudaFuncSetAttribute(bf_top2_f32_cv<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       2 * FX_MAX_DIM_T32 * 36 * (int)sizeof(float)));
+        fx_attr_set = true;
+      }
+      if (simt_tile == 64)
+        bf_top2_f32_cv<4><<<(unsigned)tiles_total, 256, smem, stream>>>(d_jobs.p, d_prefix.p, njobs, d_partial.p);
+      else
+        bf_top2_f32_cv<2><<<(unsigned)tiles_total, 256, smem, stream>>>(d_jobs.p, d_prefix.p, njobs, d_partial.p);
       OSFM_LAUNCH_CHECK();
     }
   }

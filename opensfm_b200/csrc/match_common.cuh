@@ -97,7 +97,7 @@ struct Matcher {
   long long last_total_results = 0;
   int last_npairs = 0;
   bool results_in_match_buf = true;
-  bool tc_attr_set = false;
+  bool tc_attr_set = false, fx_attr_set = false;
   std::map<int, DescSet> sets;
   std::vector<MatchJob> h_jobs;
   std::vector<int> h_prefix;

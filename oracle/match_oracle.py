@@ -61,17 +61,40 @@ def match_brute_force_symmetric(fi: np.ndarray, fj: np.ndarray, config: Dict[str
     return list(set(matches_ij).intersection(set(matches_ji)))
 
 
+def l2sqr_cv_order(f1: np.ndarray, f2: np.ndarray) -> np.ndarray:
+    """float32 sum of squared differences in the order cv2 computes it (OpenCV core `normL2Sqr_` for
+    float, x86-64 baseline of the opencv-python wheels: 4-lane universal intrinsics, no FMA): four 4-lane
+    accumulators acc[a][l] += t*t over 16-element blocks (element 16*blk + 4*a + l), combined
+    ((acc0 + acc1) + acc2) + acc3 per lane, lanes reduced (v0 + v2) + (v1 + v3), then the dim % 16 tail
+    added sequentially.  Pinned bit-for-bit against live cv2 in tests/test_match_oracle.py."""
+    a = np.ascontiguousarray(f1, dtype=np.float32)
+    b = np.ascontiguousarray(f2, dtype=np.float32)
+    n, m, dim = a.shape[0], b.shape[0], a.shape[1]
+    nblk = dim // 16
+    out = np.zeros((n, m), dtype=np.float32)
+    step = max(1, (1 << 24) // max(m * max(dim, 1), 1))
+    for q0 in range(0, n, step):
+        t = a[q0:q0 + step, None, :] - b[None, :, :]          # float32 subtraction
+        sq = t * t                                            # float32 product (rounded before the add)
+        acc = np.zeros((t.shape[0], m, 16), dtype=np.float32)
+        for blk in range(nblk):
+            acc = acc + sq[:, :, 16 * blk:16 * blk + 16]
+        acc = acc.reshape(t.shape[0], m, 4, 4)                # [a][l]
+        v = ((acc[:, :, 0] + acc[:, :, 1]) + acc[:, :, 2]) + acc[:, :, 3]
+        d = (v[:, :, 0] + v[:, :, 2]) + (v[:, :, 1] + v[:, :, 3])
+        for e in range(16 * nblk, dim):
+            d = d + sq[:, :, e]
+        out[q0:q0 + step] = d
+    return out
+
+
 def distance_matrix(f1: np.ndarray, f2: np.ndarray) -> np.ndarray:
-    """float32 distances as cv2 returns them: sqrt of the float32 sum of squared
-    differences (exact for integer-valued descriptors), or Hamming bit counts."""
+    """float32 distances as cv2 returns them: sqrt of the float32 sum of squared differences in cv2's
+    summation order, or Hamming bit counts."""
     if f1.dtype == np.uint8:
         x = np.bitwise_xor(f1[:, None, :], f2[None, :, :])
         return np.unpackbits(x, axis=2).sum(axis=2).astype(np.float32)
-    a = f1.astype(np.float64)
-    b = f2.astype(np.float64)
-    d2 = (a * a).sum(1)[:, None] + (b * b).sum(1)[None, :] - 2.0 * (a @ b.T)
-    d2 = np.maximum(d2, 0.0).astype(np.float32)
-    return np.sqrt(d2)
+    return np.sqrt(l2sqr_cv_order(f1, f2))
 
 
 def knn2_numpy(f1: np.ndarray, f2: np.ndarray, maskij: Optional[np.ndarray] = None):

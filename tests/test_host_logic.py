@@ -89,8 +89,16 @@ def test_bundle_adjuster_bookkeeping_without_gpu():
     assert pb.cam_const.tolist() == [1, 1, 0]
     assert ba.has_point("p") and not ba.has_point("q")
     assert np.allclose(ba.get_rig_instance_pose("1").rotation, [0.5, 0, 0])
+    # secondary residuals become side terms of the problem (bundle_adjuster.cc:956-971); std <= 0 adds nothing
+    ba.add_absolute_up_vector("s1", [0, 0, -2.0], 1e-3)
+    ba.add_absolute_pan("s1", 0.3, 0.0)
+    pb = ba.to_problem()
+    assert [t.type for t in pb.side_terms] == [bp.SIDE_UP_VECTOR]
+    assert np.allclose(pb.side_terms[0].consts, [0, 0, -1, 1e3]) and pb.side_terms[0].loss == bp.LOSS_CAUCHY
+    with pytest.raises(RuntimeError, match="already exist"):
+        ba.add_rig_camera("rc", T.Pose(), T.Pose(), True)   # bundle_adjuster.cc:155-158
     with pytest.raises(NotImplementedError):
-        ba.add_absolute_up_vector("s1", [0, 0, -1], 1e-3)
+        ba.add_heatmap("h", [0.0] * 16, 4, 1.0)
 
 
 def test_shard_pairs_balances_work():

@@ -45,6 +45,35 @@ def test_l2_general_float_descriptors_simt():
     assert matching.match_brute_force(a, b, CFG) == mo.match_brute_force(a, b, CFG)
 
 
+@pytest.mark.parametrize("n1,n2,dim", [(8000, 8000, 128), (3000, 4000, 64), (700, 900, 100), (500, 600, 20),
+                                       (400, 500, 384), (300, 400, 700)])
+def test_l2_general_float_exact_at_scale(n1, n2, dim):
+    """Arbitrary float descriptors (e.g. root-SIFT): bit-exact match lists vs live cv2, including near-ties --
+    the kernel sums in cv2's order (match.cu bf_top2_f32_cv).  8000 x 8000 is the C3 descriptor count."""
+    rng = np.random.RandomState(n1 + dim)
+    a = rng.rand(n1, dim).astype(np.float32)
+    b = rng.rand(n2, dim).astype(np.float32)
+    k = min(n1, n2) // 2
+    b[:k] = a[:k] + rng.normal(0, 0.02, (k, dim)).astype(np.float32)
+    b[k:k + 50] = b[:50] + np.float32(1e-7)      # near-duplicate trains: order decided by the last bits
+    for ratio in (0.8, 1.0):
+        cfg = {"lowes_ratio": ratio}
+        assert matching.match_brute_force(a, b, cfg) == mo.match_brute_force(a, b, cfg)
+    assert _pairset(matching.match_brute_force_symmetric(a, b, CFG)) == _pairset(
+        mo.match_brute_force_symmetric(a, b, CFG))
+
+
+def test_l2_integer_descriptors_16000_rows():
+    a, b = _related(16000, 15000, 77)
+    assert matching.match_brute_force(a, b, CFG) == mo.match_brute_force(a, b, CFG)
+
+
+def test_l2_float_too_long_raises():
+    a = np.zeros((4, 800), np.float32) + 0.5
+    with pytest.raises((RuntimeError, ValueError)):
+        matching.match_brute_force(a, a, CFG)
+
+
 @pytest.mark.parametrize("dim", [32, 64, 100, 128])
 def test_l2_other_dims(dim):
     rng = np.random.RandomState(dim)

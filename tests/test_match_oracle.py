@@ -70,3 +70,32 @@ def test_cube_scene_descriptors():
     f0, f1 = sc.features_of_shot(0)[0], sc.features_of_shot(1)[0]
     assert f0.dtype == np.float32 and f0.shape[1] == 128
     assert mo.match_brute_force_numpy(f0, f1, CFG) == mo.match_brute_force(f0, f1, CFG)
+
+
+@pytest.mark.parametrize("dim", [3, 16, 20, 61, 64, 100, 128, 130, 256])
+def test_cv2_float_sum_order(dim):
+    """The restated summation order of cv2's float L2 (4 lanes x 4 accumulators, mul then add, tree reduce, scalar
+    tail) reproduces cv2's distances BIT FOR BIT on arbitrary floats -- this is what makes general-float
+    matching exact by contract rather than up to near-ties."""
+    rng = np.random.RandomState(dim)
+    a = rng.randn(37, dim).astype(np.float32) * 3
+    b = rng.randn(53, dim).astype(np.float32) * 3
+    m = cv2.DescriptorMatcher_create("BruteForce")
+    m.add([b])
+    res = m.knnMatch(a, k=53)
+    D = np.zeros((37, 53), np.float32)
+    for q, lst in enumerate(res):
+        for dm in lst:
+            D[q, dm.trainIdx] = dm.distance
+    assert np.array_equal(D, mo.distance_matrix(a, b))
+
+
+def test_general_float_matches_cv2_exactly_with_near_ties():
+    rng = np.random.RandomState(5)
+    a = rng.rand(1500, 128).astype(np.float32)
+    b = rng.rand(2000, 128).astype(np.float32)
+    b[:700] = a[:700] + rng.normal(0, 0.02, (700, 128)).astype(np.float32)
+    b[1500:1600] = b[:100] + np.float32(1e-7)   # near-duplicates: distances differ in the last bits only
+    for ratio in (0.8, 1.0):
+        cfg = {"lowes_ratio": ratio}
+        assert mo.match_brute_force_numpy(a, b, cfg) == mo.match_brute_force(a, b, cfg)
