@@ -769,7 +769,12 @@ class BundleAdjuster:
 
     def run(self) -> None:
         pb = self.to_problem()
-        res = solve(pb, device=self.device, compute_reprojection_errors=self._compute_reprojection_errors)
+        self.apply_results(pb, solve(pb, device=self.device,
+                                     compute_reprojection_errors=self._compute_reprojection_errors))
+
+    def apply_results(self, pb: bp.BAProblem, res: Dict[str, Any]) -> None:
+        """Write the arrays of a solve of `pb` (= self.to_problem()) back into the per-id containers the getters
+        read.  Separate from run() so that the parity tests can push the same problem through the oracle."""
         cam_ids, inst_ids, rc_ids, shot_ids = self._order
         off = pb.cam_off
         for i, c in enumerate(cam_ids):

@@ -66,6 +66,7 @@ struct Scalars {
   double step_norm2;
   double x_norm2;
   double grad_max_bits;  // max |g| via atomicMax on the bit pattern (non-negative doubles)
+  double gdot;           // gradient . step (projected line search of bounded problems)
 };
 
 __device__ __forceinline__ double block_reduce_sum(double v) {
@@ -559,7 +560,8 @@ __global__ void ba_prior_model_change(PriorView pv, Params p, const double* scal
 __global__ void ba_update(int which, int count, const int* __restrict__ poff, const int* __restrict__ off,
                           const int* __restrict__ np, int stride, int base, const double* __restrict__ src,
                           double* __restrict__ dst, const double* __restrict__ scale, const double* __restrict__ y,
-                          Scalars* sc, int accumulate_norms, const double* __restrict__ lower = nullptr) {
+                          Scalars* sc, int accumulate_norms, const double* __restrict__ lower = nullptr,
+                          double alpha = 1.0) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   double sn = 0.0, xn = 0.0;
   if (b < count) {
@@ -570,7 +572,7 @@ __global__ void ba_update(int which, int count, const int* __restrict__ poff, co
       double val = src[o + j];
       if (g >= 0) {
         const int gi = which == 3 ? base + 3 * g + j : g + j;
-        double d = -scale[gi] * y[gi];
+        double d = -alpha * scale[gi] * y[gi];
         if (lower && val + d < lower[o + j]) d = lower[o + j] - val;   // projection onto the bound (ceres bounded LM)
         xn += val * val;
         sn += d * d;
@@ -587,6 +589,16 @@ __global__ void ba_update(int which, int count, const int* __restrict__ poff, co
       if (t2 != 0.0) atomicAdd(&sc->x_norm2, t2);
     }
   }
+}
+
+// gradient . delta with delta = -scale * y: camera side counted when cam_side != 0 (one rank), points always
+__global__ void ba_grad_dot(int n, int nc, int cam_side, const double* __restrict__ grad, const double* __restrict__ scale,
+                            const double* __restrict__ y, Scalars* sc) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  double v = 0.0;
+  if (i < n && (i >= nc || cam_side)) v = -grad[i] * scale[i] * y[i];
+  const double t = block_reduce_sum(v);
+  if (threadIdx.x == 0 && t != 0.0) atomicAdd(&sc->gdot, t);
 }
 
 // single-observation device evaluation (test hook)
@@ -889,6 +901,9 @@ void BA::run() {
     for (int i = 0; i < NE; ++i) if (!ext_const[i]) ext_blk[i] = b++;
   }
   // side terms: block references checked here (the reference's std::map::at / "doesn't exist" errors)
+  bool constrained = false;   // a free ext parameter with a finite lower bound (ceres: Problem::IsConstrained)
+  for (int i = 0; i < NE; ++i)
+    for (int j = 0; j < ext_size[i] && !ext_const[i]; ++j) constrained |= std::isfinite(ext_lower[ext_off[i] + j]);
   const int NT = (int)side_terms.size();
   std::vector<int> side_jofs(NT + 1, 0), side_rofs(NT + 1, 0);
   for (int t = 0; t < NT; ++t) {
@@ -1760,6 +1775,17 @@ void BA::run() {
     }
     // --- candidate point ---
     const int cand = cur ^ 1;
+    auto update_candidate = [&](double alpha) {   // candidate = Project(x - alpha * scale * y); |delta|^2, |x|^2
+      OSFM_CUDA(cudaMemsetAsync(&d_sc.p->step_norm2, 0, sizeof(double) * 2, stream));
+      Params a = params_of(cur), b = params_of(cand);
+      if (K) { ba_update<<<grid_for(K, 128), 128, 0, stream>>>(0, K, d_cam_poff.p, d_cam_off.p, d_cam_np.p, 0, 0, a.cam, b.cam, d_scale.p, d_y.p, d_sc.p, rank == 0, nullptr, alpha); OSFM_LAUNCH_CHECK(); }
+      if (NI) { ba_update<<<grid_for(NI, 128), 128, 0, stream>>>(1, NI, d_inst_poff.p, nullptr, nullptr, 6, 0, a.inst, b.inst, d_scale.p, d_y.p, d_sc.p, rank == 0, nullptr, alpha); OSFM_LAUNCH_CHECK(); }
+      if (NR) { ba_update<<<grid_for(NR, 128), 128, 0, stream>>>(2, NR, d_rc_poff.p, nullptr, nullptr, 6, 0, a.rc, b.rc, d_scale.p, d_y.p, d_sc.p, rank == 0, nullptr, alpha); OSFM_LAUNCH_CHECK(); }
+      if (P) { ba_update<<<grid_for(P, 128), 128, 0, stream>>>(3, P, d_pt_poff.p, nullptr, nullptr, 3, nc, a.pts, b.pts, d_scale.p, d_y.p, d_sc.p, 1, nullptr, alpha); OSFM_LAUNCH_CHECK(); }
+      if (NE) { ba_update<<<grid_for(NE, 128), 128, 0, stream>>>(0, NE, d_ext_poff.p, d_ext_off.p, d_ext_np.p, 0, 0, a.ext, b.ext, d_scale.p, d_y.p, d_sc.p, rank == 0, d_ext_lower.p, alpha); OSFM_LAUNCH_CHECK(); }
+      if (world > 1) allreduce_dev(&d_sc.p->step_norm2, 2);
+      return std::sqrt(read_scalars().step_norm2);
+    };
     {
       Params a = params_of(cur), b = params_of(cand);
       if (K) { ba_update<<<grid_for(K, 128), 128, 0, stream>>>(0, K, d_cam_poff.p, d_cam_off.p, d_cam_np.p, 0, 0, a.cam, b.cam, d_scale.p, d_y.p, d_sc.p, rank == 0); OSFM_LAUNCH_CHECK(); }
@@ -1782,7 +1808,7 @@ void BA::run() {
       if (!(rr == rr)) ok = false;
     }
     const double model_change = sm.model_change;
-    const double step_norm = std::sqrt(sm.step_norm2);
+    double step_norm = std::sqrt(sm.step_norm2);
     if (!ok || !(model_change > 0.0) || !std::isfinite(step_norm)) {
       if (++n_invalid >= 5) { termination = 2; message = "Too many consecutive invalid steps."; break; }
       radius *= 0.5;
@@ -1790,7 +1816,26 @@ void BA::run() {
       continue;
     }
     n_invalid = 0;
-    const double cand_cost = eval_cost(cand);
+    double cand_cost = eval_cost(cand);
+    if (constrained) {
+      // Ceres: a problem with parameter bounds is "constrained": TrustRegionMinimizer::DoLineSearch runs a projected
+      // Armijo search along the step (sufficient decrease 1e-4, at most 20 contractions; bisection here, Ceres'
+      // default interpolates a cubic) and the candidate is the point it accepts.  The model cost change stays
+      // that of the full step, as in Ceres.
+      OSFM_CUDA(cudaMemsetAsync(&d_sc.p->gdot, 0, sizeof(double), stream));
+      ba_grad_dot<<<grid_for(n, 256), 256, 0, stream>>>(n, nc, rank == 0, d_grad.p, d_scale.p, d_y.p, d_sc.p);
+      OSFM_LAUNCH_CHECK();
+      if (world > 1) allreduce_dev(&d_sc.p->gdot, 1);
+      const double g0 = read_scalars().gdot;
+      double alpha = 1.0;
+      bool ok_ls = false;
+      for (int ls = 0; ls < 20; ++ls) {
+        if (ls > 0) { step_norm = update_candidate(alpha); cand_cost = eval_cost(cand); }
+        if (std::isfinite(cand_cost) && cand_cost <= cost + 1e-4 * g0 * alpha) { ok_ls = true; break; }
+        alpha *= 0.5;
+      }
+      if (!ok_ls) { step_norm = update_candidate(1.0); cand_cost = eval_cost(cand); }
+    }
     if (step_norm <= ptol * (x_norm + ptol)) { termination = 0; message = "Parameter tolerance reached."; break; }
     const double cost_change = cost - cand_cost;
     if (std::fabs(cost_change) <= ftol * cost) { termination = 0; message = "Function tolerance reached."; break; }
@@ -1828,7 +1873,8 @@ void BA::run() {
     OSFM_LAUNCH_CHECK();
   }
   allreduce_dev(d_full_pts.p, 3 * (long long)Pfull);
-  OSFM_CUDA(cudaMemcpyAsync(pts.data(), d_full_pts.p, sizeof(double) * 3 * (size_t)Pfull, cudaMemcpyDeviceToHost, stream));
+  if (Pfull > 0)
+    OSFM_CUDA(cudaMemcpyAsync(pts.data(), d_full_pts.p, sizeof(double) * 3 * (size_t)Pfull, cudaMemcpyDeviceToHost, stream));
   // the reprojection errors stay on the device until osfm_ba_get_reprojection_errors fetches them
   reproj_valid = false;
   if (compute_reproj && Nfull > 0) {

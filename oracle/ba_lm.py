@@ -157,10 +157,44 @@ class OracleBA:
             self.P, _d(k[17]), _i(k[18]),
             ctypes.c_int64(self.N), _i(k[19]), _i(k[20]), _d(k[21]), _d(k[22]),
             LOSS_IDS[pb.loss_name], ctypes.c_double(pb.loss_threshold)))
+        self._set_secondary(pb)
         self.nc = L.oba_nc(self.h)
         self.npf = L.oba_npts_free(self.h)
+        k2 = self._keep2
+        # a free ext parameter with a finite lower bound makes the problem "constrained" (Ceres: is_constrained)
+        self.constrained = bool(np.any(np.repeat(k2[2] == 0, k2[0]) & np.isfinite(k2[3]))) if len(k2[0]) else False
         self.n = self.nc + 3 * self.npf
         self.ncamp = len(k[1])
+
+    def _set_secondary(self, pb: Any) -> None:
+        """Ext blocks, side terms, point priors and rig-camera priors of the problem (duck-typed: the fields of
+        opensfm_b200.ba_problem.BAProblem; absent fields = none)."""
+        c32 = lambda a: np.ascontiguousarray(a, dtype=np.int32)
+        f64 = lambda a: np.ascontiguousarray(a, dtype=np.float64)
+        ext_size = c32(getattr(pb, "ext_size", np.zeros(0)))
+        ext_values = f64(getattr(pb, "ext_values", np.zeros(0)))
+        ext_const = c32(getattr(pb, "ext_const", np.zeros(0)))
+        ext_lower = f64(getattr(pb, "ext_lower", np.zeros(0)))
+        recs, consts = pb.packed_side_terms() if hasattr(pb, "packed_side_terms") else ([], np.zeros(0))
+        ints = np.zeros((max(len(recs), 1), 21), dtype=np.int32)
+        loss_a = np.ones(max(len(recs), 1))
+        for t, (ty, nres, nb, kind, idx, loss, la, cofs, aux) in enumerate(recs):
+            ints[t] = [ty, nres, nb] + list(kind) + list(idx) + [loss, cofs] + list(aux)
+            loss_a[t] = la
+        consts = f64(consts)
+        pp_point = c32(getattr(pb, "pp_point", np.zeros(0)))
+        pp_prior = f64(getattr(pb, "pp_prior", np.zeros((0, 3))))
+        pp_sigma = f64(getattr(pb, "pp_sigma", np.zeros((0, 3))))
+        pp_alt = c32(getattr(pb, "pp_alt", np.zeros(0)))
+        rcp = getattr(pb, "rigcam_prior", None)
+        rc_prior = f64(rcp if rcp is not None else np.zeros((1, 6)))
+        rc_sigma = f64(pb.rigcam_prior_sigma if rcp is not None else np.ones((1, 6)))
+        self.n_ext = int(ext_size.sum())
+        self._keep2 = [ext_size, ext_values, ext_const, ext_lower, ints, loss_a, consts, pp_point, pp_prior, pp_sigma,
+                       pp_alt, rc_prior, rc_sigma]
+        lib().oba_set_secondary(self.h, len(ext_size), _i(ext_size), _d(ext_values), _i(ext_const), _d(ext_lower),
+                                len(recs), _i(ints), _d(loss_a), len(consts), _d(consts), len(pp_point), _i(pp_point),
+                                _d(pp_prior), _d(pp_sigma), _i(pp_alt), int(rcp is not None), _d(rc_prior), _d(rc_sigma))
 
     def __del__(self):
         try:
@@ -168,17 +202,24 @@ class OracleBA:
         except Exception:
             pass
 
+    def get_ext(self):
+        ext = np.zeros(self.n_ext)
+        lib().oba_get_ext(self.h, _d(ext))
+        return ext
+
     def get_params(self):
         cam = np.zeros(self.ncamp)
         inst = np.zeros((self.NI, 6))
         rc = np.zeros((self.NR, 6))
         pts = np.zeros((self.P, 3))
         lib().oba_get_params(self.h, _d(cam), _d(inst), _d(rc), _d(pts))
-        return cam, inst, rc, pts
+        return cam, inst, rc, pts, self.get_ext()
 
-    def set_params(self, cam, inst, rc, pts):
+    def set_params(self, cam, inst, rc, pts, ext=None):
         lib().oba_set_params(self.h, _d(np.ascontiguousarray(cam)), _d(np.ascontiguousarray(inst)),
                              _d(np.ascontiguousarray(rc)), _d(np.ascontiguousarray(pts)))
+        if ext is not None and len(ext):
+            lib().oba_set_ext(self.h, _d(np.ascontiguousarray(ext)))
 
     def plus(self, delta):
         lib().oba_plus(self.h, _d(np.ascontiguousarray(delta)))
@@ -291,9 +332,33 @@ def solve(pb: Any, max_iterations: Optional[int] = None, verbose: bool = False,
         n_invalid = 0
         delta = step * scale
         saved = ba.get_params()
+        if ba.constrained:
+            # Ceres: bounds make the problem "constrained" and TrustRegionMinimizer::DoLineSearch runs a projected
+            # Armijo search along the step before the candidate is evaluated (sufficient decrease 1e-4, at most 20
+            # contractions).  Interpolation here is BISECTION (step *= 0.5); Ceres' default fits a
+            # cubic -- the accepted step differs, the fixed points do not.  model_cost_change stays that of the
+            # full step, as in Ceres.
+            g0 = float(np.dot(g, delta))
+            alpha, ok_ls = 1.0, False
+            for _ in range(20):
+                ba.set_params(*saved)
+                ba.plus(alpha * delta)
+                c = ba.cost()
+                if np.isfinite(c) and c <= cost + 1e-4 * g0 * alpha:
+                    ok_ls = True
+                    break
+                alpha *= 0.5
+            if not ok_ls:
+                alpha = 1.0
+            delta = alpha * delta
+            ba.set_params(*saved)
         ba.plus(delta)
         cand_cost = ba.cost()
-        step_norm = float(np.linalg.norm(delta))
+        if ba.constrained:
+            # Ceres: step_norm = |x - candidate_x|, i.e. the step actually taken after projection onto the bounds
+            step_norm = float(np.sqrt(sum(((a - b) ** 2).sum() for a, b in zip(ba.get_params(), saved))))
+        else:
+            step_norm = float(np.linalg.norm(delta))
         if step_norm <= ptol * (x_norm + ptol):
             # Ceres leaves x at the pre-step value on parameter-tolerance exit
             ba.set_params(*saved)
@@ -329,9 +394,9 @@ def solve(pb: Any, max_iterations: Optional[int] = None, verbose: bool = False,
             print("it %3d cost %.9e change %.3e |g| %.3e radius %.3e" % (it, cost, cost_change, grad_max, radius))
     run_time = time.perf_counter() - t0
     final_cost, reproj = ba.cost(want_reproj=True)
-    cam, inst, rc, pts = ba.get_params()
+    cam, inst, rc, pts, ext = ba.get_params()
     return {
-        "cam_params": cam, "inst": inst, "rigcam": rc, "points": pts,
+        "cam_params": cam, "inst": inst, "rigcam": rc, "points": pts, "ext_values": ext,
         "reprojection_errors": reproj,
         "initial_cost": initial_cost, "final_cost": final_cost,
         "iterations": it, "successful_steps": n_success, "linear_solves": n_lin_solves,

@@ -18,6 +18,7 @@
 #include <vector>
 
 #include "ba_functors.hpp"
+#include "ba_side_terms.hpp"
 
 using namespace oracle;
 
@@ -101,7 +102,95 @@ struct Problem {
   struct PriorRow { double r; int col; double d; };
   std::vector<PriorRow> prior_rows;
   std::vector<double> scale;  // Jacobi column scaling, size nc + 3*npts_free (1 if unset)
+  // ---- secondary residuals (bundle_adjuster.cc:610-625, 672-790, 817-1101) ----
+  // ext blocks: camera biases (7), reconstruction scales (1), std-deviation scales (1)
+  int NE = 0;
+  std::vector<int> ext_off, ext_np, ext_poff;
+  std::vector<double> ext, ext_lower;
+  struct SideTerm { int type, nres, nblocks, kind[6], idx[6], loss; double loss_a; int cofs, aux[4]; };
+  std::vector<SideTerm> side_terms;
+  std::vector<double> side_consts;
+  struct DenseRows { int nres, ncols; int cols[MAXD]; double J[7 * MAXD]; double r[7]; };  // robustified rows
+  std::vector<DenseRows> side_rows;
+  std::vector<int> pp_of_point;            // per point: index of its prior or -1
+  std::vector<double> pp_prior, pp_sigma;  // per prior: xyz
+  std::vector<int> pp_alt;
+  std::vector<double> rc_prior, rc_prior_sigma;  // empty = no rig-camera priors
 };
+
+// parameter block (kind 0 camera, 1 rig instance, 2 rig camera, 3 ext) -> values, size, reduced column
+struct BlockRef { const double* p; int np; int col; };
+inline BlockRef block_ref(const Problem& pb, int kind, int idx) {
+  switch (kind) {
+    case 0: return {&pb.cam[pb.cam_off[idx]], pb.cam_np[idx], pb.cam_poff[idx]};
+    case 1: return {&pb.inst[6 * (size_t)idx], 6, pb.inst_poff[idx]};
+    case 2: return {&pb.rc[6 * (size_t)idx], 6, pb.rc_poff[idx]};
+    default: return {&pb.ext[pb.ext_off[idx]], pb.ext_np[idx], pb.ext_poff[idx]};
+  }
+}
+
+// Cost of the side terms at the current parameters; with_rows: also their robustified residuals and Jacobians
+// (ceres::Jet-style forward differentiation of the templated functors, Corrector with rho'' <= 0).
+inline double eval_side_terms(Problem* pb, bool with_rows) {
+  double cost = 0.0;
+  if (with_rows) pb->side_rows.assign(pb->side_terms.size(), Problem::DenseRows());
+  for (size_t t = 0; t < pb->side_terms.size(); ++t) {
+    const Problem::SideTerm& st = pb->side_terms[t];
+    BlockRef br[6];
+    int start[7] = {0};
+    for (int b = 0; b < st.nblocks; ++b) {
+      br[b] = block_ref(*pb, st.kind[b], st.idx[b]);
+      start[b + 1] = start[b] + br[b].np;
+    }
+    const int NP = start[st.nblocks];
+    const double* c = pb->side_consts.data() + st.cofs;
+    double rho[2] = {0.0, 1.0};
+    double rv[7];
+    bool ok;
+    Problem::DenseRows rows;
+    rows.nres = st.nres; rows.ncols = NP;
+    if (with_rows) {
+      std::vector<Dual> x(NP);
+      const Dual* xp[6];
+      for (int b = 0; b < st.nblocks; ++b) {
+        xp[b] = x.data() + start[b];
+        for (int q = 0; q < br[b].np; ++q) x[start[b] + q] = Dual::variable(br[b].p[q], start[b] + q);
+      }
+      Dual r[7];
+      ok = side_residual<Dual>(st.type, c, st.aux, xp, r);
+      for (int k = 0; k < st.nres; ++k) {
+        rv[k] = r[k].v;
+        for (int j = 0; j < NP; ++j) rows.J[k * MAXD + j] = r[k].d[j];
+      }
+      for (int b = 0; b < st.nblocks; ++b)
+        for (int q = 0; q < br[b].np; ++q) rows.cols[start[b] + q] = br[b].col >= 0 ? br[b].col + q : -1;
+    } else {
+      std::vector<double> x(NP);
+      const double* xp[6];
+      for (int b = 0; b < st.nblocks; ++b) {
+        xp[b] = x.data() + start[b];
+        for (int q = 0; q < br[b].np; ++q) x[start[b] + q] = br[b].p[q];
+      }
+      ok = side_residual<double>(st.type, c, st.aux, xp, rv);
+    }
+    double s = 0.0;
+    for (int k = 0; k < st.nres; ++k) s += rv[k] * rv[k];
+    if (st.loss < 0) { rho[0] = s; rho[1] = 1.0; }
+    else if (st.loss == 5) tukey_loss(st.loss_a, s, rho);
+    else loss_eval(st.loss, st.loss_a, s, rho);
+    if (!ok) { cost = std::nan(""); rho[1] = 0.0; }
+    cost += 0.5 * rho[0];
+    if (with_rows) {
+      const double w = std::sqrt(rho[1]);
+      for (int k = 0; k < st.nres; ++k) {
+        rows.r[k] = w * rv[k];
+        for (int j = 0; j < NP; ++j) rows.J[k * MAXD + j] *= w;
+      }
+      pb->side_rows[t] = rows;
+    }
+  }
+  return cost;
+}
 
 // Columns of the camera-side Jacobian of one observation:
 // local layout [camera C | instance 6 | rig camera 6].
@@ -212,6 +301,55 @@ void* oba_create(int K, const int* cam_type, const double* cam_params, const int
   return pb;
 }
 
+// Secondary residuals of the problem (call right after oba_create): ext blocks extend the reduced vector
+// [.. | free ext blocks]; term records = 21 ints each (type, nres, nblocks, kind[6], idx[6], loss, cofs, aux[4]).
+void oba_set_secondary(void* h, int NE, const int* ext_size, const double* ext_values, const int* ext_const,
+                       const double* ext_lower, int NT, const int* term_ints, const double* term_loss_a, int nconsts,
+                       const double* consts, int NPP, const int* pp_point, const double* pp_prior,
+                       const double* pp_sigma, const int* pp_alt, int has_rc_prior, const double* rc_prior,
+                       const double* rc_sigma) {
+  Problem* pb = static_cast<Problem*>(h);
+  pb->NE = NE;
+  pb->ext_off.assign(NE + 1, 0); pb->ext_np.assign(ext_size, ext_size + NE); pb->ext_poff.assign(NE, -1);
+  int off = pb->nc;
+  for (int i = 0; i < NE; ++i) {
+    pb->ext_off[i + 1] = pb->ext_off[i] + ext_size[i];
+    if (!ext_const[i]) { pb->ext_poff[i] = off; off += ext_size[i]; }
+  }
+  pb->nc = off;
+  pb->ext.assign(ext_values, ext_values + pb->ext_off[NE]);
+  pb->ext_lower.assign(ext_lower, ext_lower + pb->ext_off[NE]);
+  pb->side_terms.resize(NT);
+  for (int t = 0; t < NT; ++t) {
+    const int* q = term_ints + 21 * t;
+    Problem::SideTerm& st = pb->side_terms[t];
+    st.type = q[0]; st.nres = q[1]; st.nblocks = q[2];
+    for (int b = 0; b < 6; ++b) { st.kind[b] = q[3 + b]; st.idx[b] = q[9 + b]; }
+    st.loss = q[15]; st.cofs = q[16];
+    for (int b = 0; b < 4; ++b) st.aux[b] = q[17 + b];
+    st.loss_a = term_loss_a[t];
+  }
+  pb->side_consts.assign(consts, consts + nconsts);
+  pb->pp_of_point.assign(pb->P, -1);
+  for (int q = 0; q < NPP; ++q) pb->pp_of_point[pp_point[q]] = q;
+  pb->pp_prior.assign(pp_prior, pp_prior + 3 * (size_t)NPP);
+  pb->pp_sigma.assign(pp_sigma, pp_sigma + 3 * (size_t)NPP);
+  pb->pp_alt.assign(pp_alt, pp_alt + NPP);
+  if (has_rc_prior) {
+    pb->rc_prior.assign(rc_prior, rc_prior + 6 * (size_t)pb->NR);
+    pb->rc_prior_sigma.assign(rc_sigma, rc_sigma + 6 * (size_t)pb->NR);
+  }
+  pb->scale.assign(pb->nc + 3 * (size_t)pb->npts_free, 1.0);
+}
+void oba_get_ext(void* h, double* ext) {
+  Problem* pb = static_cast<Problem*>(h);
+  std::copy(pb->ext.begin(), pb->ext.end(), ext);
+}
+void oba_set_ext(void* h, const double* ext) {
+  Problem* pb = static_cast<Problem*>(h);
+  std::copy(ext, ext + pb->ext.size(), pb->ext.begin());
+}
+
 void oba_destroy(void* h) { delete static_cast<Problem*>(h); }
 int oba_nc(void* h) { return static_cast<Problem*>(h)->nc; }
 int oba_npts_free(void* h) { return static_cast<Problem*>(h)->npts_free; }
@@ -246,6 +384,13 @@ void oba_plus(void* h, const double* delta) {
   for (int p = 0; p < pb->P; ++p)
     if (pb->pt_poff[p] >= 0)
       for (int j = 0; j < 3; ++j) pb->pts[3 * p + j] += delta[pb->nc + 3 * pb->pt_poff[p] + j];
+  // ext blocks: projected onto their lower bounds (scales >= 0, std-deviation scales >= 1e-10; ceres bounded LM)
+  for (int i = 0; i < pb->NE; ++i)
+    if (pb->ext_poff[i] >= 0)
+      for (int j = 0; j < pb->ext_np[i]; ++j) {
+        double& v = pb->ext[pb->ext_off[i] + j];
+        v = std::max(v + delta[pb->ext_poff[i] + j], pb->ext_lower[pb->ext_off[i] + j]);
+      }
 }
 
 // Norm of the free parameters (Ceres' x_norm).
@@ -264,6 +409,9 @@ double oba_x_norm(void* h) {
   for (int p = 0; p < pb->P; ++p)
     if (pb->pt_poff[p] >= 0)
       for (int j = 0; j < 3; ++j) { const double v = pb->pts[3 * p + j]; s += v * v; }
+  for (int i = 0; i < pb->NE; ++i)
+    if (pb->ext_poff[i] >= 0)
+      for (int j = 0; j < pb->ext_np[i]; ++j) { const double v = pb->ext[pb->ext_off[i] + j]; s += v * v; }
   return std::sqrt(s);
 }
 
@@ -306,6 +454,24 @@ static void build_prior_rows(Problem* pb) {
       pb->prior_rows.push_back(row);
     }
   }
+  // DataPriorError<Pose> on every rig camera with sigma GetDefaultRigPoseSigma (bundle_adjuster.cc:779-790)
+  if (!pb->rc_prior.empty())
+    for (int i = 0; i < pb->NR; ++i) {
+      if (pb->rc_poff[i] < 0) continue;
+      for (int j = 0; j < 6; ++j) {
+        const double sc = 1.0 / std::max(pb->rc_prior_sigma[6 * i + j], DBL_EPSILON);
+        pb->prior_rows.push_back({sc * (pb->rc[6 * i + j] - pb->rc_prior[6 * i + j]), pb->rc_poff[i] + j, sc});
+      }
+    }
+  // point priors DataPriorError<Vec3d> on x, y (, z) (bundle_adjuster.cc:688-708): columns on the point side
+  for (int p = 0; p < pb->P && !pb->pp_of_point.empty(); ++p) {
+    const int q = pb->pp_of_point[p], pf = pb->pt_poff[p];
+    if (q < 0 || pf < 0) continue;
+    for (int j = 0; j < (pb->pp_alt[q] ? 3 : 2); ++j) {
+      const double sc = 1.0 / std::max(pb->pp_sigma[3 * q + j], DBL_EPSILON);
+      pb->prior_rows.push_back({sc * (pb->pts[3 * p + j] - pb->pp_prior[3 * q + j]), pb->nc + 3 * pf + j, sc});
+    }
+  }
 }
 
 // Cost = 1/2 sum_blocks rho(|r|^2) (Ceres), projections through the shared loss
@@ -335,6 +501,7 @@ double oba_cost(void* h, double* reproj) {
   }
   build_prior_rows(pb);
   for (const auto& row : pb->prior_rows) cost += 0.5 * row.r * row.r;
+  cost += eval_side_terms(pb, false);
   return cost;
 }
 
@@ -380,6 +547,7 @@ double oba_linearize(void* h) {
   }
   build_prior_rows(pb);
   for (const auto& row : pb->prior_rows) cost += 0.5 * row.r * row.r;
+  cost += eval_side_terms(pb, true);
   return cost;
 }
 
@@ -425,6 +593,15 @@ void oba_colnorm_gradient(void* h, double* colnorm2, double* grad) {
     colnorm2[row.col] += row.d * row.d;
     grad[row.col] += row.d * row.r;
   }
+  for (const auto& rows : pb->side_rows)
+    for (int j = 0; j < rows.ncols; ++j) {
+      if (rows.cols[j] < 0) continue;
+      for (int k = 0; k < rows.nres; ++k) {
+        const double v = rows.J[k * MAXD + j];
+        colnorm2[rows.cols[j]] += v * v;
+        grad[rows.cols[j]] += v * rows.r[k];
+      }
+    }
 }
 
 // Reduced camera system for the *scaled* Jacobian Js = J diag(scale) and LM
@@ -512,6 +689,15 @@ void oba_schur(void* h, const double* diag2, double* Sout, double* rhs) {
         }
       }
       if (pf < 0) continue;
+      if (!pb->pp_of_point.empty() && pb->pp_of_point[p] >= 0) {  // point prior rows: diagonal
+        const int q = pb->pp_of_point[p];
+        for (int j = 0; j < (pb->pp_alt[q] ? 3 : 2); ++j) {
+          const double d = sc[nc + 3 * pf + j] / std::max(pb->pp_sigma[3 * q + j], DBL_EPSILON);
+          const double rr = (pb->pts[3 * p + j] - pb->pp_prior[3 * q + j]) / std::max(pb->pp_sigma[3 * q + j], DBL_EPSILON);
+          V[j * 3 + j] += d * d;
+          gp[j] += d * rr;
+        }
+      }
       for (int j = 0; j < 3; ++j) V[j * 3 + j] += diag2[nc + 3 * pf + j];
       // inverse of symmetric 3x3
       double Vi[9];
@@ -555,10 +741,24 @@ void oba_schur(void* h, const double* diag2, double* Sout, double* rhs) {
     for (int i = 0; i < nc; ++i) rhs[i] += rloc[t][i];
   }
   for (const auto& row : pb->prior_rows) {
+    if (row.col >= nc) continue;  // point-side rows went into V_p / g_p above
     const double d = row.d * sc[row.col];
     Sout[(size_t)row.col * nc + row.col] += d * d;
     rhs[row.col] += d * row.r;
   }
+  for (const auto& rows : pb->side_rows)
+    for (int j1 = 0; j1 < rows.ncols; ++j1) {
+      const int c1 = rows.cols[j1];
+      if (c1 < 0) continue;
+      for (int k = 0; k < rows.nres; ++k) rhs[c1] += rows.J[k * MAXD + j1] * sc[c1] * rows.r[k];
+      for (int j2 = 0; j2 < rows.ncols; ++j2) {
+        const int c2 = rows.cols[j2];
+        if (c2 < 0) continue;
+        double v = 0.0;
+        for (int k = 0; k < rows.nres; ++k) v += rows.J[k * MAXD + j1] * rows.J[k * MAXD + j2];
+        Sout[(size_t)c1 * nc + c2] += v * sc[c1] * sc[c2];
+      }
+    }
   for (int i = 0; i < nc; ++i) Sout[(size_t)i * nc + i] += diag2[i];
 }
 
@@ -600,6 +800,15 @@ void oba_backsub(void* h, const double* diag2, double* y) {
           const double s2 = sc[nc + 3 * pf + j2];
           for (int k = 0; k < nres; ++k) V[j1 * 3 + j2] += JP[k * 3 + j1] * s1 * JP[k * 3 + j2] * s2;
         }
+      }
+    }
+    if (!pb->pp_of_point.empty() && pb->pp_of_point[p] >= 0) {
+      const int q = pb->pp_of_point[p];
+      for (int j = 0; j < (pb->pp_alt[q] ? 3 : 2); ++j) {
+        const double dd = sc[nc + 3 * pf + j] / std::max(pb->pp_sigma[3 * q + j], DBL_EPSILON);
+        const double rr = (pb->pts[3 * p + j] - pb->pp_prior[3 * q + j]) / std::max(pb->pp_sigma[3 * q + j], DBL_EPSILON);
+        V[j * 3 + j] += dd * dd;
+        t[j] += dd * rr;
       }
     }
     for (int j = 0; j < 3; ++j) V[j * 3 + j] += diag2[nc + 3 * pf + j];
@@ -645,6 +854,13 @@ double oba_model_cost_change(void* h, const double* step) {
     const double m = row.d * sc[row.col] * step[row.col];
     total += -m * (row.r + 0.5 * m);
   }
+  for (const auto& rows : pb->side_rows)
+    for (int k = 0; k < rows.nres; ++k) {
+      double m = 0.0;
+      for (int j = 0; j < rows.ncols; ++j)
+        if (rows.cols[j] >= 0) m += rows.J[k * MAXD + j] * sc[rows.cols[j]] * step[rows.cols[j]];
+      total += -m * (rows.r[k] + 0.5 * m);
+    }
   return total;
 }
 
