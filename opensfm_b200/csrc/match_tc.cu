@@ -181,8 +181,11 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 // Bounded wait: a protocol bug must surface as a trapped kernel, never as a hung GPU.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int* err_flag) {
   const uint32_t addr = smem_u32(bar);
-  const long long t0 = clock64();
-  for (;;) {
+  long long t0 = 0;
+  // try_wait suspends the thread for a hardware-defined time slice before it reports failure, so the loop is
+  // cheap; the clock is only consulted every 1024 failed slices (reading it on every poll cost more issue
+  // slots than the epilogue itself, profiles/r01_ncu_tc_v6.txt: 143M TRYWAIT + CS2R pairs per launch)
+  for (unsigned spins = 0;; ++spins) {
     uint32_t done;
     asm volatile(
         "{\n.reg .pred p;\n"
@@ -192,9 +195,13 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int* e
         : "r"(addr), "r"(parity)
         : "memory");
     if (done) return;
-    if (clock64() - t0 > 4000000000LL) {
-      atomicExch(err_flag, 1);
-      __trap();
+    if ((spins & 1023u) == 1023u) {
+      const long long now = clock64();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 4000000000LL) {
+        atomicExch(err_flag, 1);
+        __trap();
+      }
     }
   }
 }
@@ -240,6 +247,25 @@ constexpr uint32_t TC_IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(T
       : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),   \
         "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]),          \
         "=r"(v[15])                                                                                       \
+      : "r"(taddr)                                                                                        \
+      : "memory")
+
+#define OSFM_TMEM_LD64(taddr, v)                                                                          \
+  asm volatile(                                                                                           \
+      "tcgen05.ld.sync.aligned.32x32b.x64.b32 "                                                           \
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"                                           \
+      "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,"                                  \
+      "%32,%33,%34,%35,%36,%37,%38,%39,%40,%41,%42,%43,%44,%45,%46,%47,"                                  \
+      "%48,%49,%50,%51,%52,%53,%54,%55,%56,%57,%58,%59,%60,%61,%62,%63}, [%64];"                          \
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),   \
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]),          \
+        "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]),        \
+        "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]),        \
+        "=r"(v[29]), "=r"(v[30]), "=r"(v[31]), "=r"(v[32]), "=r"(v[33]), "=r"(v[34]), "=r"(v[35]),        \
+        "=r"(v[36]), "=r"(v[37]), "=r"(v[38]), "=r"(v[39]), "=r"(v[40]), "=r"(v[41]), "=r"(v[42]),        \
+        "=r"(v[43]), "=r"(v[44]), "=r"(v[45]), "=r"(v[46]), "=r"(v[47]), "=r"(v[48]), "=r"(v[49]),        \
+        "=r"(v[50]), "=r"(v[51]), "=r"(v[52]), "=r"(v[53]), "=r"(v[54]), "=r"(v[55]), "=r"(v[56]),        \
+        "=r"(v[57]), "=r"(v[58]), "=r"(v[59]), "=r"(v[60]), "=r"(v[61]), "=r"(v[62]), "=r"(v[63])         \
       : "r"(taddr)                                                                                        \
       : "memory")
 
@@ -290,7 +316,9 @@ __device__ __forceinline__ void row_update(RowState& st, float x, int idx) {
 // best, exact (predicated) updates only inside a group that beats it.  Deliberately small: the whole
 // epilogue loop body must stay resident in the instruction cache (an earlier fully unrolled version was
 // 89 KB of SASS and spent most of its time in instruction-fetch stalls, profiles/r01_*).
-__device__ __forceinline__ void row_consume16(RowState& st, const uint32_t (&v)[16], int col0) {
+template <int OFF, int NV>
+__device__ __forceinline__ void row_consume16(RowState& st, const uint32_t (&vv)[NV], int col0) {
+  const uint32_t* v = vv + OFF;   // OFF is a compile-time constant: the accesses below stay register-resident
   // minima of four groups of 4 (independent chains), one test for the common case; a triggered chunk
   // re-examines only the group(s) of 4 that beat the threshold (their updates are predicated by ptxas,
   // 7 instructions per element, so small groups matter)
@@ -421,24 +449,27 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         const int a = tilecount & 1, aph = (tilecount >> 1) & 1;
         mbar_wait(&bar_accfull[a], aph, err_flag);
         tc_fence_after();
-        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)a * TC_N;
-        const int col_base = t.t_begin + i * TC_N;
-        // two 16-column register buffers: the load of the next chunk is in flight while one is consumed
-        uint32_t va[16], vb[16];
-        constexpr int kStep = 2 * (TC_EPI_WARPS / 4);  // chunks between two visits of this warp
-        OSFM_TMEM_LD16(taddr + (2 * half) * 16, va);
-#pragma unroll 1
-        for (int cb = 2 * half; cb < TC_N / 16; cb += kStep) {
-          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-          OSFM_TMEM_LD16(taddr + (cb + 1) * 16, vb);
-          row_consume16(st, va, col_base + cb * 16);
-          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-          if (cb + kStep < TC_N / 16) OSFM_TMEM_LD16(taddr + (cb + kStep) * 16, va);
-          row_consume16(st, vb, col_base + (cb + 1) * 16);
-        }
+        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)a * TC_N + (uint32_t)half * (TC_N / 2);
+        const int col_base = t.t_begin + i * TC_N + half * (TC_N / 2);
+        // this warp's 128 columns of the tile in two 64-column loads, both in flight at once; the accumulator is
+        // handed back to the MMA issuer as soon as the values are in registers -- the TMEM stage is held for one
+        // load latency, not for the consume time (8 dependent 16-column loads per tile made the epilogue the
+        // critical path: profiles/r01_ncu_tc_v6.txt, top stall on the accumulator-full wait)
+        uint32_t va[64], vb[64];
+        OSFM_TMEM_LD64(taddr, va);
+        OSFM_TMEM_LD64(taddr + 64, vb);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&bar_accempty[a]);
+        row_consume16<0>(st, va, col_base);
+        row_consume16<16>(st, va, col_base + 16);
+        row_consume16<32>(st, va, col_base + 32);
+        row_consume16<48>(st, va, col_base + 48);
+        row_consume16<0>(st, vb, col_base + 64);
+        row_consume16<16>(st, vb, col_base + 80);
+        row_consume16<32>(st, vb, col_base + 96);
+        row_consume16<48>(st, vb, col_base + 112);
       }
       // merge the two column halves of a row (lexicographic (d^2, index), like cv2's insertion order)
       if (half == 1) {

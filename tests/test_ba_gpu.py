@@ -75,8 +75,10 @@ def test_losses(loss):
     sc = syn.cube_scene(6, 300, 2.0, with_descriptors=False)
     # ArctanLoss saturates: the cost is flat along the (free) similarity gauge, so two solvers agree on
     # cost / reprojection RMSE but may stop at different gauge representatives.
+    # (6 cameras without GPS: the similarity gauge is free, so the two solvers' iterates drift along it by a few
+    # 1e-5 when they stop on the function tolerance; 5e-5 like the other gauge-free scenes)
     _compare(syn.scene_to_problem(sc, loss_name=loss, loss_threshold=1.0), compare_params=loss != "ArctanLoss",
-             tol_rmse=1e-5 if loss == "ArctanLoss" else 1e-6)
+             tol_rmse=1e-5 if loss == "ArctanLoss" else 1e-6, tol_param=5e-5)
 
 
 def test_pose_only_and_point_only():

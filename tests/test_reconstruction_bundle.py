@@ -250,6 +250,8 @@ def test_monkey_patched_functions_give_the_same_result_as_solve():
     direct = obundle.solve(pb)
     orec.bundle(r, dict(r.cameras.items()), dict(r.rig_cameras.items()), [], cfg)
     pts = np.array([r.points[str(p)].coordinates for p in range(len(pb.points))])
-    assert np.abs(pts - direct["points"]).max() < 1e-9
+    # same engine, different observation order (per shot vs per scene): fp64 atomics and the PCG stop differ in
+    # the last digits
+    assert np.abs(pts - direct["points"]).max() < 1e-6
     inst = np.array([T.pose_to_ba_params(r.rig_instances["shot%d" % s].pose) for s in range(10)])
-    assert np.abs(inst - direct["inst"]).max() < 1e-9
+    assert np.abs(inst - direct["inst"]).max() < 1e-6
