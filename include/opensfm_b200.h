@@ -68,12 +68,28 @@ int osfm_matcher_add_u8(osfm_matcher* m, const uint8_t* desc, int n, int nbytes,
 int osfm_matcher_add_batch_f32(osfm_matcher* m, int count, const float* const* desc, const int* n, int dim, int* out_ids);
 int osfm_matcher_add_batch_u8(osfm_matcher* m, int count, const uint8_t* const* desc, const int* n, int nbytes,
                               int* out_ids);
+/* uint8-STORED descriptors compared with L2 ("BruteForce"): HAHOG / SIFT are integers 0..255 and live as uint8 on
+ * disk (opensfm/features.py:169-170, 526-534); the reference widens them to float32 on load.  Uploading the bytes
+ * and widening on the device moves a quarter of the data; results are identical to adding the float32 matrix. */
+int osfm_matcher_add_u8_l2(osfm_matcher* m, const uint8_t* desc, int n, int dim, int* out_id);
+int osfm_matcher_add_batch_u8_l2(osfm_matcher* m, int count, const uint8_t* const* desc, const int* n, int dim,
+                                 int* out_ids);
 int osfm_matcher_remove(osfm_matcher* m, int id);
 int osfm_matcher_clear(osfm_matcher* m);
 /* Enqueue matching of npairs pairs (ids_a[p], ids_b[p]).  Results stay on the
  * device until fetched.  Total result length = sum_p n(ids_a[p]). */
 int osfm_matcher_match_pairs_async(osfm_matcher* m, int npairs, const int* ids_a, const int* ids_b,
                                    double lowes_ratio, int symmetric);
+/* Guided matching (matching._match_descriptors_guided_impl, matching.py:260-338): unit bearing vectors of a
+ * resident set (n x 3 float32, feature_loader.load_bearings), then a pair list with the relative pose of image b
+ * w.r.t. image a -- pose12[p] = [R (cam b -> cam a) row-major, 9 | origin of b in a, 3] as doubles
+ * (pose.get_R_cam_to_world(), pose.get_origin()).  The epipolar mask
+ * compute_inliers_bearing_epipolar(b1, b2, pose, threshold) (matching.py:847-868,
+ * geometry/src/triangulation.cc:195-219) is evaluated on the device into a bitmask that never leaves HBM, and
+ * the pairs are matched like osfm_matcher_match_pairs_async with that mask (transposed for the b -> a pass). */
+int osfm_matcher_set_bearings(osfm_matcher* m, int id, const float* bearings_n_by_3);
+int osfm_matcher_match_pairs_guided_async(osfm_matcher* m, int npairs, const int* ids_a, const int* ids_b,
+                                          const double* pose12, double threshold, double lowes_ratio, int symmetric);
 int osfm_matcher_sync(osfm_matcher* m);
 /* Copy the last batch's results to the host: concatenated per pair, n(ids_a[p]) entries each. */
 int osfm_matcher_fetch(osfm_matcher* m, int32_t* out_match, int64_t capacity);

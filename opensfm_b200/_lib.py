@@ -54,9 +54,14 @@ SIGNATURES = {
     "osfm_matcher_add_u8": (c_int, [c_void_p, c_void_p, c_int, c_int, POINTER(c_int)]),
     "osfm_matcher_add_batch_f32": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p]),
     "osfm_matcher_add_batch_u8": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p]),
+    "osfm_matcher_add_u8_l2": (c_int, [c_void_p, c_void_p, c_int, c_int, POINTER(c_int)]),
+    "osfm_matcher_add_batch_u8_l2": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p]),
     "osfm_matcher_remove": (c_int, [c_void_p, c_int]),
     "osfm_matcher_clear": (c_int, [c_void_p]),
     "osfm_matcher_match_pairs_async": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_double, c_int]),
+    "osfm_matcher_set_bearings": (c_int, [c_void_p, c_int, c_void_p]),
+    "osfm_matcher_match_pairs_guided_async": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_double, c_double,
+                                                       c_int]),
     "osfm_matcher_sync": (c_int, [c_void_p]),
     "osfm_matcher_fetch": (c_int, [c_void_p, c_void_p, c_int64]),
     "osfm_matcher_last_device_ms": (c_int, [c_void_p, POINTER(c_float), POINTER(c_float)]),

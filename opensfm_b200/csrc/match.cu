@@ -124,7 +124,7 @@ __global__ void __launch_bounds__(256) bf_top2_simt(const MatchJob* __restrict__
       for (int j = 0; j < 4; ++j) {
         const int gt = t0 + tx * 4 + j;
         if (gq >= job.nq || gt >= t_end) continue;
-        if (job.mask && job.mask[(size_t)gq * job.mask_sq + (size_t)gt * job.mask_st] == 0) continue;
+        if (!job_allows(job, gq, gt)) continue;
         float s;
         if constexpr (U8) s = (float)acc[i][j]; else s = __fsqrt_rn(acc[i][j]);
         top2_insert(best[i], s, gt);
@@ -290,7 +290,7 @@ __global__ void __launch_bounds__(256) bf_top2_f32_cv(const MatchJob* __restrict
       for (int j = 0; j < MT; ++j) {
         const int gt = t0 + tx * MT + j;
         if (gq >= job.nq || gt >= t_end) continue;
-        if (job.mask && job.mask[(size_t)gq * job.mask_sq + (size_t)gt * job.mask_st] == 0) continue;
+        if (!job_allows(job, gq, gt)) continue;
         top2_insert(best[i], __fsqrt_rn(d2[i][j]), gt);
       }
     }
@@ -356,6 +356,87 @@ __global__ void pad_rows_kernel(const T* __restrict__ src, int n, int dim, T* __
   if (idx >= (size_t)n * dim_padded) return;
   const int r = idx / dim_padded, c = idx % dim_padded;
   dst[idx] = c < dim ? src[(size_t)r * dim + c] : T(0);
+}
+
+// ---------------------------------------------------------------------------
+// Guided matching: epipolar mask of a pair as a bitmask, built on the device.
+//
+// matching.compute_inliers_bearing_epipolar (opensfm/matching.py:847-868) ->
+// geometry::EpipolarAngleTwoBearingsMany (opensfm/src/geometry/src/triangulation.cc:195-219), fp64 on float32
+// bearings:  t^ = t / |t|,  b2w_j = R b2_j,  e1_i = (t^ x b1_i)^,  e2_j = (t^ x b2w_j)^,
+//            sym_ij = (|e1_i . b2w_j| + |b1_i . e2_j|) / 2,   mask_ij = (pi/2 - acos(sym_ij)) < threshold.
+// epi_vectors: the per-feature vectors in fp64 (and their float32 roundings).
+// epi_mask_bits: one warp per 32 x 32 block; the test runs in float32 against sin(threshold) with a guard band
+// (|error| of the float32 evaluation < 1e-6), and only elements inside the band evaluate the reference's fp64
+// expression with acos -- so the decision is the reference's for every element, at float32 cost.
+// Both layouts are written from one evaluation: F[i][j / 32] (queries of image 1) and T[j][i / 32] (the
+// transposed mask the symmetric pass needs, matching.py:774).
+// ---------------------------------------------------------------------------
+struct EpiPair {
+  const float *b1, *b2;     // bearings n x 3
+  double* v1;               // [n1][6] : b1, e1     (fp64)
+  double* v2;               // [n2][6] : b2w, e2
+  uint32_t *F, *T;
+  int n1, n2, w1, w2;       // w2 = words per row of F (over n2), w1 = words per row of T (over n1)
+  double pose[12];
+};
+__global__ void epi_vectors(const EpiPair* __restrict__ pairs) {
+  const EpiPair& p = pairs[blockIdx.y];
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const double tx = p.pose[9], ty = p.pose[10], tz = p.pose[11];
+  const double tn = sqrt(tx * tx + ty * ty + tz * tz);
+  const double t[3] = {tx / tn, ty / tn, tz / tn};
+  auto emit = [&](double* out, const double b[3]) {
+    double e[3] = {t[1] * b[2] - t[2] * b[1], t[2] * b[0] - t[0] * b[2], t[0] * b[1] - t[1] * b[0]};
+    const double en = sqrt(e[0] * e[0] + e[1] * e[1] + e[2] * e[2]);
+    out[0] = b[0]; out[1] = b[1]; out[2] = b[2];
+    out[3] = e[0] / en; out[4] = e[1] / en; out[5] = e[2] / en;
+  };
+  if (i < p.n1) {
+    const double b[3] = {(double)p.b1[3 * i], (double)p.b1[3 * i + 1], (double)p.b1[3 * i + 2]};
+    emit(p.v1 + 6 * (size_t)i, b);
+  }
+  if (i < p.n2) {
+    const double a[3] = {(double)p.b2[3 * i], (double)p.b2[3 * i + 1], (double)p.b2[3 * i + 2]};
+    const double* R = p.pose;
+    const double b[3] = {R[0] * a[0] + R[1] * a[1] + R[2] * a[2], R[3] * a[0] + R[4] * a[1] + R[5] * a[2],
+                         R[6] * a[0] + R[7] * a[1] + R[8] * a[2]};
+    emit(p.v2 + 6 * (size_t)i, b);
+  }
+}
+__global__ void __launch_bounds__(256) epi_mask_bits(const EpiPair* __restrict__ pairs, double threshold) {
+  const EpiPair& p = pairs[blockIdx.z];
+  const int lane = threadIdx.x & 31;
+  const int jb = blockIdx.x * 8 + (threadIdx.x >> 5);   // 32-column block of this warp
+  const int ib = blockIdx.y;                            // 32-row block
+  if (jb >= p.w2 || ib >= p.w1) return;
+  const int j = jb * 32 + lane, i = ib * 32 + lane;
+  const float NaNf = __int_as_float(0x7fc00000);
+  float cj[6] = {NaNf, NaNf, NaNf, NaNf, NaNf, NaNf}, ri[6] = {NaNf, NaNf, NaNf, NaNf, NaNf, NaNf};
+  if (j < p.n2) for (int e = 0; e < 6; ++e) cj[e] = (float)p.v2[6 * (size_t)j + e];
+  if (i < p.n1) for (int e = 0; e < 6; ++e) ri[e] = (float)p.v1[6 * (size_t)i + e];
+  const float s_thr = (float)sin(threshold);
+  const float lo = s_thr - 2e-6f, hi = s_thr + 2e-6f;
+  uint32_t colbits = 0;
+  for (int r = 0; r < 32; ++r) {
+    const float b0 = __shfl_sync(0xffffffffu, ri[0], r), b1 = __shfl_sync(0xffffffffu, ri[1], r),
+                b2 = __shfl_sync(0xffffffffu, ri[2], r), e0 = __shfl_sync(0xffffffffu, ri[3], r),
+                e1 = __shfl_sync(0xffffffffu, ri[4], r), e2 = __shfl_sync(0xffffffffu, ri[5], r);
+    const float sym = 0.5f * (fabsf(e0 * cj[0] + e1 * cj[1] + e2 * cj[2]) + fabsf(b0 * cj[3] + b1 * cj[4] + b2 * cj[5]));
+    bool in = sym < lo;               // NaN (missing row / column, degenerate epipolar plane) compares false
+    if (!(sym < lo) && sym < hi) {    // inside the guard band: the reference's own fp64 expression
+      const int gi = ib * 32 + r;
+      const double* a = p.v1 + 6 * (size_t)gi;
+      const double* c = p.v2 + 6 * (size_t)j;
+      const double sd = (fabs(a[3] * c[0] + a[4] * c[1] + a[5] * c[2]) + fabs(a[0] * c[3] + a[1] * c[4] + a[2] * c[5])) / 2.0;
+      in = (M_PI / 2.0 - acos(sd)) < threshold;
+    }
+    const uint32_t rowbits = __ballot_sync(0xffffffffu, in);
+    const int gi = ib * 32 + r;
+    if (lane == 0 && gi < p.n1) p.F[(size_t)gi * p.w2 + jb] = rowbits;
+    if (in) colbits |= 1u << r;
+  }
+  if (j < p.n2) p.T[(size_t)j * p.w1 + ib] = colbits;
 }
 
 // ---------------------------------------------------------------------------
@@ -429,6 +510,7 @@ void Matcher::refresh_info() {
 
 void Matcher::free_set(DescSet& s) {
   slab_release(s.slab);
+  if (s.bearings) { slab_release(s.bear_slab); s.bearings = nullptr; s.bear_slab = -1; }
   if (s.slot >= 0) {
     cudaMemsetAsync(d_info.p + 2 * s.slot, 0, 2 * sizeof(int), stream);
     free_slots.push_back(s.slot);
@@ -440,7 +522,15 @@ void Matcher::free_set(DescSet& s) {
   s.slot = -1;
 }
 
-int Matcher::add_async(const void* host, int n, int dim, bool u8) {
+// widen uint8 rows to zero-padded float32 rows (uint8-stored L2 descriptors that do not take the tensor-core path)
+__global__ void widen_rows_kernel(const uint8_t* __restrict__ src, int n, int dim, float* __restrict__ dst, int dim_padded) {
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (size_t)n * dim_padded) return;
+  const int r = idx / dim_padded, c = idx % dim_padded;
+  dst[idx] = c < dim ? (float)src[(size_t)r * dim + c] : 0.0f;
+}
+
+int Matcher::add_async(const void* host, int n, int dim, bool u8, bool u8_as_l2) {
   if (n < 0 || dim <= 0) throw ArgError("descriptor matrix must be n x dim with dim > 0");
   if (!host && n > 0) throw ArgError("null descriptor pointer");
   OSFM_CUDA(cudaSetDevice(device));
@@ -448,7 +538,9 @@ int Matcher::add_async(const void* host, int n, int dim, bool u8) {
   s.n = n;
   s.dim = dim;
   s.u8 = u8;
-  const size_t esz = u8 ? 1 : 4;
+  if (u8 && u8_as_l2) throw ArgError("a descriptor set is either Hamming or uint8-stored L2");
+  const size_t esz = u8 ? 1 : 4;          // element size of the resident rows
+  const size_t hsz = (u8 || u8_as_l2) ? 1 : 4;  // element size of the host rows
   // padded row length in bytes: multiple of DK elements (64 B for both types)
   const int row_bytes = (int)(((size_t)dim * esz + 63) / 64 * 64);
   s.dim_padded = row_bytes / 4;  // in 4-byte elements
@@ -470,18 +562,22 @@ int Matcher::add_async(const void* host, int n, int dim, bool u8) {
     else { slab_release(s.slab); throw std::runtime_error("too many resident descriptor sets"); }
   }
   if (n > 0) {
-    const bool dense = (size_t)dim * esz == (size_t)row_bytes;  // the upload already is the padded copy
+    const bool dense = !u8_as_l2 && (size_t)dim * esz == (size_t)row_bytes;  // the upload already is the padded copy
     const void* src = s.data;
     if (dense) {
       OSFM_CUDA(cudaMemcpyAsync(s.data, host, (size_t)n * row_bytes, cudaMemcpyHostToDevice, stream));
     } else {
-      staging.reserve(std::max<size_t>((size_t)n * dim * esz, (size_t)4 << 20));
-      OSFM_CUDA(cudaMemcpyAsync(staging.p, host, (size_t)n * dim * esz, cudaMemcpyHostToDevice, stream));
+      staging.reserve(std::max<size_t>((size_t)n * dim * hsz, (size_t)4 << 20));
+      OSFM_CUDA(cudaMemcpyAsync(staging.p, host, (size_t)n * dim * hsz, cudaMemcpyHostToDevice, stream));
       src = staging.p;
     }
     if (tc) {
       // one fused pass: padded copy (if needed) + exactness + norms + bf16 operands (match_tc.cu)
-      prepare_tc(s, static_cast<const float*>(src), dense ? nullptr : static_cast<float*>(s.data));
+      prepare_tc(s, src, u8_as_l2, dense ? nullptr : static_cast<float*>(s.data));
+    } else if (u8_as_l2) {
+      const size_t total = (size_t)n * s.dim_padded;
+      widen_rows_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(staging.p, n, dim, (float*)s.data, s.dim_padded);
+      OSFM_LAUNCH_CHECK();
     } else if (!dense) {
       const size_t total = (size_t)n * row_bytes / esz;
       const int threads = 256;
@@ -499,8 +595,21 @@ int Matcher::add_async(const void* host, int n, int dim, bool u8) {
   return id;
 }
 
-int Matcher::add(const void* host, int n, int dim, bool u8) {
-  const int id = add_async(host, n, dim, u8);
+void Matcher::set_bearings(int id, const float* host_n_by_3) {
+  auto it = sets.find(id);
+  if (it == sets.end()) throw ArgError("unknown descriptor set id");
+  if (!host_n_by_3) throw ArgError("null bearings");
+  OSFM_CUDA(cudaSetDevice(device));
+  DescSet& s = it->second;
+  if (!s.bearings) s.bearings = static_cast<float*>(slab_alloc(sizeof(float) * 3 * (size_t)std::max(s.n, 1), &s.bear_slab));
+  if (s.n > 0) {
+    OSFM_CUDA(cudaMemcpyAsync(s.bearings, host_n_by_3, sizeof(float) * 3 * (size_t)s.n, cudaMemcpyHostToDevice, stream));
+    OSFM_CUDA(cudaStreamSynchronize(stream));
+  }
+}
+
+int Matcher::add(const void* host, int n, int dim, bool u8, bool u8_as_l2) {
+  const int id = add_async(host, n, dim, u8, u8_as_l2);
   OSFM_CUDA(cudaStreamSynchronize(stream));  // the caller may reuse its buffer
   return id;
 }
@@ -522,7 +631,7 @@ void Matcher::clear() {
 }
 
 void Matcher::match_pairs_async(int npairs, const int* ids_a, const int* ids_b, double ratio, bool symmetric,
-                                const uint8_t* dmask) {
+                                const uint8_t* dmask, const double* pose12, double epi_threshold) {
   OSFM_CUDA(cudaSetDevice(device));
   refresh_info();
   if (npairs < 0) throw ArgError("npairs < 0");
@@ -571,13 +680,49 @@ void Matcher::match_pairs_async(int npairs, const int* ids_a, const int* ids_b, 
     }
   }
   if (any_u8 && any_f32) throw ArgError("mixed float32 / uint8 pairs in one submission");
+  // ---- guided matching: per-pair bitmasks (both layouts) built on the device ----
+  const bool guided = pose12 != nullptr;
+  std::vector<EpiPair> epi;
+  if (guided) {
+    if (dmask) throw ArgError("guided matching builds its own mask");
+    size_t words = 0, vecs = 0;
+    epi.resize(npairs);
+    for (int p = 0; p < npairs; ++p) {
+      const DescSet& A = sets.find(ids_a[p])->second;
+      const DescSet& B = sets.find(ids_b[p])->second;
+      if (!A.bearings || !B.bearings) throw ArgError("guided matching needs bearings for both images (osfm_matcher_set_bearings)");
+      EpiPair& e = epi[p];
+      e.b1 = A.bearings; e.b2 = B.bearings; e.n1 = A.n; e.n2 = B.n;
+      e.w1 = (A.n + 31) / 32; e.w2 = (B.n + 31) / 32;
+      e.F = reinterpret_cast<uint32_t*>(words); words += (size_t)A.n * e.w2;
+      e.T = reinterpret_cast<uint32_t*>(words); words += (size_t)B.n * e.w1;
+      e.v1 = reinterpret_cast<double*>(vecs); vecs += 6 * (size_t)A.n;
+      e.v2 = reinterpret_cast<double*>(vecs); vecs += 6 * (size_t)B.n;
+      std::memcpy(e.pose, pose12 + 12 * (size_t)p, sizeof(double) * 12);
+    }
+    if (words > ((size_t)1 << 29)) throw ArgError("guided submission needs more than 2 GiB of mask bits: split the pair list");
+    d_mask_bits.reserve(std::max<size_t>(words, 1));
+    d_epi_vec.reserve(std::max<size_t>(vecs, 1));
+    for (int p = 0; p < npairs; ++p) {   // offsets -> pointers
+      EpiPair& e = epi[p];
+      e.F = d_mask_bits.p + reinterpret_cast<size_t>(e.F);
+      e.T = d_mask_bits.p + reinterpret_cast<size_t>(e.T);
+      e.v1 = d_epi_vec.p + reinterpret_cast<size_t>(e.v1);
+      e.v2 = d_epi_vec.p + reinterpret_cast<size_t>(e.v2);
+      for (int d = 0; d < ndir; ++d) {
+        MatchJob& j = h_jobs[p * ndir + d];
+        j.mask_bits = d == 0 ? e.F : e.T;
+        j.mask_words = d == 0 ? e.w2 : e.w1;
+      }
+    }
+  }
   // kernel choice
   int use = 1;
   if (kernel_choice == 2) {
     if (!all_tc || dmask) throw ArgError("tcgen05 kernel forced but descriptors are not bf16-exact / norm-bounded, or a mask is set");
     use = 2;
   } else if (kernel_choice == 0 && all_tc && !dmask && any_f32 && tc_available()) {
-    use = 2;
+    use = 2;   // (guided pairs too: the tensor-core epilogue applies the bitmask)
   }
   last_kernel = use;
   last_total_results = h_out_off[npairs];
@@ -647,10 +792,25 @@ void Matcher::match_pairs_async(int npairs, const int* ids_a, const int* ids_b, 
     OSFM_CUDA(cudaMemcpyAsync(d_out_off.p, p_out_off.p, sizeof(long long) * (npairs + 1), cudaMemcpyHostToDevice,
                               stream));
   }
+  if (guided && npairs > 0) {
+    // EpiPair records travel through the (otherwise idle) epi pose buffers: sizeof(EpiPair) is a multiple of 8
+    static_assert(sizeof(EpiPair) % sizeof(double) == 0, "EpiPair packs into doubles");
+    const size_t nd = sizeof(EpiPair) / sizeof(double) * (size_t)npairs;
+    d_epi_pose.reserve(nd); p_epi_pose.reserve(nd);
+    std::memcpy(p_epi_pose.p, epi.data(), sizeof(EpiPair) * (size_t)npairs);
+    OSFM_CUDA(cudaMemcpyAsync(d_epi_pose.p, p_epi_pose.p, sizeof(EpiPair) * (size_t)npairs, cudaMemcpyHostToDevice, stream));
+    const EpiPair* dp = reinterpret_cast<const EpiPair*>(d_epi_pose.p);
+    int max_n = 1, max_w1 = 1, max_w2 = 1;
+    for (const EpiPair& e : epi) { max_n = std::max({max_n, e.n1, e.n2}); max_w1 = std::max(max_w1, e.w1); max_w2 = std::max(max_w2, e.w2); }
+    epi_vectors<<<dim3((max_n + 127) / 128, npairs), 128, 0, stream>>>(dp);
+    OSFM_LAUNCH_CHECK();
+    epi_mask_bits<<<dim3((max_w2 + 7) / 8, max_w1, npairs), 256, 0, stream>>>(dp, epi_threshold);
+    OSFM_LAUNCH_CHECK();
+  }
   OSFM_CUDA(cudaEventRecord(ev[1], stream));
   if (tiles_total > 0) {
     if (use == 2) {
-      launch_tc(*this, njobs, (int)tiles_total);
+      launch_tc(*this, njobs, (int)tiles_total, guided);
     } else if (any_u8) {
       bf_top2_simt<true><<<(unsigned)tiles_total, 256, 0, stream>>>(d_jobs.p, d_prefix.p, njobs, d_partial.p);
       OSFM_LAUNCH_CHECK();
@@ -799,13 +959,14 @@ int osfm_matcher_add_u8(osfm_matcher* m, const uint8_t* desc, int n, int nbytes,
   OSFM_API_END
 }
 
-static int add_batch(osfm_matcher* m, int count, const void* const* desc, const int* n, int dim, bool u8, int* out_ids) {
+static int add_batch(osfm_matcher* m, int count, const void* const* desc, const int* n, int dim, bool u8, int* out_ids,
+                     bool u8_as_l2 = false) {
   OSFM_API_BEGIN
   OSFM_M_LOCK
   if (count < 0 || (count > 0 && (!desc || !n || !out_ids))) throw osfm::ArgError("bad batch arguments");
   int done = 0;
   try {
-    for (; done < count; ++done) out_ids[done] = m->impl.add_async(desc[done], n[done], dim, u8);
+    for (; done < count; ++done) out_ids[done] = m->impl.add_async(desc[done], n[done], dim, u8, u8_as_l2);
     OSFM_CUDA(cudaStreamSynchronize(m->impl.stream));
   } catch (...) {
     cudaStreamSynchronize(m->impl.stream);
@@ -820,6 +981,18 @@ int osfm_matcher_add_batch_f32(osfm_matcher* m, int count, const float* const* d
 int osfm_matcher_add_batch_u8(osfm_matcher* m, int count, const uint8_t* const* desc, const int* n, int nbytes,
                               int* out_ids) {
   return add_batch(m, count, reinterpret_cast<const void* const*>(desc), n, nbytes, true, out_ids);
+}
+
+int osfm_matcher_add_u8_l2(osfm_matcher* m, const uint8_t* desc, int n, int dim, int* out_id) {
+  OSFM_API_BEGIN
+  OSFM_M_LOCK
+  if (!out_id) throw osfm::ArgError("null out_id");
+  *out_id = m->impl.add(desc, n, dim, false, true);
+  OSFM_API_END
+}
+int osfm_matcher_add_batch_u8_l2(osfm_matcher* m, int count, const uint8_t* const* desc, const int* n, int dim,
+                                 int* out_ids) {
+  return add_batch(m, count, reinterpret_cast<const void* const*>(desc), n, dim, false, out_ids, true);
 }
 
 int osfm_matcher_remove(osfm_matcher* m, int id) {
@@ -842,6 +1015,23 @@ int osfm_matcher_match_pairs_async(osfm_matcher* m, int npairs, const int* ids_a
   OSFM_M_LOCK
   if (npairs > 0 && (!ids_a || !ids_b)) throw osfm::ArgError("null pair list");
   m->impl.match_pairs_async(npairs, ids_a, ids_b, lowes_ratio, symmetric != 0, nullptr);
+  OSFM_API_END
+}
+
+int osfm_matcher_set_bearings(osfm_matcher* m, int id, const float* bearings_n_by_3) {
+  OSFM_API_BEGIN
+  OSFM_M_LOCK
+  m->impl.set_bearings(id, bearings_n_by_3);
+  OSFM_API_END
+}
+
+int osfm_matcher_match_pairs_guided_async(osfm_matcher* m, int npairs, const int* ids_a, const int* ids_b,
+                                          const double* pose12, double threshold, double lowes_ratio, int symmetric) {
+  OSFM_API_BEGIN
+  OSFM_M_LOCK
+  if (npairs > 0 && (!ids_a || !ids_b || !pose12)) throw osfm::ArgError("null pair list / poses");
+  if (!(threshold > 0.0)) throw osfm::ArgError("guided matching threshold must be positive");
+  m->impl.match_pairs_async(npairs, ids_a, ids_b, lowes_ratio, symmetric != 0, nullptr, pose12, threshold);
   OSFM_API_END
 }
 

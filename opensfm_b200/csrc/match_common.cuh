@@ -60,7 +60,15 @@ struct MatchJob {
   long long match_off;    // int32 match[match_off + q]
   const uint8_t* mask;
   long long mask_sq, mask_st;
+  // guided matching: one bit per (query, train), row-major over the queries, mask_words 32-bit words per row
+  const uint32_t* mask_bits;
+  int mask_words;
 };
+__device__ __forceinline__ bool job_allows(const MatchJob& job, int gq, int gt) {
+  if (job.mask && job.mask[(size_t)gq * job.mask_sq + (size_t)gt * job.mask_st] == 0) return false;
+  if (job.mask_bits && !((job.mask_bits[(size_t)gq * job.mask_words + (gt >> 5)] >> (gt & 31)) & 1u)) return false;
+  return true;
+}
 
 struct DescSet {
   void* data = nullptr;
@@ -78,6 +86,9 @@ struct DescSet {
   // live in d_info[slot] until refresh_info() reads them back (no host sync per add)
   int slab = -1, slot = -1;
   bool info_pending = false;
+  // unit bearing vectors of the features (n x 3 float32), for guided matching; null until set
+  float* bearings = nullptr;
+  int bear_slab = -1;
 };
 
 struct Slab {
@@ -97,7 +108,7 @@ struct Matcher {
   long long last_total_results = 0;
   int last_npairs = 0;
   bool results_in_match_buf = true;
-  bool tc_attr_set = false, fx_attr_set = false;
+  bool tc_attr_set = false, tcm_attr_set = false, fx_attr_set = false;
   std::map<int, DescSet> sets;
   std::vector<MatchJob> h_jobs;
   std::vector<int> h_prefix;
@@ -109,6 +120,9 @@ struct Matcher {
   DevBuf<int32_t> d_match, d_out;
   DevBuf<uint8_t> staging, mask_buf;
   DevBuf<int> d_flags;
+  DevBuf<uint32_t> d_mask_bits;
+  DevBuf<double> d_epi_vec, d_epi_pose;
+  PinnedBuf<double> p_epi_pose;
   PinnedBuf<MatchJob> p_jobs;
   PinnedBuf<int> p_prefix;
   PinnedBuf<long long> p_out_off;
@@ -127,27 +141,31 @@ struct Matcher {
   void* slab_alloc(size_t bytes, int* slab_idx);
   void slab_release(int idx);
   void refresh_info();
-  int add_async(const void* host, int n, int dim, bool u8);  // no host sync; the host buffer must stay valid
-  int add(const void* host, int n, int dim, bool u8);
+  // u8: Hamming descriptors.  u8_as_l2: uint8 storage of an L2 descriptor (widened to float32 on the device).
+  int add_async(const void* host, int n, int dim, bool u8, bool u8_as_l2 = false);  // no host sync; the host buffer must stay valid
+  int add(const void* host, int n, int dim, bool u8, bool u8_as_l2 = false);
   void remove(int id);
   void clear();
   void free_set(DescSet& s);
+  // guided: pose12 = npairs x 12 doubles [R cam2->cam1 row-major | origin of camera 2 in camera 1] and the angle
+  // threshold; the epipolar mask is built on the device as a bitmask (matching.py:847-868)
   void match_pairs_async(int npairs, const int* ids_a, const int* ids_b, double ratio, bool symmetric,
-                         const uint8_t* dmask);
+                         const uint8_t* dmask, const double* pose12 = nullptr, double epi_threshold = 0.0);
+  void set_bearings(int id, const float* host_n_by_3);
   void sync();
   void fetch(int32_t* out, int64_t capacity);
   void last_ms(float* total, float* kernel);
   void one_shot(const void* f1, int n1, const void* f2, int n2, int dim, bool u8, double ratio,
                 const uint8_t* mask, bool symmetric, int32_t* out);
   // match_tc.cu
-  void prepare_tc(DescSet& s, const float* src, float* padded_dst);
+  void prepare_tc(DescSet& s, const void* src, bool src_u8, float* padded_dst);
 };
 
 // match_tc.cu
 bool tc_available();
 int tc_tile_m();
 int tc_tile_n();
-void launch_tc(Matcher& m, int njobs, int ntiles);
+void launch_tc(Matcher& m, int njobs, int ntiles, bool masked);
 int tc_rows_padded(int n);
 size_t tc_operand_bytes(int rows_padded);
 bool tc_capable(int dim, bool u8, int n);

@@ -67,8 +67,11 @@ bool tc_available() {
 // [0,255]), |x|^2, max |x|^2, the zero-padded float32 row of the SIMT kernel (when it is not the
 // upload itself) and both bf16 operand roles in the UMMA core-matrix order.
 // info[0] |= 1 if any value is not bf16-exact; info[1] = max |x|^2 as float bits.
+// SrcT = float (the reference's in-memory form, features.py:169-170) or uint8_t (the on-disk form of HAHOG / SIFT
+// descriptors, uploaded as bytes and widened here: a quarter of the host->device traffic).
+template <class SrcT>
 __global__ void __launch_bounds__(256)
-    tc_prepare_set(const float* __restrict__ src, int n, int dim, int rows_padded, float* __restrict__ padded, int dim_padded,
+    tc_prepare_set(const SrcT* __restrict__ src, int n, int dim, int rows_padded, float* __restrict__ padded, int dim_padded,
                    float* __restrict__ norm, __nv_bfloat16* __restrict__ qa, __nv_bfloat16* __restrict__ tb,
                    int* __restrict__ info) {
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -81,7 +84,7 @@ __global__ void __launch_bounds__(256)
     for (int e = 0; e < 4; ++e) {
       const int k = lane * 4 + e;
       if (k < dim) {
-        v[e] = src[(size_t)row * dim + k];
+        v[e] = (float)src[(size_t)row * dim + k];
         bad |= !(v[e] >= 0.0f && v[e] <= 255.0f && v[e] == floorf(v[e]));
       }
     }
@@ -146,14 +149,18 @@ __global__ void __launch_bounds__(256)
 // src: the dense n x dim float32 upload on this stream; padded_dst: the SIMT kernel's zero-padded copy
 // to fill as well, or null when the upload already is that copy.  Asynchronous: s.tc_ok is decided by
 // Matcher::refresh_info() from d_info[s.slot].
-void Matcher::prepare_tc(DescSet& s, const float* src, float* padded_dst) {
+void Matcher::prepare_tc(DescSet& s, const void* src, bool src_u8, float* padded_dst) {
   const int rows_padded = s.rows_padded;
   const size_t op_bytes = (size_t)rows_padded * TC_ROW_BYTES;
   __nv_bfloat16* qa = reinterpret_cast<__nv_bfloat16*>(s.tc_data);
   __nv_bfloat16* tb = reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<char*>(s.tc_data) + op_bytes);
   float* norm = reinterpret_cast<float*>(reinterpret_cast<char*>(s.tc_data) + 2 * op_bytes);
-  tc_prepare_set<<<(rows_padded + 7) / 8, 256, 0, stream>>>(src, s.n, s.dim, rows_padded, padded_dst, s.dim_padded, norm, qa, tb,
-                                                           d_info.p + 2 * s.slot);
+  if (src_u8)
+    tc_prepare_set<uint8_t><<<(rows_padded + 7) / 8, 256, 0, stream>>>(static_cast<const uint8_t*>(src), s.n, s.dim, rows_padded,
+                                                                      padded_dst, s.dim_padded, norm, qa, tb, d_info.p + 2 * s.slot);
+  else
+    tc_prepare_set<float><<<(rows_padded + 7) / 8, 256, 0, stream>>>(static_cast<const float*>(src), s.n, s.dim, rows_padded,
+                                                                    padded_dst, s.dim_padded, norm, qa, tb, d_info.p + 2 * s.slot);
   OSFM_LAUNCH_CHECK();
   s.tc_q = qa;
   s.tc_t = tb;
@@ -316,31 +323,37 @@ __device__ __forceinline__ void row_update(RowState& st, float x, int idx) {
 // best, exact (predicated) updates only inside a group that beats it.  Deliberately small: the whole
 // epilogue loop body must stay resident in the instruction cache (an earlier fully unrolled version was
 // 89 KB of SASS and spent most of its time in instruction-fetch stalls, profiles/r01_*).
-template <int OFF, int NV>
-__device__ __forceinline__ void row_consume16(RowState& st, const uint32_t (&vv)[NV], int col0) {
+template <int OFF, int NV, bool MASKED>
+__device__ __forceinline__ void row_consume16(RowState& st, const uint32_t (&vv)[NV], int col0, uint32_t bits16) {
   const uint32_t* v = vv + OFF;   // OFF is a compile-time constant: the accesses below stay register-resident
   // minima of four groups of 4 (independent chains), one test for the common case; a triggered chunk
   // re-examines only the group(s) of 4 that beat the threshold (their updates are predicated by ptxas,
-  // 7 instructions per element, so small groups matter)
+  // 7 instructions per element, so small groups matter).  MASKED (guided matching): elements whose bit is
+  // clear read as +inf and can never enter the row's two best.
+  float x[16];
+#pragma unroll
+  for (int e = 0; e < 16; ++e) {
+    x[e] = __uint_as_float(v[e]);
+    if (MASKED) x[e] = ((bits16 >> e) & 1u) ? x[e] : __builtin_huge_valf();
+  }
+  if (MASKED && bits16 == 0u) return;
   float m[4];
 #pragma unroll
-  for (int g = 0; g < 4; ++g)
-    m[g] = fminf(fminf(fminf(__uint_as_float(v[g * 4]), __uint_as_float(v[g * 4 + 1])), __uint_as_float(v[g * 4 + 2])),
-                 __uint_as_float(v[g * 4 + 3]));
+  for (int g = 0; g < 4; ++g) m[g] = fminf(fminf(fminf(x[g * 4], x[g * 4 + 1]), x[g * 4 + 2]), x[g * 4 + 3]);
   if (fminf(fminf(fminf(m[0], m[1]), m[2]), m[3]) < st.q2) {
 #pragma unroll
     for (int g = 0; g < 4; ++g) {
       if (m[g] < st.q2) {
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-          const float x = __uint_as_float(v[g * 4 + e]);
-          if (x < st.q2) row_update(st, x, col0 + g * 4 + e);
+          if (x[g * 4 + e] < st.q2) row_update(st, x[g * 4 + e], col0 + g * 4 + e);
         }
       }
     }
   }
 }
 
+template <bool MASKED>
 __global__ void __launch_bounds__(TC_THREADS, 1)
     bf_top2_tc(const MatchJob* __restrict__ jobs, const int* __restrict__ tile_prefix, int njobs, int ntasks,
                Top2* __restrict__ partial, int* __restrict__ err_flag) {
@@ -456,20 +469,28 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         // load latency, not for the consume time (8 dependent 16-column loads per tile made the epilogue the
         // critical path: profiles/r01_ncu_tc_v6.txt, top stall on the accumulator-full wait)
         uint32_t va[64], vb[64];
+        uint32_t mw[4] = {0u, 0u, 0u, 0u};   // guided matching: the row's mask bits of these 128 columns
+        if (MASKED && gq < t.job.nq) {
+          const uint32_t* mrow = t.job.mask_bits + (size_t)gq * t.job.mask_words;
+          const int w0 = col_base >> 5;
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            if (w0 + q < t.job.mask_words) mw[q] = mrow[w0 + q];
+        }
         OSFM_TMEM_LD64(taddr, va);
         OSFM_TMEM_LD64(taddr + 64, vb);
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&bar_accempty[a]);
-        row_consume16<0>(st, va, col_base);
-        row_consume16<16>(st, va, col_base + 16);
-        row_consume16<32>(st, va, col_base + 32);
-        row_consume16<48>(st, va, col_base + 48);
-        row_consume16<0>(st, vb, col_base + 64);
-        row_consume16<16>(st, vb, col_base + 80);
-        row_consume16<32>(st, vb, col_base + 96);
-        row_consume16<48>(st, vb, col_base + 112);
+        row_consume16<0, 64, MASKED>(st, va, col_base, mw[0] & 0xffffu);
+        row_consume16<16, 64, MASKED>(st, va, col_base + 16, mw[0] >> 16);
+        row_consume16<32, 64, MASKED>(st, va, col_base + 32, mw[1] & 0xffffu);
+        row_consume16<48, 64, MASKED>(st, va, col_base + 48, mw[1] >> 16);
+        row_consume16<0, 64, MASKED>(st, vb, col_base + 64, mw[2] & 0xffffu);
+        row_consume16<16, 64, MASKED>(st, vb, col_base + 80, mw[2] >> 16);
+        row_consume16<32, 64, MASKED>(st, vb, col_base + 96, mw[3] & 0xffffu);
+        row_consume16<48, 64, MASKED>(st, vb, col_base + 112, mw[3] >> 16);
       }
       // merge the two column halves of a row (lexicographic (d^2, index), like cv2's insertion order)
       if (half == 1) {
@@ -506,16 +527,21 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
   }
 }
 
-void launch_tc(Matcher& m, int njobs, int ntasks) {
+void launch_tc(Matcher& m, int njobs, int ntasks, bool masked) {
   if (!m.tc_attr_set) {   // per matcher (= per device)
-    OSFM_CUDA(cudaFuncSetAttribute(bf_top2_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
+    OSFM_CUDA(cudaFuncSetAttribute(bf_top2_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
+    OSFM_CUDA(cudaFuncSetAttribute(bf_top2_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
     m.tc_attr_set = true;
   }
   m.d_flags.reserve(4);
   OSFM_CUDA(cudaMemsetAsync(m.d_flags.p + 1, 0, sizeof(int), m.stream));
   const int grid = std::min(ntasks, m.num_sms);
-  bf_top2_tc<<<grid, TC_THREADS, TC_SMEM, m.stream>>>(m.d_jobs.p, m.d_prefix.p, njobs, ntasks, m.d_partial.p,
-                                                     m.d_flags.p + 1);
+  if (masked)
+    bf_top2_tc<true><<<grid, TC_THREADS, TC_SMEM, m.stream>>>(m.d_jobs.p, m.d_prefix.p, njobs, ntasks, m.d_partial.p,
+                                                             m.d_flags.p + 1);
+  else
+    bf_top2_tc<false><<<grid, TC_THREADS, TC_SMEM, m.stream>>>(m.d_jobs.p, m.d_prefix.p, njobs, ntasks, m.d_partial.p,
+                                                              m.d_flags.p + 1);
   OSFM_LAUNCH_CHECK();
 }
 

@@ -133,17 +133,23 @@ class PairMatcher:
         if kernel:
             _lib.check(self._m.L.osfm_matcher_set_kernel(self._m.h, int(kernel)))
 
-    def add(self, key: Any, desc: np.ndarray) -> None:
+    def add(self, key: Any, desc: np.ndarray, uint8_is_l2: bool = False) -> None:
+        """uint8_is_l2: `desc` is the uint8 storage of an L2 descriptor (HAHOG / SIFT as saved by
+        opensfm/features.py:526-534), not a binary descriptor: uploaded as bytes, matched exactly like its
+        float32 form."""
         d = _prep(desc)
         out = ctypes.c_int()
-        fn = self._m.L.osfm_matcher_add_u8 if d.dtype == np.uint8 else self._m.L.osfm_matcher_add_f32
+        if d.dtype == np.uint8:
+            fn = self._m.L.osfm_matcher_add_u8_l2 if uint8_is_l2 else self._m.L.osfm_matcher_add_u8
+        else:
+            fn = self._m.L.osfm_matcher_add_f32
         _lib.check(fn(self._m.h, d.ctypes.data_as(ctypes.c_void_p), d.shape[0], d.shape[1], ctypes.byref(out)))
         if key in self._ids:
             _lib.check(self._m.L.osfm_matcher_remove(self._m.h, self._ids[key]))
         self._ids[key] = out.value
         self._n[key] = d.shape[0]
 
-    def add_many(self, items: Sequence[Tuple[Any, np.ndarray]]) -> None:
+    def add_many(self, items: Sequence[Tuple[Any, np.ndarray]], uint8_is_l2: bool = False) -> None:
         """Upload many images' descriptors with a single host synchronisation (same dtype and
         descriptor length for all; anything else goes through `add`)."""
         prepped = [(k, _prep(d)) for k, d in items]
@@ -152,13 +158,16 @@ class PairMatcher:
         d0 = prepped[0][1]
         if any(d.dtype != d0.dtype or d.shape[1] != d0.shape[1] for _, d in prepped):
             for k, d in prepped:
-                self.add(k, d)
+                self.add(k, d, uint8_is_l2)
             return
         cnt = len(prepped)
         ptrs = (ctypes.c_void_p * cnt)(*[d.ctypes.data for _, d in prepped])
         ns = np.array([d.shape[0] for _, d in prepped], dtype=np.int32)
         ids = np.empty(cnt, dtype=np.int32)
-        fn = self._m.L.osfm_matcher_add_batch_u8 if d0.dtype == np.uint8 else self._m.L.osfm_matcher_add_batch_f32
+        if d0.dtype == np.uint8:
+            fn = self._m.L.osfm_matcher_add_batch_u8_l2 if uint8_is_l2 else self._m.L.osfm_matcher_add_batch_u8
+        else:
+            fn = self._m.L.osfm_matcher_add_batch_f32
         _lib.check(fn(self._m.h, cnt, ctypes.cast(ptrs, ctypes.c_void_p), ns.ctypes.data_as(ctypes.c_void_p), d0.shape[1],
                       ids.ctypes.data_as(ctypes.c_void_p)))
         for (k, d), i in zip(prepped, ids):
@@ -180,6 +189,48 @@ class PairMatcher:
         _lib.check(self._m.L.osfm_matcher_match_pairs_async(
             self._m.h, len(pairs), ia.ctypes.data_as(ctypes.c_void_p), ib.ctypes.data_as(ctypes.c_void_p),
             float(lowes_ratio), int(symmetric)))
+
+    # -- guided matching (matching._match_descriptors_guided_impl, matching.py:260-338) ----------------------
+    def set_bearings(self, key: Any, bearings: np.ndarray) -> None:
+        """Unit bearing vectors of the image's features (n x 3), as `feature_loader.load_bearings` returns them;
+        cast to float32 like matching.compute_inliers_bearing_epipolar does (matching.py:860-861)."""
+        b = np.ascontiguousarray(bearings, dtype=np.float32)
+        if b.shape != (self._n[key], 3):
+            raise ValueError("bearings must be n x 3 for the %d descriptors of this image" % self._n[key])
+        _lib.check(self._m.L.osfm_matcher_set_bearings(self._m.h, self._ids[key], b.ctypes.data_as(ctypes.c_void_p)))
+
+    def match_pairs_guided(self, pairs: Sequence[Tuple[Any, Any]], poses: Sequence[Tuple[np.ndarray, np.ndarray]],
+                           threshold: float, config: Dict[str, Any],
+                           mask_budget_bytes: int = 1 << 30) -> Dict[Tuple[Any, Any], np.ndarray]:
+        """Guided matching of a pair list: poses[p] = (R, t) = (pose.get_R_cam_to_world(), pose.get_origin()) of
+        image b relative to image a.  Always symmetric, like the reference (matching.py:319).  The epipolar masks
+        are built on the device, `mask_budget_bytes` of them at a time."""
+        out: Dict[Tuple[Any, Any], np.ndarray] = {}
+        start = 0
+        while start < len(pairs):
+            end, used = start, 0
+            while end < len(pairs):
+                a, b = pairs[end]
+                need = (self._n[a] * ((self._n[b] + 31) // 32) + self._n[b] * ((self._n[a] + 31) // 32)) * 4
+                if end > start and used + need > mask_budget_bytes:
+                    break
+                used += need
+                end += 1
+            chunk = list(pairs[start:end])
+            ia = np.array([self._ids[a] for a, _ in chunk], dtype=np.int32)
+            ib = np.array([self._ids[b] for _, b in chunk], dtype=np.int32)
+            pose12 = np.array([np.concatenate([np.asarray(R, dtype=np.float64).reshape(9), np.asarray(t, dtype=np.float64).reshape(3)])
+                               for R, t in poses[start:end]], dtype=np.float64).reshape(-1, 12)
+            self._pairs = chunk
+            _lib.check(self._m.L.osfm_matcher_match_pairs_guided_async(
+                self._m.h, len(chunk), ia.ctypes.data_as(ctypes.c_void_p), ib.ctypes.data_as(ctypes.c_void_p),
+                pose12.ctypes.data_as(ctypes.c_void_p), float(threshold), float(config["lowes_ratio"]), 1))
+            raw = self.fetch_raw()
+            counts = np.array([self._n[a] for a, _ in chunk], dtype=np.int64)
+            for pr, lst in zip(chunk, split_match_lists(raw, counts)):
+                out[pr] = lst
+            start = end
+        return out
 
     def sync(self) -> None:
         _lib.check(self._m.L.osfm_matcher_sync(self._m.h))
@@ -209,15 +260,41 @@ class PairMatcher:
 
 
 def shard_pairs(pairs: Sequence[Tuple[Any, Any]], sizes: Dict[Any, int], world: int) -> List[List[Tuple[Any, Any]]]:
-    """Split a pair list over `world` GPUs, balancing sum(N_i * M_i) (greedy LPT).
+    """Split a pair list over `world` GPUs: balanced sum(N_i * M_i), and pairs that share an image on the same GPU
+    so that every rank uploads / keeps resident only ~1/world of the descriptor sets.
 
-    Image pairs are independent units (matching.py:83 maps a pure function over
-    them), so multi-GPU matching needs no collective: each rank matches its shard."""
-    order = sorted(range(len(pairs)), key=lambda i: -(sizes[pairs[i][0]] * sizes[pairs[i][1]]))
-    load = [0] * world
+    The images are ordered by a breadth-first walk of the pair graph (neighbouring images get neighbouring ranks in
+    the order), the pairs are sorted by that order and cut into `world` contiguous runs of equal work.  Image pairs
+    are independent units (matching.py:83 maps a pure function over them), so no collective is needed."""
+    if world <= 1 or not pairs:
+        return [list(pairs)] + [[] for _ in range(max(world - 1, 0))]
+    adj: Dict[Any, List[Any]] = {}
+    for a, b in pairs:
+        adj.setdefault(a, []).append(b)
+        adj.setdefault(b, []).append(a)
+    rank: Dict[Any, int] = {}
+    for root in adj:                       # insertion order: deterministic on every rank
+        if root in rank:
+            continue
+        queue, head = [root], 0
+        rank[root] = len(rank)
+        while head < len(queue):
+            u = queue[head]
+            head += 1
+            for v in adj[u]:
+                if v not in rank:
+                    rank[v] = len(rank)
+                    queue.append(v)
+    order = sorted(range(len(pairs)), key=lambda i: (min(rank[pairs[i][0]], rank[pairs[i][1]]),
+                                                     max(rank[pairs[i][0]], rank[pairs[i][1]]), i))
+    work = [sizes[pairs[i][0]] * sizes[pairs[i][1]] for i in order]
+    total = float(sum(work))
     shards: List[List[int]] = [[] for _ in range(world)]
-    for i in order:
-        r = min(range(world), key=lambda k: load[k])
+    acc, r = 0.0, 0
+    for i, w in zip(order, work):
+        # close the current run once it holds its share (the last rank takes the remainder)
+        if r < world - 1 and acc + 0.5 * w > total * (r + 1) / world:
+            r += 1
         shards[r].append(i)
-        load[r] += sizes[pairs[i][0]] * sizes[pairs[i][1]]
+        acc += w
     return [[pairs[i] for i in sorted(s)] for s in shards]

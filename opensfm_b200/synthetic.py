@@ -291,3 +291,36 @@ def binary_descriptors(n: int, seed: int, nbytes: int = 61) -> np.ndarray:
     """AKAZE-MLDB-sized (486 bit -> 61 byte) random binary descriptors."""
     rng = np.random.RandomState(seed)
     return rng.randint(0, 256, (n, nbytes)).astype(np.uint8)
+
+
+def guided_scene(n_images: int, n_desc: int, seed: int = 7, bearing_noise: float = 0.002, dim: int = 128):
+    """Stand-in for BASELINE configs[2] (lund sequence, HAHOG features, guided matching): `n_images`
+    cameras on an arc looking at a point cloud, each with `n_desc` features = bearings of points it sees (+ angular
+    noise) and HAHOG-like uint8-valued descriptors (the point's descriptor + small integer noise).
+    Returns (descriptors [n_images] float32 n_desc x dim, bearings [n_images] float32 n_desc x 3,
+    R_wc [n_images] 3x3 world->camera, origins [n_images])."""
+    rng = np.random.RandomState(seed)
+    n_points = int(n_desc * 1.6)
+    pts = rng.uniform(-1.0, 1.0, (n_points, 3)) * np.array([2.0, 1.0, 1.0])
+    base = hahog_like_descriptors(n_points, seed + 1, dim)
+    descs, bears, Rs, Os = [], [], [], []
+    for i in range(n_images):
+        ang = -0.6 + 1.2 * i / max(n_images - 1, 1)
+        origin = np.array([4.0 * np.sin(ang), 0.3 * np.sin(3 * ang), -4.0 * np.cos(ang)])
+        R_wc, _ = camera_pose(origin, np.zeros(3), np.array([0.0, -1.0, 0.0]))
+        idx = rng.choice(n_points, n_desc, replace=False)
+        xc = (pts[idx] - origin) @ R_wc.T
+        b = xc / np.linalg.norm(xc, axis=1, keepdims=True)
+        b = b + rng.normal(0.0, bearing_noise, b.shape)
+        b /= np.linalg.norm(b, axis=1, keepdims=True)
+        d = np.clip(base[idx] + rng.randint(-4, 5, (n_desc, dim)), 0, 255).astype(np.float32)
+        descs.append(d); bears.append(b.astype(np.float32)); Rs.append(R_wc); Os.append(origin)
+    return descs, bears, Rs, Os
+
+
+def relative_pose(R_wc_a, origin_a, R_wc_b, origin_b):
+    """(R, t) of image b relative to image a as matching.py passes them to the epipolar mask:
+    R = rotation camera b -> camera a, t = origin of camera b in camera a's frame."""
+    R = R_wc_a @ R_wc_b.T
+    t = R_wc_a @ (np.asarray(origin_b) - np.asarray(origin_a))
+    return R, t

@@ -126,3 +126,23 @@ def match_brute_force_symmetric_numpy(fi, fj, config, maskij=None) -> List[Tuple
     mij = set(match_brute_force_numpy(fi, fj, config, maskij))
     mji = set((b, a) for a, b in match_brute_force_numpy(fj, fi, config, None if maskij is None else maskij.T))
     return list(mij & mji)
+
+
+def epipolar_mask(b1: np.ndarray, b2: np.ndarray, R: np.ndarray, t: np.ndarray, threshold: float) -> np.ndarray:
+    """matching.compute_inliers_bearing_epipolar (opensfm/matching.py:847-868) around
+    geometry::EpipolarAngleTwoBearingsMany (opensfm/src/geometry/src/triangulation.cc:195-219), restated in numpy
+    fp64: bearings are cast to float32 first (matching.py:860-861), R = pose.get_R_cam_to_world(),
+    t = pose.get_origin() of image 2 relative to image 1.  Returns the boolean n1 x n2 mask."""
+    b1 = np.asarray(b1).astype(np.float32).astype(np.float64)
+    b2 = np.asarray(b2).astype(np.float32).astype(np.float64)
+    R = np.asarray(R, dtype=np.float64).reshape(3, 3)
+    t = np.asarray(t, dtype=np.float64).reshape(3)
+    tn = t / np.linalg.norm(t)
+    b2w = b2 @ R.T
+    with np.errstate(invalid="ignore", divide="ignore"):
+        e1 = np.cross(tn, b1)
+        e1 = e1 / np.linalg.norm(e1, axis=1, keepdims=True)
+        e2 = np.cross(tn, b2w)
+        e2 = e2 / np.linalg.norm(e2, axis=1, keepdims=True)
+        sym = (np.abs(e1 @ b2w.T) + np.abs(b1 @ e2.T)) / 2.0
+        return (np.pi / 2.0 - np.arccos(sym)) < threshold

@@ -177,3 +177,48 @@ def test_threads_share_nothing():
     [t.start() for t in ts]
     [t.join() for t in ts]
     assert all(o == ref for o in out)
+
+
+def test_uint8_stored_l2_descriptors_match_their_float32_form():
+    """HAHOG / SIFT-uchar uploaded as bytes (osfm_matcher_add_u8_l2) give exactly the float32 results."""
+    a, b = _related(1500, 1700, 31)
+    pm = matching.PairMatcher()
+    pm.add("a", a.astype(np.uint8), uint8_is_l2=True)
+    pm.add("b", b.astype(np.uint8), uint8_is_l2=True)
+    got = pm.match_pairs([("a", "b")], CFG, symmetric=False)[("a", "b")]
+    assert pm.last_kernel() == 2
+    assert [tuple(x) for x in got.tolist()] == mo.match_brute_force(a, b, CFG)
+    pm.add_many([("c", a.astype(np.uint8)), ("d", b.astype(np.uint8))], uint8_is_l2=True)
+    sym = pm.match_pairs([("c", "d")], CFG)[("c", "d")]
+    assert _pairset(sym) == _pairset(mo.match_brute_force_symmetric(a, b, CFG))
+    # a short descriptor (no tensor-core operands) goes through the widening kernel
+    a20, b20 = a[:300, :20], b[:400, :20]
+    pm.add("e", a20.astype(np.uint8), uint8_is_l2=True)
+    pm.add("f", b20.astype(np.uint8), uint8_is_l2=True)
+    got20 = pm.match_pairs([("e", "f")], CFG, symmetric=False)[("e", "f")]
+    assert [tuple(x) for x in got20.tolist()] == mo.match_brute_force(np.ascontiguousarray(a20), np.ascontiguousarray(b20), CFG)
+
+
+@pytest.mark.parametrize("n_desc,kernel", [(900, 0), (900, 1), (2500, 0)])
+def test_guided_matching_matches_the_reference_mask_and_matcher(n_desc, kernel):
+    """matching._match_descriptors_guided_impl (matching.py:260-338): epipolar mask from bearings + relative pose
+    (fp64, built on the device as a bitmask) and symmetric brute-force matching under it -- against the numpy
+    restatement of EpipolarAngleTwoBearingsMany + live cv2 with the byte mask."""
+    descs, bears, Rs, Os = syn.guided_scene(4, n_desc, seed=n_desc)
+    pm = matching.PairMatcher(kernel=kernel)
+    for i in range(4):
+        pm.add(i, descs[i])
+        pm.set_bearings(i, bears[i])
+    pairs = [(0, 1), (1, 2), (0, 3), (3, 2)]
+    poses = [syn.relative_pose(Rs[a], Os[a], Rs[b], Os[b]) for a, b in pairs]
+    thr = 0.006   # config.py guided_matching_threshold
+    got = pm.match_pairs_guided(pairs, poses, thr, CFG, mask_budget_bytes=3 * n_desc * n_desc // 8 * 2)
+    assert pm.last_kernel() == (1 if kernel == 1 else 2)
+    total = 0
+    for (a, b), (R, t) in zip(pairs, poses):
+        mask = mo.epipolar_mask(bears[a], bears[b], R, t, thr)
+        ref = mo.match_brute_force_symmetric(descs[a], descs[b], CFG, mask)
+        assert _pairset(got[(a, b)]) == _pairset(ref), (a, b)
+        total += len(ref)
+        assert 0.001 < mask.mean() < 0.2
+    assert total > 50
