@@ -409,6 +409,157 @@ __global__ void __launch_bounds__(256, WCT ? 3 : 2) ba_colnorm_grad_seg(BAView v
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// The same camera-side sums with the observation tiles staged by the TMA engine (cp.async.bulk + mbarrier).
+// The residual / Jacobian planes of a chunk of a segment (<= 8 points seen by the same k shots) are, per plane,
+// one contiguous run of 8 * np * k bytes: a warp stages the 2 + 2 * 9 runs of a chunk into its shared-memory
+// tile with one bulk copy each (lane 0 issues them, all complete on one mbarrier), double-buffered so that the
+// copy of the next chunk is in flight while the current one is reduced.  Lane l owns the accumulators
+// (shot c, column j) = l, l + 32, l + 64 and walks the points of the chunk in shared memory: no shuffles, no
+// atomics until the segment's k * 9 sums are flushed.  wc == 9, nres == 2 (one 3-parameter camera + pose per
+// shot: BASELINE configs[1..3]); chunks whose runs are not 16-byte aligned are staged with plain loads.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int CG_WARPS = 4;
+constexpr int CG_ROWS = 20;                         // r[2] + Jc[2 * 9]
+constexpr int CG_PCHUNK = 8, CG_KMAX = 16;          // points per chunk, shots per segment (= SEG_KMAX, ba_reduced.cuh)
+constexpr int CG_OBS = CG_PCHUNK * CG_KMAX;         // observations per chunk
+constexpr int CG_STAGE_DOUBLES = CG_ROWS * CG_OBS;
+constexpr int CG_SMEM = CG_WARPS * 2 * CG_STAGE_DOUBLES * (int)sizeof(double);   // 163,840 bytes
+
+__device__ __forceinline__ uint32_t cg_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void cg_mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = cg_smem_u32(bar);
+  for (;;) {
+    uint32_t done;
+    asm volatile(
+        "{\n.reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n}\n"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (done) return;
+  }
+}
+
+__global__ void __launch_bounds__(32 * CG_WARPS, 1)
+    ba_colnorm_grad_tma(BAView v, const int* __restrict__ seg_start, int nseg, double* colnorm2, double* grad) {
+  extern __shared__ __align__(128) double cg_tiles[];
+  __shared__ __align__(8) uint64_t bars[CG_WARPS][2];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int w = 0; w < CG_WARPS; ++w)
+      for (int st = 0; st < 2; ++st)
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(cg_smem_u32(&bars[w][st])), "r"(1));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  double* tile[2] = {cg_tiles + (size_t)(warp * 2) * CG_STAGE_DOUBLES, cg_tiles + (size_t)(warp * 2 + 1) * CG_STAGE_DOUBLES};
+  const size_t N = (size_t)v.N;
+  const int gw = blockIdx.x * CG_WARPS + warp, nw = gridDim.x * CG_WARPS;
+  uint32_t phase[2] = {0u, 0u};
+
+  // stage chunk [pc0, pc0 + np) of a segment with k shots into tile[st]; returns whether the TMA path was used
+  auto stage = [&](int st, int pc0, int np, int k) -> bool {
+    const long long ibase = v.pt_start[pc0];
+    const int run = np * k;
+    const bool aligned = ((ibase | (long long)run | (long long)N) & 1LL) == 0;   // 16-byte aligned runs in every plane
+    if (aligned) {
+      if (lane == 0) {
+        const uint32_t bytes = (uint32_t)run * 8u;
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(cg_smem_u32(&bars[warp][st])),
+                     "r"(bytes * CG_ROWS)
+                     : "memory");
+        for (int row = 0; row < CG_ROWS; ++row) {
+          const double* src = (row < 2 ? v.r + (size_t)row * N : v.Jc + (size_t)(row - 2) * N) + ibase;
+          asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                           cg_smem_u32(tile[st] + row * CG_OBS)),
+                       "l"(src), "r"(bytes), "r"(cg_smem_u32(&bars[warp][st]))
+                       : "memory");
+        }
+      }
+    } else {
+      for (int idx = lane; idx < CG_ROWS * run; idx += 32) {
+        const int row = idx / run, e = idx - row * run;
+        tile[st][row * CG_OBS + e] = (row < 2 ? v.r + (size_t)row * N : v.Jc + (size_t)(row - 2) * N)[ibase + e];
+      }
+    }
+    return aligned;
+  };
+
+  // (segment, chunk) walk of this warp, one step ahead for the prefetch
+  int s = gw, pc = 0, p_end = 0, k = 0;
+  auto open_segment = [&]() {
+    while (s < nseg) {
+      pc = seg_start[s]; p_end = seg_start[s + 1];
+      if (pc < p_end) { k = (int)(v.pt_start[pc + 1] - v.pt_start[pc]); return true; }
+      s += nw;
+    }
+    return false;
+  };
+  if (!open_segment()) return;
+  int st = 0;
+  bool cur_tma = stage(0, pc, min(CG_PCHUNK, p_end - pc), k);
+  double n2[3] = {0.0, 0.0, 0.0}, gr[3] = {0.0, 0.0, 0.0};
+  while (true) {
+    const int np = min(CG_PCHUNK, p_end - pc);
+    const int cur_k = k, cur_pc = pc;
+    const bool last_chunk = pc + np >= p_end;
+    // next (segment, chunk)
+    int ns = s, npc = pc + np, np_end = p_end, nk = k;
+    bool have_next = true;
+    if (last_chunk) {
+      ns = s + nw;
+      have_next = false;
+      while (ns < nseg) {
+        npc = seg_start[ns]; np_end = seg_start[ns + 1];
+        if (npc < np_end) { nk = (int)(v.pt_start[npc + 1] - v.pt_start[npc]); have_next = true; break; }
+        ns += nw;
+      }
+    }
+    bool next_tma = false;
+    if (have_next) next_tma = stage(st ^ 1, npc, min(CG_PCHUNK, np_end - npc), nk);
+    if (cur_tma) { cg_mbar_wait(&bars[warp][st], phase[st]); phase[st] ^= 1u; }
+    else __syncwarp();
+    // reduce the chunk: accumulator a = c * 9 + j
+    const double* T = tile[st];
+    const int nacc = cur_k * 9;
+#pragma unroll
+    for (int u = 0; u < 3; ++u) {
+      const int a = lane + 32 * u;
+      if (a < nacc) {
+        const int c = a / 9, j = a - c * 9;
+        for (int pi = 0; pi < np; ++pi) {
+          const int e = pi * cur_k + c;
+          const double j0 = T[(2 + j) * CG_OBS + e], j1 = T[(2 + 9 + j) * CG_OBS + e];
+          n2[u] += j0 * j0 + j1 * j1;
+          gr[u] += j0 * T[e] + j1 * T[CG_OBS + e];
+        }
+      }
+    }
+    __syncwarp();   // the tile may be overwritten by the copy issued two steps from now
+    if (last_chunk) {
+      const long long base = v.pt_start[seg_start[s]];
+#pragma unroll
+      for (int u = 0; u < 3; ++u) {
+        const int a = lane + 32 * u;
+        if (a < nacc) {
+          const int c = a / 9, j = a - c * 9;
+          const ObsCols oc = obs_cols(v, base + c);
+          const int col = oc.col(j);
+          if (col >= 0) { atomicAdd(&colnorm2[col], n2[u]); atomicAdd(&grad[col], gr[u]); }
+        }
+        n2[u] = 0.0; gr[u] = 0.0;
+      }
+    }
+    (void)cur_pc;
+    if (!have_next) break;
+    s = ns; pc = npc; p_end = np_end; k = nk;
+    cur_tma = next_tma;
+    st ^= 1;
+  }
+}
+
 __global__ void ba_prior_colnorm_grad(PriorView pv, Params p, double* colnorm2, double* grad) {
   const int row = blockIdx.x * blockDim.x + threadIdx.x;
   if (row >= pv.n_cam_rows + pv.n_pos_rows) return;
@@ -459,6 +610,7 @@ __global__ void ba_grad_max(const double* grad, int n, Scalars* sc) {
 
 }  // namespace osfm
 #include "ba_reduced.cuh"
+static_assert(osfm::CG_KMAX == osfm::SEG_KMAX, "colnorm tiles hold the widest segment");
 #include "ba_side.cuh"
 #include "ba_order.cuh"
 namespace osfm {
@@ -759,7 +911,7 @@ struct BA {
   int pcg_smem = 0;
   DevBuf<int> d_pcg_grplo;
   DevBuf<unsigned long long> d_prof;
-  bool seg_attr = false, mma_attr = false;   // per handle (= per device): dynamic shared-memory opt-in done
+  bool seg_attr = false, mma_attr = false, cg_attr = false;   // per handle (= per device): dynamic shared-memory opt-in done
   DevBuf<long long> d_tab_off, d_tab_sizes;
   DevBuf<int> d_tab;
   PcgPipe pcg_pipe{};
@@ -1248,7 +1400,16 @@ void BA::run() {
       ba_colnorm_grad_points<<<grid_for(N, 256), 256, 0, stream>>>(v, d_colnorm2.p, d_grad.p);
       OSFM_LAUNCH_CHECK();
       if (nseg > 0) {
-        if (wc == 9)
+        // OSFM_BA_COLNORM_TMA=0: the shuffle kernel instead of the bulk-copy staged one (A/B switch)
+        static const bool use_tma = []() { const char* e = getenv("OSFM_BA_COLNORM_TMA"); return !(e && e[0] == '0'); }();
+        if (wc == 9 && nres == 2 && use_tma) {
+          if (!cg_attr) {
+            OSFM_CUDA(cudaFuncSetAttribute(ba_colnorm_grad_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, CG_SMEM));
+            cg_attr = true;
+          }
+          const int grid = std::max(1, std::min(num_sms, (nseg + CG_WARPS - 1) / CG_WARPS));
+          ba_colnorm_grad_tma<<<grid, 32 * CG_WARPS, CG_SMEM, stream>>>(v, d_seg_start.p, nseg, d_colnorm2.p, d_grad.p);
+        } else if (wc == 9)
           ba_colnorm_grad_seg<9><<<grid_for((long long)nseg * 32, 256), 256, 0, stream>>>(v, d_seg_start.p, nseg, d_colnorm2.p, d_grad.p);
         else
           ba_colnorm_grad_seg<0><<<grid_for((long long)nseg * 32, 256), 256, 0, stream>>>(v, d_seg_start.p, nseg, d_colnorm2.p, d_grad.p);

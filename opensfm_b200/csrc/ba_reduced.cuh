@@ -856,7 +856,17 @@ __global__ void __launch_bounds__(SM_THREADS, 2)
     sm.lp_of[tid] = (unsigned char)lp;
     sm.bb_of[tid] = (unsigned char)(tid - lp * k);
   }
-  for (int t = tid; t < 3 * SM_KC * SM_LD; t += SM_THREADS) (&sm.Yt[0][0])[t] = 0.0;
+  // every (row < 3 np, column < ncols) entry of the operand buffers is rewritten by each chunk; only the padding
+  // columns [ncols, SM_LD) the 8-wide tiles can touch have to read as zero (zeroing all 57 KB cost 5k clocks per
+  // segment, profiles/README.md)
+  {
+    const int padc = SM_LD - ncols;
+    for (int t = tid; t < 3 * SM_KC * padc; t += SM_THREADS) {
+      const int arr = t / (SM_KC * padc), rem = t - arr * (SM_KC * padc);
+      const int kk = rem / padc, cc = ncols + rem - kk * padc;
+      (arr == 0 ? sm.Yt : arr == 1 ? sm.Wt : sm.Jt)[kk][cc] = 0.0;
+    }
+  }
   mark(0);
 
   // ---- my tiles of the upper triangle of nt x nt 8x8 tiles.  Slots 0..SM_NEAR-1 take the tiles that can
@@ -901,6 +911,18 @@ __global__ void __launch_bounds__(SM_THREADS, 2)
         sm.Yt[kk][cc] = 0.0; sm.Wt[kk][cc] = 0.0; sm.Jt[kk][cc] = 0.0;
       }
     }
+    // items (c2 = item >> 7, observation = item & 127): coalesced plane reads of the camera-side Jacobian, issued
+    // first so that their latency overlaps the per-observation / per-point loads below
+    constexpr int ITEMS = ((WC ? WC : SEG_WCMAX) * 128 + SM_THREADS - 1) / SM_THREADS;
+    double jall[ITEMS][3];
+#pragma unroll
+    for (int it = 0; it < ITEMS; ++it) {
+      const int t = tid + it * SM_THREADS;
+      const int c2 = t >> 7, off = t & 127;
+#pragma unroll
+      for (int q = 0; q < 3; ++q)
+        jall[it][q] = (c2 < wc && off < run && q < nres) ? v.Jc[((size_t)q * wc + c2) * N + (size_t)(ibase + off)] : 0.0;
+    }
     // per-observation / per-point data of the chunk, loaded once (not once per camera-side column)
     if (tid < run) {
       const size_t i = (size_t)(ibase + tid);
@@ -927,17 +949,6 @@ __global__ void __launch_bounds__(SM_THREADS, 2)
     }
     __syncthreads();
     mark(2);
-    // items (c2 = item >> 7, observation = item & 127): coalesced plane reads of the camera-side Jacobian
-    constexpr int ITEMS = ((WC ? WC : SEG_WCMAX) * 128 + SM_THREADS - 1) / SM_THREADS;
-    double jall[ITEMS][3];   // all of this thread's plane reads in flight before the first use
-#pragma unroll
-    for (int it = 0; it < ITEMS; ++it) {
-      const int t = tid + it * SM_THREADS;
-      const int c2 = t >> 7, off = t & 127;
-#pragma unroll
-      for (int q = 0; q < 3; ++q)
-        jall[it][q] = (c2 < wc && off < run && q < nres) ? v.Jc[((size_t)q * wc + c2) * N + (size_t)(ibase + off)] : 0.0;
-    }
 #pragma unroll
     for (int it = 0; it < ITEMS; ++it) {
       const int t = tid + it * SM_THREADS;

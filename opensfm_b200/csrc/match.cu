@@ -405,24 +405,29 @@ __global__ void epi_vectors(const EpiPair* __restrict__ pairs) {
   }
 }
 __global__ void __launch_bounds__(256) epi_mask_bits(const EpiPair* __restrict__ pairs, double threshold) {
+  // the 32 rows of the block: [b1 | e1] as float32, read by every lane of the warp (shared-memory broadcast;
+  // the first version moved them with 6 shuffles per row and was shuffle-bound at 6e11 elements/s)
+  __shared__ float rows[8][32][8];
   const EpiPair& p = pairs[blockIdx.z];
-  const int lane = threadIdx.x & 31;
-  const int jb = blockIdx.x * 8 + (threadIdx.x >> 5);   // 32-column block of this warp
-  const int ib = blockIdx.y;                            // 32-row block
-  if (jb >= p.w2 || ib >= p.w1) return;
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int jb = blockIdx.x * 8 + wib;   // 32-column block of this warp
+  const int ib = blockIdx.y;             // 32-row block
+  if (jb >= p.w2 || ib >= p.w1) return;  // warp-uniform
   const int j = jb * 32 + lane, i = ib * 32 + lane;
   const float NaNf = __int_as_float(0x7fc00000);
-  float cj[6] = {NaNf, NaNf, NaNf, NaNf, NaNf, NaNf}, ri[6] = {NaNf, NaNf, NaNf, NaNf, NaNf, NaNf};
+  float cj[6] = {NaNf, NaNf, NaNf, NaNf, NaNf, NaNf};
   if (j < p.n2) for (int e = 0; e < 6; ++e) cj[e] = (float)p.v2[6 * (size_t)j + e];
-  if (i < p.n1) for (int e = 0; e < 6; ++e) ri[e] = (float)p.v1[6 * (size_t)i + e];
+  for (int e = 0; e < 6; ++e) rows[wib][lane][e] = i < p.n1 ? (float)p.v1[6 * (size_t)i + e] : NaNf;
+  __syncwarp();
   const float s_thr = (float)sin(threshold);
   const float lo = s_thr - 2e-6f, hi = s_thr + 2e-6f;
   uint32_t colbits = 0;
+#pragma unroll 4
   for (int r = 0; r < 32; ++r) {
-    const float b0 = __shfl_sync(0xffffffffu, ri[0], r), b1 = __shfl_sync(0xffffffffu, ri[1], r),
-                b2 = __shfl_sync(0xffffffffu, ri[2], r), e0 = __shfl_sync(0xffffffffu, ri[3], r),
-                e1 = __shfl_sync(0xffffffffu, ri[4], r), e2 = __shfl_sync(0xffffffffu, ri[5], r);
-    const float sym = 0.5f * (fabsf(e0 * cj[0] + e1 * cj[1] + e2 * cj[2]) + fabsf(b0 * cj[3] + b1 * cj[4] + b2 * cj[5]));
+    const float4 ra = *reinterpret_cast<const float4*>(&rows[wib][r][0]);
+    const float2 rb = *reinterpret_cast<const float2*>(&rows[wib][r][4]);
+    // ra = (b1.x, b1.y, b1.z, e1.x), rb = (e1.y, e1.z)
+    const float sym = 0.5f * (fabsf(ra.w * cj[0] + rb.x * cj[1] + rb.y * cj[2]) + fabsf(ra.x * cj[3] + ra.y * cj[4] + ra.z * cj[5]));
     bool in = sym < lo;               // NaN (missing row / column, degenerate epipolar plane) compares false
     if (!(sym < lo) && sym < hi) {    // inside the guard band: the reference's own fp64 expression
       const int gi = ib * 32 + r;

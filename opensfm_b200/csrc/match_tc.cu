@@ -34,8 +34,9 @@
 
 namespace osfm {
 
-constexpr int TC_M = 128;
-constexpr int TC_N = 256;
+constexpr int TC_M = 256;                // query rows per task: two M = 128 MMAs share every train tile
+constexpr int TC_MH = 128;               // rows of one MMA (TMEM lanes)
+constexpr int TC_N = 128;                // train rows per tile
 constexpr int TC_KD = 128;               // descriptor dims carried
 constexpr int TC_KP = 144;               // padded K (9 x UMMA_K)
 constexpr int TC_KCH = TC_KP / 8;        // 16-byte K chunks per row
@@ -167,7 +168,7 @@ void Matcher::prepare_tc(DescSet& s, const void* src, bool src_u8, float* padded
   s.tc_norm = norm;
   s.info_pending = true;
 }
-int tc_rows_padded(int n) { return (n + TC_N - 1) / TC_N * TC_N; }
+int tc_rows_padded(int n) { return (n + TC_M - 1) / TC_M * TC_M; }   // whole query tiles (and whole train tiles)
 size_t tc_operand_bytes(int rows_padded) { return 2 * (size_t)rows_padded * TC_ROW_BYTES + (size_t)rows_padded * sizeof(float); }
 bool tc_capable(int dim, bool u8, int n) { return !u8 && dim <= TC_KD && n > 0 && tc_available(); }
 
@@ -245,7 +246,7 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
 // cute::UMMA::InstrDescriptor: c_format F32 (1) @4, a/b format BF16 (1) @7/@10, K-major both,
 // n_dim = N>>3 @17, m_dim = M>>4 @24
 constexpr uint32_t TC_IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TC_N >> 3) << 17) |
-                              ((uint32_t)(TC_M >> 4) << 24);
+                              ((uint32_t)(TC_MH >> 4) << 24);
 
 #define OSFM_TMEM_LD16(taddr, v)                                                                          \
   asm volatile(                                                                                           \
@@ -361,7 +362,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
   __shared__ __align__(8) uint64_t bar_qfull[2], bar_qempty[2], bar_full[TC_STAGES], bar_empty[TC_STAGES],
       bar_accfull[2], bar_accempty[2];
   __shared__ uint32_t tmem_base_smem;
-  __shared__ float4 merge_buf[TC_M];
 
   uint8_t* q_smem[2] = {smem, smem + TC_Q_BYTES};
   uint8_t* t_smem[TC_STAGES];
@@ -423,18 +423,24 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         const int b = n & 1, qph = (n >> 1) & 1;
         mbar_wait(&bar_qfull[b], qph, err_flag);
         const uint64_t adesc0 = make_smem_desc(smem_u32(q_smem[b]));
+        const uint64_t adesc1 = make_smem_desc(smem_u32(q_smem[b]) + (TC_MH / 8) * TC_SBO);   // query rows 128..255
         for (int i = 0; i < t.ntiles; ++i, ++tilecount) {
           const int a = tilecount & 1, aph = (tilecount >> 1) & 1;
           mbar_wait(&bar_accempty[a], aph ^ 1, err_flag);
           mbar_wait(&bar_full[stage], ph, err_flag);
           tc_fence_after();
           const uint64_t bdesc0 = make_smem_desc(smem_u32(t_smem[stage]));
-          const uint32_t d_tmem = tmem_base + (uint32_t)a * TC_N;
+          // accumulator stage a = TMEM columns [256 a, 256 a + 256): query rows 0..127 in the first 128 columns,
+          // 128..255 in the second.  Both MMAs read the same train tile from shared memory: every byte the TMA
+          // engine brings in feeds 256 query rows (the M = 128 x N = 256 tile moved twice the bytes per output
+          // and was bound by the L2 -> SM path, profiles/README.md round 2)
+          const uint32_t d_tmem = tmem_base + (uint32_t)a * (2 * TC_N);
 #pragma unroll
           for (int k = 0; k < TC_KP / 16; ++k) {
             // one UMMA_K = 16 bf16 = two core matrices = 256 bytes along K
             const uint64_t koff = (uint64_t)((k * 2 * TC_LBO) >> 4);
             tc_mma_bf16(d_tmem, adesc0 + koff, bdesc0 + koff, TC_IDESC, k > 0 ? 1u : 0u);
+            tc_mma_bf16(d_tmem + TC_N, adesc1 + koff, bdesc0 + koff, TC_IDESC, k > 0 ? 1u : 0u);
           }
           tc_commit(&bar_empty[stage]);   // smem stage reusable when these MMAs retire
           tc_commit(&bar_accfull[a]);     // accumulator complete
@@ -444,12 +450,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
       }
     }
   } else {
-    // ===== epilogue: warps 2..9; a warp may only touch TMEM lanes 32*(warp%4)..+31.  The two warps
-    // of a quarter take alternating pairs of 16-column chunks, so each SM sub-partition always has two
-    // independent instruction streams (the single-warp version was latency-bound, profiles/r01_ncu_tc_v2) =====
+    // ===== epilogue: warps 2..9; a warp may only touch TMEM lanes 32*(warp%4)..+31.  The two warps of a lane
+    // quarter take the two query halves of the task (rows 0..127 / 128..255 = the two accumulators of a stage), so
+    // each SM sub-partition always has two independent instruction streams and every thread owns one query row =====
     const int quarter = warp & 3;
     const int half = (warp - 2) >> 2;
-    const int row_in_tile = quarter * 32 + lane;
+    const int row_in_tile = half * TC_MH + quarter * 32 + lane;
     int tilecount = 0;
     for (int task = blockIdx.x; task < ntasks; task += gridDim.x) {
       const TcTask t = tc_decode(jobs, tile_prefix, njobs, task);
@@ -462,9 +468,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         const int a = tilecount & 1, aph = (tilecount >> 1) & 1;
         mbar_wait(&bar_accfull[a], aph, err_flag);
         tc_fence_after();
-        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)a * TC_N + (uint32_t)half * (TC_N / 2);
-        const int col_base = t.t_begin + i * TC_N + half * (TC_N / 2);
-        // this warp's 128 columns of the tile in two 64-column loads, both in flight at once; the accumulator is
+        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)a * (2 * TC_N) + (uint32_t)half * TC_N;
+        const int col_base = t.t_begin + i * TC_N;
+        // this row's 128 columns of the tile in two 64-column loads, both in flight at once; the accumulator is
         // handed back to the MMA issuer as soon as the values are in registers -- the TMEM stage is held for one
         // load latency, not for the consume time (8 dependent 16-column loads per tile made the epilogue the
         // critical path: profiles/r01_ncu_tc_v6.txt, top stall on the accumulator-full wait)
@@ -492,22 +498,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         row_consume16<32, 64, MASKED>(st, vb, col_base + 96, mw[3] & 0xffffu);
         row_consume16<48, 64, MASKED>(st, vb, col_base + 112, mw[3] >> 16);
       }
-      // merge the two column halves of a row (lexicographic (d^2, index), like cv2's insertion order)
-      if (half == 1) {
-        merge_buf[row_in_tile] = make_float4(st.q1, __int_as_float(st.i1), st.q2, __int_as_float(st.i2));
-      }
-      asm volatile("bar.sync 1, %0;" ::"r"(32 * TC_EPI_WARPS) : "memory");
-      if (half == 0) {
-        const float4 o = merge_buf[row_in_tile];
-        Top2 a2;
-        a2.s1 = st.q1; a2.i1 = st.i1; a2.s2 = st.q2; a2.i2 = st.i2;
-        Top2 b2;
-        b2.s1 = o.x; b2.i1 = __float_as_int(o.y); b2.s2 = o.z; b2.i2 = __float_as_int(o.w);
-        top2_merge(a2, b2);
-        st.q1 = a2.s1; st.i1 = a2.i1; st.q2 = a2.s2; st.i2 = a2.i2;
-      }
-      asm volatile("bar.sync 1, %0;" ::"r"(32 * TC_EPI_WARPS) : "memory");
-      if (half == 0 && gq < t.job.nq) {
+      if (gq < t.job.nq) {
         // partial results of this kernel are squared distances (exact integers in fp32)
         Top2 out;
         out.s1 = st.i1 >= 0 ? fmaxf(st.q1 + na, 0.0f) : __builtin_huge_valf();

@@ -259,6 +259,62 @@ class PairMatcher:
         return dict(zip(self._pairs, split_match_lists(raw, counts)))
 
 
+def unfilter_matches(matches: np.ndarray, m1: np.ndarray, m2: np.ndarray) -> np.ndarray:
+    """matching.unfilter_matches (matching.py:932-936): indexes in the masked feature sets -> indexes in the original
+    sets, vectorised."""
+    matches = np.asarray(matches, dtype=np.int64).reshape(-1, 2)
+    i1, i2 = np.flatnonzero(m1), np.flatnonzero(m2)
+    return np.stack([i1[matches[:, 0]], i2[matches[:, 1]]], axis=1) if len(matches) else np.zeros((0, 2), dtype=np.int64)
+
+
+def match_images_with_pairs(descriptors: Dict[Any, np.ndarray], pairs: Sequence[Tuple[Any, Any]], config: Dict[str, Any],
+                            robust_filter=None, feature_masks: Optional[Dict[Any, np.ndarray]] = None,
+                            guided: Optional[Dict[str, Any]] = None, device: int = 0, rank: int = 0, world: int = 1,
+                            uint8_is_l2: bool = False) -> Dict[Tuple[Any, Any], np.ndarray]:
+    """The pair loop of `matching.match_images_with_pairs` / `matching.match` (matching.py:63-98, 563-634) as one
+    batched submission: every image's descriptors are uploaded once, the pair list (this rank's shard of it) is
+    matched in one launch sequence, then per pair the reference's post-processing runs on the host:
+
+      * fewer than config["robust_matching_min_match"] descriptor matches -> empty result (:583-590);
+      * `robust_filter(im1, im2, matches) -> matches` (the geometric verification `_match_robust_impl`, :547-560 --
+        host-side geometry, outside this engine) if given, and the same gate on its output (:629-631);
+      * `unfilter_matches` when both images have a feature mask (:596-600).
+
+    descriptors: image -> the (masked) descriptor matrix `feature_loader.load_all_data(masked=True)` returns.
+    guided: None, or {"bearings": image -> n x 3, "poses": (im1, im2) -> (R, t), "threshold": rad}: pairs with a
+    pose are matched under the epipolar mask (`_match_descriptors_guided_impl`), always symmetric.
+    Returns {(im1, im2): int array [K, 2]} for this rank's pairs; `opensfm_b200.dist.gather_pair_results` merges
+    the ranks."""
+    sizes = {k: len(v) for k, v in descriptors.items()}
+    mine = shard_pairs(list(pairs), sizes, world)[rank] if world > 1 else list(pairs)
+    pm = PairMatcher(device=device)
+    needed = sorted({i for p in mine for i in p}, key=lambda k: str(k))
+    pm.add_many([(k, descriptors[k]) for k in needed], uint8_is_l2=uint8_is_l2)
+    gp = [p for p in mine if guided is not None and p in guided["poses"]]
+    up = [p for p in mine if not (guided is not None and p in guided["poses"])]
+    raw: Dict[Tuple[Any, Any], np.ndarray] = {}
+    if up:
+        raw.update(pm.match_pairs(up, config))
+    if gp:
+        for k in {i for p in gp for i in p}:
+            pm.set_bearings(k, guided["bearings"][k])
+        raw.update(pm.match_pairs_guided(gp, [guided["poses"][p] for p in gp], guided["threshold"], config))
+    min_match = int(config.get("robust_matching_min_match", 20))
+    out: Dict[Tuple[Any, Any], np.ndarray] = {}
+    empty = np.zeros((0, 2), dtype=np.int64)
+    for p in mine:
+        m = raw[p]
+        if len(m) < min_match:
+            out[p] = empty
+            continue
+        if robust_filter is not None:
+            m = np.asarray(robust_filter(p[0], p[1], m), dtype=np.int64).reshape(-1, 2)
+        if feature_masks is not None and feature_masks.get(p[0]) is not None and feature_masks.get(p[1]) is not None:
+            m = unfilter_matches(m, feature_masks[p[0]], feature_masks[p[1]])
+        out[p] = empty if len(m) < min_match else m
+    return out
+
+
 def shard_pairs(pairs: Sequence[Tuple[Any, Any]], sizes: Dict[Any, int], world: int) -> List[List[Tuple[Any, Any]]]:
     """Split a pair list over `world` GPUs: balanced sum(N_i * M_i), and pairs that share an image on the same GPU
     so that every rank uploads / keeps resident only ~1/world of the descriptor sets.

@@ -183,3 +183,14 @@ def test_bench_reference_arm_prints_the_contract_line():
         assert key in line, key
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["cpu_baseline"]["kind"] in ("port", "reference")
     assert line["match"]["value"] > 0
+
+
+def test_unfilter_matches_follows_the_reference():
+    m1 = np.array([1, 0, 1, 1, 0, 1], dtype=bool)
+    m2 = np.array([0, 1, 1, 0, 1], dtype=bool)
+    matches = np.array([[0, 2], [3, 0], [1, 1]])
+    # reference: [(flatnonzero(m1)[a], flatnonzero(m2)[b])] (matching.py:932-936)
+    i1, i2 = np.flatnonzero(m1), np.flatnonzero(m2)
+    want = np.array([(i1[a], i2[b]) for a, b in matches])
+    assert np.array_equal(matching.unfilter_matches(matches, m1, m2), want)
+    assert matching.unfilter_matches(np.zeros((0, 2)), m1, m2).shape == (0, 2)

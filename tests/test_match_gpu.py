@@ -222,3 +222,42 @@ def test_guided_matching_matches_the_reference_mask_and_matcher(n_desc, kernel):
         total += len(ref)
         assert 0.001 < mask.mean() < 0.2
     assert total > 50
+
+
+def test_match_images_with_pairs_driver_applies_the_reference_gates():
+    """matching.match (matching.py:563-634): min-match gate, robust filter hand-off, unfilter_matches."""
+    rng = np.random.RandomState(3)
+    feats, masks = {}, {}
+    base = syn.hahog_like_descriptors(900, 400)
+    for i in range(4):
+        idx = rng.choice(900, 600, replace=False)
+        feats["im%d" % i] = np.clip(base[idx] + rng.randint(-3, 4, (600, 128)), 0, 255).astype(np.float32)
+        m = np.zeros(800, dtype=bool)
+        m[rng.choice(800, 600, replace=False)] = True
+        masks["im%d" % i] = m
+    feats["junk"] = syn.hahog_like_descriptors(600, 999)          # shares nothing: fails the min-match gate
+    masks["junk"] = np.ones(600, dtype=bool)
+    pairs = [("im0", "im1"), ("im1", "im2"), ("im0", "junk"), ("im2", "im3")]
+    cfg = dict(CFG, robust_matching_min_match=20, symmetric_matching=True)
+    calls = []
+
+    def robust(im1, im2, m):
+        calls.append((im1, im2))
+        return m[::2]                                              # stand-in for the geometric verification
+
+    got = matching.match_images_with_pairs(feats, pairs, cfg, robust_filter=robust, feature_masks=masks)
+    for p in pairs:
+        ref = np.array(sorted(mo.match_brute_force_symmetric(feats[p[0]], feats[p[1]], cfg)), dtype=np.int64).reshape(-1, 2)
+        if len(ref) < 20:
+            assert p == ("im0", "junk") and len(got[p]) == 0 and p not in calls
+            continue
+        assert p in calls
+        want = matching.unfilter_matches(np.array(sorted(map(tuple, got_raw(p, feats, cfg))))[::2], masks[p[0]], masks[p[1]])
+        assert np.array_equal(np.array(sorted(map(tuple, got[p].tolist()))), np.array(sorted(map(tuple, want.tolist()))))
+
+
+def got_raw(p, feats, cfg):
+    # the device's own symmetric list in its (query-ordered) order: what the robust filter stand-in received
+    pm = matching.PairMatcher()
+    pm.add_many([(k, feats[k]) for k in p])
+    return pm.match_pairs([p], cfg)[p].tolist()
