@@ -93,6 +93,11 @@ int osfm_matcher_match_pairs_guided_async(osfm_matcher* m, int npairs, const int
 int osfm_matcher_sync(osfm_matcher* m);
 /* Copy the last batch's results to the host: concatenated per pair, n(ids_a[p]) entries each. */
 int osfm_matcher_fetch(osfm_matcher* m, int32_t* out_match, int64_t capacity);
+/* The last batch as the reference's lists: (query, train) int32 rows packed pair after pair in query order
+ * (matching.py:749-756, 775-777), compacted on the device.  offsets_out[npairs + 1] = first row of every pair,
+ * *total_rows = offsets_out[npairs] rows written to pairs_out (capacity_rows >= sum of n(ids_a[p]) always fits). */
+int osfm_matcher_fetch_pairs(osfm_matcher* m, int64_t* offsets_out, int32_t* pairs_out, int64_t capacity_rows,
+                             int64_t* total_rows);
 /* Milliseconds spent on the device by the last batch (CUDA events on the matcher's stream). */
 int osfm_matcher_last_device_ms(osfm_matcher* m, float* ms_total, float* ms_distance_kernel);
 /* 0 = pick automatically, 1 = force the exact SIMT kernel, 2 = force the tcgen05 kernel
@@ -100,6 +105,17 @@ int osfm_matcher_last_device_ms(osfm_matcher* m, float* ms_total, float* ms_dist
 int osfm_matcher_set_kernel(osfm_matcher* m, int which);
 /* Which distance kernel the last batch used: 1 = SIMT, 2 = tcgen05. */
 int osfm_matcher_last_kernel(osfm_matcher* m);
+
+/* WORDS matcher: features::match_using_words (opensfm/src/features/src/matching.cc:24-88; pyfeatures, called by
+ * matching.match_words, matching.py:636-656).  words1: n1 x words_per_feature nearest visual words of every feature
+ * of image 1; words2: the nearest word of every feature of image 2 (words2[:, 0] in the reference's call).
+ * out_match[i] = matched feature of image 2 or -1; the reference returns the rows (i, out_match[i]) with a match. */
+int osfm_match_words(osfm_matcher* m, const float* f1, int n1, const int32_t* words1, int words_per_feature,
+                     const float* f2, int n2, const int32_t* words2, int dim, float lowes_ratio, int max_checks,
+                     int32_t* out_match);
+/* features::compute_vlad_distances (matching.cc:122-145): Euclidean distance of VLAD descriptor `query` to each of
+ * the n descriptors (n x dim float32, row-major); out_n[query] = 0. */
+int osfm_vlad_distances(osfm_matcher* m, const float* vlad, int n, int dim, int query, double* out_n);
 
 /* ------------------------------------------------------------------------
  * BA
@@ -172,7 +188,16 @@ enum {
   OSFM_SIDE_UP_VECTOR = 0, OSFM_SIDE_PAN = 1, OSFM_SIDE_TILT = 2, OSFM_SIDE_ROLL = 3, OSFM_SIDE_RELATIVE_MOTION = 4,
   OSFM_SIDE_RELATIVE_ROTATION = 5, OSFM_SIDE_COMMON_POSITION = 6, OSFM_SIDE_LINEAR_MOTION = 7,
   OSFM_SIDE_TRANSLATION_PRIOR = 8, OSFM_SIDE_PARAMETER_BARRIER = 9, OSFM_SIDE_STD_DEVIATION = 10,
-  OSFM_SIDE_POSITION_PRIOR = 11, OSFM_SIDE_NUM_TYPES = 12
+  OSFM_SIDE_POSITION_PRIOR = 11,
+  /* ReconstructionAlignment (opensfm/src/bundle/reconstruction_alignment.h:140-365): "shots" are rig-instance blocks
+   * holding [R | t] world-to-camera, "reconstructions" are 7-parameter ext blocks [R | t | scale] (scale >= 0.1):
+   *   RA_RELATIVE_MOTION             [reconstruction, shot]  c = Rtai[6], scale_matrix[36]
+   *   RA_ABSOLUTE_POSITION           [shot]                  c = position[3], 1/std
+   *   RA_RELATIVE_ABSOLUTE_POSITION  [reconstruction]        c = position[3], shot[6], 1/std
+   *   RA_COMMON_POINT                [reconstruction a, b]   c = point_a[3], point_b[3], 1/std
+   *   RA_COMMON_CAMERA               [reconstruction a, b]   c = shot_a[6], shot_b[6], 1/std_centre, 1/std_rotation */
+  OSFM_SIDE_RA_RELATIVE_MOTION = 12, OSFM_SIDE_RA_ABSOLUTE_POSITION = 13, OSFM_SIDE_RA_RELATIVE_ABSOLUTE_POSITION = 14,
+  OSFM_SIDE_RA_COMMON_POINT = 15, OSFM_SIDE_RA_COMMON_CAMERA = 16, OSFM_SIDE_NUM_TYPES = 17
 };
 typedef struct {
   int32_t type, nres, nblocks;

@@ -64,9 +64,13 @@ SIGNATURES = {
                                                        c_int]),
     "osfm_matcher_sync": (c_int, [c_void_p]),
     "osfm_matcher_fetch": (c_int, [c_void_p, c_void_p, c_int64]),
+    "osfm_matcher_fetch_pairs": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, POINTER(c_int64)]),
     "osfm_matcher_last_device_ms": (c_int, [c_void_p, POINTER(c_float), POINTER(c_float)]),
     "osfm_matcher_set_kernel": (c_int, [c_void_p, c_int]),
     "osfm_matcher_last_kernel": (c_int, [c_void_p]),
+    "osfm_match_words": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_float,
+                                  c_int, c_void_p]),
+    "osfm_vlad_distances": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "osfm_ba_create": (c_int, [c_int, POINTER(c_void_p)]),
     "osfm_ba_destroy": (c_int, [c_void_p]),
     "osfm_camera_num_params": (c_int, [c_int]),

@@ -53,7 +53,10 @@ LOSS_NONE, LOSS_CAUCHY, LOSS_TUKEY = -1, 3, 5
 # block kinds of a side term / ids of the side-term types (include/opensfm_b200.h)
 SB_CAM, SB_INST, SB_RIGCAM, SB_EXT = 0, 1, 2, 3
 (SIDE_UP_VECTOR, SIDE_PAN, SIDE_TILT, SIDE_ROLL, SIDE_RELATIVE_MOTION, SIDE_RELATIVE_ROTATION, SIDE_COMMON_POSITION,
- SIDE_LINEAR_MOTION, SIDE_TRANSLATION_PRIOR, SIDE_PARAMETER_BARRIER, SIDE_STD_DEVIATION, SIDE_POSITION_PRIOR) = range(12)
+ SIDE_LINEAR_MOTION, SIDE_TRANSLATION_PRIOR, SIDE_PARAMETER_BARRIER, SIDE_STD_DEVIATION, SIDE_POSITION_PRIOR,
+ SIDE_RA_RELATIVE_MOTION, SIDE_RA_ABSOLUTE_POSITION, SIDE_RA_RELATIVE_ABSOLUTE_POSITION, SIDE_RA_COMMON_POINT,
+ SIDE_RA_COMMON_CAMERA) = range(17)
+LOSS_SOFTLONE = 2
 
 
 @dataclass

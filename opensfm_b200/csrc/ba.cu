@@ -132,6 +132,11 @@ __global__ void __launch_bounds__(128, NB) ba_linearize(BAView v, Params p, Scal
       if (nres == 3) s += r[2] * r[2];
       double w;
       cost = 0.5 * robust_loss(v.loss, v.loss_a, s, &w);
+      // a residual block whose parameter blocks are all constant is not part of the minimised cost (ceres removes
+      // it from the reduced program; its value only enters Summary::fixed_cost)
+      if (v.cam_poff[cam] < 0 && v.inst_poff[v.shot_inst[shot]] < 0 && (!use_rc || v.rc_poff[v.shot_rc[shot]] < 0) &&
+          v.pt_poff[pt] < 0)
+        cost = 0.0;
     } else {
       double r[3], jc[3 * MAX_CAM_PARAMS], jri[18], jrc[18], jp[9];
       const int nres = observation_eval(type, camp, ri, rc, use_rc, X, ox, oy, v.obs_isig[i], r, jc, jri, jrc, jp);
@@ -140,6 +145,8 @@ __global__ void __launch_bounds__(128, NB) ba_linearize(BAView v, Params p, Scal
       double w;
       cost = 0.5 * robust_loss(v.loss, v.loss_a, s, &w);
       const bool pfree = v.pt_poff[pt] >= 0;
+      if (!pfree && v.cam_poff[cam] < 0 && v.inst_poff[v.shot_inst[shot]] < 0 && (!use_rc || v.rc_poff[v.shot_rc[shot]] < 0))
+        cost = 0.0;   // all blocks constant: not part of the minimised cost (see MODE 0)
       const size_t N = (size_t)v.N;
       for (int k = 0; k < v.nres; ++k) {
         const bool live = k < nres;

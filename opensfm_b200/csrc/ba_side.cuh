@@ -156,6 +156,21 @@ OSFM_HD T diff_between_angles(const T& a, double b) {
   return d;
 }
 
+// reconstruction_alignment.h:224-234: point of the world frame -> frame of a reconstruction [R | t | scale]
+template <class T>
+OSFM_HD void ra_transform_point(const T* rec, const double* point, T* out) {
+  const T p[3] = {(T(point[0]) - rec[3]) / rec[6], (T(point[1]) - rec[4]) / rec[6], (T(point[2]) - rec[5]) / rec[6]};
+  const T Rt[3] = {-rec[0], -rec[1], -rec[2]};
+  aa_rotate_point(Rt, p, out);
+}
+// optical centre -R^t t of a constant shot [R | t] (world-to-camera parametrisation of RAShot)
+OSFM_HD void ra_shot_centre(const double* shot, double* c) {
+  const double Rt[3] = {-shot[0], -shot[1], -shot[2]};
+  double v[3];
+  aa_rotate_point<double>(Rt, shot + 3, v);
+  c[0] = -v[0]; c[1] = -v[1]; c[2] = -v[2];
+}
+
 // ---- term records ----------------------------------------------------------------------------
 constexpr int SIDE_MAX_BLOCKS = 6;
 constexpr int SIDE_MAX_RES = 7;
@@ -362,6 +377,74 @@ __device__ bool side_eval(const SideTerm& t, const double* __restrict__ c, T* co
       }
       return true;
     }
+    // ---- ReconstructionAlignment (opensfm/src/bundle/reconstruction_alignment.h): shots [R | t] world-to-camera,
+    //      reconstructions [R | t | scale] ----
+    case OSFM_SIDE_RA_RELATIVE_MOTION: {          // :140-197; blocks [reconstruction a, shot i]; c = Rtai[6], scale_matrix[36]
+      const T* rec = x[0]; const T* shot = x[1];
+      const T Rit[3] = {-shot[0], -shot[1], -shot[2]};
+      const T Rai[3] = {T(c[0]), T(c[1]), T(c[2])};
+      const T tai[3] = {T(c[3]), T(c[4]), T(c[5])};
+      const T Rait[3] = {-Rai[0], -Rai[1], -Rai[2]};
+      T qRai[4], qRa[4], qRit[4], q1[4], q2[4], e[6];
+      aa_to_quat(Rai, qRai); aa_to_quat(rec, qRa); aa_to_quat(Rit, qRit);
+      quat_product(qRa, qRit, q1);
+      quat_product(qRai, q1, q2);
+      quat_to_aa(q2, e);
+      T a[3], b[3], d[3];
+      aa_rotate_point(Rait, tai, a);
+      aa_rotate_point(Rit, shot + 3, b);
+      aa_rotate_point(rec, b, d);
+      for (int k = 0; k < 3; ++k) e[3 + k] = a[k] - rec[6] * d[k] + rec[3 + k];
+      for (int i = 0; i < 6; ++i) {
+        T s(0.0);
+        for (int j = 0; j < 6; ++j) s = s + T(c[6 + 6 * i + j]) * e[j];
+        r[i] = s;
+      }
+      return true;
+    }
+    case OSFM_SIDE_RA_ABSOLUTE_POSITION: {        // :199-222; block [shot]; c = prior[3], 1/std
+      const T* shot = x[0];
+      const T Rit[3] = {-shot[0], -shot[1], -shot[2]};
+      T v[3];
+      aa_rotate_point(Rit, shot + 3, v);
+      for (int k = 0; k < 3; ++k) r[k] = T(c[3]) * (T(c[k]) + v[k]);
+      return true;
+    }
+    case OSFM_SIDE_RA_RELATIVE_ABSOLUTE_POSITION: {   // :236-265; block [reconstruction]; c = prior[3], shot[6], 1/std
+      double centre[3];
+      ra_shot_centre(c + 3, centre);
+      T tr[3];
+      ra_transform_point(x[0], centre, tr);
+      for (int k = 0; k < 3; ++k) r[k] = T(c[9]) * (T(c[k]) - tr[k]);
+      return true;
+    }
+    case OSFM_SIDE_RA_COMMON_POINT: {             // :267-296; blocks [reconstruction a, b]; c = pa[3], pb[3], 1/std
+      T ta[3], tb[3];
+      ra_transform_point(x[0], c, ta);
+      ra_transform_point(x[1], c + 3, tb);
+      const T sf = x[0][6] + x[1][6];
+      for (int k = 0; k < 3; ++k) r[k] = T(c[6]) * sf * (ta[k] - tb[k]);
+      return true;
+    }
+    case OSFM_SIDE_RA_COMMON_CAMERA: {            // :298-365; blocks [reconstruction a, b]; c = shot_a[6], shot_b[6], 1/std_centre, 1/std_rotation
+      double pa[3], pb[3];
+      ra_shot_centre(c, pa);
+      ra_shot_centre(c + 6, pb);
+      T wa[3], wb[3];
+      ra_transform_point(x[0], pa, wa);
+      ra_transform_point(x[1], pb, wb);
+      const T Rbt[3] = {-x[1][0], -x[1][1], -x[1][2]};
+      const T Rbit[3] = {T(-c[6]), T(-c[7]), T(-c[8])};
+      const T Rai[3] = {T(c[0]), T(c[1]), T(c[2])};
+      T qRai[4], qRa[4], qRbt[4], qRbit[4], q1[4], q2[4], q3[4], e[3];
+      aa_to_quat(Rai, qRai); aa_to_quat(x[0], qRa); aa_to_quat(Rbt, qRbt); aa_to_quat(Rbit, qRbit);
+      quat_product(qRai, qRa, q1);
+      quat_product(q1, qRbt, q2);
+      quat_product(q2, qRbit, q3);
+      quat_to_aa(q3, e);
+      for (int k = 0; k < 3; ++k) { r[k] = e[k] * T(c[13]); r[3 + k] = T(c[12]) * (wa[k] - wb[k]); }
+      return true;
+    }
   }
   return false;
 }
@@ -417,7 +500,9 @@ __global__ void __launch_bounds__(SIDE_THREADS)
   if (j == 0) {
     double* ro = sv.r + sv.rofs[blockIdx.x];
     for (int q = 0; q < t.nres; ++q) ro[q] = w * r[q].v;
-    if (with_cost) atomicAdd(&sc_out->cost, 0.5 * rho);
+    bool any_free = false;   // all blocks constant: ceres drops the residual block from the minimised cost
+    for (int k = 0; k < t.nblocks; ++k) any_free |= sc.b[k].col >= 0;
+    if (with_cost && any_free) atomicAdd(&sc_out->cost, 0.5 * rho);
   }
 }
 
@@ -441,6 +526,9 @@ __global__ void side_cost(SideView sv, BAView v, BlkMaps bm, Params p, Scalars* 
     double w;
     cst = 0.5 * side_loss(t.loss, t.loss_a, s, &w);
     if (!ok) cst = __longlong_as_double(0x7ff8000000000000LL);
+    bool any_free = false;
+    for (int k = 0; k < t.nblocks; ++k) any_free |= sc.b[k].col >= 0;
+    if (!any_free) cst = 0.0;
   }
   const double tot = block_reduce_sum(cst);
   if (threadIdx.x == 0 && tot != 0.0) atomicAdd(&sc_out->cost, tot);

@@ -121,6 +121,9 @@ struct Matcher {
   DevBuf<uint8_t> staging, mask_buf;
   DevBuf<int> d_flags;
   DevBuf<uint32_t> d_mask_bits;
+  DevBuf<int> d_pair_counts;
+  DevBuf<long long> d_pair_off;
+  DevBuf<int32_t> d_pairs;
   DevBuf<double> d_epi_vec, d_epi_pose;
   PinnedBuf<double> p_epi_pose;
   PinnedBuf<MatchJob> p_jobs;
@@ -154,6 +157,7 @@ struct Matcher {
   void set_bearings(int id, const float* host_n_by_3);
   void sync();
   void fetch(int32_t* out, int64_t capacity);
+  long long fetch_pairs(long long* offsets_out, int32_t* pairs_out, long long capacity_rows);
   void last_ms(float* total, float* kernel);
   void one_shot(const void* f1, int n1, const void* f2, int n2, int dim, bool u8, double ratio,
                 const uint8_t* mask, bool symmetric, int32_t* out);

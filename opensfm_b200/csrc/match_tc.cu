@@ -401,9 +401,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         const TcTask t = tc_decode(jobs, tile_prefix, njobs, task);
         const int b = n & 1, qph = (n >> 1) & 1;
         mbar_wait(&bar_qempty[b], qph ^ 1, err_flag);
-        mbar_expect_tx(&bar_qfull[b], TC_Q_BYTES);
+        // the last query tile of a job may hold <= 128 rows: only its first half is loaded and multiplied
+        const uint32_t qbytes = (t.job.nq - t.q0 > TC_MH) ? TC_Q_BYTES : TC_Q_BYTES / 2;
+        mbar_expect_tx(&bar_qfull[b], qbytes);
         bulk_copy_g2s(q_smem[b], reinterpret_cast<const uint8_t*>(t.job.q_tc) + (size_t)t.q0 * TC_ROW_BYTES,
-                      TC_Q_BYTES, &bar_qfull[b]);
+                      qbytes, &bar_qfull[b]);
         for (int i = 0; i < t.ntiles; ++i) {
           mbar_wait(&bar_empty[stage], ph ^ 1, err_flag);
           mbar_expect_tx(&bar_full[stage], TC_T_BYTES);
@@ -424,6 +426,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         mbar_wait(&bar_qfull[b], qph, err_flag);
         const uint64_t adesc0 = make_smem_desc(smem_u32(q_smem[b]));
         const uint64_t adesc1 = make_smem_desc(smem_u32(q_smem[b]) + (TC_MH / 8) * TC_SBO);   // query rows 128..255
+        const bool two = t.job.nq - t.q0 > TC_MH;   // a short last tile skips the second MMA (its rows do not exist)
         for (int i = 0; i < t.ntiles; ++i, ++tilecount) {
           const int a = tilecount & 1, aph = (tilecount >> 1) & 1;
           mbar_wait(&bar_accempty[a], aph ^ 1, err_flag);
@@ -440,7 +443,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
             // one UMMA_K = 16 bf16 = two core matrices = 256 bytes along K
             const uint64_t koff = (uint64_t)((k * 2 * TC_LBO) >> 4);
             tc_mma_bf16(d_tmem, adesc0 + koff, bdesc0 + koff, TC_IDESC, k > 0 ? 1u : 0u);
-            tc_mma_bf16(d_tmem + TC_N, adesc1 + koff, bdesc0 + koff, TC_IDESC, k > 0 ? 1u : 0u);
+            if (two) tc_mma_bf16(d_tmem + TC_N, adesc1 + koff, bdesc0 + koff, TC_IDESC, k > 0 ? 1u : 0u);
           }
           tc_commit(&bar_empty[stage]);   // smem stage reusable when these MMAs retire
           tc_commit(&bar_accfull[a]);     // accumulator complete

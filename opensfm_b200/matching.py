@@ -130,6 +130,8 @@ class PairMatcher:
         self._ids: Dict[Any, int] = {}
         self._n: Dict[Any, int] = {}
         self._keep: Dict[Any, np.ndarray] = {}
+        self._rows: Optional[np.ndarray] = None
+        self._pairs: List[Tuple[Any, Any]] = []
         if kernel:
             _lib.check(self._m.L.osfm_matcher_set_kernel(self._m.h, int(kernel)))
 
@@ -225,9 +227,7 @@ class PairMatcher:
             _lib.check(self._m.L.osfm_matcher_match_pairs_guided_async(
                 self._m.h, len(chunk), ia.ctypes.data_as(ctypes.c_void_p), ib.ctypes.data_as(ctypes.c_void_p),
                 pose12.ctypes.data_as(ctypes.c_void_p), float(threshold), float(config["lowes_ratio"]), 1))
-            raw = self.fetch_raw()
-            counts = np.array([self._n[a] for a, _ in chunk], dtype=np.int64)
-            for pr, lst in zip(chunk, split_match_lists(raw, counts)):
+            for pr, lst in zip(chunk, self.fetch_lists()):
                 out[pr] = lst
             start = end
         return out
@@ -240,6 +240,21 @@ class PairMatcher:
         out = np.empty(max(total, 1), dtype=np.int32)
         _lib.check(self._m.L.osfm_matcher_fetch(self._m.h, out.ctypes.data_as(ctypes.c_void_p), total))
         return out[:total]
+
+    def fetch_lists(self) -> List[np.ndarray]:
+        """The last batch as one [K, 2] (query, train) array per pair, compacted on the device
+        (osfm_matcher_fetch_pairs): the host only slices one packed buffer."""
+        npairs = len(self._pairs)
+        cap = sum(self._n[a] for a, _ in self._pairs)
+        if self._rows is None or len(self._rows) < max(cap, 1):
+            self._rows = np.empty((max(cap, 1), 2), dtype=np.int32)
+        offs = np.empty(npairs + 1, dtype=np.int64)
+        total = ctypes.c_int64()
+        _lib.check(self._m.L.osfm_matcher_fetch_pairs(self._m.h, offs.ctypes.data_as(ctypes.c_void_p),
+                                                      self._rows.ctypes.data_as(ctypes.c_void_p), cap, ctypes.byref(total)))
+        rows = self._rows[:total.value].copy()
+        o = offs.tolist()
+        return [rows[o[p]:o[p + 1]] for p in range(npairs)]
 
     def device_ms(self) -> Tuple[float, float]:
         a, b = ctypes.c_float(), ctypes.c_float()
@@ -254,9 +269,55 @@ class PairMatcher:
         if symmetric is None:
             symmetric = bool(config.get("symmetric_matching", True))  # config.py:101
         self.submit(pairs, config["lowes_ratio"], symmetric)
-        raw = self.fetch_raw()
-        counts = np.array([self._n[a] for a, _ in self._pairs], dtype=np.int64)
-        return dict(zip(self._pairs, split_match_lists(raw, counts)))
+        return dict(zip(self._pairs, self.fetch_lists()))
+
+
+def match_words(f1: np.ndarray, words1: np.ndarray, f2: np.ndarray, words2: np.ndarray, config: Dict[str, Any],
+                device: int = 0) -> np.ndarray:
+    """matching.match_words (matching.py:636-656) -> pyfeatures.match_using_words
+    (opensfm/src/features/src/matching.cc:24-88) on the GPU.  Returns the int array [K, 2] of (feature of image 1,
+    feature of image 2) the reference returns; like the reference it reads every column of `words1` and the first
+    column of `words2`."""
+    f1 = np.ascontiguousarray(f1, dtype=np.float32)
+    f2 = np.ascontiguousarray(f2, dtype=np.float32)
+    w1 = np.ascontiguousarray(words1, dtype=np.int32)
+    w1 = w1.reshape(len(f1), -1)
+    w2 = np.ascontiguousarray(np.asarray(words2).reshape(len(f2), -1)[:, 0], dtype=np.int32)
+    if f1.ndim != 2 or f2.ndim != 2 or f1.shape[1] != f2.shape[1]:
+        raise ValueError("descriptor matrices must be n x dim with the same dim")
+    out = np.full(len(f1), -1, dtype=np.int32)
+    m = _thread_matcher(device)
+    _lib.check(m.L.osfm_match_words(m.h, f1.ctypes.data_as(ctypes.c_void_p), len(f1), w1.ctypes.data_as(ctypes.c_void_p),
+                                    w1.shape[1], f2.ctypes.data_as(ctypes.c_void_p), len(f2),
+                                    w2.ctypes.data_as(ctypes.c_void_p), f1.shape[1], float(config["lowes_ratio"]),
+                                    int(config["bow_num_checks"]), out.ctypes.data_as(ctypes.c_void_p)))
+    q = np.flatnonzero(out >= 0)
+    return np.stack([q, out[q]], axis=1).astype(np.int32)
+
+
+def match_words_symmetric(f1: np.ndarray, words1: np.ndarray, f2: np.ndarray, words2: np.ndarray,
+                          config: Dict[str, Any], device: int = 0) -> List[Tuple[int, int]]:
+    """matching.match_words_symmetric (matching.py:659-680)."""
+    mij = {(int(a), int(b)) for a, b in match_words(f1, words1, f2, words2, config, device)}
+    mji = {(int(b), int(a)) for a, b in match_words(f2, words2, f1, words1, config, device)}
+    return list(mij & mji)
+
+
+def vlad_distances(image: Any, other_images: Sequence[Any], histograms: Dict[Any, np.ndarray], device: int = 0):
+    """pairs_selection.vlad_distances (pairs_selection.py:690-708) -> pyfeatures.compute_vlad_distances
+    (features/src/matching.cc:122-145): (image, distances, other images) with the candidates that have a VLAD
+    descriptor, `image` itself skipped."""
+    if image not in histograms:
+        return image, [], []
+    others = [o for o in other_images if o != image and o in histograms]
+    if not others:
+        return image, [], []
+    mat = np.ascontiguousarray(np.stack([histograms[image]] + [histograms[o] for o in others]), dtype=np.float32)
+    out = np.zeros(len(mat), dtype=np.float64)
+    m = _thread_matcher(device)
+    _lib.check(m.L.osfm_vlad_distances(m.h, mat.ctypes.data_as(ctypes.c_void_p), mat.shape[0], mat.shape[1], 0,
+                                       out.ctypes.data_as(ctypes.c_void_p)))
+    return image, out[1:].tolist(), others
 
 
 def unfilter_matches(matches: np.ndarray, m1: np.ndarray, m2: np.ndarray) -> np.ndarray:

@@ -179,7 +179,9 @@ inline double eval_side_terms(Problem* pb, bool with_rows) {
     else if (st.loss == 5) tukey_loss(st.loss_a, s, rho);
     else loss_eval(st.loss, st.loss_a, s, rho);
     if (!ok) { cost = std::nan(""); rho[1] = 0.0; }
-    cost += 0.5 * rho[0];
+    bool any_free = false;  // Ceres removes residual blocks whose parameter blocks are all constant (fixed_cost)
+    for (int b = 0; b < st.nblocks; ++b) any_free |= br[b].col >= 0;
+    if (any_free) cost += 0.5 * rho[0];
     if (with_rows) {
       const double w = std::sqrt(rho[1]);
       for (int k = 0; k < st.nres; ++k) {
@@ -207,6 +209,14 @@ inline ObsCols obs_cols(const Problem& pb, int shot) {
   oc.goff[2] = pb.shot_use_rc[shot] ? pb.rc_poff[pb.shot_rc[shot]] : -1; oc.lsz[2] = 6;
   oc.lstart[2] = oc.lsz[0] + 6;
   return oc;
+}
+
+// every parameter block of the observation's residual block is constant: Ceres drops the block from the reduced
+// program (its cost only enters Summary::fixed_cost, not the minimised cost the tolerances look at)
+inline bool obs_all_constant(const Problem& pb, int64_t i) {
+  const int shot = pb.obs_shot[i];
+  return pb.cam_poff[pb.shot_cam[shot]] < 0 && pb.inst_poff[pb.shot_inst[shot]] < 0 &&
+         (!pb.shot_use_rc[shot] || pb.rc_poff[pb.shot_rc[shot]] < 0) && pb.pt_poff[pb.obs_point[i]] < 0;
 }
 
 }  // namespace
@@ -494,7 +504,7 @@ double oba_cost(void* h, double* reproj) {
     for (int k = 0; k < nres; ++k) s += r[k] * r[k];
     double rho[2];
     loss_eval(pb->loss, pb->loss_a, s, rho);
-    cost += 0.5 * rho[0];
+    if (!obs_all_constant(*pb, i)) cost += 0.5 * rho[0];
     if (reproj) {
       for (int k = 0; k < 3; ++k) reproj[3 * i + k] = k < nres ? r[k] * pb->obs_sigma[i] : 0.0;
     }
@@ -529,7 +539,7 @@ double oba_linearize(void* h) {
     for (int k = 0; k < nres; ++k) s += r[k] * r[k];
     double rho[2];
     loss_eval(pb->loss, pb->loss_a, s, rho);
-    cost += 0.5 * rho[0];
+    if (!obs_all_constant(*pb, i)) cost += 0.5 * rho[0];
     const double w = std::sqrt(rho[1]);
     pb->obs_nres[i] = nres;
     double* R = &pb->r[3 * i];

@@ -156,8 +156,20 @@ V3<T> ShotRotation(T const* const* p, int inst, int rc) {
 enum SideType {
   SIDE_UP_VECTOR = 0, SIDE_PAN, SIDE_TILT, SIDE_ROLL, SIDE_RELATIVE_MOTION, SIDE_RELATIVE_ROTATION,
   SIDE_COMMON_POSITION, SIDE_LINEAR_MOTION, SIDE_TRANSLATION_PRIOR, SIDE_PARAMETER_BARRIER, SIDE_STD_DEVIATION,
-  SIDE_POSITION_PRIOR
+  SIDE_POSITION_PRIOR, SIDE_RA_RELATIVE_MOTION, SIDE_RA_ABSOLUTE_POSITION, SIDE_RA_RELATIVE_ABSOLUTE_POSITION,
+  SIDE_RA_COMMON_POINT, SIDE_RA_COMMON_CAMERA
 };
+
+// reconstruction_alignment.h:224-234
+template <class T>
+void transform_point(const T* const reconstruction, const double* point, T* transformed) {
+  const T* const R = reconstruction + 0;
+  const T* const t = reconstruction + 3;
+  const T& scale = reconstruction[6];
+  T p_t_s[3] = {(T(point[0]) - t[0]) / scale, (T(point[1]) - t[1]) / scale, (T(point[2]) - t[2]) / scale};
+  T Rt[3] = {-R[0], -R[1], -R[2]};
+  AngleAxisRotatePoint(Rt, p_t_s, transformed);
+}
 
 // Returns false when the functor cannot be evaluated (RelativeMotionError with a zero scale).
 template <class T>
@@ -301,6 +313,102 @@ bool side_residual(int type, const double* c, const int* aux, T const* const* p,
         T scale = T(c[3 + k]);
         if (c[6] != 0.0) scale = scale / p[2][0];
         r[k] = scale * (inst[3 + k] - point);
+      }
+      return true;
+    }
+    // ---- ReconstructionAlignment functors (reconstruction_alignment.h) ----
+    case SIDE_RA_RELATIVE_MOTION: {  // :140-197
+      const T* const reconstruction_a = p[0];
+      const T* const shot_i = p[1];
+      T rr[6];
+      const T* const Ri = shot_i + 0;
+      const T* const Ra = reconstruction_a + 0;
+      T Rit[3] = {-Ri[0], -Ri[1], -Ri[2]};
+      const T* const ti = shot_i + 3;
+      const T* const ta = reconstruction_a + 3;
+      const T* const scale_a = reconstruction_a + 6;
+      T Rai[3] = {T(c[0]), T(c[1]), T(c[2])};
+      T tai[3] = {T(c[3]), T(c[4]), T(c[5])};
+      T Rait[3] = {-Rai[0], -Rai[1], -Rai[2]};
+      T qRai[4], qRa[4], qRit[4], qRa_Rit[4], qRai_Ra_Rit[4];
+      AngleAxisToQuaternion(Rai, qRai);
+      AngleAxisToQuaternion(Ra, qRa);
+      AngleAxisToQuaternion(Rit, qRit);
+      QuaternionProduct(qRa, qRit, qRa_Rit);
+      QuaternionProduct(qRai, qRa_Rit, qRai_Ra_Rit);
+      T Rai_Ra_Rit[3];
+      QuaternionToAngleAxis(qRai_Ra_Rit, Rai_Ra_Rit);
+      rr[0] = Rai_Ra_Rit[0]; rr[1] = Rai_Ra_Rit[1]; rr[2] = Rai_Ra_Rit[2];
+      T Rait_tai[3], Rit_ti[3], Ra_Rit_ti[3];
+      AngleAxisRotatePoint(Rait, tai, Rait_tai);
+      AngleAxisRotatePoint(Rit, ti, Rit_ti);
+      AngleAxisRotatePoint(Ra, Rit_ti, Ra_Rit_ti);
+      for (int k = 0; k < 3; ++k) rr[3 + k] = Rait_tai[k] - scale_a[0] * Ra_Rit_ti[k] + ta[k];
+      for (int i = 0; i < 6; ++i) {
+        r[i] = T(0.0);
+        for (int j = 0; j < 6; ++j) r[i] = r[i] + T(c[6 + 6 * i + j]) * rr[j];
+      }
+      return true;
+    }
+    case SIDE_RA_ABSOLUTE_POSITION: {  // :199-222
+      const T* const shot_i = p[0];
+      T Rit[3] = {-shot_i[0], -shot_i[1], -shot_i[2]};
+      T Rit_ti[3];
+      AngleAxisRotatePoint(Rit, shot_i + 3, Rit_ti);
+      for (int k = 0; k < 3; ++k) r[k] = T(c[3]) * (T(c[k]) + Rit_ti[k]);
+      return true;
+    }
+    case SIDE_RA_RELATIVE_ABSOLUTE_POSITION: {  // :236-265
+      const double* const Ri = c + 3;
+      const double* const ti = c + 6;
+      double Rit[3] = {-Ri[0], -Ri[1], -Ri[2]};
+      double Rit_ti[3];
+      AngleAxisRotatePoint(Rit, ti, Rit_ti);
+      double minus_Rit_ti[3] = {-Rit_ti[0], -Rit_ti[1], -Rit_ti[2]};
+      T transformed[3];
+      transform_point(p[0], minus_Rit_ti, transformed);
+      for (int k = 0; k < 3; ++k) r[k] = T(c[9]) * (T(c[k]) - transformed[k]);
+      return true;
+    }
+    case SIDE_RA_COMMON_POINT: {  // :267-296
+      T transformed_pai[3], transformed_pbi[3];
+      transform_point(p[0], c, transformed_pai);
+      transform_point(p[1], c + 3, transformed_pbi);
+      const T scale_factor = p[0][6] + p[1][6];
+      for (int k = 0; k < 3; ++k) r[k] = T(c[6]) * scale_factor * (transformed_pai[k] - transformed_pbi[k]);
+      return true;
+    }
+    case SIDE_RA_COMMON_CAMERA: {  // :298-365
+      const double* const rotation_ai = c;
+      const double* const rotation_bi = c + 6;
+      const double* const translation_ai = c + 3;
+      const double* const translation_bi = c + 9;
+      double pose_ai[3], pose_bi[3];
+      const double rotation_ait[3] = {-rotation_ai[0], -rotation_ai[1], -rotation_ai[2]};
+      AngleAxisRotatePoint(rotation_ait, translation_ai, pose_ai);
+      const double rotation_bit[3] = {-rotation_bi[0], -rotation_bi[1], -rotation_bi[2]};
+      AngleAxisRotatePoint(rotation_bit, translation_bi, pose_bi);
+      for (int i = 0; i < 3; ++i) { pose_ai[i] = -pose_ai[i]; pose_bi[i] = -pose_bi[i]; }
+      T world_pose_ai[3], world_pose_bi[3];
+      transform_point(p[0], pose_ai, world_pose_ai);
+      transform_point(p[1], pose_bi, world_pose_bi);
+      const T* const Ra = p[0];
+      const T* const Rb = p[1];
+      const T Rbt[3] = {-Rb[0], -Rb[1], -Rb[2]};
+      const T Rbit[3] = {T(-rotation_bi[0]), T(-rotation_bi[1]), T(-rotation_bi[2])};
+      const T Rai[3] = {T(rotation_ai[0]), T(rotation_ai[1]), T(rotation_ai[2])};
+      T qRai[4], qRa[4], qRbt[4], qRbit[4], qRai_qRa[4], qRai_qRa_qRbt[4], qRai_qRa_qRbt_qRbit[4];
+      AngleAxisToQuaternion(Rai, qRai);
+      AngleAxisToQuaternion(Ra, qRa);
+      AngleAxisToQuaternion(Rbt, qRbt);
+      AngleAxisToQuaternion(Rbit, qRbit);
+      QuaternionProduct(qRai, qRa, qRai_qRa);
+      QuaternionProduct(qRai_qRa, qRbt, qRai_qRa_qRbt);
+      QuaternionProduct(qRai_qRa_qRbt, qRbit, qRai_qRa_qRbt_qRbit);
+      QuaternionToAngleAxis(qRai_qRa_qRbt_qRbit, r);
+      for (int i = 0; i < 3; ++i) {
+        r[i] = r[i] * T(c[13]);
+        r[3 + i] = T(c[12]) * (world_pose_ai[i] - world_pose_bi[i]);
       }
       return true;
     }

@@ -146,3 +146,36 @@ def epipolar_mask(b1: np.ndarray, b2: np.ndarray, R: np.ndarray, t: np.ndarray, 
         e2 = e2 / np.linalg.norm(e2, axis=1, keepdims=True)
         sym = (np.abs(e1 @ b2w.T) + np.abs(b1 @ e2.T)) / 2.0
         return (np.pi / 2.0 - np.arccos(sym)) < threshold
+
+
+def match_using_words(f1: np.ndarray, words1: np.ndarray, f2: np.ndarray, words2_first: np.ndarray, lowes_ratio: float,
+                      max_checks: int) -> np.ndarray:
+    """features::MatchUsingWords restated (opensfm/src/features/src/matching.cc:15-72): multimap word -> features of
+    image 2 (equal words in insertion order), per feature of image 1 the walk over its words, float32 distances
+    summed in dimension order (np.cumsum in float32 is sequential), strict `<` updates, the `checks >= max_checks`
+    break after a word, and the float32 ratio test (a single candidate passes: second best = inf)."""
+    f1 = np.asarray(f1, dtype=np.float32)
+    f2 = np.asarray(f2, dtype=np.float32)
+    words1 = np.asarray(words1).reshape(len(f1), -1)
+    index2 = {}
+    for i, w in enumerate(np.asarray(words2_first).ravel().tolist()):
+        index2.setdefault(int(w), []).append(i)
+    out = []
+    ratio = np.float32(lowes_ratio)
+    for i in range(len(f1)):
+        best = second = np.float32(np.inf)
+        best_match, checks = -1, 0
+        for j in range(words1.shape[1]):
+            for match in index2.get(int(words1[i, j]), []):
+                t = f1[i] - f2[match]
+                d = np.sqrt(np.cumsum(t * t, dtype=np.float32)[-1])
+                if d < best:
+                    second, best, best_match = best, d, match
+                elif d < second:
+                    second = d
+                checks += 1
+            if checks >= max_checks:
+                break
+        if best < np.float32(ratio * second):
+            out.append((i, best_match))
+    return np.array(out, dtype=np.int32).reshape(-1, 2)

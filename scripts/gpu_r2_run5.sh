@@ -1,0 +1,13 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 1500 python -m pytest tests -m gpu -q --timeout 900 -x > gpurun_out/r2_run5_all.log 2>&1; echo "pytest exit: $?"; tail -12 gpurun_out/r2_run5_all.log
+( time timeout 1500 python bench.py > gpurun_out/r2_bench_v3.json 2> gpurun_out/r2_bench_v3.err ) 2> gpurun_out/r2_bench_v3.time; echo "bench exit: $?"; tail -3 gpurun_out/r2_bench_v3.err
+python - <<'PY'
+import json
+try:
+    d=json.loads(open('gpurun_out/r2_bench_v3.json').read().strip().splitlines()[-1])
+    print('BA', d['value'], d['value_run'], d['ba_ms_per_step'], 'e2e', d['e2e']['value'], d['roofline']['frac'])
+    m=d['match']; print('MATCH', m['value'], m['e2e']['value'], m['roofline']['frac'])
+    g=d['extras']['match_guided']; print('guided', g['value'], g['device_ms'], g['distance_kernel_ms'], g['e2e']['value'])
+except Exception as e: print('parse failed', e)
+PY

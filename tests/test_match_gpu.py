@@ -261,3 +261,43 @@ def got_raw(p, feats, cfg):
     pm = matching.PairMatcher()
     pm.add_many([(k, feats[k]) for k in p])
     return pm.match_pairs([p], cfg)[p].tolist()
+
+
+@pytest.mark.parametrize("integer", [True, False])
+def test_words_matcher_matches_the_restated_reference(integer):
+    """features::match_using_words (features/src/matching.cc:24-88) incl. its candidate order, the max_checks break
+    and the single-candidate case."""
+    rng = np.random.RandomState(5)
+    n1, n2, vocab, k = 700, 800, 120, 5
+    if integer:
+        a, b = _related(n1, n2, 55)
+    else:
+        a = rng.rand(n1, 128).astype(np.float32)
+        b = rng.rand(n2, 128).astype(np.float32)
+        b[:300] = a[:300] + rng.normal(0, 0.02, (300, 128)).astype(np.float32)
+    centers = a[rng.choice(n1, vocab, replace=False)]
+
+    def nearest_words(f, kk):
+        d = ((f[:, None, :].astype(np.float64) - centers[None].astype(np.float64)) ** 2).sum(2)
+        return np.argsort(d, axis=1, kind="stable")[:, :kk].astype(np.int32)
+
+    w1, w2 = nearest_words(a, k), nearest_words(b, k)
+    for checks in (20, 3):
+        cfg = {"lowes_ratio": 0.8, "bow_num_checks": checks}
+        got = matching.match_words(a, w1, b, w2, cfg)
+        ref = mo.match_using_words(a, w1, b, w2[:, 0], 0.8, checks)
+        assert np.array_equal(got, ref)
+    sym = matching.match_words_symmetric(a, w1, b, w2, {"lowes_ratio": 0.8, "bow_num_checks": 20})
+    r12 = {tuple(x) for x in mo.match_using_words(a, w1, b, w2[:, 0], 0.8, 20).tolist()}
+    r21 = {(y, x) for x, y in mo.match_using_words(b, w2, a, w1[:, 0], 0.8, 20).tolist()}
+    assert set(sym) == (r12 & r21) and len(sym) > 20
+
+
+def test_vlad_distances():
+    rng = np.random.RandomState(1)
+    hist = {"im%d" % i: rng.normal(0, 1, 64 * 128).astype(np.float32) for i in range(9)}
+    im, dist, others = matching.vlad_distances("im3", ["im%d" % i for i in range(9)] + ["missing"], hist)
+    assert im == "im3" and "im3" not in others and "missing" not in others and len(others) == 8
+    want = [float(np.linalg.norm(hist["im3"].astype(np.float64) - hist[o].astype(np.float64))) for o in others]
+    assert np.allclose(dist, want, rtol=1e-6)
+    assert matching.vlad_distances("nope", ["im0"], hist) == ("nope", [], [])
