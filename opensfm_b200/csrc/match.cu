@@ -492,43 +492,59 @@ __global__ void epi_vectors(const EpiPair* __restrict__ pairs) {
   }
 }
 __global__ void __launch_bounds__(256) epi_mask_bits(const EpiPair* __restrict__ pairs, double threshold) {
-  // the 32 rows of the block: [b1 | e1] as float32, read by every lane of the warp (shared-memory broadcast;
-  // the first version moved them with 6 shuffles per row and was shuffle-bound at 6e11 elements/s)
-  __shared__ float rows[8][32][8];
+  // One CTA = 256 x 256 elements = 8 x 8 blocks of 32 x 32; warp w owns column block w and walks the 8 row blocks.
+  // The 32 rows of a block ([b1 | e1] as float32) sit in shared memory and are read by every lane (broadcast);
+  // the row words (F) and column words (T) of the whole CTA tile are staged in shared memory and written as full
+  // 32-byte runs -- one word per (row, block) scattered straight to HBM made the kernel store-bound at 7e11
+  // elements/s.
+  __shared__ __align__(16) float rows[32][8];
+  __shared__ uint32_t sF[256][8], sT[256][8];
   const EpiPair& p = pairs[blockIdx.z];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-  const int jb = blockIdx.x * 8 + wib;   // 32-column block of this warp
-  const int ib = blockIdx.y;             // 32-row block
-  if (jb >= p.w2 || ib >= p.w1) return;  // warp-uniform
-  const int j = jb * 32 + lane, i = ib * 32 + lane;
+  const int jb0 = blockIdx.x * 8, ib0 = blockIdx.y * 8;
+  if (jb0 >= p.w2 || ib0 >= p.w1) return;   // CTA-uniform (pairs of different sizes share the grid)
+  const int jb = jb0 + wib;
+  const int j = jb * 32 + lane;
   const float NaNf = __int_as_float(0x7fc00000);
   float cj[6] = {NaNf, NaNf, NaNf, NaNf, NaNf, NaNf};
   if (j < p.n2) for (int e = 0; e < 6; ++e) cj[e] = (float)p.v2[6 * (size_t)j + e];
-  for (int e = 0; e < 6; ++e) rows[wib][lane][e] = i < p.n1 ? (float)p.v1[6 * (size_t)i + e] : NaNf;
-  __syncwarp();
   const float s_thr = (float)sin(threshold);
   const float lo = s_thr - 2e-6f, hi = s_thr + 2e-6f;
-  uint32_t colbits = 0;
-#pragma unroll 4
-  for (int r = 0; r < 32; ++r) {
-    const float4 ra = *reinterpret_cast<const float4*>(&rows[wib][r][0]);
-    const float2 rb = *reinterpret_cast<const float2*>(&rows[wib][r][4]);
-    // ra = (b1.x, b1.y, b1.z, e1.x), rb = (e1.y, e1.z)
-    const float sym = 0.5f * (fabsf(ra.w * cj[0] + rb.x * cj[1] + rb.y * cj[2]) + fabsf(ra.x * cj[3] + ra.y * cj[4] + ra.z * cj[5]));
-    bool in = sym < lo;               // NaN (missing row / column, degenerate epipolar plane) compares false
-    if (!(sym < lo) && sym < hi) {    // inside the guard band: the reference's own fp64 expression
+  for (int ibl = 0; ibl < 8; ++ibl) {
+    const int ib = ib0 + ibl;
+    __syncthreads();   // previous row block consumed
+    if (threadIdx.x < 192) {
+      const int r = threadIdx.x / 6, e = threadIdx.x - r * 6;
       const int gi = ib * 32 + r;
-      const double* a = p.v1 + 6 * (size_t)gi;
-      const double* c = p.v2 + 6 * (size_t)j;
-      const double sd = (fabs(a[3] * c[0] + a[4] * c[1] + a[5] * c[2]) + fabs(a[0] * c[3] + a[1] * c[4] + a[2] * c[5])) / 2.0;
-      in = (M_PI / 2.0 - acos(sd)) < threshold;
+      rows[r][e] = gi < p.n1 ? (float)p.v1[6 * (size_t)gi + e] : NaNf;
     }
-    const uint32_t rowbits = __ballot_sync(0xffffffffu, in);
-    const int gi = ib * 32 + r;
-    if (lane == 0 && gi < p.n1) p.F[(size_t)gi * p.w2 + jb] = rowbits;
-    if (in) colbits |= 1u << r;
+    __syncthreads();
+    uint32_t colbits = 0;
+#pragma unroll 4
+    for (int r = 0; r < 32; ++r) {
+      const float4 ra = *reinterpret_cast<const float4*>(&rows[r][0]);   // b1.x, b1.y, b1.z, e1.x
+      const float2 rb = *reinterpret_cast<const float2*>(&rows[r][4]);   // e1.y, e1.z
+      const float sym = 0.5f * (fabsf(ra.w * cj[0] + rb.x * cj[1] + rb.y * cj[2]) + fabsf(ra.x * cj[3] + ra.y * cj[4] + ra.z * cj[5]));
+      bool in = sym < lo;               // NaN (missing row / column, degenerate epipolar plane) compares false
+      if (!(sym < lo) && sym < hi) {    // inside the guard band: the reference's own fp64 expression
+        const double* a = p.v1 + 6 * (size_t)(ib * 32 + r);
+        const double* c = p.v2 + 6 * (size_t)j;
+        const double sd = (fabs(a[3] * c[0] + a[4] * c[1] + a[5] * c[2]) + fabs(a[0] * c[3] + a[1] * c[4] + a[2] * c[5])) / 2.0;
+        in = (M_PI / 2.0 - acos(sd)) < threshold;
+      }
+      const uint32_t rowbits = __ballot_sync(0xffffffffu, in);
+      if (lane == 0) sF[ibl * 32 + r][wib] = rowbits;
+      if (in) colbits |= 1u << r;
+    }
+    sT[wib * 32 + lane][ibl] = colbits;
   }
-  if (j < p.n2) p.T[(size_t)j * p.w1 + ib] = colbits;
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < 256 * 8; idx += 256) {
+    const int r = idx >> 3, w = idx & 7;
+    const int gi = ib0 * 32 + r, gj = jb0 * 32 + r;
+    if (gi < p.n1 && jb0 + w < p.w2) p.F[(size_t)gi * p.w2 + jb0 + w] = sF[r][w];
+    if (gj < p.n2 && ib0 + w < p.w1) p.T[(size_t)gj * p.w1 + ib0 + w] = sT[r][w];
+  }
 }
 
 // ---------------------------------------------------------------------------
@@ -896,7 +912,7 @@ void Matcher::match_pairs_async(int npairs, const int* ids_a, const int* ids_b, 
     for (const EpiPair& e : epi) { max_n = std::max({max_n, e.n1, e.n2}); max_w1 = std::max(max_w1, e.w1); max_w2 = std::max(max_w2, e.w2); }
     epi_vectors<<<dim3((max_n + 127) / 128, npairs), 128, 0, stream>>>(dp);
     OSFM_LAUNCH_CHECK();
-    epi_mask_bits<<<dim3((max_w2 + 7) / 8, max_w1, npairs), 256, 0, stream>>>(dp, epi_threshold);
+    epi_mask_bits<<<dim3((max_w2 + 7) / 8, (max_w1 + 7) / 8, npairs), 256, 0, stream>>>(dp, epi_threshold);
     OSFM_LAUNCH_CHECK();
   }
   OSFM_CUDA(cudaEventRecord(ev[1], stream));
