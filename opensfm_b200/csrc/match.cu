@@ -654,12 +654,13 @@ int Matcher::add_async(const void* host, int n, int dim, bool u8, bool u8_as_l2)
   s.dim_padded = row_bytes / 4;  // in 4-byte elements
   s.row_bytes = row_bytes;
   const bool tc = tc_capable(dim, u8, n);
+  const bool h8 = u8 && h8_capable(dim, n);     // Hamming on the tensor cores: +-1 fp8 operands
   const size_t data_bytes = ((size_t)std::max(n, 1) * row_bytes + 255) / 256 * 256;
-  s.rows_padded = tc ? tc_rows_padded(n) : 0;
-  const size_t tc_bytes = tc ? tc_operand_bytes(s.rows_padded) : 0;
+  s.rows_padded = (tc || h8) ? tc_rows_padded(n) : 0;
+  const size_t tc_bytes = tc ? tc_operand_bytes(s.rows_padded) : h8 ? h8_operand_bytes(s.rows_padded) : 0;
   char* chunk = static_cast<char*>(slab_alloc(data_bytes + tc_bytes, &s.slab));
   s.data = chunk;
-  s.tc_data = tc ? chunk + data_bytes : nullptr;
+  s.tc_data = (tc || h8) ? chunk + data_bytes : nullptr;
   if (tc) {
     if (d_info.p == nullptr) {
       d_info.reserve(2 * (size_t)MAX_SLOTS);
@@ -696,6 +697,7 @@ int Matcher::add_async(const void* host, int n, int dim, bool u8, bool u8_as_l2)
         pad_rows_kernel<float><<<blocks, threads, 0, stream>>>((const float*)staging.p, n, dim, (float*)s.data, row_bytes / 4);
       OSFM_LAUNCH_CHECK();
     }
+    if (h8) prepare_h8(s, static_cast<const uint8_t*>(s.data), row_bytes);
   }
   const int id = next_id++;
   sets[id] = s;
@@ -749,7 +751,7 @@ void Matcher::match_pairs_async(int npairs, const int* ids_a, const int* ids_b, 
   h_jobs.assign(njobs, MatchJob());
   h_prefix.assign(njobs + 1, 0);
   h_out_off.assign(npairs + 1, 0);
-  bool any_u8 = false, any_f32 = false, all_tc = true;
+  bool any_u8 = false, any_f32 = false, all_tc = true, all_h8 = true;
   long long total_qtiles = 0;
   int max_nq = 0, max_dim_padded = 0;
   for (int p = 0; p < npairs; ++p) {
@@ -765,6 +767,7 @@ void Matcher::match_pairs_async(int npairs, const int* ids_a, const int* ids_b, 
     // d^2 <= (|a| + |b|)^2 <= 2 (|a|^2 + |b|^2) must stay below 2^22 for the d^2-space ranking of the
     // tcgen05 kernel to equal cv2's sqrt-space ranking (float32 sqrt injective on integers < 2^22)
     all_tc &= (!A.u8 && A.tc_ok && B.tc_ok && 2.0f * (A.tc_max_norm + B.tc_max_norm) < 4194304.0f);
+    all_h8 &= (A.u8 && A.tc_ok && B.tc_ok && A.tc_q != nullptr && B.tc_q != nullptr);
     h_out_off[p + 1] = h_out_off[p] + A.n;
     for (int d = 0; d < ndir; ++d) {
       MatchJob& j = h_jobs[p * ndir + d];
@@ -831,6 +834,8 @@ void Matcher::match_pairs_async(int npairs, const int* ids_a, const int* ids_b, 
     use = 2;
   } else if (kernel_choice == 0 && all_tc && !dmask && any_f32 && tc_available()) {
     use = 2;   // (guided pairs too: the tensor-core epilogue applies the bitmask)
+  } else if (kernel_choice == 0 && all_h8 && any_u8 && !dmask && !guided && npairs > 0 && tc_available()) {
+    use = 3;   // Hamming as a +-1 fp8 contraction (match_tc.cu bf_top2_tc_h8)
   }
   last_kernel = use;
   last_total_results = h_out_off[npairs];
@@ -844,14 +849,14 @@ void Matcher::match_pairs_async(int npairs, const int* ids_a, const int* ids_b, 
       throw ArgError("float32 descriptors longer than 704 elements are not supported by the exact matcher");
     simt_tile = max_dim_padded > FX_MAX_DIM_T64 ? 32 : 64;
   }
-  const int tile_m = use == 2 ? tc_tile_m() : simt_tile;
-  const int chunk_unit = use == 2 ? tc_tile_n() : simt_tile;
+  const int tile_m = use == 2 ? tc_tile_m() : use == 3 ? h8_tile_m() : simt_tile;
+  const int chunk_unit = use == 2 ? tc_tile_n() : use == 3 ? h8_tile_n() : simt_tile;
   long long tiles_total = 0;
-  if (use == 2 || simt_tile != BM) {
+  if (use >= 2 || simt_tile != BM) {
     total_qtiles = 0;
     for (auto& j : h_jobs) { j.qtiles = (j.nq + tile_m - 1) / tile_m; total_qtiles += j.qtiles; }
   }
-  const long long target = (long long)num_sms * (use == 2 ? 2 : 4);
+  const long long target = (long long)num_sms * (use >= 2 ? 2 : 4);
   long long partial_total = 0, match_total = 0;
   for (int i = 0; i < njobs; ++i) {
     MatchJob& j = h_jobs[i];
@@ -919,6 +924,8 @@ void Matcher::match_pairs_async(int npairs, const int* ids_a, const int* ids_b, 
   if (tiles_total > 0) {
     if (use == 2) {
       launch_tc(*this, njobs, (int)tiles_total, guided);
+    } else if (use == 3) {
+      launch_tc_h8(*this, njobs, (int)tiles_total);
     } else if (any_u8) {
       bf_top2_simt<true><<<(unsigned)tiles_total, 256, 0, stream>>>(d_jobs.p, d_prefix.p, njobs, d_partial.p);
       OSFM_LAUNCH_CHECK();

@@ -108,7 +108,7 @@ struct Matcher {
   long long last_total_results = 0;
   int last_npairs = 0;
   bool results_in_match_buf = true;
-  bool tc_attr_set = false, tcm_attr_set = false, fx_attr_set = false;
+  bool tc_attr_set = false, tcm_attr_set = false, fx_attr_set = false, h8_attr_set = false;
   std::map<int, DescSet> sets;
   std::vector<MatchJob> h_jobs;
   std::vector<int> h_prefix;
@@ -163,6 +163,7 @@ struct Matcher {
                 const uint8_t* mask, bool symmetric, int32_t* out);
   // match_tc.cu
   void prepare_tc(DescSet& s, const void* src, bool src_u8, float* padded_dst);
+  void prepare_h8(DescSet& s, const uint8_t* src, int src_stride);   // +-1 fp8 operands of a Hamming set
 };
 
 // match_tc.cu
@@ -173,5 +174,11 @@ void launch_tc(Matcher& m, int njobs, int ntiles, bool masked);
 int tc_rows_padded(int n);
 size_t tc_operand_bytes(int rows_padded);
 bool tc_capable(int dim, bool u8, int n);
+// tensor-core Hamming (match_tc.cu)
+int h8_tile_m();
+int h8_tile_n();
+size_t h8_operand_bytes(int rows_padded);
+bool h8_capable(int nbytes, int n);
+void launch_tc_h8(Matcher& m, int njobs, int ntiles);
 
 }  // namespace osfm

@@ -521,6 +521,274 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
   }
 }
 
+// ===========================================================================================================
+// Hamming distance on the tensor cores ("BruteForce-Hamming": AKAZE MLDB 61 bytes, ORB 32 bytes).
+//
+// Bits become +-1 in fp8 (E4M3: +1 = 0x38, -1 = 0xB8, both exact): for two descriptors a, b of nbits bits
+//     sum_i a_i b_i = (#equal bits) - (#different bits) = nbits - 2 H(a, b),
+// so with the train operand negated the fp32 accumulator is 2 H - nbits, an exact integer, and its ranking inside
+// a query row is cv2's ranking by Hamming distance (ties -> lowest index through the same epilogue as the L2
+// kernel).  K = 512 fp8 per row; positions beyond nbits are 0 in real rows of both roles (they add nothing),
+// +1 in every query row and +448 in the *padding* rows of a train set, so a padding train scores
+// >= 8 * 448 - nbits > any real one and is never selected (needs >= 8 spare positions: nbytes <= 63).
+// `tcgen05.mma.kind::f8f6f4`, M = 128, N = 128, K = 32 x 16; operands in the same no-swizzle K-major core-matrix
+// order as the bf16 kernel (a core matrix row is 16 bytes = 16 fp8), 512 B per row.  1 CTA / SM, 10 warps:
+// bulk-copy producer (Q tile single-buffered: 64 KB, T tiles 2 x 64 KB), MMA issuer (2 accumulator stages of 128
+// TMEM columns), 8 epilogue warps = 4 lane quarters x 2 column halves (one 64-column TMEM load per warp and tile).
+// The popcount kernel this replaces is bound by the POPC pipe (16 / clk / SM): 2.1e11 pairs/s at 74 % of that roof.
+// ===========================================================================================================
+constexpr int H8_M = 128, H8_N = 128;
+constexpr int H8_ROW_BYTES = 512;
+constexpr int H8_KCH = H8_ROW_BYTES / 16;         // 16-byte K chunks per row
+constexpr int H8_SBO = H8_KCH * 128;              // bytes between 8-row groups
+constexpr int H8_Q_BYTES = H8_M * H8_ROW_BYTES;   // 65536
+constexpr int H8_T_BYTES = H8_N * H8_ROW_BYTES;   // 65536
+constexpr int H8_STAGES = 2;
+constexpr int H8_SMEM = H8_Q_BYTES + H8_STAGES * H8_T_BYTES;   // 196608
+// c_format F32 (1) @4, a/b format E4M3 (0) @7/@10, K-major, n_dim = N>>3 @17, m_dim = M>>4 @24
+constexpr uint32_t H8_IDESC = (1u << 4) | ((uint32_t)(H8_N >> 3) << 17) | ((uint32_t)(H8_M >> 4) << 24);
+
+int h8_tile_m() { return H8_M; }
+int h8_tile_n() { return H8_N; }
+size_t h8_operand_bytes(int rows_padded) { return 2 * (size_t)rows_padded * H8_ROW_BYTES; }
+bool h8_capable(int nbytes, int n) { return nbytes >= 1 && nbytes <= 63 && n > 0 && tc_available(); }
+
+// one thread per (row, 16-byte K chunk): 16 bits of the source row -> 16 fp8 values in both roles
+__global__ void __launch_bounds__(256)
+    h8_prepare_set(const uint8_t* __restrict__ src, int n, int nbytes, int src_stride, int rows_padded, uint8_t* __restrict__ qa,
+                   uint8_t* __restrict__ tb) {
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (size_t)rows_padded * H8_KCH) return;
+  const int row = (int)(idx / H8_KCH), c = (int)(idx % H8_KCH);
+  const int nbits = nbytes * 8;
+  __align__(16) uint8_t a[16], b[16];
+#pragma unroll
+  for (int e = 0; e < 16; ++e) {
+    const int bit = c * 16 + e;
+    uint8_t va = 0, vb = 0;
+    if (row < n) {
+      if (bit < nbits) {
+        const int on = (src[(size_t)row * src_stride + (bit >> 3)] >> (bit & 7)) & 1;
+        va = on ? 0x38 : 0xB8;   // +1 / -1
+        vb = on ? 0xB8 : 0x38;   // negated
+      } else {
+        va = 0x38;               // +1 against the padding trains' markers
+      }
+    } else if (bit >= nbits) {
+      vb = 0x7E;                 // +448: a padding train can never win
+    }
+    a[e] = va; b[e] = vb;
+  }
+  const size_t off = ((size_t)(row >> 3) * H8_KCH + c) * 128 + (row & 7) * 16;
+  *reinterpret_cast<uint4*>(qa + off) = *reinterpret_cast<const uint4*>(a);
+  *reinterpret_cast<uint4*>(tb + off) = *reinterpret_cast<const uint4*>(b);
+}
+
+void Matcher::prepare_h8(DescSet& s, const uint8_t* src, int src_stride) {
+  const size_t op_bytes = (size_t)s.rows_padded * H8_ROW_BYTES;
+  uint8_t* qa = reinterpret_cast<uint8_t*>(s.tc_data);
+  uint8_t* tb = qa + op_bytes;
+  const size_t total = (size_t)s.rows_padded * H8_KCH;
+  h8_prepare_set<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(src, s.n, s.dim, src_stride, s.rows_padded, qa, tb);
+  OSFM_LAUNCH_CHECK();
+  s.tc_q = reinterpret_cast<const __nv_bfloat16*>(qa);
+  s.tc_t = reinterpret_cast<const __nv_bfloat16*>(tb);
+  s.tc_norm = nullptr;
+  s.tc_ok = true;
+}
+
+__device__ __forceinline__ void tc_mma_f8(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n.reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f8f6f4 [%0], %1, %2, %3, p;\n}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ uint64_t h8_smem_desc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3fff);
+  d |= (uint64_t)((TC_LBO >> 4) & 0x3fff) << 16;
+  d |= (uint64_t)((H8_SBO >> 4) & 0x3fff) << 32;
+  d |= (uint64_t)1 << 46;
+  return d;
+}
+
+struct H8Task {
+  MatchJob job;
+  int q0, t_begin, ntiles, chunk;
+};
+__device__ __forceinline__ H8Task h8_decode(const MatchJob* jobs, const int* tile_prefix, int njobs, int task) {
+  int lo = 0, hi = njobs - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (tile_prefix[mid] <= task) lo = mid; else hi = mid - 1;
+  }
+  H8Task t;
+  t.job = jobs[lo];
+  const int local = task - tile_prefix[lo];
+  const int qtile = local / t.job.nchunks;
+  t.chunk = local % t.job.nchunks;
+  t.q0 = qtile * H8_M;
+  t.t_begin = t.chunk * t.job.chunk_len;
+  const int t_end = min(t.job.nt, t.t_begin + t.job.chunk_len);
+  t.ntiles = (t_end - t.t_begin + H8_N - 1) / H8_N;
+  return t;
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+    bf_top2_tc_h8(const MatchJob* __restrict__ jobs, const int* __restrict__ tile_prefix, int njobs, int ntasks,
+                  Top2* __restrict__ partial, int* __restrict__ err_flag) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ __align__(8) uint64_t bar_qfull, bar_qempty, bar_full[H8_STAGES], bar_empty[H8_STAGES], bar_accfull[2],
+      bar_accempty[2];
+  __shared__ uint32_t tmem_base_smem;
+  __shared__ float4 merge_buf[H8_M];
+  uint8_t* q_smem = smem;
+  uint8_t* t_smem[H8_STAGES];
+#pragma unroll
+  for (int st = 0; st < H8_STAGES; ++st) t_smem[st] = smem + H8_Q_BYTES + st * H8_T_BYTES;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    mbar_init(&bar_qfull, 1);
+    mbar_init(&bar_qempty, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&bar_accfull[i], 1);
+      mbar_init(&bar_accempty[i], TC_EPI_WARPS);
+    }
+    for (int i = 0; i < H8_STAGES; ++i) {
+      mbar_init(&bar_full[i], 1);
+      mbar_init(&bar_empty[i], 1);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 256;" ::"r"(smem_u32(&tmem_base_smem))
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_smem;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0, ph = 0, n = 0;
+      for (int task = blockIdx.x; task < ntasks; task += gridDim.x, ++n) {
+        const H8Task t = h8_decode(jobs, tile_prefix, njobs, task);
+        mbar_wait(&bar_qempty, (n & 1) ^ 1, err_flag);
+        mbar_expect_tx(&bar_qfull, H8_Q_BYTES);
+        bulk_copy_g2s(q_smem, reinterpret_cast<const uint8_t*>(t.job.q_tc) + (size_t)t.q0 * H8_ROW_BYTES, H8_Q_BYTES, &bar_qfull);
+        for (int i = 0; i < t.ntiles; ++i) {
+          mbar_wait(&bar_empty[stage], ph ^ 1, err_flag);
+          mbar_expect_tx(&bar_full[stage], H8_T_BYTES);
+          bulk_copy_g2s(t_smem[stage],
+                        reinterpret_cast<const uint8_t*>(t.job.t_tc) + (size_t)(t.t_begin + i * H8_N) * H8_ROW_BYTES,
+                        H8_T_BYTES, &bar_full[stage]);
+          if (++stage == H8_STAGES) { stage = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      int stage = 0, ph = 0, n = 0, tilecount = 0;
+      for (int task = blockIdx.x; task < ntasks; task += gridDim.x, ++n) {
+        const H8Task t = h8_decode(jobs, tile_prefix, njobs, task);
+        mbar_wait(&bar_qfull, n & 1, err_flag);
+        const uint64_t adesc0 = h8_smem_desc(smem_u32(q_smem));
+        for (int i = 0; i < t.ntiles; ++i, ++tilecount) {
+          const int a = tilecount & 1, aph = (tilecount >> 1) & 1;
+          mbar_wait(&bar_accempty[a], aph ^ 1, err_flag);
+          mbar_wait(&bar_full[stage], ph, err_flag);
+          tc_fence_after();
+          const uint64_t bdesc0 = h8_smem_desc(smem_u32(t_smem[stage]));
+          const uint32_t d_tmem = tmem_base + (uint32_t)a * H8_N;
+#pragma unroll
+          for (int k = 0; k < H8_ROW_BYTES / 32; ++k) {
+            // one UMMA_K = 32 fp8 = two core matrices = 256 bytes along K
+            const uint64_t koff = (uint64_t)((k * 2 * TC_LBO) >> 4);
+            tc_mma_f8(d_tmem, adesc0 + koff, bdesc0 + koff, H8_IDESC, k > 0 ? 1u : 0u);
+          }
+          tc_commit(&bar_empty[stage]);
+          tc_commit(&bar_accfull[a]);
+          if (++stage == H8_STAGES) { stage = 0; ph ^= 1; }
+        }
+        tc_commit(&bar_qempty);
+      }
+    }
+  } else {
+    const int quarter = warp & 3;
+    const int half = (warp - 2) >> 2;          // column half of the 128-wide tile
+    const int row_in_tile = quarter * 32 + lane;
+    int tilecount = 0;
+    for (int task = blockIdx.x; task < ntasks; task += gridDim.x) {
+      const H8Task t = h8_decode(jobs, tile_prefix, njobs, task);
+      const int gq = t.q0 + row_in_tile;
+      const float nbits = (float)(t.job.dim * 8);
+      RowState st;
+      st.q1 = st.q2 = __builtin_huge_valf();
+      st.i1 = st.i2 = -1;
+      for (int i = 0; i < t.ntiles; ++i, ++tilecount) {
+        const int a = tilecount & 1, aph = (tilecount >> 1) & 1;
+        mbar_wait(&bar_accfull[a], aph, err_flag);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)a * H8_N + (uint32_t)half * 64;
+        const int col_base = t.t_begin + i * H8_N + half * 64;
+        uint32_t va[64];
+        OSFM_TMEM_LD64(taddr, va);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bar_accempty[a]);
+        row_consume16<0, 64, false>(st, va, col_base, 0u);
+        row_consume16<16, 64, false>(st, va, col_base + 16, 0u);
+        row_consume16<32, 64, false>(st, va, col_base + 32, 0u);
+        row_consume16<48, 64, false>(st, va, col_base + 48, 0u);
+      }
+      // merge the two column halves of a row (lexicographic (distance, index), like cv2's insertion order)
+      if (half == 1) merge_buf[row_in_tile] = make_float4(st.q1, __int_as_float(st.i1), st.q2, __int_as_float(st.i2));
+      asm volatile("bar.sync 1, %0;" ::"r"(32 * TC_EPI_WARPS) : "memory");
+      if (half == 0) {
+        const float4 o = merge_buf[row_in_tile];
+        Top2 a2, b2;
+        a2.s1 = st.q1; a2.i1 = st.i1; a2.s2 = st.q2; a2.i2 = st.i2;
+        b2.s1 = o.x; b2.i1 = __float_as_int(o.y); b2.s2 = o.z; b2.i2 = __float_as_int(o.w);
+        top2_merge(a2, b2);
+        if (gq < t.job.nq) {
+          Top2 out;   // accumulator = 2 H - nbits  ->  the Hamming distance cv2 reports (an integer as float)
+          out.s1 = a2.i1 >= 0 ? (a2.s1 + nbits) * 0.5f : __builtin_huge_valf();
+          out.i1 = a2.i1;
+          out.s2 = a2.i2 >= 0 ? (a2.s2 + nbits) * 0.5f : __builtin_huge_valf();
+          out.i2 = a2.i2;
+          partial[t.job.partial_off + (size_t)t.chunk * t.job.nq + gq] = out;
+        }
+      }
+      asm volatile("bar.sync 1, %0;" ::"r"(32 * TC_EPI_WARPS) : "memory");
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;" ::"r"(tmem_base) : "memory");
+  }
+}
+
+void launch_tc_h8(Matcher& m, int njobs, int ntasks) {
+  if (!m.h8_attr_set) {
+    OSFM_CUDA(cudaFuncSetAttribute(bf_top2_tc_h8, cudaFuncAttributeMaxDynamicSharedMemorySize, H8_SMEM));
+    m.h8_attr_set = true;
+  }
+  m.d_flags.reserve(4);
+  OSFM_CUDA(cudaMemsetAsync(m.d_flags.p + 1, 0, sizeof(int), m.stream));
+  const int grid = std::min(ntasks, m.num_sms);
+  bf_top2_tc_h8<<<grid, TC_THREADS, H8_SMEM, m.stream>>>(m.d_jobs.p, m.d_prefix.p, njobs, ntasks, m.d_partial.p, m.d_flags.p + 1);
+  OSFM_LAUNCH_CHECK();
+}
+
 void launch_tc(Matcher& m, int njobs, int ntasks, bool masked) {
   if (!m.tc_attr_set) {   // per matcher (= per device)
     OSFM_CUDA(cudaFuncSetAttribute(bf_top2_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));

@@ -8,6 +8,7 @@ import json
 import subprocess
 import sys
 
+OUT = "profiles/r02_traffic.json"
 UNIT = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
 
 
@@ -30,7 +31,7 @@ def main(paths):
         e["dram_bytes_per_launch"] = e["dram_bytes"] / e["launches"]
         e["ncu_time_per_launch"] = e.pop("ncu_time") / e["launches"]
         del e["dram_bytes"]
-    json.dump(out, open("profiles/r01_traffic.json", "w"), indent=1, sort_keys=True)
+    json.dump(out, open(OUT, "w"), indent=1, sort_keys=True)
     print(json.dumps(out, indent=1, sort_keys=True))
 
 

@@ -112,6 +112,30 @@ def test_hamming(nbytes):
         mo.match_brute_force_symmetric(u1, u2, CFG))
 
 
+@pytest.mark.parametrize("nbytes,n1,n2", [(61, 3000, 2700), (32, 1234, 4321), (4, 600, 700), (63, 130, 129)])
+def test_hamming_tensor_core_kernel(nbytes, n1, n2):
+    """Binary descriptors with at most 63 bytes run as a +-1 fp8 contraction on the tensor cores (kernel id 3);
+    results are cv2's, ties included (4-byte descriptors: nearly every row has tied candidates), and equal to the
+    popcount kernel's."""
+    u1 = syn.binary_descriptors(n1, 11, nbytes)
+    u2 = syn.binary_descriptors(n2, 12, nbytes)
+    k = min(n1, n2) // 3
+    u2[:k] = u1[:k]
+    u2[:k, :2] ^= 9
+    got = {}
+    for kernel in (0, 1):
+        pm = matching.PairMatcher(kernel=kernel)
+        pm.add("a", u1)
+        pm.add("b", u2)
+        got[kernel] = pm.match_pairs([("a", "b")], CFG, symmetric=False)[("a", "b")]
+        assert pm.last_kernel() == (3 if kernel == 0 else 1)
+        sym = pm.match_pairs([("a", "b")], CFG, symmetric=True)[("a", "b")]
+        assert _pairset(sym) == _pairset(mo.match_brute_force_symmetric(u1, u2, CFG))
+    want = np.asarray(mo.match_brute_force(u1, u2, CFG), dtype=np.int64).reshape(-1, 2)
+    assert np.array_equal(np.asarray(got[0], dtype=np.int64).reshape(-1, 2), want)
+    assert np.array_equal(np.asarray(got[1], dtype=np.int64).reshape(-1, 2), want)
+
+
 def test_empty_inputs():
     a = np.zeros((0, 128), np.float32)
     b = syn.hahog_like_descriptors(10, 1)
