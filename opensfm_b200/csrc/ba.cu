@@ -617,6 +617,27 @@ __global__ void ba_grad_max(const double* grad, int n, Scalars* sc) {
 
 }  // namespace osfm
 #include "ba_reduced.cuh"
+#include "ba_schur_pipe.cuh"
+
+#include <tuple>
+#include <utility>
+
+namespace osfm {
+// The PCG kernels synchronise the whole grid through their own barrier (flags in global memory): every CTA must be
+// resident at the same time.  A cooperative launch makes the runtime check that (it fails with
+// cudaErrorCooperativeLaunchTooLarge instead of deadlocking when the grid cannot be co-resident).
+template <typename... KArgs, size_t... I>
+inline void launch_cooperative_impl(void (*kern)(KArgs...), int grid, int block, size_t smem, cudaStream_t st,
+                                    std::tuple<KArgs...>& a, std::index_sequence<I...>) {
+  void* ptrs[] = {static_cast<void*>(&std::get<I>(a))...};
+  OSFM_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(kern), dim3(grid), dim3(block), ptrs, smem, st));
+}
+template <typename... KArgs, typename... Args>
+inline void launch_cooperative(void (*kern)(KArgs...), int grid, int block, size_t smem, cudaStream_t st, Args&&... args) {
+  std::tuple<KArgs...> a(std::forward<Args>(args)...);
+  launch_cooperative_impl(kern, grid, block, smem, st, a, std::index_sequence_for<KArgs...>{});
+}
+}  // namespace osfm
 static_assert(osfm::CG_KMAX == osfm::SEG_KMAX, "colnorm tiles hold the widest segment");
 #include "ba_side.cuh"
 #include "ba_order.cuh"
@@ -920,6 +941,11 @@ struct BA {
   DevBuf<unsigned long long> d_prof;
   bool seg_attr = false, mma_attr = false, cg_attr = false;   // per handle (= per device): dynamic shared-memory opt-in done
   DevBuf<long long> d_tab_off, d_tab_sizes;
+  DevBuf<int> d_sp_nch, d_sp_chunk0;       // chunks per segment / first chunk of every segment (ba_schur_pipe)
+  DevBuf<SchurChunk> d_sp_chunks;
+  DevBuf<int> d_sp_ftab;                   // flush destinations per segment (sp_flush_tables)
+  int sp_nchunks = 0;
+  bool sp_attr = false;
   DevBuf<int> d_tab;
   PcgPipe pcg_pipe{};
   bool pcg_pipe_ok = false;
@@ -1723,6 +1749,8 @@ void BA::run() {
   }
   // per-segment tables of the tensor-core Schur kernel (columns, block offsets, Jacobi scales): constant from here on
   static const bool use_mma = []() { const char* e = getenv("OSFM_BA_SCHUR_MMA"); return !(e && e[0] == '0'); }();
+  bool use_pipe = false;
+  sp_nchunks = 0;
   if (nseg > 0 && use_mma && nblk > 0) {
     d_tab_off.reserve((size_t)nseg + 1); d_tab_sizes.reserve((size_t)nseg + 1);
     ba_seg_table_sizes<<<grid_for(nseg + 1, 256), 256, 0, stream>>>(v, d_seg_start.p, nseg, d_tab_sizes.p);
@@ -1738,6 +1766,30 @@ void BA::run() {
     d_tab.reserve((size_t)total_ints + 2);
     ba_seg_tables<<<nseg, 128, 0, stream>>>(v, bm, bsr, d_seg_start.p, d_scale.p, d_tab_off.p, d_tab.p);
     OSFM_LAUNCH_CHECK();
+    // chunk list of the persistent Schur kernel (ba_schur_pipe.cuh)
+    static const bool pipe_on = []() { const char* e = getenv("OSFM_BA_SCHUR_PIPE"); return !(e && e[0] == '0'); }();
+    // (the flush table holds offset << 2: the reduced system must stay below 2^29 doubles; 20 KB of table per segment)
+    use_pipe = pipe_on && v.nres * (wc + 4) <= SP_ROWS && s_upper_total + (long long)nc_pad < (1LL << 29) &&
+               (long long)nseg * SP_FT_SEG * (long long)sizeof(int) <= (8LL << 30);
+    if (use_pipe) {
+      d_sp_nch.reserve((size_t)nseg + 1); d_sp_chunk0.reserve((size_t)nseg + 1);
+      sp_chunk_counts<<<grid_for(nseg + 1, 256), 256, 0, stream>>>(v, d_seg_start.p, nseg, d_sp_nch.p);
+      OSFM_LAUNCH_CHECK();
+      size_t tb2 = 0;
+      cub::DeviceScan::ExclusiveSum(nullptr, tb2, d_sp_nch.p, d_sp_chunk0.p, nseg + 1, stream);
+      d_cub.reserve(tb2 + 256);
+      tb2 = d_cub.cap;
+      OSFM_CUDA(cub::DeviceScan::ExclusiveSum(d_cub.p, tb2, d_sp_nch.p, d_sp_chunk0.p, nseg + 1, stream));
+      OSFM_CUDA(cudaMemcpyAsync(&sp_nchunks, d_sp_chunk0.p + nseg, sizeof(int), cudaMemcpyDeviceToHost, stream));
+      OSFM_CUDA(cudaStreamSynchronize(stream));
+      d_sp_chunks.reserve((size_t)sp_nchunks + 1);
+      sp_fill_chunks<<<grid_for((long long)nseg * 32, 256), 256, 0, stream>>>(v, d_seg_start.p, nseg, d_sp_chunk0.p, d_tab_off.p,
+                                                                            d_sp_chunks.p);
+      OSFM_LAUNCH_CHECK();
+      d_sp_ftab.reserve((size_t)nseg * SP_FT_SEG);
+      sp_flush_tables<<<nseg, SP_CONS_THREADS, 0, stream>>>(v, d_seg_start.p, d_tab_off.p, d_tab.p, d_sp_ftab.p);
+      OSFM_LAUNCH_CHECK();
+    }
   }
   // |x| of the free parameters
   auto x_norm_of = [&](int b) -> double {
@@ -1794,18 +1846,46 @@ void BA::run() {
           }
           unsigned long long* prof = nullptr;
           if (trace_on) {
-            d_prof.reserve(8);
-            OSFM_CUDA(cudaMemsetAsync(d_prof.p, 0, 8 * sizeof(unsigned long long), stream));
+            d_prof.reserve(16);
+            OSFM_CUDA(cudaMemsetAsync(d_prof.p, 0, 16 * sizeof(unsigned long long), stream));
             prof = d_prof.p;
           }
-          if (wc == 9)
+          if (use_pipe && sp_nchunks > 0) {
+            if (!sp_attr) {
+              OSFM_CUDA(cudaFuncSetAttribute(ba_schur_pipe<9, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SpSmem)));
+              OSFM_CUDA(cudaFuncSetAttribute(ba_schur_pipe<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SpSmem)));
+              OSFM_CUDA(cudaFuncSetAttribute(ba_schur_pipe<9, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SpSmem)));
+              OSFM_CUDA(cudaFuncSetAttribute(ba_schur_pipe<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SpSmem)));
+              sp_attr = true;
+            }
+            const int grid = std::max(1, std::min(num_sms, sp_nchunks));
+            auto kern = wc == 9 ? (prof ? ba_schur_pipe<9, true> : ba_schur_pipe<9, false>)
+                                : (prof ? ba_schur_pipe<0, true> : ba_schur_pipe<0, false>);
+            kern<<<grid, SP_THREADS, sizeof(SpSmem), stream>>>(v, d_sp_chunks.p, sp_nchunks, d_tab.p, d_scale.p, d_Vinv.p, d_Vig.p,
+                                                              d_sp_ftab.p, d_S_p, d_rhs_p, prof);
+            if (trace_on) {
+              OSFM_LAUNCH_CHECK();
+              unsigned long long hp[16];
+              OSFM_CUDA(cudaMemcpyAsync(hp, d_prof.p, sizeof(hp), cudaMemcpyDeviceToHost, stream));
+              OSFM_CUDA(cudaStreamSynchronize(stream));
+              const unsigned long long nch = std::max<unsigned long long>(hp[3], 1);
+              fprintf(stderr, "[osfm_ba] ba_schur_pipe (%d CTAs, %llu chunks) producer clocks / chunk: copy wait %llu buffer wait %llu build %llu\n",
+                      grid, hp[3], hp[0] / nch, hp[1] / nch, hp[2] / nch);
+              for (int gI = 0; gI < 2; ++gI) {
+                const unsigned long long ns = std::max<unsigned long long>(hp[8 + 5 * gI], 1);
+                fprintf(stderr, "[osfm_ba]   consumer group %d clocks / segment (%llu segments): tables %llu operand wait %llu mma %llu flush %llu\n",
+                        gI, hp[8 + 5 * gI], hp[4 + 5 * gI] / ns, hp[5 + 5 * gI] / ns, hp[6 + 5 * gI] / ns, hp[7 + 5 * gI] / ns);
+              }
+              prof = nullptr;
+            }
+          } else if (wc == 9)
             ba_schur_mma<9><<<nseg, SM_THREADS, sizeof(SegMmaSmem), stream>>>(v, d_seg_start.p, d_tab_off.p, d_tab.p, d_scale.p,
                                                                              d_Vinv.p, d_Vig.p, d_S_p, d_rhs_p, prof);
           else
             ba_schur_mma<0><<<nseg, SM_THREADS, sizeof(SegMmaSmem), stream>>>(v, d_seg_start.p, d_tab_off.p, d_tab.p, d_scale.p,
                                                                              d_Vinv.p, d_Vig.p, d_S_p, d_rhs_p, prof);
           OSFM_LAUNCH_CHECK();
-          if (trace_on) {
+          if (trace_on && prof) {
             unsigned long long hp[8];
             OSFM_CUDA(cudaMemcpyAsync(hp, d_prof.p, sizeof(hp), cudaMemcpyDeviceToHost, stream));
             OSFM_CUDA(cudaStreamSynchronize(stream));
@@ -1873,8 +1953,8 @@ void BA::run() {
       const int max_pcg = std::min(2 * nc + 100, 5000);
       bool solved = false;
       if (pcg_pipe_ok) {
-        pcg_pipelined<<<pcg_grid, PCG_THREADS, pcg_pipe_smem, stream>>>(d_Spcg.p, lay, bsr, d_Minv.p, d_rhs_p, d_px.p, d_pz.p,
-                                                                        d_pp.p, d_pcg.p, nc, max_pcg, 1e-16, pcg_pipe);
+        launch_cooperative(pcg_pipelined, pcg_grid, PCG_THREADS, pcg_pipe_smem, stream, d_Spcg.p, lay, bsr, d_Minv.p, d_rhs_p,
+                           d_px.p, d_pz.p, d_pp.p, d_pcg.p, nc, max_pcg, 1e-16, pcg_pipe);
         OSFM_LAUNCH_CHECK();
         OSFM_CUDA(cudaMemcpyAsync(h_pcg.p, d_pcg.p, PCG_STATE_HEADER, cudaMemcpyDeviceToHost, stream));
         OSFM_CUDA(cudaStreamSynchronize(stream));
@@ -1893,13 +1973,11 @@ void BA::run() {
       }
       if (!solved) {
         if (pcg_resident)
-          pcg_persistent<true><<<pcg_grid, PCG_THREADS, pcg_smem, stream>>>(d_Spcg.p, lay, bsr, d_Minv.p, d_rhs_p, d_px.p,
-                                                                            d_pr.p, d_pz.p, d_pp.p, d_pAp.p, d_Ap.p, d_pcg.p,
-                                                                            nc, max_pcg, 1e-16, pcg_res);
+          launch_cooperative(pcg_persistent<true>, pcg_grid, PCG_THREADS, pcg_smem, stream, d_Spcg.p, lay, bsr, d_Minv.p,
+                             d_rhs_p, d_px.p, d_pr.p, d_pz.p, d_pp.p, d_pAp.p, d_Ap.p, d_pcg.p, nc, max_pcg, 1e-16, pcg_res);
         else
-          pcg_persistent<false><<<pcg_grid, PCG_THREADS, 0, stream>>>(d_Spcg.p, lay, bsr, d_Minv.p, d_rhs_p, d_px.p, d_pr.p,
-                                                                      d_pz.p, d_pp.p, d_pAp.p, d_Ap.p, d_pcg.p, nc, max_pcg,
-                                                                      1e-16, pcg_res);
+          launch_cooperative(pcg_persistent<false>, pcg_grid, PCG_THREADS, 0, stream, d_Spcg.p, lay, bsr, d_Minv.p, d_rhs_p,
+                             d_px.p, d_pr.p, d_pz.p, d_pp.p, d_pAp.p, d_Ap.p, d_pcg.p, nc, max_pcg, 1e-16, pcg_res);
         OSFM_LAUNCH_CHECK();
       }
       OSFM_CUDA(cudaMemcpyAsync(d_y.p, d_px.p, sizeof(double) * nc, cudaMemcpyDeviceToDevice, stream));

@@ -77,8 +77,12 @@ def test_losses(loss):
     # cost / reprojection RMSE but may stop at different gauge representatives.
     # (6 cameras without GPS: the similarity gauge is free, so the two solvers' iterates drift along it by a few
     # 1e-5 when they stop on the function tolerance; 5e-5 like the other gauge-free scenes)
+    # ArctanLoss (non-convex, 48 iterations until the 1e-6 function tolerance stops both solvers): the two final
+    # costs agree to a few times that tolerance, not better -- a different summation order in the Schur kernel
+    # moves the last digits of every iterate.
     _compare(syn.scene_to_problem(sc, loss_name=loss, loss_threshold=1.0), compare_params=loss != "ArctanLoss",
-             tol_rmse=1e-5 if loss == "ArctanLoss" else 1e-6, tol_param=5e-5)
+             tol_rmse=1e-5 if loss == "ArctanLoss" else 1e-6, tol_param=5e-5,
+             tol_cost=5e-6 if loss == "ArctanLoss" else 1e-6)
 
 
 def test_pose_only_and_point_only():
@@ -234,7 +238,7 @@ def test_degenerate_inputs():
 
 
 def test_kernel_variants_agree():
-    """The default path (fp64 tensor-core segment Schur, pipelined PCG with S resident in shared memory) and the
+    """The default path (persistent fp64 tensor-core segment Schur, pipelined PCG with S resident in shared memory) and the
     kernels it replaces (per-point ba_schur, SIMT segment kernel, classic / streamed PCG) must give the same solve."""
     import os
     import subprocess
@@ -249,14 +253,14 @@ def test_kernel_variants_agree():
         "np.save(sys.argv[1], np.concatenate([[r['summary']['final_cost'], r['summary']['iterations']], r['points'].ravel()]))\n"
     ) % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     out = {}
-    variants = {"default": {}, "generic_schur": {"OSFM_BA_SEGMENT_SCHUR": "0"}, "simt_seg_schur": {"OSFM_BA_SCHUR_MMA": "0"}, "classic_pcg": {"OSFM_BA_PCG_PIPELINED": "0"}, "b128_barrier": {"OSFM_BA_PCG_B128": "1"},
+    variants = {"default": {}, "generic_schur": {"OSFM_BA_SEGMENT_SCHUR": "0"}, "simt_seg_schur": {"OSFM_BA_SCHUR_MMA": "0"}, "cta_per_segment_schur": {"OSFM_BA_SCHUR_PIPE": "0"}, "classic_pcg": {"OSFM_BA_PCG_PIPELINED": "0"}, "b128_barrier": {"OSFM_BA_PCG_B128": "1"},
                 "streamed_pcg": {"OSFM_BA_PCG_PIPELINED": "0", "OSFM_BA_PCG_RESIDENT": "0"}}
     for name, extra in variants.items():
         path = "/tmp/osfm_variant_%s.npy" % name
         env = dict(os.environ, **extra)
         subprocess.run([sys.executable, "-c", code, path], check=True, env=env, timeout=600)
         out[name] = np.load(path)
-    for name in ("generic_schur", "simt_seg_schur", "classic_pcg", "b128_barrier", "streamed_pcg"):
+    for name in ("generic_schur", "simt_seg_schur", "cta_per_segment_schur", "classic_pcg", "b128_barrier", "streamed_pcg"):
         assert out["default"][1] == out[name][1]
         assert abs(out["default"][0] - out[name][0]) <= 1e-9 * out["default"][0]
         assert np.abs(out["default"][2:] - out[name][2:]).max() < 1e-8
