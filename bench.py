@@ -543,7 +543,7 @@ def main():
         wc_ = s["jac_planes"] / 2.0 - 4.0  # jac_planes = nres * (wc + 4), nres = 2
         fma = npts * (kk * wc_) ** 2 * 3
         tf = 2.0 * fma / (kern["ba_schur"]["ms"] * 1e-3) / 1e12
-        kern["ba_schur"]["kernels"] = "ba_point_blocks + ba_schur_mma<wc> (fp64 mma.m8n8k4)"
+        kern["ba_schur"]["kernels"] = "ba_point_blocks + ba_schur_pipe<wc> (fp64 mma.m8n8k4, persistent producer / consumer CTAs)"
         kern["ba_schur"]["fp64_tflops"] = tf
         kern["ba_schur"]["fp64_peak_tflops"] = FP64_TENSOR_PEAK_TFLOPS
         kern["ba_schur"]["fp64_frac"] = tf / FP64_TENSOR_PEAK_TFLOPS
@@ -551,7 +551,7 @@ def main():
                                          "(full square); peak = DMMA/DFMA rate measured by scripts/bench_dmma.cu")
     dom = max((k for k in kern if "bytes" in kern[k]), key=lambda k: kern[k]["share"])
     ach = kern[dom]["bytes"] / (kern[dom]["ms"] * 1e-3) / 1e9
-    dom_traffic = dram("ba_point_blocks", "ba_schur_mma<9>", "ba_schur_mma<0>", "ba_schur") if dom == "ba_schur" else dram("ba_linearize<1>")
+    dom_traffic = dram("ba_point_blocks", "ba_schur_pipe<9>", "ba_schur_pipe<0>", "ba_schur_mma<9>", "ba_schur_mma<0>", "ba_schur") if dom == "ba_schur" else dram("ba_linearize<1>")
     roofline = {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": pk["hbm"], "unit": "GB/s",
                 "frac": ach / pk["hbm"], "traffic": dom_traffic, "peak_source": pk["source"], "kernels": kern}
     flops = 2.0 * 128.0 * my_pair_work * K
