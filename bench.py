@@ -551,14 +551,14 @@ def main():
                                          "(full square); peak = DMMA/DFMA rate measured by scripts/bench_dmma.cu")
     dom = max((k for k in kern if "bytes" in kern[k]), key=lambda k: kern[k]["share"])
     ach = kern[dom]["bytes"] / (kern[dom]["ms"] * 1e-3) / 1e9
-    dom_traffic = dram("ba_point_blocks", "ba_schur_pipe<9>", "ba_schur_pipe<0>", "ba_schur_mma<9>", "ba_schur_mma<0>", "ba_schur") if dom == "ba_schur" else dram("ba_linearize<1>")
+    dom_traffic = dram("ba_point_blocks", "ba_schur_pipe<9, 0>", "ba_schur_pipe<0, 0>", "ba_schur_mma<9>", "ba_schur_mma<0>", "ba_schur") if dom == "ba_schur" else dram("ba_linearize<1, 3>") or dram("ba_linearize<1>")
     roofline = {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": pk["hbm"], "unit": "GB/s",
                 "frac": ach / pk["hbm"], "traffic": dom_traffic, "peak_source": pk["source"], "kernels": kern}
     flops = 2.0 * 128.0 * my_pair_work * K
     tc_ach = flops / (mt_kernel_ms * 1e-3) / 1e12
     mt_roof = {"kernel": "bf_top2_tc" if pm.last_kernel() == 2 else "bf_top2_f32_cv", "bound": "tensor",
                "achieved": tc_ach, "peak": pk["bf16_sustained"], "unit": "TFLOP/s", "frac": tc_ach / pk["bf16_sustained"],
-               "traffic": dram("bf_top2_tc", "bf_top2_tc<false>"), "peak_source": pk["source"] + ", sustained bf16",
+               "traffic": dram("bf_top2_tc<0>") or dram("bf_top2_tc", "bf_top2_tc<false>"), "peak_source": pk["source"] + ", sustained bf16",
                "note": "2*128 flop per descriptor pair per direction (SURVEY 8d); kernel time = distance kernel only"}
 
     line = None
