@@ -97,19 +97,24 @@ __device__ __forceinline__ void atomic_max_nonneg(double* addr, double v) {
 // MODE 2: unscaled reprojection errors (bundle_adjuster.cc:531-566), written in original order.
 // NB = minimum resident CTAs per SM the register allocation is held to (the kernel is latency-bound: at its
 // natural 156 registers only 12 warps fit on an SM).
-template <int MODE, int NB = 3>
+// TYPE >= 0: every camera of the problem has this projection type and no shot goes through a rig camera: the
+// model dispatch, the parameter count and the Jacobian block sizes become compile-time constants, the blocks
+// live in registers instead of a local-memory frame.
+template <int MODE, int NB = 3, int TYPE = -1>
 __global__ void __launch_bounds__(128, NB) ba_linearize(BAView v, Params p, Scalars* sc, double* reproj) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   double cost = 0.0;
   if (i < v.N) {
     const int shot = v.obs_shot[i];
     const int cam = v.shot_cam[shot];
-    const int type = v.cam_type[cam];
-    const int C = v.cam_np[cam];
-    const bool use_rc = v.shot_use_rc[shot] != 0;
+    const int type = TYPE >= 0 ? TYPE : v.cam_type[cam];
+    const int C = TYPE >= 0 ? model_num_params(TYPE >= 0 ? TYPE : 0) : v.cam_np[cam];
+    const bool use_rc = TYPE >= 0 ? false : v.shot_use_rc[shot] != 0;
     const int pt = v.obs_point[i];
     double camp[MAX_CAM_PARAMS], ri[6], rc[6], X[3];
-    for (int j = 0; j < C; ++j) camp[j] = p.cam[v.cam_off[cam] + j];
+#pragma unroll
+    for (int j = 0; j < MAX_CAM_PARAMS; ++j)
+      if (j < C) camp[j] = p.cam[v.cam_off[cam] + j];
 #pragma unroll
     for (int j = 0; j < 6; ++j) ri[j] = p.inst[6 * (size_t)v.shot_inst[shot] + j];
     if (use_rc) {
@@ -148,6 +153,28 @@ __global__ void __launch_bounds__(128, NB) ba_linearize(BAView v, Params p, Scal
       if (!pfree && v.cam_poff[cam] < 0 && v.inst_poff[v.shot_inst[shot]] < 0 && (!use_rc || v.rc_poff[v.shot_rc[shot]] < 0))
         cost = 0.0;   // all blocks constant: not part of the minimised cost (see MODE 0)
       const size_t N = (size_t)v.N;
+      if (TYPE >= 0) {
+        // uniform projection type, no rig cameras: nres = 2 rows, wc = C + 6 columns, all indices compile-time
+        constexpr int CC = TYPE == PT_PERSPECTIVE ? 3 : TYPE == PT_FISHEYE ? 3 : TYPE == PT_BROWN ? 9 : 1;
+        const int wcl = v.wc;
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+          v.r[k * N + i] = w * r[k];
+          double* jcrow = v.Jc + (size_t)k * wcl * N + i;
+#pragma unroll
+          for (int j = 0; j < CC; ++j) jcrow[(size_t)j * N] = w * jc[k * CC + j];
+#pragma unroll
+          for (int j = 0; j < 6; ++j) jcrow[(size_t)(CC + j) * N] = w * jri[k * 6 + j];
+          for (int j = CC + 6; j < wcl; ++j) jcrow[(size_t)j * N] = 0.0;
+#pragma unroll
+          for (int j = 0; j < 3; ++j) v.Jp[((size_t)k * 3 + j) * N + i] = pfree ? w * jp[k * 3 + j] : 0.0;
+        }
+        for (int k = 2; k < v.nres; ++k) {
+          v.r[k * N + i] = 0.0;
+          for (int j = 0; j < wcl; ++j) v.Jc[((size_t)k * wcl + j) * N + i] = 0.0;
+          for (int j = 0; j < 3; ++j) v.Jp[((size_t)k * 3 + j) * N + i] = 0.0;
+        }
+      } else
       for (int k = 0; k < v.nres; ++k) {
         const bool live = k < nres;
         v.r[k * N + i] = live ? w * r[k] : 0.0;
@@ -450,7 +477,8 @@ __device__ __forceinline__ void cg_mbar_wait(uint64_t* bar, uint32_t parity) {
 }
 
 __global__ void __launch_bounds__(32 * CG_WARPS, 1)
-    ba_colnorm_grad_tma(BAView v, const int* __restrict__ seg_start, int nseg, double* colnorm2, double* grad) {
+    ba_colnorm_grad_tma(BAView v, const int* __restrict__ seg_start, int nseg, const long long* __restrict__ tab_off,
+                        const int* __restrict__ tab, double* colnorm2, double* grad) {
   extern __shared__ __align__(128) double cg_tiles[];
   __shared__ __align__(8) uint64_t bars[CG_WARPS][2];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -551,9 +579,14 @@ __global__ void __launch_bounds__(32 * CG_WARPS, 1)
       for (int u = 0; u < 3; ++u) {
         const int a = lane + 32 * u;
         if (a < nacc) {
-          const int c = a / 9, j = a - c * 9;
-          const ObsCols oc = obs_cols(v, base + c);
-          const int col = oc.col(j);
+          int col;
+          if (tab) {   // per-segment column table (ba_seg_tables): one load instead of the shot -> camera -> offset chain
+            col = tab[tab_off[s] + a];
+          } else {
+            const int c = a / 9, j = a - c * 9;
+            const ObsCols oc = obs_cols(v, base + c);
+            col = oc.col(j);
+          }
           if (col >= 0) { atomicAdd(&colnorm2[col], n2[u]); atomicAdd(&grad[col], gr[u]); }
         }
         n2[u] = 0.0; gr[u] = 0.0;
@@ -945,6 +978,8 @@ struct BA {
   DevBuf<SchurChunk> d_sp_chunks;
   DevBuf<int> d_sp_ftab;                   // flush destinations per segment (sp_flush_tables)
   int sp_nchunks = 0;
+  bool cc_attr = false;
+  bool have_seg_tab = false;               // ba_seg_tables has run for this problem (gcol of every segment column)
   bool sp_attr = false;
   DevBuf<int> d_tab;
   PcgPipe pcg_pipe{};
@@ -1155,6 +1190,15 @@ void BA::run() {
   static const bool use_seg = []() { const char* e = getenv("OSFM_BA_SEGMENT_SCHUR"); return !(e && e[0] == '0'); }();
   // register budget of ba_linearize<1> (A/B switch): 3, 4 or 5 resident CTAs per SM
   static const int lin_nb = []() { const char* e = getenv("OSFM_BA_LIN_NB"); return e ? atoi(e) : LIN_NB_DEFAULT; }();
+  // one projection type for all cameras and no rig-camera shots -> specialised linearisation kernels
+  static const bool lin_special = []() { const char* e = getenv("OSFM_BA_LIN_SPECIAL"); return !(e && e[0] == '0'); }();
+  int uniform_type = -1;
+  if (lin_special && K > 0) {
+    uniform_type = cam_type[0];
+    for (int k = 1; k < K; ++k) if (cam_type[k] != uniform_type) uniform_type = -1;
+    for (int s = 0; s < S && uniform_type >= 0; ++s) if (shot_use_rc[s]) uniform_type = -1;
+    if (uniform_type != PT_PERSPECTIVE && uniform_type != PT_BROWN && uniform_type != PT_FISHEYE) uniform_type = -1;
+  }
   if (Nfull >= (1LL << 31)) throw ArgError("too many observations");
   const int P = Pfull > rank ? (Pfull - rank + world - 1) / world : 0;
   const size_t Nfz = (size_t)std::max<long long>(Nfull, 1), Pz = (size_t)std::max(P, 1);
@@ -1400,7 +1444,10 @@ void BA::run() {
   auto eval_cost = [&](int b) -> double {
     OSFM_CUDA(cudaMemsetAsync(&d_sc.p->cost, 0, sizeof(double), stream));
     if (N > 0) {
-      ba_linearize<0><<<grid_for(N, 128), 128, 0, stream>>>(v, params_of(b), d_sc.p, nullptr);
+      if (uniform_type == PT_PERSPECTIVE) ba_linearize<0, 3, PT_PERSPECTIVE><<<grid_for(N, 128), 128, 0, stream>>>(v, params_of(b), d_sc.p, nullptr);
+      else if (uniform_type == PT_BROWN) ba_linearize<0, 3, PT_BROWN><<<grid_for(N, 128), 128, 0, stream>>>(v, params_of(b), d_sc.p, nullptr);
+      else if (uniform_type == PT_FISHEYE) ba_linearize<0, 3, PT_FISHEYE><<<grid_for(N, 128), 128, 0, stream>>>(v, params_of(b), d_sc.p, nullptr);
+      else ba_linearize<0><<<grid_for(N, 128), 128, 0, stream>>>(v, params_of(b), d_sc.p, nullptr);
       OSFM_LAUNCH_CHECK();
     }
     if (npr_local > 0) {
@@ -1425,7 +1472,10 @@ void BA::run() {
     OSFM_CUDA(cudaMemsetAsync(d_grad.p, 0, sizeof(double) * nz, stream));
     if (N > 0) {
       tm_lin.start(stream);
-      if (lin_nb == 5) ba_linearize<1, 5><<<grid_for(N, 128), 128, 0, stream>>>(v, params_of(b), d_sc.p, nullptr);
+      if (uniform_type == PT_PERSPECTIVE) ba_linearize<1, 5, PT_PERSPECTIVE><<<grid_for(N, 128), 128, 0, stream>>>(v, params_of(b), d_sc.p, nullptr);
+      else if (uniform_type == PT_BROWN) ba_linearize<1, 4, PT_BROWN><<<grid_for(N, 128), 128, 0, stream>>>(v, params_of(b), d_sc.p, nullptr);
+      else if (uniform_type == PT_FISHEYE) ba_linearize<1, 5, PT_FISHEYE><<<grid_for(N, 128), 128, 0, stream>>>(v, params_of(b), d_sc.p, nullptr);
+      else if (lin_nb == 5) ba_linearize<1, 5><<<grid_for(N, 128), 128, 0, stream>>>(v, params_of(b), d_sc.p, nullptr);
       else if (lin_nb == 4) ba_linearize<1, 4><<<grid_for(N, 128), 128, 0, stream>>>(v, params_of(b), d_sc.p, nullptr);
       else ba_linearize<1, 3><<<grid_for(N, 128), 128, 0, stream>>>(v, params_of(b), d_sc.p, nullptr);
       OSFM_LAUNCH_CHECK();
@@ -1435,13 +1485,22 @@ void BA::run() {
       if (nseg > 0) {
         // OSFM_BA_COLNORM_TMA=0: the shuffle kernel instead of the bulk-copy staged one (A/B switch)
         static const bool use_tma = []() { const char* e = getenv("OSFM_BA_COLNORM_TMA"); return !(e && e[0] == '0'); }();
-        if (wc == 9 && nres == 2 && use_tma) {
+        if (wc == 9 && nres == 2 && use_tma && have_seg_tab && sp_nchunks > 0) {
+          // chunk list + segment tables exist (every call but the first of a run): no dependent index loads
+          if (!cc_attr) {
+            OSFM_CUDA(cudaFuncSetAttribute(ba_colnorm_grad_chunks, cudaFuncAttributeMaxDynamicSharedMemorySize, CC_SMEM));
+            cc_attr = true;
+          }
+          const int grid = std::max(1, std::min(num_sms, (sp_nchunks + CC_WARPS - 1) / CC_WARPS));
+          ba_colnorm_grad_chunks<<<grid, 32 * CC_WARPS, CC_SMEM, stream>>>(v, d_sp_chunks.p, sp_nchunks, d_tab.p, d_colnorm2.p, d_grad.p);
+        } else if (wc == 9 && nres == 2 && use_tma) {
           if (!cg_attr) {
             OSFM_CUDA(cudaFuncSetAttribute(ba_colnorm_grad_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, CG_SMEM));
             cg_attr = true;
           }
           const int grid = std::max(1, std::min(num_sms, (nseg + CG_WARPS - 1) / CG_WARPS));
-          ba_colnorm_grad_tma<<<grid, 32 * CG_WARPS, CG_SMEM, stream>>>(v, d_seg_start.p, nseg, d_colnorm2.p, d_grad.p);
+          ba_colnorm_grad_tma<<<grid, 32 * CG_WARPS, CG_SMEM, stream>>>(v, d_seg_start.p, nseg, have_seg_tab ? d_tab_off.p : nullptr,
+                                                                        have_seg_tab ? d_tab.p : nullptr, d_colnorm2.p, d_grad.p);
         } else if (wc == 9)
           ba_colnorm_grad_seg<9><<<grid_for((long long)nseg * 32, 256), 256, 0, stream>>>(v, d_seg_start.p, nseg, d_colnorm2.p, d_grad.p);
         else
@@ -1741,6 +1800,8 @@ void BA::run() {
   std::string message = "Maximum number of iterations reached.";
 
   double grad_max = 0.0;
+  have_seg_tab = false;   // the tables / chunk list of a previous run() do not describe this problem
+  sp_nchunks = 0;
   double cost = linearize(cur, &grad_max);
   const double initial_cost = cost;
   if (n > 0) {
@@ -1748,9 +1809,14 @@ void BA::run() {
     OSFM_LAUNCH_CHECK();
   }
   // per-segment tables of the tensor-core Schur kernel (columns, block offsets, Jacobi scales): constant from here on
-  static const bool use_mma = []() { const char* e = getenv("OSFM_BA_SCHUR_MMA"); return !(e && e[0] == '0'); }();
+  static const bool mma_on = []() { const char* e = getenv("OSFM_BA_SCHUR_MMA"); return !(e && e[0] == '0'); }();
+  // The tensor-core kernels add the same-shot blocks J^T J only in the tiles (t, t) and (t, t + 1): a shot's wc
+  // columns must not span three 8-wide tiles, i.e. wc <= 9.  Wider camera sides (Brown: 9 + 6, rig cameras: + 6)
+  // use the SIMT segment kernels.
+  const bool use_mma = mma_on && wc <= 9;
   bool use_pipe = false;
   sp_nchunks = 0;
+  have_seg_tab = false;
   if (nseg > 0 && use_mma && nblk > 0) {
     d_tab_off.reserve((size_t)nseg + 1); d_tab_sizes.reserve((size_t)nseg + 1);
     ba_seg_table_sizes<<<grid_for(nseg + 1, 256), 256, 0, stream>>>(v, d_seg_start.p, nseg, d_tab_sizes.p);
@@ -1766,6 +1832,7 @@ void BA::run() {
     d_tab.reserve((size_t)total_ints + 2);
     ba_seg_tables<<<nseg, 128, 0, stream>>>(v, bm, bsr, d_seg_start.p, d_scale.p, d_tab_off.p, d_tab.p);
     OSFM_LAUNCH_CHECK();
+    have_seg_tab = true;
     // chunk list of the persistent Schur kernel (ba_schur_pipe.cuh)
     static const bool pipe_on = []() { const char* e = getenv("OSFM_BA_SCHUR_PIPE"); return !(e && e[0] == '0'); }();
     // (the flush table holds offset << 2: the reduced system must stay below 2^29 doubles; 20 KB of table per segment)

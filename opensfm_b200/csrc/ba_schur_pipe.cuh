@@ -40,6 +40,7 @@ constexpr int SP_SLOTS = SM_NT + 1;                 // tiles of a row pair (p, n
 constexpr int SP_NPAIR9 = 9 * (SEG_KMAX * (SEG_KMAX + 1) / 2);
 static_assert(2 * SP_OBS == SP_PROD_THREADS, "two producer threads per observation of a chunk");
 static_assert(2 * SP_CONS_WARPS >= SM_NT, "a consumer warp per pair of tile rows");
+static_assert((SP_ROWS / 2) - 4 <= 9, "same-shot blocks are only accumulated in the tiles (t, t) and (t, t + 1): wc <= 9");
 
 struct SchurChunk {      // 48 bytes, read with three 16-byte loads
   long long ibase;       // first observation of the chunk (sorted order)
@@ -198,6 +199,122 @@ __global__ void __launch_bounds__(SP_CONS_THREADS)
       }
       out[(j * 2 + el) * 32] = code;
     }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Camera-side gradient and squared column norms over the chunk list (wc == 9, nres == 2): ba_colnorm_grad_tma
+// (ba.cu) walks seg_start / pt_start with three dependent loads per chunk before it can issue the next copy; here a
+// warp owns a contiguous range of chunks (cut at segment starts), reads one 48-byte entry per chunk (the entry of
+// chunk n + 1 is in registers while chunk n is reduced) and takes the global columns from the per-segment table.
+// Staging as there: one bulk copy (TMA engine) per plane row and chunk, two stages per warp, one mbarrier each.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int CC_WARPS = 5;
+constexpr int CC_ROWS = 20;                       // r[2] + Jc[2 * 9]
+constexpr int CC_STAGE_DOUBLES = CC_ROWS * SP_OBS;
+constexpr int CC_SMEM = CC_WARPS * 2 * CC_STAGE_DOUBLES * (int)sizeof(double);   // 204,800 bytes
+
+__global__ void __launch_bounds__(32 * CC_WARPS, 1)
+    ba_colnorm_grad_chunks(BAView v, const SchurChunk* __restrict__ chunks, int nchunks, const int* __restrict__ tab,
+                           double* colnorm2, double* grad) {
+  extern __shared__ __align__(128) double cc_tiles[];
+  __shared__ __align__(8) unsigned long long bars[CC_WARPS][2];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int w = 0; w < CC_WARPS; ++w)
+      for (int st = 0; st < 2; ++st) sp_mbar_init(&bars[w][st], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  double* tile[2] = {cc_tiles + (size_t)(warp * 2) * CC_STAGE_DOUBLES, cc_tiles + (size_t)(warp * 2 + 1) * CC_STAGE_DOUBLES};
+  const size_t N = (size_t)v.N;
+  const int gw = blockIdx.x * CC_WARPS + warp, nw = gridDim.x * CC_WARPS;
+  auto cut = [&](int b) -> int {
+    if (b <= 0) return 0;
+    const long long c = (long long)b * nchunks / nw;
+    if (c >= nchunks) return nchunks;
+    const SchurChunk e = sp_load_chunk(chunks, (int)c);
+    return e.seg_chunk0 == (int)c ? (int)c : e.seg_chunk0 + e.seg_nch;
+  };
+  const int c_lo = cut(gw), c_hi = cut(gw + 1);
+  if (c_lo >= c_hi) return;
+
+  // returns whether the bulk-copy path was used (every plane run 16-byte aligned)
+  auto stage = [&](int st, const SchurChunk& e) -> bool {
+    const int run = e.np * e.k;
+    const bool aligned = ((e.ibase | (long long)run | (long long)N) & 1LL) == 0;
+    if (aligned) {
+      if (lane == 0) {
+        const uint32_t bytes = (uint32_t)run * 8u;
+        const uint32_t bar = sp_saddr(&bars[warp][st]);
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes * CC_ROWS) : "memory");
+        for (int row = 0; row < CC_ROWS; ++row) {
+          const double* src = (row < 2 ? v.r + (size_t)row * N : v.Jc + (size_t)(row - 2) * N) + e.ibase;
+          asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                           sp_saddr(tile[st] + row * SP_OBS)),
+                       "l"(src), "r"(bytes), "r"(bar)
+                       : "memory");
+        }
+      }
+    } else {
+      for (int idx = lane; idx < CC_ROWS * run; idx += 32) {
+        const int row = idx / run, el = idx - row * run;
+        tile[st][row * SP_OBS + el] = (row < 2 ? v.r + (size_t)row * N : v.Jc + (size_t)(row - 2) * N)[e.ibase + el];
+      }
+    }
+    return aligned;
+  };
+
+  SchurChunk e = sp_load_chunk(chunks, c_lo);
+  bool cur_tma = stage(0, e);
+  unsigned phase0 = 0u, phase1 = 0u;
+  double n2[3] = {0.0, 0.0, 0.0}, gr[3] = {0.0, 0.0, 0.0};
+  int col[3] = {-1, -1, -1};
+  for (int n = c_lo; n < c_hi; ++n) {
+    const int st = (n - c_lo) & 1;
+    SchurChunk en = e;
+    bool next_tma = false;
+    if (n + 1 < c_hi) {
+      en = sp_load_chunk(chunks, n + 1);
+      next_tma = stage(st ^ 1, en);
+    }
+    const int k = e.k, np = e.np, nacc = k * 9;
+    if (n == e.seg_chunk0) {
+#pragma unroll
+      for (int u = 0; u < 3; ++u) {
+        const int a = lane + 32 * u;
+        col[u] = a < nacc ? __ldg(tab + e.tab_off + a) : -1;
+        n2[u] = 0.0; gr[u] = 0.0;
+      }
+    }
+    if (cur_tma) {
+      sp_mbar_wait(&bars[warp][st], st ? phase1 : phase0);
+      if (st) phase1 ^= 1u; else phase0 ^= 1u;
+    } else {
+      __syncwarp();
+    }
+    const double* T = tile[st];
+#pragma unroll
+    for (int u = 0; u < 3; ++u) {
+      const int a = lane + 32 * u;
+      if (a < nacc) {
+        const int c = a / 9, j = a - c * 9;
+        for (int pi = 0; pi < np; ++pi) {
+          const int el = pi * k + c;
+          const double j0 = T[(2 + j) * SP_OBS + el], j1 = T[(2 + 9 + j) * SP_OBS + el];
+          n2[u] += j0 * j0 + j1 * j1;
+          gr[u] += j0 * T[el] + j1 * T[SP_OBS + el];
+        }
+      }
+    }
+    __syncwarp();   // the tile may be overwritten by the copy issued in the next iteration
+    if (n == e.seg_chunk0 + e.seg_nch - 1) {
+#pragma unroll
+      for (int u = 0; u < 3; ++u)
+        if (col[u] >= 0) { atomicAdd(&colnorm2[col[u]], n2[u]); atomicAdd(&grad[col[u]], gr[u]); }
+    }
+    e = en;
+    cur_tma = next_tma;
   }
 }
 

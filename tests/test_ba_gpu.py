@@ -138,7 +138,7 @@ def test_bundle_adjuster_api_roundtrip():
         ba.run()
 
 
-def _mixed_problem(seed=0, rig=False, free_rig=False):
+def _mixed_problem(seed=0, rig=False, free_rig=False, only=None):
     """6 instances looking at a point cloud through different camera models (and, optionally, a
     two-camera rig so that the two-pose path of projection_errors.h:95-149 runs)."""
     from scipy.spatial.transform import Rotation
@@ -146,6 +146,8 @@ def _mixed_problem(seed=0, rig=False, free_rig=False):
     rng = np.random.RandomState(seed)
     types = [bp.PERSPECTIVE, bp.BROWN, bp.FISHEYE, bp.FISHEYE_OPENCV, bp.RADIAL, bp.SPHERICAL, bp.DUAL,
              bp.SIMPLE_RADIAL, bp.FISHEYE62, bp.FISHEYE624]
+    if only is not None:
+        types = [only] * 6
     params = {
         bp.PERSPECTIVE: [-0.05, 0.01, 0.8], bp.BROWN: [-0.05, 0.01, 0.001, 0.001, -0.001, 0.8, 1.0, 0.01, -0.01],
         bp.FISHEYE: [-0.02, 0.005, 0.7], bp.FISHEYE_OPENCV: [-0.02, 0.005, 0.001, 0.0, 0.7, 1.0, 0.0, 0.01],
@@ -207,6 +209,13 @@ def test_all_camera_models_in_one_problem():
     _compare(_mixed_problem(0), tol_param=5e-5)
 
 
+@pytest.mark.parametrize("ptype", ["PERSPECTIVE", "BROWN", "FISHEYE"])
+def test_uniform_camera_type_uses_the_specialised_linearisation(ptype):
+    """One projection type for every camera and no rig cameras: ba_linearize<.., TYPE> (compile-time model) runs;
+    it must agree with the oracle like the generic kernel does."""
+    _compare(_mixed_problem(3, only=getattr(bp, ptype)), tol_param=5e-5)
+
+
 def test_rig_cameras_two_pose_path():
     _compare(_mixed_problem(1, rig=True), tol_param=5e-5)
     _compare(_mixed_problem(2, rig=True, free_rig=True), tol_param=5e-5)
@@ -253,14 +262,14 @@ def test_kernel_variants_agree():
         "np.save(sys.argv[1], np.concatenate([[r['summary']['final_cost'], r['summary']['iterations']], r['points'].ravel()]))\n"
     ) % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     out = {}
-    variants = {"default": {}, "generic_schur": {"OSFM_BA_SEGMENT_SCHUR": "0"}, "simt_seg_schur": {"OSFM_BA_SCHUR_MMA": "0"}, "cta_per_segment_schur": {"OSFM_BA_SCHUR_PIPE": "0"}, "classic_pcg": {"OSFM_BA_PCG_PIPELINED": "0"}, "b128_barrier": {"OSFM_BA_PCG_B128": "1"},
+    variants = {"default": {}, "generic_schur": {"OSFM_BA_SEGMENT_SCHUR": "0"}, "simt_seg_schur": {"OSFM_BA_SCHUR_MMA": "0"}, "cta_per_segment_schur": {"OSFM_BA_SCHUR_PIPE": "0"}, "generic_linearize": {"OSFM_BA_LIN_SPECIAL": "0"}, "classic_pcg": {"OSFM_BA_PCG_PIPELINED": "0"}, "b128_barrier": {"OSFM_BA_PCG_B128": "1"},
                 "streamed_pcg": {"OSFM_BA_PCG_PIPELINED": "0", "OSFM_BA_PCG_RESIDENT": "0"}}
     for name, extra in variants.items():
         path = "/tmp/osfm_variant_%s.npy" % name
         env = dict(os.environ, **extra)
         subprocess.run([sys.executable, "-c", code, path], check=True, env=env, timeout=600)
         out[name] = np.load(path)
-    for name in ("generic_schur", "simt_seg_schur", "cta_per_segment_schur", "classic_pcg", "b128_barrier", "streamed_pcg"):
+    for name in ("generic_schur", "simt_seg_schur", "cta_per_segment_schur", "generic_linearize", "classic_pcg", "b128_barrier", "streamed_pcg"):
         assert out["default"][1] == out[name][1]
         assert abs(out["default"][0] - out[name][0]) <= 1e-9 * out["default"][0]
         assert np.abs(out["default"][2:] - out[name][2:]).max() < 1e-8
