@@ -941,6 +941,7 @@ struct BA {
   DevBuf<double> d_r, d_Jc, d_Jp, d_Sbuf, d_Vinv, d_gp, d_slots;
   DevBuf<double> d_scale, d_colnorm2, d_grad, d_diag, d_y, d_bs_t;
   DevBuf<double> d_px, d_pr, d_pz, d_pp, d_pAp, d_Minv, d_reproj, d_full_pts;
+  DevBuf<double> d_Wdef;                   // [PCG_ND][nc] deflation vectors of the pipelined PCG (pcg_gauge_vectors)
   DevBuf<int> d_blk_off, d_blk_sz, d_cam_blk, d_inst_blk, d_rc_blk;
   // block-sparse reduced system (ba_reduced.cuh)
   DevBuf<unsigned long long> d_tkeys, d_skeys, d_skeys2, d_rkeys, d_rkeys2;
@@ -1753,11 +1754,16 @@ void BA::run() {
       const long long off_S = up16(8 * col_max), off_Minv = off_S + up16(8 * ent_max);
       const long long off_vec = off_Minv + 8LL * grp_max * MAXB * MAXB, off_cols = off_vec + up16(24LL * rows_max);
       const long long off_rows = off_cols + up16(2 * col_max);
-      const long long total = off_rows + 36LL * rows_max + 4LL * (grp_max + 1);
+      const long long off_defl = up16(off_rows + 36LL * rows_max + 4LL * (grp_max + 1));
+      // own rows of the deflation vectors W and of S W, then the gather buffer of the wide barrier
+      const long long total = off_defl + 2LL * PCG_ND * 8 * rows_max + 8LL * PCG_NW * G;
+      cudaFuncAttributes pipe_attr{};
+      OSFM_CUDA(cudaFuncGetAttributes(&pipe_attr, pcg_pipelined));
       static const bool allow_pipe = []() { const char* e = getenv("OSFM_BA_PCG_PIPELINED"); return !(e && e[0] == '0'); }();
       int max_smem = 0;
       OSFM_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
-      pcg_pipe_ok = allow_pipe && nc <= 65535 && rows_max <= PCG_THREADS && ent_max < (1LL << 30) && total + 1024 <= max_smem;
+      pcg_pipe_ok = allow_pipe && nc <= 65535 && rows_max <= PCG_THREADS && ent_max < (1LL << 30) &&
+                    total + (long long)pipe_attr.sharedSizeBytes + 1024 <= max_smem;
       pcg_pipe_smem = pcg_pipe_ok ? (int)total : 0;
       pcg_pipe = PcgPipe{};
       if (pcg_pipe_ok) {
@@ -1765,6 +1771,7 @@ void BA::run() {
         pcg_pipe.grp_lo = d_pcg_grplo.p; pcg_pipe.off_S = (int)off_S; pcg_pipe.off_Minv = (int)off_Minv;
         pcg_pipe.off_vec = (int)off_vec; pcg_pipe.off_cols = (int)off_cols; pcg_pipe.off_rows = (int)off_rows;
         pcg_pipe.max_rows = rows_max; pcg_pipe.max_groups = grp_max; pcg_pipe.max_cols = (int)col_max;
+        pcg_pipe.off_defl = (int)off_defl; pcg_pipe.Wdef = nullptr;
         // 128-bit barrier words (value + generation in one strong 16-byte access): measured SLOWER than flags + slots
         // on B200 (PCG 8.69 vs 8.05 ms at C4), so it is opt-in: OSFM_BA_PCG_B128=1
         static const bool allow_b128 = []() { const char* e = getenv("OSFM_BA_PCG_B128"); return e && e[0] == '1'; }();
@@ -1807,6 +1814,16 @@ void BA::run() {
   if (n > 0) {
     ba_make_scale<<<grid_for(n, 256), 256, 0, stream>>>(d_colnorm2.p, d_scale.p, n);
     OSFM_LAUNCH_CHECK();
+  }
+  // deflation vectors of the reduced solve: the similarity gauge at the initial poses, in the scaled variables
+  static const bool deflate_on = []() { const char* e = getenv("OSFM_BA_PCG_DEFLATE"); return !(e && e[0] == '0'); }();
+  pcg_pipe.Wdef = nullptr;
+  if (deflate_on && pcg_pipe_ok && !pcg_pipe.b128 && NI > 0 && nc > 0) {
+    d_Wdef.reserve((size_t)PCG_ND * nc);
+    OSFM_CUDA(cudaMemsetAsync(d_Wdef.p, 0, sizeof(double) * PCG_ND * (size_t)nc, stream));
+    pcg_gauge_vectors<<<grid_for(NI, 128), 128, 0, stream>>>(NI, d_inst_poff.p, params_of(cur).inst, d_scale.p, nc, d_Wdef.p);
+    OSFM_LAUNCH_CHECK();
+    pcg_pipe.Wdef = d_Wdef.p;
   }
   // per-segment tables of the tensor-core Schur kernel (columns, block offsets, Jacobi scales): constant from here on
   static const bool mma_on = []() { const char* e = getenv("OSFM_BA_SCHUR_MMA"); return !(e && e[0] == '0'); }();

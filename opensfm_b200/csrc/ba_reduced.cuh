@@ -1223,6 +1223,8 @@ struct PcgState {
   long long prof[8];                   // CTA 0 / thread 0 clock64 totals per phase (OSFM_BA_TRACE)
   // per-CTA partial sums of the reduction riding on the barrier (double-buffered by generation parity)
   double slot[2][PCG_MAX_CTAS][4];
+  // wide payload of the deflated solver: 3 dot products + PCG_ND projections (double-buffered by generation parity)
+  double slotx[2][PCG_MAX_CTAS][12];
   // per-CTA arrival generation, one 128-byte line each (packed flags cost 9.3k clk per barrier,
   // strided ones 4.4k: scripts/bench_barrier.cu)
   unsigned flags[PCG_MAX_CTAS * PCG_FLAG_STRIDE];
@@ -1476,9 +1478,13 @@ __global__ void __launch_bounds__(PCG_THREADS, 1)
 // The recurrences drift from the true residual earlier than classic CG; the kernel reports
 // converged = 0 on stagnation / breakdown and the host re-solves with pcg_persistent.
 // ---------------------------------------------------------------------------
+constexpr int PCG_ND = 7;   // deflation vectors: the similarity gauge of the rig instances (3 translations, 3 rotations, scale)
+constexpr int PCG_NW = 10;  // doubles per CTA on the wide barrier: gamma, delta, |r|^2, PCG_ND projections
 struct PcgPipe {
   const int* grp_lo;  // [grid + 1] group range of every CTA (balanced by stored entries)
   int off_S, off_Minv, off_vec, off_cols, off_rows;  // byte offsets into dynamic shared memory; mp at 0
+  int off_defl;       // [2][PCG_ND][max_rows] doubles: own rows of W and of S W
+  const double* Wdef; // [PCG_ND][nc] deflation vectors (scaled variables), or null: plain PCG
   int max_cols;
   int max_rows, max_groups;
   int b128;   // 1: grid_reduce3_b128 (<= 160 CTAs, >= 480 threads), 0: flags + slots
@@ -1591,6 +1597,115 @@ __device__ __forceinline__ void grid_reduce3(PcgState* st, unsigned nblocks, uns
   __syncthreads();
 }
 
+// Deflation vectors of the reduced system: the similarity gauge of the rig instances at the current poses.
+// Instance block = [r (camera -> world angle-axis) | t (camera origin)], x_cam = R(-r) (X - t).  Under the world map
+// X -> s Q X + T:  t -> s Q t + T,  R(r) -> Q R(r), i.e. to first order
+//   translation e_a:  dt = e_a;   rotation w = e_a:  dr = J_l(r)^-1 e_a, dt = e_a x t;   scale:  dt = t,
+// in the Jacobi-scaled variables (x = scale * x_scaled).  Intrinsics, rig cameras and ext blocks do not move.
+// When nothing fixes the gauge these seven directions carry the smallest eigenvalues of the reduced system
+// (only the LM damping acts on them); with priors / fixed shots they are ordinary vectors and deflating them is harmless.
+__global__ void pcg_gauge_vectors(int NI, const int* __restrict__ inst_poff, const double* __restrict__ inst,
+                                  const double* __restrict__ scale, int nc, double* __restrict__ W) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= NI) return;
+  const int c0 = inst_poff[i];
+  if (c0 < 0) return;
+  const double r[3] = {inst[6 * (size_t)i], inst[6 * (size_t)i + 1], inst[6 * (size_t)i + 2]};
+  const double t[3] = {inst[6 * (size_t)i + 3], inst[6 * (size_t)i + 4], inst[6 * (size_t)i + 5]};
+  // J_l^-1 = I - K / 2 + g K^2,  K = [r]x,  g = 1 / th^2 - (1 + cos th) / (2 th sin th)
+  const double th2 = r[0] * r[0] + r[1] * r[1] + r[2] * r[2];
+  double g = 1.0 / 12.0;
+  if (th2 > 1e-8) {
+    const double th = sqrt(th2);
+    g = 1.0 / th2 - (1.0 + cos(th)) / (2.0 * th * sin(th));
+  }
+  const double K[9] = {0.0, -r[2], r[1], r[2], 0.0, -r[0], -r[1], r[0], 0.0};
+  double J[9];
+  for (int a = 0; a < 3; ++a)
+    for (int b = 0; b < 3; ++b) {
+      double k2 = 0.0;
+      for (int c = 0; c < 3; ++c) k2 += K[a * 3 + c] * K[c * 3 + b];
+      J[a * 3 + b] = (a == b ? 1.0 : 0.0) - 0.5 * K[a * 3 + b] + g * k2;
+    }
+  double inv_s[6];
+  for (int j = 0; j < 6; ++j) inv_s[j] = 1.0 / scale[c0 + j];
+  for (int a = 0; a < 3; ++a) {
+    W[(size_t)a * nc + c0 + 3 + a] = inv_s[3 + a];                                   // translation
+    for (int b = 0; b < 3; ++b) W[(size_t)(3 + a) * nc + c0 + b] = J[b * 3 + a] * inv_s[b];   // rotation: dr
+    // e_a x t
+    const int a1 = (a + 1) % 3, a2 = (a + 2) % 3;
+    W[(size_t)(3 + a) * nc + c0 + 3 + a1] = -t[a2] * inv_s[3 + a1];
+    W[(size_t)(3 + a) * nc + c0 + 3 + a2] = t[a1] * inv_s[3 + a2];
+    W[(size_t)6 * nc + c0 + 3 + a] = t[a] * inv_s[3 + a];                            // scale
+  }
+}
+
+// The same barrier with PCG_NW doubles per CTA (thread t < PCG_NW publishes value t; thread t < nblocks collects CTA t).
+// Built for latency, the only thing that matters here: the owners of the CTA's rows (threads < nactive) reduce their
+// PCG_NW values with interleaved shuffles; a collector loads the whole slot of its CTA with independent 16-byte loads
+// and drops it into shared memory (gather[t][.]), where warp i < PCG_NW sums column i over the CTAs in a fixed order
+// (bit-identical totals in every CTA).  Not inlined: the kernel calls it from seven places and the loop body has to
+// stay resident in the instruction cache (inlined copies made an iteration 20k clocks slower; loading the slot values
+// one by one in a rolled loop cost 10 L2 round trips).
+__device__ __noinline__ void grid_reduce_wide(PcgState* st, unsigned nblocks, unsigned* gen_io, double* vals /* [PCG_THREADS / 32][PCG_NW] */,
+                                              double* gather /* [nblocks][PCG_NW] */, const double* in, double* out, int nactive) {
+  const unsigned gen = ++(*gen_io);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int wact = (nactive + 31) >> 5;
+  if (warp < wact) {
+    double a[PCG_NW];
+#pragma unroll
+    for (int i = 0; i < PCG_NW; ++i) a[i] = in[i];
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+#pragma unroll
+      for (int i = 0; i < PCG_NW; ++i) a[i] += __shfl_xor_sync(0xffffffffu, a[i], o);
+    }
+    if (lane == 0) {
+#pragma unroll
+      for (int i = 0; i < PCG_NW; ++i) vals[warp * PCG_NW + i] = a[i];
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < PCG_NW) {
+    double sa = 0.0;
+    for (int w = 0; w < wact; ++w) sa += vals[w * PCG_NW + threadIdx.x];
+    __stcg(&st->slotx[gen & 1][blockIdx.x][threadIdx.x], sa);
+  }
+  __syncthreads();  // the slot (and every other global write of this CTA) happens-before thread 0's release
+  // (one thread summing and writing all PCG_NW values, to save this barrier, measured slower: 14.0k vs 12.7k clocks)
+  if (threadIdx.x == 0)
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(&st->flags[blockIdx.x * PCG_FLAG_STRIDE]), "r"(gen) : "memory");
+  if (threadIdx.x < nblocks) {
+    const long long t0 = clock64();
+    unsigned cur;
+    do {
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(cur) : "l"(&st->flags[threadIdx.x * PCG_FLAG_STRIDE]) : "memory");
+      if (clock64() - t0 > 8000000000LL) __trap();
+    } while ((int)(cur - gen) < 0);
+    const double2* sl = reinterpret_cast<const double2*>(st->slotx[gen & 1][threadIdx.x]);
+    double2 v[PCG_NW / 2];
+#pragma unroll
+    for (int i = 0; i < PCG_NW / 2; ++i) v[i] = __ldcg(sl + i);
+    double2* dst = reinterpret_cast<double2*>(gather + threadIdx.x * PCG_NW);
+#pragma unroll
+    for (int i = 0; i < PCG_NW / 2; ++i) dst[i] = v[i];
+  }
+  __syncthreads();
+  if (warp < PCG_NW) {   // warp i sums value i over the CTAs: lane l takes CTAs l, l + 32, ... in order, then a fixed tree
+    double sa = 0.0;
+    for (unsigned c = lane; c < nblocks; c += 32) sa += gather[c * PCG_NW + warp];
+#pragma unroll
+    for (int o = 16; o; o >>= 1) sa += __shfl_xor_sync(0xffffffffu, sa, o);
+    if (lane == 0) vals[warp] = sa;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < PCG_NW; ++i) out[i] = vals[i];
+  __syncthreads();
+}
+static_assert(PCG_THREADS / 32 >= PCG_NW, "a warp per value of the wide barrier");
+
 __global__ void __launch_bounds__(PCG_THREADS, 1)
     pcg_pipelined(const double* __restrict__ Spcg, PcgLayout L, BsrView h, const double* __restrict__ Minv,
                   const double* __restrict__ rhs, double* __restrict__ x_out, double* mbuf0, double* mbuf1, PcgState* st,
@@ -1619,6 +1734,14 @@ __global__ void __launch_bounds__(PCG_THREADS, 1)
   int* unit_nr = unit_lr0 + R.max_rows;
   __shared__ double part_s[PCG_THREADS / 8][3];   // per 8-lane group: partial sums of its unit's rows
   __shared__ int s_nunits;
+  // deflation (R.Wdef != null): own rows of W and A W, (W^T A W)^-1, W^T b projected through it
+  __shared__ double redw[PCG_THREADS / 32][PCG_NW];
+  __shared__ double Einv_s[PCG_ND * PCG_ND], c0_s[PCG_ND];
+  __shared__ int s_defl;
+  double* Wd_s = reinterpret_cast<double*>(pcg_smem + R.off_defl);
+  double* AW_s = Wd_s + PCG_ND * R.max_rows;
+  double* gather_s = AW_s + PCG_ND * R.max_rows;   // [gridDim.x][PCG_NW]: the slots of all CTAs on the wide barrier
+  const int MR = R.max_rows;
   double* mbuf[2] = {mbuf0, mbuf1};
   unsigned bar_gen = 0;
 
@@ -1742,17 +1865,147 @@ __global__ void __launch_bounds__(PCG_THREADS, 1)
     }
   };
 
-  // ---- init: x = 0, r = b, u = M^-1 r, w = S u, m = M^-1 w ----
+  // ---- deflation set-up: A W (PCG_ND mat-vecs, no barrier: W is known everywhere), E = W^T A W, W^T b ----
+  // Deflated CG (Saad, Yeung, Erhel, Guyomarc'h 2000) in its projected form: with Q = W E^-1 W^T and P = I - A Q solve
+  // P A y = P b by (pipelined) PCG, then x = Q b + (I - Q A) y.  P A is symmetric positive semi-definite and the true
+  // residual b - A x equals the residual of the projected system, so the stopping rule is unchanged.  The projection
+  // of a mat-vec, A m -> A m - A W E^-1 (A W)^T m, needs the PCG_ND numbers (A W)^T m of the vector m the barrier
+  // exchanges anyway: they ride on that barrier, an iteration still costs one.
   const bool mine = tid < nrows;
   const int gi = mine ? row_gidx[tid] : 0;
-  double xr = 0.0, rr_ = mine ? rhs[gi] : 0.0, u = 0.0, w = 0.0, z = 0.0, q = 0.0, sv_ = 0.0, p = 0.0;
+  const double bi = mine ? rhs[gi] : 0.0;
+  bool defl = R.Wdef != nullptr;
+  double bb;
+  if (defl) {
+    __syncthreads();   // S_s / cols_s of my rows were loaded by other warps
+#pragma unroll 1
+    for (int j = 0; j < PCG_ND; ++j) {
+      if (mine) Wd_s[j * MR + tid] = R.Wdef[(size_t)j * nc + gi];
+      stage(R.Wdef + (size_t)j * nc);
+      __syncthreads();
+      matvec();
+      __syncthreads();
+      if (mine) AW_s[j * MR + tid] = n_s[tid];
+      __syncthreads();
+    }
+    // 28 entries of the symmetric E, W^T b (7), b^T b: four wide reductions
+    double E[PCG_ND * PCG_ND], wb[PCG_ND];
+    bb = 0.0;
+    int e_idx = 0;
+    double in[PCG_NW], out[PCG_NW];
+    double collected[40];
+    for (int pass = 0; pass < 4; ++pass) {
+#pragma unroll
+      for (int q = 0; q < PCG_NW; ++q) {
+        const int idx = pass * PCG_NW + q;   // 0..27: E(a <= b) row-major upper; 28..34: W^T b; 35: b^T b
+        double val = 0.0;
+        if (mine) {
+          if (idx < 28) {
+            int a = 0, rem = idx;
+            while (rem >= PCG_ND - a) { rem -= PCG_ND - a; ++a; }
+            const int b2 = a + rem;
+            val = Wd_s[a * MR + tid] * AW_s[b2 * MR + tid];
+          } else if (idx < 35) {
+            val = Wd_s[(idx - 28) * MR + tid] * bi;
+          } else if (idx == 35) {
+            val = bi * bi;
+          }
+        }
+        in[q] = val;
+      }
+      grid_reduce_wide(st, gridDim.x, &bar_gen, &redw[0][0], gather_s, in, out, nrows);
+#pragma unroll
+      for (int q = 0; q < PCG_NW; ++q) collected[pass * PCG_NW + q] = out[q];
+    }
+    (void)e_idx;
+    if (tid == 0) {
+      // every CTA factorises the same 7 x 7 matrix: identical decisions everywhere
+      int idx = 0;
+      for (int a = 0; a < PCG_ND; ++a)
+        for (int b2 = a; b2 < PCG_ND; ++b2) { E[a * PCG_ND + b2] = collected[idx]; E[b2 * PCG_ND + a] = collected[idx]; ++idx; }
+      for (int a = 0; a < PCG_ND; ++a) wb[a] = collected[28 + a];
+      double Lc[PCG_ND * PCG_ND];
+      bool ok = true;
+      double dmax = 0.0;
+      for (int a = 0; a < PCG_ND; ++a) dmax = fmax(dmax, E[a * PCG_ND + a]);
+      for (int j = 0; j < PCG_ND && ok; ++j) {
+        double dd = E[j * PCG_ND + j];
+        for (int k2 = 0; k2 < j; ++k2) dd -= Lc[j * PCG_ND + k2] * Lc[j * PCG_ND + k2];
+        if (!(dd > 1e-12 * dmax) || !(dmax > 0.0)) { ok = false; break; }
+        dd = sqrt(dd);
+        Lc[j * PCG_ND + j] = dd;
+        for (int i2 = j + 1; i2 < PCG_ND; ++i2) {
+          double sv2 = E[i2 * PCG_ND + j];
+          for (int k2 = 0; k2 < j; ++k2) sv2 -= Lc[i2 * PCG_ND + k2] * Lc[j * PCG_ND + k2];
+          Lc[i2 * PCG_ND + j] = sv2 / dd;
+        }
+      }
+      if (ok) {
+        for (int cidx = 0; cidx < PCG_ND; ++cidx) {   // E^-1 column by column
+          double y[PCG_ND];
+          for (int i2 = 0; i2 < PCG_ND; ++i2) {
+            double sv2 = (i2 == cidx) ? 1.0 : 0.0;
+            for (int k2 = 0; k2 < i2; ++k2) sv2 -= Lc[i2 * PCG_ND + k2] * y[k2];
+            y[i2] = sv2 / Lc[i2 * PCG_ND + i2];
+          }
+          for (int i2 = PCG_ND - 1; i2 >= 0; --i2) {
+            double sv2 = y[i2];
+            for (int k2 = i2 + 1; k2 < PCG_ND; ++k2) sv2 -= Lc[k2 * PCG_ND + i2] * y[k2];
+            y[i2] = sv2 / Lc[i2 * PCG_ND + i2];
+          }
+          for (int i2 = 0; i2 < PCG_ND; ++i2) Einv_s[i2 * PCG_ND + cidx] = y[i2];
+        }
+        for (int a = 0; a < PCG_ND; ++a) {
+          double sv2 = 0.0;
+          for (int b2 = 0; b2 < PCG_ND; ++b2) sv2 += Einv_s[a * PCG_ND + b2] * wb[b2];
+          c0_s[a] = sv2;
+        }
+      }
+      s_defl = ok ? 1 : 0;
+    }
+    __syncthreads();
+    bb = collected[35];
+    defl = s_defl != 0;   // dependent / vanishing vectors (e.g. every rig instance fixed): plain PCG
+  }
+  // c = E^-1 t for the PCG_ND projections in t
+  auto coarse = [&](const double* t, double* c) {
+#pragma unroll
+    for (int a = 0; a < PCG_ND; ++a) {
+      double sv2 = 0.0;
+#pragma unroll
+      for (int b2 = 0; b2 < PCG_ND; ++b2) sv2 += Einv_s[a * PCG_ND + b2] * t[b2];
+      c[a] = sv2;
+    }
+  };
+  // sum_j (A W)_j[row] c_j for the own row
+  auto aw_dot = [&](const double* c) -> double {
+    double sv2 = 0.0;
+#pragma unroll
+    for (int j = 0; j < PCG_ND; ++j) sv2 += AW_s[j * MR + tid] * c[j];
+    return sv2;
+  };
+
+  // ---- init: y = 0, r = P b, u = M^-1 r, w = P A u, m = M^-1 w ----
+  double xr = 0.0, rr_ = bi, u = 0.0, w = 0.0, z = 0.0, q = 0.0, sv_ = 0.0, p = 0.0;
+  if (defl && mine) rr_ = bi - aw_dot(c0_s);
   if (mine) w_s[tid] = rr_;
   __syncthreads();
   group_solve(mbuf[0]);
-  double d0, d1, d2;
-  if (R.b128) grid_reduce3_b128(st, gridDim.x, bar_gen, 0.0, 0.0, mine ? rr_ * rr_ : 0.0, d0, d1, d2, red);
-  else grid_reduce3(st, gridDim.x, bar_gen, 0.0, 0.0, mine ? rr_ * rr_ : 0.0, d0, d1, d2, red);
-  const double bb = d2;
+  double tc[PCG_ND];   // E^-1 (A W)^T (vector on the barrier)
+  if (defl) {
+    __syncthreads();   // g_s of my row was written by the warp that solved its group
+    double in[PCG_NW], out[PCG_NW];
+    in[0] = 0.0; in[1] = 0.0; in[2] = 0.0;
+#pragma unroll
+    for (int j = 0; j < PCG_ND; ++j) in[3 + j] = mine ? AW_s[j * MR + tid] * g_s[tid] : 0.0;
+    grid_reduce_wide(st, gridDim.x, &bar_gen, &redw[0][0], gather_s, in, out, nrows);
+    coarse(out + 3, tc);
+  } else {
+    double d0, d1, d2;
+    if (R.b128) grid_reduce3_b128(st, gridDim.x, bar_gen, 0.0, 0.0, mine ? rr_ * rr_ : 0.0, d0, d1, d2, red);
+    else grid_reduce3(st, gridDim.x, bar_gen, 0.0, 0.0, mine ? rr_ * rr_ : 0.0, d0, d1, d2, red);
+    bb = d2;
+  }
   const double tol2 = tol2_rel * bb;
   double rr = bb;
   int it = 0, converged = 0;
@@ -1762,7 +2015,7 @@ __global__ void __launch_bounds__(PCG_THREADS, 1)
     __syncthreads();
     matvec();
     __syncthreads();
-    if (mine) { w = n_s[tid]; w_s[tid] = w; }
+    if (mine) { w = n_s[tid] - (defl ? aw_dot(tc) : 0.0); w_s[tid] = w; }
     __syncthreads();
     group_solve(mbuf[1]);
     double gamma_prev = 1.0, alpha_prev = 1.0, best = bb;
@@ -1770,7 +2023,16 @@ __global__ void __launch_bounds__(PCG_THREADS, 1)
     for (;; ++it) {
       const long long tk0 = clock64();
       double gamma, delta;
-      if (R.b128)
+      if (defl) {
+        __syncthreads();   // g_s (m of my row) comes from another warp's group solve
+        double in[PCG_NW], out[PCG_NW];
+        in[0] = mine ? rr_ * u : 0.0; in[1] = mine ? w * u : 0.0; in[2] = mine ? rr_ * rr_ : 0.0;
+#pragma unroll
+        for (int j = 0; j < PCG_ND; ++j) in[3 + j] = mine ? AW_s[j * MR + tid] * g_s[tid] : 0.0;   // (A W)^T m of the m being exchanged
+        grid_reduce_wide(st, gridDim.x, &bar_gen, &redw[0][0], gather_s, in, out, nrows);
+        gamma = out[0]; delta = out[1]; rr = out[2];
+        coarse(out + 3, tc);
+      } else if (R.b128)
         grid_reduce3_b128(st, gridDim.x, bar_gen, mine ? rr_ * u : 0.0, mine ? w * u : 0.0, mine ? rr_ * rr_ : 0.0, gamma, delta, rr,
                    red);
       else
@@ -1791,7 +2053,7 @@ __global__ void __launch_bounds__(PCG_THREADS, 1)
       const double beta = it > 0 ? gamma / gamma_prev : 0.0;
       const double alpha = it > 0 ? gamma / (delta - beta * gamma / alpha_prev) : gamma / delta;
       if (mine) {
-        const double mo = g_s[tid], nn = n_s[tid];
+        const double mo = g_s[tid], nn = n_s[tid] - (defl ? aw_dot(tc) : 0.0);   // P A m
         z = nn + beta * z;
         q = mo + beta * q;
         sv_ = w + beta * sv_;
@@ -1813,6 +2075,21 @@ __global__ void __launch_bounds__(PCG_THREADS, 1)
     }
   } else {
     converged = 1;
+  }
+  if (defl) {
+    // x = Q b + y - Q A y = y + W (c0 - E^-1 (A W)^T y)
+    double in[PCG_NW], out[PCG_NW];
+    in[0] = 0.0; in[1] = 0.0; in[2] = 0.0;
+#pragma unroll
+    for (int j = 0; j < PCG_ND; ++j) in[3 + j] = mine ? AW_s[j * MR + tid] * xr : 0.0;
+    grid_reduce_wide(st, gridDim.x, &bar_gen, &redw[0][0], gather_s, in, out, nrows);
+    coarse(out + 3, tc);
+    if (mine) {
+      double add = 0.0;
+#pragma unroll
+      for (int j = 0; j < PCG_ND; ++j) add += Wd_s[j * MR + tid] * (c0_s[j] - tc[j]);
+      xr += add;
+    }
   }
   if (mine) x_out[gi] = xr;
   if (blockIdx.x == 0 && tid == 0) { st->iterations = it; st->rr_final = rr; st->converged = converged; }
