@@ -551,7 +551,7 @@ def main():
                                          "(full square); peak = DMMA/DFMA rate measured by scripts/bench_dmma.cu")
     dom = max((k for k in kern if "bytes" in kern[k]), key=lambda k: kern[k]["share"])
     ach = kern[dom]["bytes"] / (kern[dom]["ms"] * 1e-3) / 1e9
-    dom_traffic = dram("ba_point_blocks", "ba_schur_pipe<9, 0>", "ba_schur_pipe<0, 0>", "ba_schur_mma<9>", "ba_schur_mma<0>", "ba_schur") if dom == "ba_schur" else dram("ba_linearize<1, 3>") or dram("ba_linearize<1>")
+    dom_traffic = dram("ba_point_blocks", "ba_schur_pipe<9, 0>", "ba_schur_pipe<0, 0>", "ba_schur_mma<9>", "ba_schur_mma<0>", "ba_schur") if dom == "ba_schur" else dram("ba_linearize<1, 5, 0>") or dram("ba_linearize<1, 3>") or dram("ba_linearize<1>")
     roofline = {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": pk["hbm"], "unit": "GB/s",
                 "frac": ach / pk["hbm"], "traffic": dom_traffic, "peak_source": pk["source"], "kernels": kern}
     flops = 2.0 * 128.0 * my_pair_work * K

@@ -281,7 +281,10 @@ class BAProblem:
             kw[k] = v.copy() if isinstance(v, np.ndarray) else (list(v) if isinstance(v, list) else v)
         return BAProblem(**kw)
 
-    def validate(self) -> None:
+    def validate(self, check_indices: bool = True) -> None:
+        """Shape / range checks.  bundle.solve passes check_indices=False: the observation indices are range-checked
+        on the device while the sort keys are built (ba_order.cuh, "observation references a shot / point that does
+        not exist"), and four numpy passes over 2M entries cost more than the whole device-side ordering."""
         K = len(self.cam_type)
         ncp = int(self.cam_off[-1])
         assert self.cam_params.shape == (ncp,)
@@ -291,7 +294,7 @@ class BAProblem:
         NI, NR, S, P, N = len(self.inst), len(self.rigcam), len(self.shot_inst), len(self.points), len(self.obs_shot)
         assert self.inst.shape == (NI, 6) and self.rigcam.shape == (NR, 6) and self.points.shape == (P, 3)
         assert self.obs_xy.shape == (N, 2) and self.obs_sigma.shape == (N,)
-        if N:
+        if N and check_indices:
             assert self.obs_shot.min() >= 0 and self.obs_shot.max() < S
             assert self.obs_point.min() >= 0 and self.obs_point.max() < P
         if S:

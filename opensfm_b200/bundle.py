@@ -70,7 +70,7 @@ def solve(pb: bp.BAProblem, device: int = 0, rank: int = 0, world: int = 1, allr
 
     `out` may hold preallocated C-contiguous float64 arrays "points" (P, 3) and "reprojection_errors"
     (N, 3) to receive the results (page-locked buffers make the device->host copy a plain DMA)."""
-    pb.validate()
+    pb.validate(check_indices=False)
     L = _lib.load()
     h = _handle(int(device)).h
     if True:
