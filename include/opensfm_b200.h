@@ -103,8 +103,10 @@ int osfm_matcher_last_device_ms(osfm_matcher* m, float* ms_total, float* ms_dist
 /* 0 = pick automatically, 1 = force the exact SIMT kernel, 2 = force the tcgen05 kernel
  * (fails at match time if the descriptors are not exactly representable). */
 int osfm_matcher_set_kernel(osfm_matcher* m, int which);
-/* Which distance kernel the last batch used: 1 = SIMT, 2 = tcgen05. */
+/* Which distance kernel the last batch used: 1 = SIMT, 2 = tcgen05 (L2), 3 = tcgen05 fp8 (Hamming). */
 int osfm_matcher_last_kernel(osfm_matcher* m);
+/* Device memory held by the matcher's descriptor slabs (bytes reserved / bytes in use by live sets). */
+int osfm_matcher_device_bytes(osfm_matcher* m, int64_t* reserved, int64_t* in_use);
 
 /* WORDS matcher: features::match_using_words (opensfm/src/features/src/matching.cc:24-88; pyfeatures, called by
  * matching.match_words, matching.py:636-656).  words1: n1 x words_per_feature nearest visual words of every feature

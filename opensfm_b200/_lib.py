@@ -68,6 +68,7 @@ SIGNATURES = {
     "osfm_matcher_last_device_ms": (c_int, [c_void_p, POINTER(c_float), POINTER(c_float)]),
     "osfm_matcher_set_kernel": (c_int, [c_void_p, c_int]),
     "osfm_matcher_last_kernel": (c_int, [c_void_p]),
+    "osfm_matcher_device_bytes": (c_int, [c_void_p, POINTER(c_int64), POINTER(c_int64)]),
     "osfm_match_words": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_float,
                                   c_int, c_void_p]),
     "osfm_vlad_distances": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),

@@ -2092,6 +2092,21 @@ __global__ void __launch_bounds__(PCG_THREADS, 1)
     }
   }
   if (mine) x_out[gi] = xr;
+  // The residual above is the recurred one, which drifts from b - S x in pipelined CG: check the true residual of the
+  // returned x with one more exchange and mat-vec, and hand the solve to the classic kernel if it is not what was claimed.
+  if (converged && bb > 0.0 && !R.b128) {
+    if (mine) mbuf[0][gi] = xr;
+    double d0, d1, d2;
+    grid_reduce3(st, gridDim.x, bar_gen, 0.0, 0.0, 0.0, d0, d1, d2, red);   // x of every CTA is visible
+    stage(mbuf[0]);
+    __syncthreads();
+    matvec();
+    __syncthreads();
+    const double tr = mine ? bi - n_s[tid] : 0.0;
+    grid_reduce3(st, gridDim.x, bar_gen, 0.0, 0.0, tr * tr, d0, d1, d2, red);
+    rr = d2;
+    if (!(rr <= 4.0 * tol2)) converged = 0;
+  }
   if (blockIdx.x == 0 && tid == 0) { st->iterations = it; st->rr_final = rr; st->converged = converged; }
 }
 

@@ -569,6 +569,19 @@ Matcher::~Matcher() {
 
 void* Matcher::slab_alloc(size_t bytes, int* slab_idx) {
   bytes = (bytes + 255) / 256 * 256;
+  // first fit in the released ranges, then the bump pointers, then a new slab
+  for (size_t i = 0; i < slabs.size(); ++i) {
+    Slab& sl = slabs[i];
+    for (size_t r = 0; r < sl.free_ranges.size(); ++r) {
+      if (sl.free_ranges[r].second < bytes) continue;
+      void* p = sl.base + sl.free_ranges[r].first;
+      if (sl.free_ranges[r].second == bytes) sl.free_ranges.erase(sl.free_ranges.begin() + r);
+      else { sl.free_ranges[r].first += bytes; sl.free_ranges[r].second -= bytes; }
+      ++sl.live;
+      *slab_idx = (int)i;
+      return p;
+    }
+  }
   for (size_t i = 0; i < slabs.size(); ++i) {
     Slab& sl = slabs[i];
     if (sl.cap - sl.used >= bytes) {
@@ -593,10 +606,19 @@ void* Matcher::slab_alloc(size_t bytes, int* slab_idx) {
   return sl.base;
 }
 
-void Matcher::slab_release(int idx) {
+void Matcher::slab_release(int idx, void* ptr, size_t bytes) {   // callers synchronise the stream before releasing
   if (idx < 0) return;
   Slab& sl = slabs[idx];
-  if (--sl.live == 0) sl.used = 0;  // callers synchronise the stream before releasing
+  if (--sl.live == 0) { sl.used = 0; sl.free_ranges.clear(); return; }
+  bytes = (bytes + 255) / 256 * 256;
+  if (!ptr || bytes == 0) return;
+  size_t off = (size_t)(static_cast<char*>(ptr) - sl.base);
+  auto& fr = sl.free_ranges;
+  auto it = std::lower_bound(fr.begin(), fr.end(), std::make_pair(off, (size_t)0));
+  it = fr.insert(it, std::make_pair(off, bytes));
+  if (it + 1 != fr.end() && it->first + it->second == (it + 1)->first) { it->second += (it + 1)->second; fr.erase(it + 1); }
+  if (it != fr.begin() && (it - 1)->first + (it - 1)->second == it->first) { (it - 1)->second += it->second; it = fr.erase(it) - 1; }
+  if (it->first + it->second == sl.used) { sl.used = it->first; fr.erase(it); }   // the tail goes back to the bump pointer
 }
 
 // exactness flags / max norms of the sets added since the last call (one D2H copy for all of them)
@@ -617,8 +639,8 @@ void Matcher::refresh_info() {
 }
 
 void Matcher::free_set(DescSet& s) {
-  slab_release(s.slab);
-  if (s.bearings) { slab_release(s.bear_slab); s.bearings = nullptr; s.bear_slab = -1; }
+  slab_release(s.slab, s.data, s.slab_bytes);
+  if (s.bearings) { slab_release(s.bear_slab, s.bearings, s.bear_bytes); s.bearings = nullptr; s.bear_slab = -1; }
   if (s.slot >= 0) {
     cudaMemsetAsync(d_info.p + 2 * s.slot, 0, 2 * sizeof(int), stream);
     free_slots.push_back(s.slot);
@@ -658,7 +680,8 @@ int Matcher::add_async(const void* host, int n, int dim, bool u8, bool u8_as_l2)
   const size_t data_bytes = ((size_t)std::max(n, 1) * row_bytes + 255) / 256 * 256;
   s.rows_padded = (tc || h8) ? tc_rows_padded(n) : 0;
   const size_t tc_bytes = tc ? tc_operand_bytes(s.rows_padded) : h8 ? h8_operand_bytes(s.rows_padded) : 0;
-  char* chunk = static_cast<char*>(slab_alloc(data_bytes + tc_bytes, &s.slab));
+  s.slab_bytes = data_bytes + tc_bytes;
+  char* chunk = static_cast<char*>(slab_alloc(s.slab_bytes, &s.slab));
   s.data = chunk;
   s.tc_data = (tc || h8) ? chunk + data_bytes : nullptr;
   if (tc) {
@@ -668,7 +691,7 @@ int Matcher::add_async(const void* host, int n, int dim, bool u8, bool u8_as_l2)
     }
     if (!free_slots.empty()) { s.slot = free_slots.back(); free_slots.pop_back(); }
     else if (next_slot < MAX_SLOTS) s.slot = next_slot++;
-    else { slab_release(s.slab); throw std::runtime_error("too many resident descriptor sets"); }
+    else { slab_release(s.slab, chunk, s.slab_bytes); throw std::runtime_error("too many resident descriptor sets"); }
   }
   if (n > 0) {
     const bool dense = !u8_as_l2 && (size_t)dim * esz == (size_t)row_bytes;  // the upload already is the padded copy
@@ -711,7 +734,10 @@ void Matcher::set_bearings(int id, const float* host_n_by_3) {
   if (!host_n_by_3) throw ArgError("null bearings");
   OSFM_CUDA(cudaSetDevice(device));
   DescSet& s = it->second;
-  if (!s.bearings) s.bearings = static_cast<float*>(slab_alloc(sizeof(float) * 3 * (size_t)std::max(s.n, 1), &s.bear_slab));
+  if (!s.bearings) {
+    s.bear_bytes = sizeof(float) * 3 * (size_t)std::max(s.n, 1);
+    s.bearings = static_cast<float*>(slab_alloc(s.bear_bytes, &s.bear_slab));
+  }
   if (s.n > 0) {
     OSFM_CUDA(cudaMemcpyAsync(s.bearings, host_n_by_3, sizeof(float) * 3 * (size_t)s.n, cudaMemcpyHostToDevice, stream));
     OSFM_CUDA(cudaStreamSynchronize(stream));
@@ -1222,5 +1248,19 @@ int osfm_matcher_set_kernel(osfm_matcher* m, int which) {
 }
 
 int osfm_matcher_last_kernel(osfm_matcher* m) { return m ? m->impl.last_kernel : 0; }
+int osfm_matcher_device_bytes(osfm_matcher* m, int64_t* reserved, int64_t* in_use) {
+  OSFM_API_BEGIN
+  if (!m || !reserved || !in_use) throw osfm::ArgError("null argument");
+  std::lock_guard<std::mutex> lock(m->mu);
+  int64_t cap = 0, used = 0;
+  for (const auto& sl : m->impl.slabs) {
+    cap += (int64_t)sl.cap;
+    used += (int64_t)sl.used;
+    for (const auto& fr : sl.free_ranges) used -= (int64_t)fr.second;
+  }
+  *reserved = cap;
+  *in_use = used;
+  OSFM_API_END
+}
 
 }  // extern "C"

@@ -85,6 +85,7 @@ struct DescSet {
   // device memory comes from the matcher's slabs; the exactness flag / max norm of a freshly added set
   // live in d_info[slot] until refresh_info() reads them back (no host sync per add)
   int slab = -1, slot = -1;
+  size_t slab_bytes = 0, bear_bytes = 0;   // sizes of the two slab allocations (data + operands; bearings)
   bool info_pending = false;
   // unit bearing vectors of the features (n x 3 float32), for guided matching; null until set
   float* bearings = nullptr;
@@ -93,8 +94,11 @@ struct DescSet {
 
 struct Slab {
   char* base = nullptr;
-  size_t cap = 0, used = 0;
+  size_t cap = 0, used = 0;   // bump pointer
   int live = 0;
+  // ranges below `used` that were released while neighbours stayed live: (offset, bytes), sorted, coalesced.
+  // A long-lived matcher that replaces descriptor sets key by key reuses them instead of growing.
+  std::vector<std::pair<size_t, size_t>> free_ranges;
 };
 
 struct Matcher {
@@ -142,7 +146,7 @@ struct Matcher {
   int next_slot = 0;
   static constexpr int MAX_SLOTS = 1 << 16;
   void* slab_alloc(size_t bytes, int* slab_idx);
-  void slab_release(int idx);
+  void slab_release(int idx, void* ptr, size_t bytes);
   void refresh_info();
   // u8: Hamming descriptors.  u8_as_l2: uint8 storage of an L2 descriptor (widened to float32 on the device).
   int add_async(const void* host, int n, int dim, bool u8, bool u8_as_l2 = false);  // no host sync; the host buffer must stay valid

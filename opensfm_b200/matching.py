@@ -264,6 +264,12 @@ class PairMatcher:
     def last_kernel(self) -> int:
         return self._m.L.osfm_matcher_last_kernel(self._m.h)
 
+    def device_bytes(self) -> Tuple[int, int]:
+        """(bytes reserved by the descriptor slabs, bytes in use by live descriptor sets)."""
+        a, b = ctypes.c_int64(), ctypes.c_int64()
+        _lib.check(self._m.L.osfm_matcher_device_bytes(self._m.h, ctypes.byref(a), ctypes.byref(b)))
+        return a.value, b.value
+
     def match_pairs(self, pairs: Sequence[Tuple[Any, Any]], config: Dict[str, Any],
                     symmetric: Optional[bool] = None) -> Dict[Tuple[Any, Any], np.ndarray]:
         if symmetric is None:

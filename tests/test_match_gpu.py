@@ -136,6 +136,24 @@ def test_hamming_tensor_core_kernel(nbytes, n1, n2):
     assert np.array_equal(np.asarray(got[1], dtype=np.int64).reshape(-1, 2), want)
 
 
+def test_replacing_descriptor_sets_key_by_key_reuses_device_memory():
+    """A long-lived matcher that replaces the descriptors of its keys one at a time (add allocates the new set before
+    the old one is removed) must not grow: the slab allocator reuses released ranges."""
+    pm = matching.PairMatcher()
+    descs = [syn.hahog_like_descriptors(3000, 100 + i) for i in range(6)]
+    for i, d in enumerate(descs):
+        pm.add(i, d)
+    reserved0, used0 = pm.device_bytes()
+    for rnd in range(40):
+        k = rnd % 6
+        pm.add(k, syn.hahog_like_descriptors(3000, 1000 + rnd))
+    reserved1, used1 = pm.device_bytes()
+    assert reserved1 == reserved0, (reserved0, reserved1)
+    assert used1 <= used0 + used0 // 4
+    a, b = syn.hahog_like_descriptors(3000, 1000 + 36), syn.hahog_like_descriptors(3000, 1000 + 37)
+    assert _pairset(pm.match_pairs([(0, 1)], CFG)[(0, 1)]) == _pairset(mo.match_brute_force_symmetric(a, b, CFG))
+
+
 def test_empty_inputs():
     a = np.zeros((0, 128), np.float32)
     b = syn.hahog_like_descriptors(10, 1)
