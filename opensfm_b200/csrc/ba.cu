@@ -1756,7 +1756,7 @@ void BA::run() {
       const long long off_rows = off_cols + up16(2 * col_max);
       const long long off_defl = up16(off_rows + 36LL * rows_max + 4LL * (grp_max + 1));
       // own rows of the deflation vectors W and of S W, then the gather buffer of the wide barrier
-      const long long total = off_defl + 2LL * PCG_ND * 8 * rows_max + 8LL * PCG_NW * G;
+      const long long total = off_defl + 2LL * PCG_ND * 8 * rows_max + 8LL * PCG_NW * G + 8LL * PCG_NW * rows_max;
       cudaFuncAttributes pipe_attr{};
       OSFM_CUDA(cudaFuncGetAttributes(&pipe_attr, pcg_pipelined));
       static const bool allow_pipe = []() { const char* e = getenv("OSFM_BA_PCG_PIPELINED"); return !(e && e[0] == '0'); }();
@@ -2045,10 +2045,13 @@ void BA::run() {
         solved = h_pcg.p->converged != 0;
         pcg_pipe_its = h_pcg.p->iterations;
         if (trace_on)
-          fprintf(stderr, "[osfm_ba] pipelined pcg %d its converged %d, CTA0 clocks/it: stage %lld matvec %lld reduce %lld update %lld\n",
+          fprintf(stderr, "[osfm_ba] pipelined pcg %d its converged %d, CTA0 clocks/it: stage %lld matvec %lld reduce %lld update %lld"
+                  " | wide barrier (all calls / its): own sums %lld release %lld collect %lld column sums %lld\n",
                   h_pcg.p->iterations, h_pcg.p->converged, h_pcg.p->prof[0] / std::max(pcg_pipe_its, 1),
                   h_pcg.p->prof[1] / std::max(pcg_pipe_its, 1), h_pcg.p->prof[2] / std::max(pcg_pipe_its, 1),
-                  h_pcg.p->prof[3] / std::max(pcg_pipe_its, 1));
+                  h_pcg.p->prof[3] / std::max(pcg_pipe_its, 1), h_pcg.p->prof[4] / std::max(pcg_pipe_its, 1),
+                  h_pcg.p->prof[5] / std::max(pcg_pipe_its, 1), h_pcg.p->prof[6] / std::max(pcg_pipe_its, 1),
+                  h_pcg.p->prof[7] / std::max(pcg_pipe_its, 1));
         if (!solved) {  // stagnation / breakdown of the pipelined recurrences: classic PCG from scratch
           pcg_total += pcg_pipe_its;
           ++pcg_fallbacks;

@@ -1640,42 +1640,35 @@ __global__ void pcg_gauge_vectors(int NI, const int* __restrict__ inst_poff, con
   }
 }
 
-// The same barrier with PCG_NW doubles per CTA (thread t < PCG_NW publishes value t; thread t < nblocks collects CTA t).
-// Built for latency, the only thing that matters here: the owners of the CTA's rows (threads < nactive) reduce their
-// PCG_NW values with interleaved shuffles; a collector loads the whole slot of its CTA with independent 16-byte loads
-// and drops it into shared memory (gather[t][.]), where warp i < PCG_NW sums column i over the CTAs in a fixed order
-// (bit-identical totals in every CTA).  Not inlined: the kernel calls it from seven places and the loop body has to
-// stay resident in the instruction cache (inlined copies made an iteration 20k clocks slower; loading the slot values
-// one by one in a rolled loop cost 10 L2 round trips).
-__device__ __noinline__ void grid_reduce_wide(PcgState* st, unsigned nblocks, unsigned* gen_io, double* vals /* [PCG_THREADS / 32][PCG_NW] */,
-                                              double* gather /* [nblocks][PCG_NW] */, const double* in, double* out, int nactive) {
+// The same barrier with PCG_NW doubles per CTA.  Built for latency, the only thing that matters here, and around one
+// measurement: arguments and results must not live in local memory -- every poll of the barrier invalidates L1
+// (ld.acquire -> CCTL.IVALL), so a stack array written before the call and read inside it is an L2 round trip (the
+// version with in[] / out[] arrays spent 2.9k + 2.5k clocks per call on that).  Protocol: the owners of the CTA's rows
+// (threads < nactive) have written their PCG_NW contributions to inrow[thread][.] in shared memory; warp i sums
+// column i and publishes it in the CTA's slot; thread 0 releases the flag; thread t < nblocks acquires CTA t's flag,
+// loads its slot with independent 16-byte loads and drops it into gather[t][.]; warp i sums column i over the CTAs
+// in a fixed order (bit-identical totals in every CTA) into vals[i], which the caller reads.  Not inlined: the kernel
+// calls it from seven places and the loop body has to stay resident in the instruction cache.
+__device__ __noinline__ void grid_reduce_wide(PcgState* st, unsigned nblocks, unsigned* gen_io, double* vals /* [PCG_NW] */,
+                                              double* gather /* [nblocks][PCG_NW] */, const double* inrow /* [nactive][PCG_NW] */,
+                                              int nactive) {
   const unsigned gen = ++(*gen_io);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int wact = (nactive + 31) >> 5;
-  if (warp < wact) {
-    double a[PCG_NW];
-#pragma unroll
-    for (int i = 0; i < PCG_NW; ++i) a[i] = in[i];
-#pragma unroll
-    for (int o = 16; o; o >>= 1) {
-#pragma unroll
-      for (int i = 0; i < PCG_NW; ++i) a[i] += __shfl_xor_sync(0xffffffffu, a[i], o);
-    }
-    if (lane == 0) {
-#pragma unroll
-      for (int i = 0; i < PCG_NW; ++i) vals[warp * PCG_NW + i] = a[i];
-    }
-  }
-  __syncthreads();
-  if (threadIdx.x < PCG_NW) {
+  const bool probe = blockIdx.x == 0 && threadIdx.x == 0;   // st->prof[4..7]: own sums, release, collection, column sums
+  long long tq = probe ? clock64() : 0;
+  __syncthreads();   // inrow is complete
+  if (warp < PCG_NW) {
     double sa = 0.0;
-    for (int w = 0; w < wact; ++w) sa += vals[w * PCG_NW + threadIdx.x];
-    __stcg(&st->slotx[gen & 1][blockIdx.x][threadIdx.x], sa);
+    for (int r = lane; r < nactive; r += 32) sa += inrow[r * PCG_NW + warp];
+#pragma unroll
+    for (int o = 16; o; o >>= 1) sa += __shfl_xor_sync(0xffffffffu, sa, o);
+    if (lane == 0) __stcg(&st->slotx[gen & 1][blockIdx.x][warp], sa);
   }
   __syncthreads();  // the slot (and every other global write of this CTA) happens-before thread 0's release
-  // (one thread summing and writing all PCG_NW values, to save this barrier, measured slower: 14.0k vs 12.7k clocks)
+  if (probe) { const long long now = clock64(); st->prof[4] += now - tq; tq = now; }
   if (threadIdx.x == 0)
     asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(&st->flags[blockIdx.x * PCG_FLAG_STRIDE]), "r"(gen) : "memory");
+  if (probe) { const long long now = clock64(); st->prof[5] += now - tq; tq = now; }
   if (threadIdx.x < nblocks) {
     const long long t0 = clock64();
     unsigned cur;
@@ -1692,6 +1685,7 @@ __device__ __noinline__ void grid_reduce_wide(PcgState* st, unsigned nblocks, un
     for (int i = 0; i < PCG_NW / 2; ++i) dst[i] = v[i];
   }
   __syncthreads();
+  if (probe) { const long long now = clock64(); st->prof[6] += now - tq; tq = now; }
   if (warp < PCG_NW) {   // warp i sums value i over the CTAs: lane l takes CTAs l, l + 32, ... in order, then a fixed tree
     double sa = 0.0;
     for (unsigned c = lane; c < nblocks; c += 32) sa += gather[c * PCG_NW + warp];
@@ -1700,9 +1694,7 @@ __device__ __noinline__ void grid_reduce_wide(PcgState* st, unsigned nblocks, un
     if (lane == 0) vals[warp] = sa;
   }
   __syncthreads();
-#pragma unroll
-  for (int i = 0; i < PCG_NW; ++i) out[i] = vals[i];
-  __syncthreads();
+  if (probe) st->prof[7] += clock64() - tq;
 }
 static_assert(PCG_THREADS / 32 >= PCG_NW, "a warp per value of the wide barrier");
 
@@ -1736,11 +1728,13 @@ __global__ void __launch_bounds__(PCG_THREADS, 1)
   __shared__ int s_nunits;
   // deflation (R.Wdef != null): own rows of W and A W, (W^T A W)^-1, W^T b projected through it
   __shared__ double redw[PCG_THREADS / 32][PCG_NW];
-  __shared__ double Einv_s[PCG_ND * PCG_ND], c0_s[PCG_ND];
+  __shared__ double Einv_s[PCG_ND * PCG_ND], c0_s[PCG_ND], tc_s[PCG_ND];
   __shared__ int s_defl;
   double* Wd_s = reinterpret_cast<double*>(pcg_smem + R.off_defl);
   double* AW_s = Wd_s + PCG_ND * R.max_rows;
   double* gather_s = AW_s + PCG_ND * R.max_rows;   // [gridDim.x][PCG_NW]: the slots of all CTAs on the wide barrier
+  double* inrow_s = gather_s + PCG_NW * gridDim.x; // [max_rows][PCG_NW]: what the owners of the rows put on it
+  double* wide_s = &redw[0][0];                    // [PCG_NW]: its totals
   const int MR = R.max_rows;
   double* mbuf[2] = {mbuf0, mbuf1};
   unsigned bar_gen = 0;
@@ -1892,7 +1886,6 @@ __global__ void __launch_bounds__(PCG_THREADS, 1)
     double E[PCG_ND * PCG_ND], wb[PCG_ND];
     bb = 0.0;
     int e_idx = 0;
-    double in[PCG_NW], out[PCG_NW];
     double collected[40];
     for (int pass = 0; pass < 4; ++pass) {
 #pragma unroll
@@ -1911,11 +1904,12 @@ __global__ void __launch_bounds__(PCG_THREADS, 1)
             val = bi * bi;
           }
         }
-        in[q] = val;
+        if (mine) inrow_s[tid * PCG_NW + q] = val;
       }
-      grid_reduce_wide(st, gridDim.x, &bar_gen, &redw[0][0], gather_s, in, out, nrows);
+      grid_reduce_wide(st, gridDim.x, &bar_gen, wide_s, gather_s, inrow_s, nrows);
 #pragma unroll
-      for (int q = 0; q < PCG_NW; ++q) collected[pass * PCG_NW + q] = out[q];
+      for (int q = 0; q < PCG_NW; ++q) collected[pass * PCG_NW + q] = wide_s[q];
+      __syncthreads();   // wide_s / inrow_s are rewritten by the next pass
     }
     (void)e_idx;
     if (tid == 0) {
@@ -1967,15 +1961,16 @@ __global__ void __launch_bounds__(PCG_THREADS, 1)
     bb = collected[35];
     defl = s_defl != 0;   // dependent / vanishing vectors (e.g. every rig instance fixed): plain PCG
   }
-  // c = E^-1 t for the PCG_ND projections in t
-  auto coarse = [&](const double* t, double* c) {
-#pragma unroll
-    for (int a = 0; a < PCG_ND; ++a) {
+  // tc_s = E^-1 t for the PCG_ND projections the wide barrier left in wide_s[3..]: seven threads, not all 512 (49 DFMA
+  // each) -- and no per-thread copy of the result in registers (the kernel sits at its 128-register limit)
+  auto coarse = [&]() {
+    if (tid < PCG_ND) {
       double sv2 = 0.0;
 #pragma unroll
-      for (int b2 = 0; b2 < PCG_ND; ++b2) sv2 += Einv_s[a * PCG_ND + b2] * t[b2];
-      c[a] = sv2;
+      for (int b2 = 0; b2 < PCG_ND; ++b2) sv2 += Einv_s[tid * PCG_ND + b2] * wide_s[3 + b2];
+      tc_s[tid] = sv2;
     }
+    __syncthreads();
   };
   // sum_j (A W)_j[row] c_j for the own row
   auto aw_dot = [&](const double* c) -> double {
@@ -1991,15 +1986,16 @@ __global__ void __launch_bounds__(PCG_THREADS, 1)
   if (mine) w_s[tid] = rr_;
   __syncthreads();
   group_solve(mbuf[0]);
-  double tc[PCG_ND];   // E^-1 (A W)^T (vector on the barrier)
   if (defl) {
     __syncthreads();   // g_s of my row was written by the warp that solved its group
-    double in[PCG_NW], out[PCG_NW];
-    in[0] = 0.0; in[1] = 0.0; in[2] = 0.0;
+    if (mine) {
+      double* ir = inrow_s + tid * PCG_NW;
+      ir[0] = 0.0; ir[1] = 0.0; ir[2] = 0.0;
 #pragma unroll
-    for (int j = 0; j < PCG_ND; ++j) in[3 + j] = mine ? AW_s[j * MR + tid] * g_s[tid] : 0.0;
-    grid_reduce_wide(st, gridDim.x, &bar_gen, &redw[0][0], gather_s, in, out, nrows);
-    coarse(out + 3, tc);
+      for (int j = 0; j < PCG_ND; ++j) ir[3 + j] = AW_s[j * MR + tid] * g_s[tid];
+    }
+    grid_reduce_wide(st, gridDim.x, &bar_gen, wide_s, gather_s, inrow_s, nrows);
+    coarse();
   } else {
     double d0, d1, d2;
     if (R.b128) grid_reduce3_b128(st, gridDim.x, bar_gen, 0.0, 0.0, mine ? rr_ * rr_ : 0.0, d0, d1, d2, red);
@@ -2015,7 +2011,7 @@ __global__ void __launch_bounds__(PCG_THREADS, 1)
     __syncthreads();
     matvec();
     __syncthreads();
-    if (mine) { w = n_s[tid] - (defl ? aw_dot(tc) : 0.0); w_s[tid] = w; }
+    if (mine) { w = n_s[tid] - (defl ? aw_dot(tc_s) : 0.0); w_s[tid] = w; }
     __syncthreads();
     group_solve(mbuf[1]);
     double gamma_prev = 1.0, alpha_prev = 1.0, best = bb;
@@ -2025,13 +2021,15 @@ __global__ void __launch_bounds__(PCG_THREADS, 1)
       double gamma, delta;
       if (defl) {
         __syncthreads();   // g_s (m of my row) comes from another warp's group solve
-        double in[PCG_NW], out[PCG_NW];
-        in[0] = mine ? rr_ * u : 0.0; in[1] = mine ? w * u : 0.0; in[2] = mine ? rr_ * rr_ : 0.0;
+        if (mine) {
+          double* ir = inrow_s + tid * PCG_NW;
+          ir[0] = rr_ * u; ir[1] = w * u; ir[2] = rr_ * rr_;
 #pragma unroll
-        for (int j = 0; j < PCG_ND; ++j) in[3 + j] = mine ? AW_s[j * MR + tid] * g_s[tid] : 0.0;   // (A W)^T m of the m being exchanged
-        grid_reduce_wide(st, gridDim.x, &bar_gen, &redw[0][0], gather_s, in, out, nrows);
-        gamma = out[0]; delta = out[1]; rr = out[2];
-        coarse(out + 3, tc);
+          for (int j = 0; j < PCG_ND; ++j) ir[3 + j] = AW_s[j * MR + tid] * g_s[tid];   // (A W)^T m of the m being exchanged
+        }
+        grid_reduce_wide(st, gridDim.x, &bar_gen, wide_s, gather_s, inrow_s, nrows);
+        gamma = wide_s[0]; delta = wide_s[1]; rr = wide_s[2];
+        coarse();
       } else if (R.b128)
         grid_reduce3_b128(st, gridDim.x, bar_gen, mine ? rr_ * u : 0.0, mine ? w * u : 0.0, mine ? rr_ * rr_ : 0.0, gamma, delta, rr,
                    red);
@@ -2053,7 +2051,7 @@ __global__ void __launch_bounds__(PCG_THREADS, 1)
       const double beta = it > 0 ? gamma / gamma_prev : 0.0;
       const double alpha = it > 0 ? gamma / (delta - beta * gamma / alpha_prev) : gamma / delta;
       if (mine) {
-        const double mo = g_s[tid], nn = n_s[tid] - (defl ? aw_dot(tc) : 0.0);   // P A m
+        const double mo = g_s[tid], nn = n_s[tid] - (defl ? aw_dot(tc_s) : 0.0);   // P A m
         z = nn + beta * z;
         q = mo + beta * q;
         sv_ = w + beta * sv_;
@@ -2078,16 +2076,18 @@ __global__ void __launch_bounds__(PCG_THREADS, 1)
   }
   if (defl) {
     // x = Q b + y - Q A y = y + W (c0 - E^-1 (A W)^T y)
-    double in[PCG_NW], out[PCG_NW];
-    in[0] = 0.0; in[1] = 0.0; in[2] = 0.0;
+    if (mine) {
+      double* ir = inrow_s + tid * PCG_NW;
+      ir[0] = 0.0; ir[1] = 0.0; ir[2] = 0.0;
 #pragma unroll
-    for (int j = 0; j < PCG_ND; ++j) in[3 + j] = mine ? AW_s[j * MR + tid] * xr : 0.0;
-    grid_reduce_wide(st, gridDim.x, &bar_gen, &redw[0][0], gather_s, in, out, nrows);
-    coarse(out + 3, tc);
+      for (int j = 0; j < PCG_ND; ++j) ir[3 + j] = AW_s[j * MR + tid] * xr;
+    }
+    grid_reduce_wide(st, gridDim.x, &bar_gen, wide_s, gather_s, inrow_s, nrows);
+    coarse();
     if (mine) {
       double add = 0.0;
 #pragma unroll
-      for (int j = 0; j < PCG_ND; ++j) add += Wd_s[j * MR + tid] * (c0_s[j] - tc[j]);
+      for (int j = 0; j < PCG_ND; ++j) add += Wd_s[j * MR + tid] * (c0_s[j] - tc_s[j]);
       xr += add;
     }
   }
