@@ -814,6 +814,22 @@ __global__ void ba_grad_dot(int n, int nc, int cam_side, const double* __restric
   if (threadIdx.x == 0 && t != 0.0) atomicAdd(&sc->gdot, t);
 }
 
+// Model cost change of the step without another pass over the Jacobian.  Ceres evaluates
+//   model_cost_change = -step^T (g + H step / 2),   H = J^T J, g = J^T r   (trust_region_minimizer.cc)
+// from J step; the step solves (H + D) step = -g (D = LM diagonal / radius), so H step = -g - D step and
+//   model_cost_change = (y^T g_s + y^T D y) / 2,   step = -y, g_s = scale * grad   (scaled variables)
+// exactly when the linear system is solved exactly, and to the solver's 1e-8 relative residual here (every term of H
+// and g -- observations, priors, side terms -- is in the system that was solved).  Replaces ba_model_change +
+// ba_prior_model_change + side_model_change + ba_point_prior<2>: 447 MB of plane reads per LM iteration.
+__global__ void ba_model_change_alg(int n, int nc, int cam_side, const double* __restrict__ grad, const double* __restrict__ scale,
+                                    const double* __restrict__ diag, double inv_radius, const double* __restrict__ y, Scalars* sc) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  double v = 0.0;
+  if (i < n && (i >= nc || cam_side)) v = 0.5 * y[i] * (grad[i] * scale[i] + diag[i] * inv_radius * y[i]);
+  const double t = block_reduce_sum(v);
+  if (threadIdx.x == 0 && t != 0.0) atomicAdd(&sc->model_change, t);
+}
+
 // single-observation device evaluation (test hook)
 __global__ void ba_eval_one(int type, const double* in, int use_rc, double* out, int* nres_out) {
   // in: cam[16] ri[6] rc[6] X[3] obs[2] isig[1]
@@ -2090,6 +2106,13 @@ void BA::run() {
       tm_back.stop(stream);
     }
     OSFM_CUDA(cudaMemsetAsync(&d_sc.p->model_change, 0, sizeof(double) * 3, stream));  // model_change, step_norm2, x_norm2
+    static const bool mc_explicit = []() { const char* e = getenv("OSFM_BA_MODEL_CHANGE_EXPLICIT"); return e && e[0] == '1'; }();
+    if (!mc_explicit) {
+      if (n > 0) {
+        ba_model_change_alg<<<grid_for(n, 256), 256, 0, stream>>>(n, nc, rank == 0, d_grad.p, d_scale.p, d_diag.p, inv_radius, d_y.p, d_sc.p);
+        OSFM_LAUNCH_CHECK();
+      }
+    } else {
     if (N > 0) {
       ba_model_change<<<grid_for(N, 256), 256, 0, stream>>>(v, d_scale.p, d_y.p, d_sc.p);
       OSFM_LAUNCH_CHECK();
@@ -2105,6 +2128,7 @@ void BA::run() {
     if (have_pp && P > 0) {
       ba_point_prior<2><<<grid_for(P, 128), 128, 0, stream>>>(ppv, v, params_of(cur), d_scale.p, d_y.p, nullptr, nullptr, nullptr, d_sc.p);
       OSFM_LAUNCH_CHECK();
+    }
     }
     // --- candidate point ---
     const int cand = cur ^ 1;

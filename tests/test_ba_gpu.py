@@ -262,14 +262,14 @@ def test_kernel_variants_agree():
         "np.save(sys.argv[1], np.concatenate([[r['summary']['final_cost'], r['summary']['iterations']], r['points'].ravel()]))\n"
     ) % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     out = {}
-    variants = {"default": {}, "generic_schur": {"OSFM_BA_SEGMENT_SCHUR": "0"}, "simt_seg_schur": {"OSFM_BA_SCHUR_MMA": "0"}, "cta_per_segment_schur": {"OSFM_BA_SCHUR_PIPE": "0"}, "generic_linearize": {"OSFM_BA_LIN_SPECIAL": "0"}, "undeflated_pcg": {"OSFM_BA_PCG_DEFLATE": "0"}, "classic_pcg": {"OSFM_BA_PCG_PIPELINED": "0"}, "b128_barrier": {"OSFM_BA_PCG_B128": "1"},
+    variants = {"default": {}, "generic_schur": {"OSFM_BA_SEGMENT_SCHUR": "0"}, "simt_seg_schur": {"OSFM_BA_SCHUR_MMA": "0"}, "cta_per_segment_schur": {"OSFM_BA_SCHUR_PIPE": "0"}, "generic_linearize": {"OSFM_BA_LIN_SPECIAL": "0"}, "undeflated_pcg": {"OSFM_BA_PCG_DEFLATE": "0"}, "explicit_model_change": {"OSFM_BA_MODEL_CHANGE_EXPLICIT": "1"}, "classic_pcg": {"OSFM_BA_PCG_PIPELINED": "0"}, "b128_barrier": {"OSFM_BA_PCG_B128": "1"},
                 "streamed_pcg": {"OSFM_BA_PCG_PIPELINED": "0", "OSFM_BA_PCG_RESIDENT": "0"}}
     for name, extra in variants.items():
         path = "/tmp/osfm_variant_%s.npy" % name
         env = dict(os.environ, **extra)
         subprocess.run([sys.executable, "-c", code, path], check=True, env=env, timeout=600)
         out[name] = np.load(path)
-    for name in ("generic_schur", "simt_seg_schur", "cta_per_segment_schur", "generic_linearize", "undeflated_pcg", "classic_pcg", "b128_barrier", "streamed_pcg"):
+    for name in ("generic_schur", "simt_seg_schur", "cta_per_segment_schur", "generic_linearize", "undeflated_pcg", "explicit_model_change", "classic_pcg", "b128_barrier", "streamed_pcg"):
         assert out["default"][1] == out[name][1]
         assert abs(out["default"][0] - out[name][0]) <= 1e-9 * out["default"][0]
         # the solvers that do not deflate the gauge directions stop with a different (larger) error along those
