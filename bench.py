@@ -437,7 +437,7 @@ def main():
 
     def ba_step():
         t0 = time.perf_counter()
-        res = bundle.solve(pb, device=local, rank=rank, world=world, allreduce=allreduce, out=ba_out)
+        res = bundle.solve(pb, device=local, rank=rank, world=world, allreduce=allreduce, out=ba_out, pinned_inputs=True)
         return res, time.perf_counter() - t0
 
     def match_resident():

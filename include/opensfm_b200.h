@@ -152,6 +152,12 @@ int osfm_ba_set_shots(osfm_ba* ba, int n, const int32_t* rig_instance, const int
 int osfm_ba_set_points(osfm_ba* ba, int n, const double* xyz, const int32_t* constant);
 int osfm_ba_set_observations(osfm_ba* ba, int64_t n, const int32_t* shot, const int32_t* point,
                              const double* xy, const double* std_deviation);
+/* The same for PAGE-LOCKED arrays: the indices are on the device when the call returns, xy and std_deviation may
+ * still be in flight on a copy stream (osfm_ba_run waits for them right before the kernel that needs them, i.e. the
+ * upload overlaps the device-side ordering): both arrays must stay valid and unchanged until osfm_ba_run returns.
+ * With pageable memory the copies are staged by the driver and the call behaves like osfm_ba_set_observations. */
+int osfm_ba_set_observations_async(osfm_ba* ba, int64_t n, const int32_t* shot, const int32_t* point,
+                                   const double* xy, const double* std_deviation);
 
 /* Rig-camera pose priors: DataPriorError<Pose> with sigma GetDefaultRigPoseSigma, one per rig camera
  * (bundle_adjuster.cc:779-790; residual dropped when the rig camera is constant).  prior6 / sigma6: n x 6

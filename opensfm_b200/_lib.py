@@ -81,6 +81,7 @@ SIGNATURES = {
     "osfm_ba_set_shots": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "osfm_ba_set_points": (c_int, [c_void_p, c_int, c_void_p, c_void_p]),
     "osfm_ba_set_observations": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "osfm_ba_set_observations_async": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]),
     "osfm_ba_set_rig_camera_priors": (c_int, [c_void_p, c_void_p, c_void_p]),
     "osfm_ba_set_point_priors": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "osfm_ba_set_ext_blocks": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),

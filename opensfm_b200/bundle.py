@@ -59,7 +59,7 @@ def _p(a: np.ndarray):
 
 def solve(pb: bp.BAProblem, device: int = 0, rank: int = 0, world: int = 1, allreduce=None,
           stream: Optional[int] = None, compute_reprojection_errors: bool = True,
-          out: Optional[Dict[str, np.ndarray]] = None) -> Dict[str, Any]:
+          out: Optional[Dict[str, np.ndarray]] = None, pinned_inputs: bool = False) -> Dict[str, Any]:
     """Run the GPU bundle adjustment on a BAProblem.  Returns updated parameter arrays,
     unscaled reprojection errors (bundle_adjuster.cc:1196-1208) and the run summary.
 
@@ -69,7 +69,9 @@ def solve(pb: bp.BAProblem, device: int = 0, rank: int = 0, world: int = 1, allr
     pointer `ptr` across ranks (see opensfm_b200.dist; used with gloo in the CPU tests).
 
     `out` may hold preallocated C-contiguous float64 arrays "points" (P, 3) and "reprojection_errors"
-    (N, 3) to receive the results (page-locked buffers make the device->host copy a plain DMA)."""
+    (N, 3) to receive the results (page-locked buffers make the device->host copy a plain DMA).
+    `pinned_inputs`: the observation arrays of `pb` are page-locked; their upload then overlaps the device-side
+    ordering (osfm_ba_set_observations_async; the arrays are kept alive here until the solve returns)."""
     pb.validate(check_indices=False)
     L = _lib.load()
     h = _handle(int(device)).h
@@ -90,7 +92,8 @@ def solve(pb: bp.BAProblem, device: int = 0, rank: int = 0, world: int = 1, allr
         k5 = [f64(pb.points), i32(pb.point_const)]
         _lib.check(L.osfm_ba_set_points(h, P, *[_p(a) for a in k5]))
         k6 = [i32(pb.obs_shot), i32(pb.obs_point), f64(pb.obs_xy), f64(pb.obs_sigma)]
-        _lib.check(L.osfm_ba_set_observations(h, N, *[_p(a) for a in k6]))
+        set_obs = L.osfm_ba_set_observations_async if pinned_inputs else L.osfm_ba_set_observations
+        _lib.check(set_obs(h, N, *[_p(a) for a in k6]))
         # secondary residuals: always (re)set, the handle is reused between solves
         if pb.rigcam_prior is not None:
             k7 = [f64(pb.rigcam_prior), f64(pb.rigcam_prior_sigma)]

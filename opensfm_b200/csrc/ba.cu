@@ -915,6 +915,10 @@ static void nccl_check(int rc, const char* what) {
 struct BA {
   int device = 0;
   cudaStream_t own_stream = nullptr, stream = nullptr;
+  // osfm_ba_set_observations_async: the measurement arrays travel on their own stream while run() already sorts the indices
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t ev_obs = nullptr;
+  bool obs_pending = false;
   // host copies of the problem
   std::vector<int> cam_type, cam_const, cam_prior_log;
   std::vector<double> cam_params, cam_prior, cam_prior_sigma;
@@ -1016,6 +1020,8 @@ struct BA {
     OSFM_CUDA(cudaSetDevice(device));
     OSFM_CUDA(cudaStreamCreateWithFlags(&own_stream, cudaStreamNonBlocking));
     stream = own_stream;
+    OSFM_CUDA(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
+    OSFM_CUDA(cudaEventCreateWithFlags(&ev_obs, cudaEventDisableTiming));
     h_sc.reserve(1);
     h_pcg.reserve(1);
     OSFM_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, device));
@@ -1023,6 +1029,8 @@ struct BA {
   ~BA() {
     cudaSetDevice(device);
     if (nccl_comm) { try { nccl_api().CommDestroy(nccl_comm); } catch (...) {} }
+    if (copy_stream) { cudaStreamSynchronize(copy_stream); cudaStreamDestroy(copy_stream); }
+    if (ev_obs) cudaEventDestroy(ev_obs);
     if (own_stream) cudaStreamDestroy(own_stream);
   }
 
@@ -1287,6 +1295,10 @@ void BA::run() {
     const size_t Nz0 = (size_t)std::max<long long>(N, 1);
     d_obs_orig.reserve(Nz0); d_obs_shot.reserve(Nz0); d_obs_point.reserve(Nz0);
     d_obs_x.reserve(Nz0); d_obs_y.reserve(Nz0); d_obs_isig.reserve(Nz0);
+  }
+  if (obs_pending) {   // image coordinates / standard deviations uploaded by osfm_ba_set_observations_async
+    OSFM_CUDA(cudaStreamWaitEvent(stream, ev_obs, 0));
+    obs_pending = false;
   }
   ord_gather_obs<<<grid_for(Nfull, 256), 256, 0, stream>>>(okeys, ovals, Nfull, d_g_pt_start.p, d_inv_order.p, d_pt_start.p, world,
                                                            rank, d_raw_xy.p, d_raw_sigma.p, d_obs_orig.p, d_obs_shot.p,
@@ -2448,6 +2460,7 @@ int osfm_ba_set_observations(osfm_ba* ba, int64_t n, const int32_t* shot, const 
   // straight to the device: the ordering, the index checks and the 1/sigma happen there (ba_order.cuh)
   auto& b = ba->impl;
   OSFM_CUDA(cudaSetDevice(b.device));
+  if (b.obs_pending) { OSFM_CUDA(cudaStreamSynchronize(b.copy_stream)); b.obs_pending = false; }
   const size_t nz = (size_t)std::max<int64_t>(n, 1);
   b.d_raw_shot.reserve(nz); b.d_raw_point.reserve(nz); b.d_raw_xy.reserve(2 * nz); b.d_raw_sigma.reserve(nz);
   if (n > 0) {
@@ -2455,6 +2468,31 @@ int osfm_ba_set_observations(osfm_ba* ba, int64_t n, const int32_t* shot, const 
     OSFM_CUDA(cudaMemcpyAsync(b.d_raw_point.p, point, sizeof(int32_t) * n, cudaMemcpyHostToDevice, b.own_stream));
     OSFM_CUDA(cudaMemcpyAsync(b.d_raw_xy.p, xy, sizeof(double) * 2 * n, cudaMemcpyHostToDevice, b.own_stream));
     OSFM_CUDA(cudaMemcpyAsync(b.d_raw_sigma.p, std_deviation, sizeof(double) * n, cudaMemcpyHostToDevice, b.own_stream));
+    OSFM_CUDA(cudaStreamSynchronize(b.own_stream));
+  }
+  b.n_obs_full = n;
+  b.has_run = false;
+  OSFM_API_END
+}
+int osfm_ba_set_observations_async(osfm_ba* ba, int64_t n, const int32_t* shot, const int32_t* point, const double* xy,
+                                   const double* std_deviation) {
+  OSFM_API_BEGIN
+  OSFM_BA_CHECK
+  if (n < 0 || (n > 0 && (!shot || !point || !xy || !std_deviation))) throw ArgError("bad observation arrays");
+  auto& b = ba->impl;
+  OSFM_CUDA(cudaSetDevice(b.device));
+  if (b.obs_pending) { OSFM_CUDA(cudaStreamSynchronize(b.copy_stream)); b.obs_pending = false; }
+  const size_t nz = (size_t)std::max<int64_t>(n, 1);
+  b.d_raw_shot.reserve(nz); b.d_raw_point.reserve(nz); b.d_raw_xy.reserve(2 * nz); b.d_raw_sigma.reserve(nz);
+  if (n > 0) {
+    // the indices are what the ordering needs first: they are on the device when the call returns; the measurements
+    // follow on the copy stream and run() waits for them (an event) right before the kernel that gathers them
+    OSFM_CUDA(cudaMemcpyAsync(b.d_raw_shot.p, shot, sizeof(int32_t) * n, cudaMemcpyHostToDevice, b.own_stream));
+    OSFM_CUDA(cudaMemcpyAsync(b.d_raw_point.p, point, sizeof(int32_t) * n, cudaMemcpyHostToDevice, b.own_stream));
+    OSFM_CUDA(cudaMemcpyAsync(b.d_raw_xy.p, xy, sizeof(double) * 2 * n, cudaMemcpyHostToDevice, b.copy_stream));
+    OSFM_CUDA(cudaMemcpyAsync(b.d_raw_sigma.p, std_deviation, sizeof(double) * n, cudaMemcpyHostToDevice, b.copy_stream));
+    OSFM_CUDA(cudaEventRecord(b.ev_obs, b.copy_stream));
+    b.obs_pending = true;
     OSFM_CUDA(cudaStreamSynchronize(b.own_stream));
   }
   b.n_obs_full = n;
@@ -2520,7 +2558,13 @@ int osfm_ba_set_stream(osfm_ba* ba, void* cuda_stream) {
 int osfm_ba_run(osfm_ba* ba) {
   OSFM_API_BEGIN
   OSFM_BA_CHECK
-  ba->impl.run();
+  try {
+    ba->impl.run();
+  } catch (...) {
+    // an asynchronous observation upload must not outlive the call: the caller may free its arrays now
+    if (ba->impl.obs_pending) { cudaStreamSynchronize(ba->impl.copy_stream); ba->impl.obs_pending = false; }
+    throw;
+  }
   OSFM_API_END
 }
 int osfm_ba_get_summary(osfm_ba* ba, osfm_ba_summary* out) {

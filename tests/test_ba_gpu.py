@@ -85,6 +85,24 @@ def test_losses(loss):
              tol_cost=5e-6 if loss == "ArctanLoss" else 1e-6)
 
 
+def test_async_observation_upload_gives_the_same_solve():
+    """pinned_inputs=True: image coordinates / standard deviations travel on a copy stream while run() sorts the indices
+    (osfm_ba_set_observations_async); with page-locked and with pageable arrays the solve is the one of the default path."""
+    import torch
+
+    sc = syn.cube_scene(10, 1000, 1.0, with_descriptors=False)
+    pb = syn.scene_to_problem(sc)
+    ref = bundle.solve(pb)
+    got = bundle.solve(pb, pinned_inputs=True)   # pageable: the driver stages the copies
+    assert got["summary"]["final_cost"] == ref["summary"]["final_cost"]
+    for name in ("obs_shot", "obs_point", "obs_xy", "obs_sigma"):
+        setattr(pb, name, torch.from_numpy(np.ascontiguousarray(getattr(pb, name))).pin_memory().numpy())
+    for _ in range(3):
+        got = bundle.solve(pb, pinned_inputs=True)
+        assert abs(got["summary"]["final_cost"] - ref["summary"]["final_cost"]) <= 1e-12 * ref["summary"]["final_cost"]
+        assert np.abs(got["points"] - ref["points"]).max() < 1e-9
+
+
 def test_pose_only_and_point_only():
     sc = syn.cube_scene(6, 400, 1.0, with_descriptors=False)
     pb = syn.scene_to_problem(sc, optimize_cameras=False)
