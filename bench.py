@@ -224,6 +224,98 @@ def run_reference(args, rank, world):
 # --------------------------------------------------------------------------------------
 # extras (N = 1): the other BASELINE configs and the non-tensor-core matcher paths
 # --------------------------------------------------------------------------------------
+def run_c5():
+    """BASELINE configs[4] stand-in ("opensfm/large" submodel split): the C4 scene's 500 cameras in 4 overlapping
+    submodels, one bundle adjustment per submodel, each result moved into a gauge of its own (what independent
+    reconstructions come back in), then opensfm.large.tools.align_reconstructions' problem (soft camera constraints:
+    one relative-motion term per (submodel, shot) + one absolute GPS position per shot, opensfm/large/tools.py:120-159)
+    through opensfm_b200.alignment.ReconstructionAlignment.  Pair-list matching of the submodels is the sharded matching
+    of the headline line.  Reports times; the alignment is checked against the similarities that were applied."""
+    from scipy.spatial.transform import Rotation
+
+    from opensfm_b200 import alignment, ba_problem as bp, bundle
+
+    pb, _, _, _ = build_workload("c4")
+    S = len(pb.inst)
+    ranges = [(0, 140), (120, 265), (245, 390), (370, S)]
+    off = np.asarray(pb.cam_off)
+    out = {"workload": "BASELINE configs[4] stand-in: the C4 scene in 4 overlapping submodels (%s cameras), BA per submodel, "
+                       "then ReconstructionAlignment with soft camera constraints + GPS" % "/".join(str(b - a) for a, b in ranges),
+           "submodels": []}
+    rng = np.random.RandomState(5)
+    results = []
+    t_ba = 0.0
+    for m, (a, b) in enumerate(ranges):
+        sel = (pb.obs_shot >= a) & (pb.obs_shot < b)
+        o_shot, o_pt = pb.obs_shot[sel] - a, pb.obs_point[sel]
+        cnt = np.bincount(o_pt, minlength=len(pb.points))
+        keep_pt = cnt >= 2
+        ok = keep_pt[o_pt]
+        remap = np.cumsum(keep_pt) - 1
+        sub = bp.make_problem(
+            [bp.PERSPECTIVE] * (b - a), [pb.cam_params[off[k]:off[k + 1]] for k in range(a, b)], pb.inst[a:b], pb.points[keep_pt],
+            o_shot[ok].astype(np.int32), remap[o_pt[ok]].astype(np.int32), pb.obs_xy[sel][ok], pb.obs_sigma[sel][ok],
+            prior_sd=dict(focal_sd=0.01, aspect_ratio_sd=0.01, c_sd=0.01, k1_sd=0.01, k2_sd=0.01, p1_sd=0.01, p2_sd=0.01,
+                          k3_sd=0.01, k4_sd=0.01),
+            loss_name=pb.loss_name, loss_threshold=pb.loss_threshold, max_iterations=pb.max_iterations)
+        bundle.solve(sub)   # warm-up (allocations)
+        t0 = time.perf_counter()
+        r = bundle.solve(sub)
+        dt = time.perf_counter() - t0
+        t_ba += dt
+        s = r["summary"]
+        out["submodels"].append({"cameras": b - a, "points": int(keep_pt.sum()), "observations": int(ok.sum()),
+                                 "lm_iterations": s["iterations"], "device_ms": s["time_device_ms"], "wall_ms": 1e3 * dt,
+                                 "obs_per_s": ok.sum() * s["iterations"] / (s["time_device_ms"] * 1e-3)})
+        results.append((a, b, r["inst"]))
+    # every submodel comes back in its own gauge: X' = s Q X + T
+    gauges = [(float(rng.uniform(0.8, 1.25)), Rotation.from_rotvec(rng.normal(0, 0.2, 3)).as_matrix(), rng.normal(0, 2.0, 3))
+              for _ in results]
+    gps_noise = rng.normal(0, 0.05, (S, 3))
+    cov = np.diag([1e-5, 1e-5, 1e-5, 1e-2, 1e-2, 1e-2])
+    sm = np.linalg.inv(np.linalg.cholesky(cov)).T   # scale_matrix of opensfm/large/tools.py
+
+    def make_alignment():
+        ra = alignment.ReconstructionAlignment()
+        added = set()
+        for m, (a, b, inst) in enumerate(results):
+            sc, Q, T = gauges[m]
+            ra.add_reconstruction("rec%d" % m, 0, 0, 0, 0, 0, 0, 1, False)
+            for k in range(a, b):
+                R_cw = Rotation.from_rotvec(inst[k - a, :3]).as_matrix()
+                origin = inst[k - a, 3:]
+                R_cw2, origin2 = Q @ R_cw, sc * Q @ origin + T          # pose of the shot in the submodel's own gauge
+                R_wc2 = R_cw2.T
+                rv, tv = Rotation.from_matrix(R_wc2).as_rotvec(), -R_wc2 @ origin2   # OpenSfM pose: x_cam = R x_world + t
+                name = "shot%d" % k
+                if name not in added:
+                    ra.add_shot(name, rv[0], rv[1], rv[2], tv[0], tv[1], tv[2], False)
+                    gps = origin + gps_noise[k]   # positions in the common (GPS) frame
+                    ra.add_absolute_position_constraint(name, gps[0], gps[1], gps[2], 1.0)
+                    added.add(name)
+                rmc = alignment.RARelativeMotionConstraint("rec%d" % m, name, rv[0], rv[1], rv[2], tv[0], tv[1], tv[2])
+                for i in range(6):
+                    for j in range(6):
+                        rmc.set_scale_matrix(i, j, sm[i, j])
+                ra.add_relative_motion_constraint(rmc)
+        return ra, len(added)
+
+    make_alignment()[0].run()   # warm-up
+    ra, n_shots = make_alignment()
+    t0 = time.perf_counter()
+    ra.run()
+    t_ra = time.perf_counter() - t0
+    # the reconstruction similarity must undo the gauge: compare the recovered scale with 1 / s
+    err = 0.0
+    for m, (sc, Q, T) in enumerate(gauges):
+        rec = ra.get_reconstruction("rec%d" % m)
+        err = max(err, min(abs(rec.scale * sc - 1.0), abs(rec.scale / sc - 1.0)))   # either direction convention
+    out.update({"ba_wall_ms": 1e3 * t_ba, "alignment_wall_ms": 1e3 * t_ra, "alignment_terms": n_shots + sum(b - a for a, b in ranges),
+                "alignment_report": ra.brief_report().strip().splitlines()[-1] if ra.brief_report() else "",
+                "alignment_scale_error": float(err), "total_wall_ms": 1e3 * (t_ba + t_ra)})
+    return out
+
+
 def run_extras(pk, clocks_mhz, with_cpu):
     import torch
 
@@ -593,6 +685,10 @@ def main():
                 line["extras"] = run_extras(pk, clk.get("sm_mhz"), not args.no_cpu_baseline)
             except Exception as e:  # the extras never take the headline line down
                 line["extras"] = {"error": repr(e)}
+            try:
+                line["extras"]["c5"] = run_c5()
+            except Exception as e:
+                line["extras"]["c5"] = {"error": repr(e)}
         if not args.no_cpu_baseline and world == 1:
             its = CPU_BA_ITERATIONS.get(args.workload, 5)
             v, it, dt = cpu_ba_sample(pb, its)
