@@ -94,7 +94,8 @@ def test_async_observation_upload_gives_the_same_solve():
     pb = syn.scene_to_problem(sc)
     ref = bundle.solve(pb)
     got = bundle.solve(pb, pinned_inputs=True)   # pageable: the driver stages the copies
-    assert got["summary"]["final_cost"] == ref["summary"]["final_cost"]
+    # (not bit-equal: the fp64 atomics of the Schur flush land in a different order from run to run)
+    assert abs(got["summary"]["final_cost"] - ref["summary"]["final_cost"]) <= 1e-12 * ref["summary"]["final_cost"]
     for name in ("obs_shot", "obs_point", "obs_xy", "obs_sigma"):
         setattr(pb, name, torch.from_numpy(np.ascontiguousarray(getattr(pb, name))).pin_memory().numpy())
     for _ in range(3):
