@@ -335,6 +335,17 @@ def test_words_matcher_matches_the_restated_reference(integer):
     assert set(sym) == (r12 & r21) and len(sym) > 20
 
 
+def test_words_matcher_reproduces_the_reference_known_answer():
+    """opensfm/test/test_matching.py:50-70 on the CUDA kernel: every feature matches its noisy copy."""
+    from test_match_oracle import words_known_answer_case
+
+    f1, w1, f2, w2 = words_known_answer_case()
+    matches = matching.match_words(f1, w1, f2, w2, {"lowes_ratio": 0.8, "bow_num_checks": 20})
+    assert len(matches) == len(f1)
+    assert all(i == j for i, j in matches)
+    assert np.array_equal(matches, mo.match_using_words(f1, w1, f2, w2[:, 0], 0.8, 20))
+
+
 def test_vlad_distances():
     rng = np.random.RandomState(1)
     hist = {"im%d" % i: rng.normal(0, 1, 64 * 128).astype(np.float32) for i in range(9)}

@@ -99,3 +99,29 @@ def test_general_float_matches_cv2_exactly_with_near_ties():
     for ratio in (0.8, 1.0):
         cfg = {"lowes_ratio": ratio}
         assert mo.match_brute_force_numpy(a, b, cfg) == mo.match_brute_force(a, b, cfg)
+
+
+def words_known_answer_case():
+    """The inputs of the reference's own known-answer test for the WORDS matcher (opensfm/test/test_matching.py:23-70):
+    f1 random normal rows of the unit-norm matrix, f2 = f1 + noise / 500, the `bow_words_to_match` = 50 closest visual
+    words of every feature in the reference's 10000-word vocabulary (tests/golden/words_golden.npz, made from that file
+    by tests/golden/make_words_golden.py).  Expected answer there: every feature matches its own copy,
+    `len(matches) == nfeatures` and `i == j` for all of them."""
+    import importlib.util
+    import os
+
+    here = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    spec = importlib.util.spec_from_file_location("make_words_golden", os.path.join(here, "make_words_golden.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    g = np.load(os.path.join(here, "words_golden.npz"))
+    f1, f2 = mod.example_features(int(g["seed"]), int(g["nfeatures"]))
+    return f1, g["w1"].astype(np.int32), f2, g["w2"].astype(np.int32)
+
+
+def test_words_matcher_reproduces_the_reference_known_answer():
+    """opensfm/test/test_matching.py:50-70 with its own assertions (lowes_ratio 0.8, bow_num_checks 20)."""
+    f1, w1, f2, w2 = words_known_answer_case()
+    matches = mo.match_using_words(f1, w1, f2, w2[:, 0], 0.8, 20)
+    assert len(matches) == len(f1)
+    assert all(i == j for i, j in matches)
