@@ -224,7 +224,7 @@ def run_reference(args, rank, world):
 # --------------------------------------------------------------------------------------
 # extras (N = 1): the other BASELINE configs and the non-tensor-core matcher paths
 # --------------------------------------------------------------------------------------
-def run_c5():
+def run_c5(workload="c4"):
     """BASELINE configs[4] stand-in ("opensfm/large" submodel split): the C4 scene's 500 cameras in 4 overlapping
     submodels, one bundle adjustment per submodel, each result moved into a gauge of its own (what independent
     reconstructions come back in), then opensfm.large.tools.align_reconstructions' problem (soft camera constraints:
@@ -235,9 +235,10 @@ def run_c5():
 
     from opensfm_b200 import alignment, ba_problem as bp, bundle
 
-    pb, _, _, _ = build_workload("c4")
+    pb, _, _, _ = build_workload(workload)
     S = len(pb.inst)
-    ranges = [(0, 140), (120, 265), (245, 390), (370, S)]
+    # four overlapping index ranges: (0, 140), (120, 265), (245, 390), (370, 500) for the 500 cameras of C4
+    ranges = [(0, int(0.28 * S)), (int(0.24 * S), int(0.53 * S)), (int(0.49 * S), int(0.78 * S)), (int(0.74 * S), S)]
     off = np.asarray(pb.cam_off)
     out = {"workload": "BASELINE configs[4] stand-in: the C4 scene in 4 overlapping submodels (%s cameras), BA per submodel, "
                        "then ReconstructionAlignment with soft camera constraints + GPS" % "/".join(str(b - a) for a, b in ranges),

@@ -194,3 +194,36 @@ def test_unfilter_matches_follows_the_reference():
     want = np.array([(i1[a], i2[b]) for a, b in matches])
     assert np.array_equal(matching.unfilter_matches(matches, m1, m2), want)
     assert matching.unfilter_matches(np.zeros((0, 2)), m1, m2).shape == (0, 2)
+
+
+def test_bench_submodel_workload_host_logic(monkeypatch):
+    """bench.py run_c5 (BASELINE configs[4] stand-in) with the GPU calls stubbed out: the four sub-problems and the
+    alignment problem it builds are valid, every shot is added once and constrained once per submodel it belongs to."""
+    import importlib
+    import os
+    import sys
+
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    bench = importlib.import_module("bench")
+    from opensfm_b200 import alignment, bundle
+
+    seen = {"solve": 0, "problems": []}
+
+    def fake_solve(pb, **kw):
+        pb.validate()
+        seen["solve"] += 1
+        return {"inst": pb.inst.copy(), "summary": {"iterations": 5, "time_device_ms": 1.0}}
+
+    def fake_run(self):
+        pb = self.to_problem()
+        pb.validate()
+        seen["problems"].append((len(pb.inst), len(pb.ext_size), len(pb.side_terms)))
+
+    monkeypatch.setattr(bundle, "solve", fake_solve)
+    monkeypatch.setattr(alignment.ReconstructionAlignment, "run", fake_run)
+    monkeypatch.setattr(alignment.ReconstructionAlignment, "brief_report", lambda self: "stub")
+    out = bench.run_c5("c2")
+    cams = [m["cameras"] for m in out["submodels"]]
+    assert cams == [14, 14, 15, 13] and seen["solve"] == 8            # warm-up + timed solve per submodel
+    assert seen["problems"] == [(50, 4, 50 + sum(cams))] * 2          # 50 GPS terms + one relative motion per (submodel, shot)
+    assert out["alignment_terms"] == 50 + sum(cams)
