@@ -26,7 +26,10 @@ iteration), MATCH shards the pair list (pairs sharing images on the same GPU); t
 
 Sub-records measured once per run at N = 1 (`extras`, outside the K timed steps): guided matching on the
 BASELINE configs[2] stand-in (29 images x 8000 HAHOG-like descriptors, epipolar mask built on the device),
-AKAZE-size Hamming, general float32 (cv2-order exact kernel), and the configs[1] scene (50 cameras / 5k points).
+AKAZE- / ORB-size Hamming (fp8 tensor-core kernel), general float32 (cv2-order exact kernel), the configs[1] scene
+(50 cameras / 5k points) and a configs[4] stand-in (`c5`: four overlapping submodels of the scene, a bundle adjustment
+each, then the ReconstructionAlignment problem of opensfm/large/tools.py).  The e2e BA leg uploads its page-locked
+observation arrays with osfm_ba_set_observations_async (`pinned_inputs=True`).
 """
 from __future__ import annotations
 
