@@ -292,6 +292,6 @@ def test_kernel_variants_agree():
         assert out["default"][1] == out[name][1]
         assert abs(out["default"][0] - out[name][0]) <= 1e-9 * out["default"][0]
         # the solvers that do not deflate the gauge directions stop with a different (larger) error along those
-        # weakly determined directions: same cost to 1e-9, points to 1e-6; everything else is the same solve
+        # weakly determined directions: same cost to 1e-9, points to 2e-6; everything else is the same solve
         plain = name in ("undeflated_pcg", "classic_pcg", "b128_barrier", "streamed_pcg")
-        assert np.abs(out["default"][2:] - out[name][2:]).max() < (1e-6 if plain else 1e-8)
+        assert np.abs(out["default"][2:] - out[name][2:]).max() < (2e-6 if plain else 1e-8)   # measured 3e-7 / 1e-9
